@@ -1,0 +1,217 @@
+/*
+ * qgt_b200.h — thin C-ABI of the sm_100a statevector + quantum-geometric-tensor library.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, `extern "C"`, no C++ or
+ * torch types.  Every reference entry point on the hot path is a short
+ * C wrapper over these calls (see include/quantum_geometric/ and
+ * quantum_geometric_tensor_b200/csrc/compat/).  All paths are relative to the reference
+ * tree tsotchke/quantum_geometric_tensor.
+ *
+ * What each group replaces
+ *   qgt_b200_state_*  / qgt_b200_apply_circuit
+ *       -> sim_init / sim_execute_circuit / sim_get_statevector
+ *          (src/quantum_geometric/hardware/quantum_simulator.c:57,499,677) and
+ *          init_simulator_state / simulate_circuit_cpu
+ *          (src/quantum_geometric/hardware/quantum_simulator_cpu.c:98,761)
+ *   qgt_b200_qgt
+ *       -> geometric_compute_full_qgt (src/quantum_geometric/core/quantum_geometric_curvature.c:289),
+ *          geometric_compute_fubini_study_metric (core/quantum_geometric_metric.c:353),
+ *          compute_quantum_geometric_tensor (core/quantum_geometric_tensor_network.c:1058),
+ *          diffgeo_compute_fubini_study / diffgeo_compute_berry_curvature
+ *          (src/quantum_geometric/distributed/differential_geometry.c:2819,2864)
+ *   qgt_b200_gram
+ *       -> the three 2^n-long dot loops of compute_quantum_geometric_tensor
+ *          (core/quantum_geometric_tensor_network.c:1127-1175) for caller-supplied columns
+ *   qgt_b200_natural_gradient
+ *       -> compute_regularized_natural_gradient (core/quantum_geometric_gradient.c:2887)
+ *   qgt_b200_dist_*
+ *       -> init_distributed_state / sync_quantum_states
+ *          (src/quantum_geometric/distributed/quantum_distributed_operations.c:260,289) and the
+ *          NCCL calls of core/multi_gpu_operations.c:46-264
+ *
+ * Conventions
+ *   - amplitudes are complex double, interleaved (re, im), index bit q = qubit q (qubit 0 = LSB),
+ *     exactly the layout of `double complex[2^n]` in the reference simulator;
+ *   - status codes are the reference's qgt_error_t values (core/error_codes.h:17-110);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     QGT_B200_ERR_NO_DEVICE and writes nothing.
+ */
+#ifndef QGT_B200_H
+#define QGT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QGT_B200_ABI_VERSION 1
+
+/* ---- status (numerically equal to the reference's qgt_error_t) ------------------------- */
+enum {
+    QGT_B200_OK               = 0,
+    QGT_B200_ERR_INVALID_ARG  = -1,   /* QGT_ERROR_INVALID_PARAMETER   */
+    QGT_B200_ERR_NO_MEMORY    = -2,   /* QGT_ERROR_MEMORY_ALLOCATION   */
+    QGT_B200_ERR_DIMENSION    = -3,   /* QGT_ERROR_DIMENSION_MISMATCH  */
+    QGT_B200_ERR_INVALID_STATE= -4,   /* QGT_ERROR_INVALID_STATE       */
+    QGT_B200_ERR_HARDWARE     = -6,   /* QGT_ERROR_HARDWARE_FAILURE    */
+    QGT_B200_ERR_UNSUPPORTED  = -7,   /* QGT_ERROR_NOT_IMPLEMENTED     */
+    QGT_B200_ERR_INTERNAL     = -15,  /* QGT_ERROR_INTERNAL            */
+    QGT_B200_ERR_NOT_INIT     = -18,  /* QGT_ERROR_NOT_INITIALIZED     */
+    QGT_B200_ERR_CIRCUIT      = -36,  /* QGT_ERROR_INVALID_CIRCUIT     */
+    QGT_B200_ERR_NO_DEVICE    = -31   /* QGT_ERROR_INVALID_HARDWARE    */
+};
+
+/* ---- gate kinds: numeric values follow gate_type_t (core/quantum_base_types.h:32-72) ---- */
+enum {
+    QGT_B200_GATE_I = 0, QGT_B200_GATE_X = 1, QGT_B200_GATE_Y = 2, QGT_B200_GATE_Z = 3,
+    QGT_B200_GATE_H = 4, QGT_B200_GATE_S = 5, QGT_B200_GATE_T = 6,
+    QGT_B200_GATE_RX = 7, QGT_B200_GATE_RY = 8, QGT_B200_GATE_RZ = 9,
+    QGT_B200_GATE_CNOT = 10, QGT_B200_GATE_CY = 11, QGT_B200_GATE_CZ = 12, QGT_B200_GATE_SWAP = 13,
+    QGT_B200_GATE_U1 = 15, QGT_B200_GATE_PHASE = 19,
+    QGT_B200_GATE_CRX = 22, QGT_B200_GATE_CRY = 23, QGT_B200_GATE_CRZ = 24, QGT_B200_GATE_CH = 25,
+    QGT_B200_GATE_SDG = 26, QGT_B200_GATE_TDG = 27, QGT_B200_GATE_SX = 29,
+    QGT_B200_GATE_ZZ = 35,
+    /* not in gate_type_t: the QAOA cost layer exp(-i*angle*E_z) of algorithms/qaoa.c:344-372,
+       E_z from the circuit's edge list / vertex weights (qaoa.c:236-294) */
+    QGT_B200_GATE_COST = 100
+};
+
+/* One gate.  angle_effective = scale * theta[param] + angle   (param >= 0)
+ *                            = angle                           (param <  0)
+ * For two-qubit kinds `control` is the control qubit (CNOT/CY/CZ/CH/CR*) or the second qubit
+ * (SWAP/ZZ); it is ignored (set -1) otherwise. */
+typedef struct qgt_b200_gate {
+    int32_t kind;
+    int32_t target;
+    int32_t control;
+    int32_t param;
+    double  angle;
+    double  scale;
+} qgt_b200_gate;
+
+typedef struct qgt_b200_edge { int32_t i, j; double weight; } qgt_b200_edge;
+
+enum { QGT_B200_INIT_ZERO = 0, QGT_B200_INIT_PLUS = 1 };
+
+/* A parameterised circuit.  All pointers are HOST pointers, read during the call only. */
+typedef struct qgt_b200_circuit {
+    int32_t              num_qubits;
+    int32_t              num_params;      /* length of theta[] */
+    const qgt_b200_gate* gates;
+    size_t               num_gates;
+    const qgt_b200_edge* edges;           /* for QGT_B200_GATE_COST, may be NULL */
+    size_t               num_edges;
+    const double*        vertex_weights;  /* num_qubits doubles or NULL */
+    int32_t              initial_state;   /* QGT_B200_INIT_* */
+} qgt_b200_circuit;
+
+typedef struct qgt_b200_ctx qgt_b200_ctx;      /* one per process and GPU */
+typedef struct qgt_b200_state qgt_b200_state;  /* a device-resident statevector (or shard) */
+
+/* ---- library / device -------------------------------------------------------------------- */
+int         qgt_b200_abi_version(void);
+int         qgt_b200_device_count(void);                 /* 0 when no usable sm_100 device */
+const char* qgt_b200_last_error(void);                   /* thread-local message */
+const char* qgt_b200_error_string(int status);
+
+int  qgt_b200_create(qgt_b200_ctx** out, int device);    /* device = CUDA ordinal */
+void qgt_b200_destroy(qgt_b200_ctx* ctx);
+/* workspace cap in bytes for derivative columns (0 = 85 % of free HBM at first use) */
+int  qgt_b200_set_workspace_limit(qgt_b200_ctx* ctx, size_t bytes);
+/* tuning knob: tile qubits per sweep (10..12), 0 = default */
+int  qgt_b200_set_option(qgt_b200_ctx* ctx, const char* key, double value);
+
+/* ---- statevector ------------------------------------------------------------------------- */
+int  qgt_b200_state_create(qgt_b200_ctx* ctx, int num_qubits, qgt_b200_state** out);
+void qgt_b200_state_destroy(qgt_b200_state* st);
+int  qgt_b200_state_init(qgt_b200_state* st, int initial_state);                 /* |0..0> or |+>^n */
+int  qgt_b200_state_upload(qgt_b200_state* st, const double* host_amps);          /* 2^n (re,im) */
+int  qgt_b200_state_download(const qgt_b200_state* st, double* host_amps);
+int  qgt_b200_state_norm2(const qgt_b200_state* st, double* out);
+void* qgt_b200_state_device_ptr(qgt_b200_state* st);                             /* raw device pointer */
+
+/* Apply `circuit` (its gates only; circuit->initial_state is ignored) to the state in place. */
+int  qgt_b200_apply_circuit(qgt_b200_state* st, const qgt_b200_circuit* circuit, const double* theta);
+
+/* Host-buffer convenience used by simulate_circuit_cpu: H2D, sweeps, D2H in one call. */
+int  qgt_b200_simulate_host(qgt_b200_ctx* ctx, double* host_amps, int num_qubits,
+                            const qgt_b200_circuit* circuit, const double* theta);
+
+/* ---- quantum geometric tensor ------------------------------------------------------------- */
+/* Full QGT of |psi(theta)> = U(theta)|init>:  Q = <d_mu psi|d_nu psi> - <d_mu psi|psi><psi|d_nu psi>.
+ * Outputs are HOST buffers, row-major P x P, any of them may be NULL:
+ *   metric  = Re Q            (Fubini-Study, core/quantum_geometric_metric.c:353)
+ *   berry   = Im Q            (core/quantum_geometric_curvature.c:201; diffgeo's F = -2*berry)
+ *   q_full  = Q interleaved (re,im)
+ * If `psi_out` (a state with the same qubit count) is given it receives psi(theta). */
+int  qgt_b200_qgt(qgt_b200_ctx* ctx, const qgt_b200_circuit* circuit, const double* theta,
+                  double* metric, double* berry, double* q_full, qgt_b200_state* psi_out);
+
+/* Same formula for caller-supplied derivative columns (device or host pointers are detected):
+ * psi[dim], dpsi[P*dim] row-major as in diffgeo_compute_fubini_study. */
+int  qgt_b200_gram(qgt_b200_ctx* ctx, const double* psi, const double* dpsi, size_t dim, size_t num_params,
+                   double* metric, double* berry, double* q_full);
+
+/* Derivative column d_mu psi written to `out` (device state) — for tests and callers that want J. */
+int  qgt_b200_derivative(qgt_b200_ctx* ctx, const qgt_b200_circuit* circuit, const double* theta,
+                         int mu, qgt_b200_state* out);
+
+/* Regularised natural-gradient step on the real metric: out = (G + lambda I)^-1 grad with the
+ * adaptive-lambda / pseudo-inverse semantics of core/quantum_geometric_gradient.c:2721-2964. */
+typedef struct qgt_b200_natgrad_config {
+    double regularization;        /* lambda, default 1e-4 */
+    double condition_threshold;   /* 1e8 */
+    int    adaptive;              /* 1 */
+    int    pseudoinverse_fallback;/* 1 */
+    double singular_cutoff;       /* 1e-10 */
+} qgt_b200_natgrad_config;
+int  qgt_b200_natural_gradient(qgt_b200_ctx* ctx, const double* metric, const double* grad, size_t num_params,
+                               const qgt_b200_natgrad_config* cfg, double* out, double* lambda_used);
+
+/* Energy gradient d<E>/d theta for the diagonal cost observable of a COST circuit or a sum of Z_i Z_j /
+ * Z_i terms, by the adjoint method on device (feeds the natural-gradient step of config 2). */
+int  qgt_b200_expectation_gradient(qgt_b200_ctx* ctx, const qgt_b200_circuit* circuit, const double* theta,
+                                   double* energy, double* grad);
+
+/* ---- statistics of the last qgt/apply call (for bench.py and the roofline) ----------------- */
+typedef struct qgt_b200_stats {
+    double ms_total;          /* device time of the whole call (CUDA events) */
+    double ms_sweep;          /* time in gate-sweep kernels */
+    double ms_gram;           /* time in Gram kernels */
+    double ms_other;
+    double sweep_bytes;       /* algorithmic bytes moved by sweep launches (32*D or 16*D+16*D per column pass) */
+    double gram_flops;        /* algorithmic real flops of Gram launches (8*na*nb*D) */
+    double gram_bytes;
+    int64_t sweep_launches;
+    int64_t gram_launches;
+    int64_t other_launches;
+    int64_t sweep_column_passes;
+    int32_t num_runs;         /* fused sweeps the circuit was cut into */
+    int32_t resident_columns; /* b */
+    int32_t blocks;           /* number of resident blocks */
+    int32_t tile_qubits;
+} qgt_b200_stats;
+int  qgt_b200_get_stats(qgt_b200_ctx* ctx, qgt_b200_stats* out);
+
+/* Debug/verification: textual dump of the fused-run plan and the column schedule for a circuit
+ * (no device needed).  Returns bytes written (excluding NUL) or a negative status. */
+long qgt_b200_plan_dump(const qgt_b200_circuit* circuit, int tile_qubits, int reg_qubits,
+                        size_t column_slots, char* buf, size_t buflen);
+
+/* ---- multi-GPU (one process per GPU; amplitudes sharded on the top log2(world) qubits) ------ */
+#define QGT_B200_IPC_HANDLE_BYTES 64
+#define QGT_B200_NCCL_ID_BYTES    128
+int  qgt_b200_dist_unique_id(uint8_t id[QGT_B200_NCCL_ID_BYTES]);          /* rank 0 creates, host broadcasts */
+int  qgt_b200_dist_init(qgt_b200_ctx* ctx, int rank, int world, const uint8_t id[QGT_B200_NCCL_ID_BYTES]);
+int  qgt_b200_dist_world(const qgt_b200_ctx* ctx, int* rank, int* world);
+/* peer-memory exchange buffers: every rank exports its handle, the host all-gathers them */
+int  qgt_b200_dist_export_ipc(qgt_b200_ctx* ctx, size_t local_bytes, uint8_t handle[QGT_B200_IPC_HANDLE_BYTES]);
+int  qgt_b200_dist_import_ipc(qgt_b200_ctx* ctx, const uint8_t* handles /* world * 64 */);
+int  qgt_b200_dist_barrier(qgt_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QGT_B200_H */
