@@ -196,8 +196,8 @@ typedef struct qgt_b200_stats {
 int  qgt_b200_get_stats(qgt_b200_ctx* ctx, qgt_b200_stats* out);
 
 /* Debug/verification: textual dump of the fused-run plan and the column schedule for a circuit
- * (no device needed).  Returns bytes written (excluding NUL) or a negative status. */
-long qgt_b200_plan_dump(const qgt_b200_circuit* circuit, int tile_qubits, int reg_qubits,
+ * (no device needed; theta may be NULL = all zeros).  Returns the JSON length (excluding NUL) or a negative status. */
+long qgt_b200_plan_dump(const qgt_b200_circuit* circuit, const double* theta, int tile_qubits, int reg_qubits,
                         size_t column_slots, char* buf, size_t buflen);
 
 /* ---- multi-GPU (one process per GPU; amplitudes sharded on the top log2(world) qubits) ------ */

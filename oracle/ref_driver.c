@@ -47,6 +47,16 @@ static int ref_run_range(SimulatorState* st, const qgt_b200_circuit* c, const do
         if (!ref_supported(g->kind)) { rc = -7; break; }
         double p[4] = { ref_angle(g, theta), 0, 0, 0 };
         int rot = (g->kind == GATE_RX || g->kind == GATE_RY || g->kind == GATE_RZ);
+        if (g->kind == GATE_SWAP) {
+            /* sim_add_gate stores a control qubit only for CNOT/CZ (quantum_simulator.c:461-476), so a
+             * SWAP added through it always pairs the target with qubit 0 at execution (:509-510) — a
+             * reference defect.  Drive the reference's own decomposition
+             * SWAP = CNOT(a,b) CNOT(b,a) CNOT(a,b) (:269-275) through its CNOT path instead. */
+            uint32_t a = (uint32_t)g->control, b = (uint32_t)g->target;
+            if (!sim_add_gate(circ, GATE_CNOT, b, a, NULL) || !sim_add_gate(circ, GATE_CNOT, a, b, NULL) ||
+                !sim_add_gate(circ, GATE_CNOT, b, a, NULL)) rc = -2;
+            continue;
+        }
         if (!sim_add_gate(circ, (gate_type_t)g->kind, (uint32_t)g->target,
                           (uint32_t)(g->control < 0 ? 0 : g->control), rot ? p : NULL)) rc = -2;
     }

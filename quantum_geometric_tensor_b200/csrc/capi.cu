@@ -1,0 +1,771 @@
+// capi.cu — the C-ABI of include/qgt_b200.h: context, device memory, program executor.
+//
+// No CPU fallback: every compute entry point needs a CUDA device and reports
+// QGT_B200_ERR_NO_DEVICE otherwise (north star: "backend dispatch ... targets only the new sm_100a
+// library with no CPU fallback"; contrast gpu_malloc's malloc fallback in the reference,
+// src/quantum_geometric/core/quantum_geometric_gpu.c:30-61).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qgt_b200.h"
+#include "ctx.hpp"
+#include "kernels.cuh"
+#include "plan.hpp"
+
+using namespace qgt;
+
+namespace qgt {
+thread_local std::string g_last_error;
+
+int fail(int status, const std::string& msg) {
+    g_last_error = msg;
+    return status;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    g_last_error = buf;
+    return e == cudaErrorMemoryAllocation ? QGT_B200_ERR_NO_MEMORY : QGT_B200_ERR_HARDWARE;
+}
+
+int DevBuf::reserve(size_t n) {
+    if (n <= bytes) return QGT_B200_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&ptr, n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    bytes = n;
+    return QGT_B200_OK;
+}
+
+void DevBuf::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; bytes = 0;
+}
+
+void Timer::begin(cudaStream_t st, int cat) {
+    if (!enabled) return;
+    if (used + 2 > events.size()) {
+        const size_t old = events.size();
+        events.resize(old + 64);
+        for (size_t i = old; i < events.size(); i++) cudaEventCreate(&events[i]);
+    }
+    cats.push_back(cat);
+    cudaEventRecord(events[used], st);
+}
+
+void Timer::end(cudaStream_t st) {
+    if (!enabled) return;
+    cudaEventRecord(events[used + 1], st);
+    used += 2;
+}
+
+void Timer::collect(double ms[3]) {
+    ms[0] = ms[1] = ms[2] = 0.0;
+    for (size_t i = 0; i < cats.size(); i++) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, events[2 * i], events[2 * i + 1]);
+        ms[cats[i]] += t;
+    }
+    cats.clear();
+    used = 0;
+}
+
+Timer::~Timer() {
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+}
+}  // namespace qgt
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int qgt_b200_abi_version(void) { return QGT_B200_ABI_VERSION; }
+
+int qgt_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+const char* qgt_b200_last_error(void) { return g_last_error.c_str(); }
+
+const char* qgt_b200_error_string(int s) {
+    switch (s) {
+    case QGT_B200_OK: return "success";
+    case QGT_B200_ERR_INVALID_ARG: return "invalid argument";
+    case QGT_B200_ERR_NO_MEMORY: return "out of memory";
+    case QGT_B200_ERR_DIMENSION: return "dimension mismatch";
+    case QGT_B200_ERR_INVALID_STATE: return "invalid state";
+    case QGT_B200_ERR_HARDWARE: return "CUDA failure";
+    case QGT_B200_ERR_UNSUPPORTED: return "not implemented";
+    case QGT_B200_ERR_INTERNAL: return "internal error";
+    case QGT_B200_ERR_NOT_INIT: return "not initialized";
+    case QGT_B200_ERR_CIRCUIT: return "invalid circuit";
+    case QGT_B200_ERR_NO_DEVICE: return "no sm_100 CUDA device (this library has no CPU fallback)";
+    default: return "unknown status";
+    }
+}
+
+int qgt_b200_create(qgt_b200_ctx** out, int device) {
+    if (!out) return fail(QGT_B200_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(QGT_B200_ERR_NO_DEVICE, "no CUDA device visible; qgt_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(QGT_B200_ERR_INVALID_ARG, "device ordinal out of range");
+    cudaDeviceProp p;
+    cudaError_t e = cudaGetDeviceProperties(&p, device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    if (p.major != 10) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "device %d is sm_%d%d; this library ships sm_100a code only", device, p.major, p.minor);
+        return fail(QGT_B200_ERR_NO_DEVICE, buf);
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    qgt_b200_ctx* c = new qgt_b200_ctx();
+    c->device = device;
+    c->num_sms = p.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    *out = c;
+    return QGT_B200_OK;
+}
+
+void qgt_b200_destroy(qgt_b200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    qgt::dist_shutdown(c);
+    c->arena.release(); c->img_runs.release(); c->img_ops.release(); c->img_subs.release();
+    c->items.release(); c->aux.release(); c->partial.release(); c->cmat.release(); c->outbuf.release();
+    c->edges.release(); c->vweights.release(); c->scratch.release();
+    if (c->pinned) cudaFreeHost(c->pinned);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int qgt_b200_set_workspace_limit(qgt_b200_ctx* c, size_t bytes) {
+    if (!c) return fail(QGT_B200_ERR_INVALID_ARG, "ctx is NULL");
+    c->ws_limit = bytes;
+    return QGT_B200_OK;
+}
+
+int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
+    if (!c || !key) return fail(QGT_B200_ERR_INVALID_ARG, "ctx/key is NULL");
+    const std::string k(key);
+    if (k == "tile_qubits") { if (value) c->opt.tile_qubits = (int)value; }
+    else if (k == "low_qubits") c->opt.low_qubits = (int)value;
+    else if (k == "max_ops_per_run") c->opt.max_ops_per_run = (int)value;
+    else if (k == "profile") c->timer.enabled = value != 0;
+    else if (k == "max_slots") c->max_slots = (size_t)value;
+    else return fail(QGT_B200_ERR_INVALID_ARG, "unknown option " + k);
+    return QGT_B200_OK;
+}
+
+int qgt_b200_get_stats(qgt_b200_ctx* c, qgt_b200_stats* out) {
+    if (!c || !out) return fail(QGT_B200_ERR_INVALID_ARG, "ctx/out is NULL");
+    *out = c->stats;
+    return QGT_B200_OK;
+}
+
+// ---- statevector ---------------------------------------------------------------------------------
+int qgt_b200_state_create(qgt_b200_ctx* c, int n, qgt_b200_state** out) {
+    if (!c || !out) return fail(QGT_B200_ERR_INVALID_ARG, "ctx/out is NULL");
+    *out = nullptr;
+    if (n < 1 || n > QGT_MAX_QUBITS) return fail(QGT_B200_ERR_INVALID_ARG, "num_qubits out of range");
+    int gbits = 0;
+    while ((1 << gbits) < c->world) gbits++;
+    if (n - gbits < 1) return fail(QGT_B200_ERR_INVALID_ARG, "state too small for this many ranks");
+    cudaSetDevice(c->device);
+    qgt_b200_state* s = new qgt_b200_state();
+    s->ctx = c; s->n = n; s->nloc = n - gbits; s->D = (uint64_t)1 << s->nloc;
+    cudaError_t e = cudaMalloc((void**)&s->d, s->D * sizeof(cplx));
+    if (e != cudaSuccess) { delete s; return cuda_fail(e, "cudaMalloc(state)"); }
+    s->owns = true;
+    *out = s;
+    return qgt_b200_state_init(s, QGT_B200_INIT_ZERO);
+}
+
+void qgt_b200_state_destroy(qgt_b200_state* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    if (s->owns && s->d) cudaFree(s->d);
+    delete s;
+}
+
+int qgt_b200_state_init(qgt_b200_state* s, int initial_state) {
+    if (!s) return fail(QGT_B200_ERR_INVALID_ARG, "state is NULL");
+    if (initial_state != QGT_B200_INIT_ZERO && initial_state != QGT_B200_INIT_PLUS)
+        return fail(QGT_B200_ERR_INVALID_ARG, "unknown initial state");
+    qgt_b200_ctx* c = s->ctx;
+    cudaSetDevice(c->device);
+    const double amp = std::pow(2.0, -0.5 * s->n);
+    cudaError_t e = launch_init_state(s->d, s->D, initial_state, amp, (uint64_t)c->rank * s->D, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "init kernel");
+    e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "init sync");
+    return QGT_B200_OK;
+}
+
+int qgt_b200_state_upload(qgt_b200_state* s, const double* host) {
+    if (!s || !host) return fail(QGT_B200_ERR_INVALID_ARG, "state/host is NULL");
+    cudaSetDevice(s->ctx->device);
+    cudaError_t e = cudaMemcpyAsync(s->d, host, s->D * sizeof(cplx), cudaMemcpyHostToDevice, s->ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "state upload");
+    return QGT_B200_OK;
+}
+
+int qgt_b200_state_download(const qgt_b200_state* s, double* host) {
+    if (!s || !host) return fail(QGT_B200_ERR_INVALID_ARG, "state/host is NULL");
+    cudaSetDevice(s->ctx->device);
+    cudaError_t e = cudaMemcpyAsync(host, s->d, s->D * sizeof(cplx), cudaMemcpyDeviceToHost, s->ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "state download");
+    return QGT_B200_OK;
+}
+
+int qgt_b200_state_norm2(const qgt_b200_state* s, double* out) {
+    if (!s || !out) return fail(QGT_B200_ERR_INVALID_ARG, "state/out is NULL");
+    qgt_b200_ctx* c = s->ctx;
+    cudaSetDevice(c->device);
+    int rc = c->scratch.reserve(256);
+    if (rc) return rc;
+    cudaError_t e = launch_norm2(s->d, s->D, (double*)c->scratch.ptr, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "norm kernel");
+    double v = 0;
+    e = cudaMemcpyAsync(&v, c->scratch.ptr, sizeof v, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "norm readback");
+    rc = qgt::dist_allreduce_host(c, &v, 1);
+    if (rc) return rc;
+    *out = v;
+    return QGT_B200_OK;
+}
+
+void* qgt_b200_state_device_ptr(qgt_b200_state* s) { return s ? (void*)s->d : nullptr; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// executor
+// ------------------------------------------------------------------------------------------------
+namespace qgt {
+
+static int check_circuit(const qgt_b200_circuit* circ, const double* theta) {
+    if (!circ) return fail(QGT_B200_ERR_INVALID_ARG, "circuit is NULL");
+    if (circ->num_params > 0 && !theta) return fail(QGT_B200_ERR_INVALID_ARG, "theta is NULL");
+    if (circ->num_params < 0) return fail(QGT_B200_ERR_INVALID_ARG, "num_params < 0");
+    return QGT_B200_OK;
+}
+
+// upload the device image of a plan and the circuit's cost table
+int upload_plan(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan& plan, PlanImage& img) {
+    build_image(plan, img);
+    int rc;
+    if ((rc = c->img_runs.reserve(std::max<size_t>(1, img.runs.size()) * sizeof(QgtDevRun)))) return rc;
+    if ((rc = c->img_ops.reserve(std::max<size_t>(1, img.ops.size()) * sizeof(QgtDevOp)))) return rc;
+    if ((rc = c->img_subs.reserve(std::max<size_t>(1, img.subs.size()) * sizeof(QgtDevSubPass)))) return rc;
+    cudaError_t e = cudaSuccess;
+    if (!img.runs.empty()) e = cudaMemcpyAsync(c->img_runs.ptr, img.runs.data(), img.runs.size() * sizeof(QgtDevRun), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && !img.ops.empty()) e = cudaMemcpyAsync(c->img_ops.ptr, img.ops.data(), img.ops.size() * sizeof(QgtDevOp), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && !img.subs.empty()) e = cudaMemcpyAsync(c->img_subs.ptr, img.subs.data(), img.subs.size() * sizeof(QgtDevSubPass), cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "plan upload");
+    c->cost.edges = nullptr; c->cost.num_edges = 0; c->cost.vertex_weights = nullptr; c->cost.n = circ.num_qubits;
+    if (circ.num_edges && circ.edges) {
+        std::vector<QgtDevEdge> ed(circ.num_edges);
+        for (size_t k = 0; k < circ.num_edges; k++) {
+            if (circ.edges[k].i < 0 || circ.edges[k].i >= circ.num_qubits || circ.edges[k].j < 0 || circ.edges[k].j >= circ.num_qubits)
+                return fail(QGT_B200_ERR_CIRCUIT, "edge endpoint out of range");
+            ed[k].i = circ.edges[k].i; ed[k].j = circ.edges[k].j; ed[k].w = circ.edges[k].weight;
+        }
+        if ((rc = c->edges.reserve(ed.size() * sizeof(QgtDevEdge)))) return rc;
+        e = cudaMemcpyAsync(c->edges.ptr, ed.data(), ed.size() * sizeof(QgtDevEdge), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // `ed` is a local
+        if (e != cudaSuccess) return cuda_fail(e, "edge upload");
+        c->cost.edges = (const QgtDevEdge*)c->edges.ptr; c->cost.num_edges = (int)ed.size();
+    }
+    if (circ.vertex_weights) {
+        if ((rc = c->vweights.reserve(circ.num_qubits * sizeof(double)))) return rc;
+        e = cudaMemcpyAsync(c->vweights.ptr, circ.vertex_weights, circ.num_qubits * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "vertex weight upload");
+        c->cost.vertex_weights = (const double*)c->vweights.ptr;
+    }
+    return QGT_B200_OK;
+}
+
+struct SweepBatch { int run; size_t item_off; int nitems; int out_of_place; };
+
+// one fused sweep launch over `cols` (slot pointers resolved by the caller)
+static int do_sweep(qgt_b200_ctx* c, const CircuitPlan& plan, int run, const QgtSweepItem* d_items, int nitems,
+                    uint64_t shard_tiles) {
+    SweepLaunch a;
+    a.runs = (const QgtDevRun*)c->img_runs.ptr;
+    a.ops = (const QgtDevOp*)c->img_ops.ptr;
+    a.subs = (const QgtDevSubPass*)c->img_subs.ptr;
+    a.run_idx = run;
+    a.items = d_items;
+    a.nitems = nitems;
+    a.ntiles = shard_tiles;
+    a.ct = c->cost;
+    const int K = plan.runs[run].K;
+    const int R = (int)plan.runs[run].subs.empty() ? std::min(plan.opt.reg_qubits, K) : (int)plan.runs[run].subs[0].reg_local.size();
+    c->timer.begin(c->stream, 0);
+    cudaError_t e = launch_sweep(a, K, R, c->num_sms, c->stream);
+    c->timer.end(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sweep launch");
+    c->stats.sweep_launches++;
+    c->stats.sweep_column_passes += nitems;
+    return QGT_B200_OK;
+}
+
+// Apply every run of `plan` to the column at `d` in place.
+int apply_plan_inplace(qgt_b200_ctx* c, const CircuitPlan& plan, cplx* d, uint64_t D) {
+    if (plan.runs.empty()) return QGT_B200_OK;
+    int rc = c->items.reserve(sizeof(QgtSweepItem));
+    if (rc) return rc;
+    QgtSweepItem it;
+    std::memset(&it, 0, sizeof it);
+    it.src = d; it.dst = d; it.ovr_op = -1; it.accumulate = 0;
+    cudaError_t e = cudaMemcpyAsync(c->items.ptr, &it, sizeof it, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "item upload");
+    for (size_t r = 0; r < plan.runs.size(); r++) {
+        const uint64_t ntiles = D >> plan.runs[r].K;
+        if ((rc = do_sweep(c, plan, (int)r, (const QgtSweepItem*)c->items.ptr, 1, ntiles))) return rc;
+        c->stats.sweep_bytes += 32.0 * (double)D;
+    }
+    return QGT_B200_OK;
+}
+
+static int gram_ksplit(const qgt_b200_ctx* c, int tiles, uint64_t D) {
+    const uint64_t by_len = std::max<uint64_t>(1, D / 256);
+    uint64_t want = (uint64_t)std::max(1, (c->num_sms * 3 + tiles - 1) / tiles);
+    want = std::min<uint64_t>(want, by_len);
+    return (int)std::min<uint64_t>(want, 1024);
+}
+
+// executes a Program on `nslots` columns of D amplitudes each living at arena + slot*D
+int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan& plan, const Program& prog,
+                cplx* arena, uint64_t D, cplx* cmat /* (P+1)^2 device */) {
+    const int P = plan.P;
+    // ---- pack every launch's arguments and upload them once ------------------------------------
+    std::vector<QgtSweepItem> items;
+    std::vector<const cplx*> ptrs;
+    std::vector<int> ids;
+    struct GramRec { size_t a_off, b_off, aid_off, bid_off; int na, nb; bool symmetric; };
+    std::vector<size_t> item_off(prog.instrs.size(), 0);
+    std::vector<GramRec> grec(prog.instrs.size());
+    size_t partial_bytes = 0;
+    for (size_t i = 0; i < prog.instrs.size(); i++) {
+        const Instr& in = prog.instrs[i];
+        if (in.kind == INSTR_SWEEP) {
+            item_off[i] = items.size();
+            const Run& run = plan.runs[in.run];
+            for (const SweepCol& sc : in.cols) {
+                QgtSweepItem it;
+                std::memset(&it, 0, sizeof it);
+                it.src = arena + (size_t)sc.src * D;
+                it.dst = arena + (size_t)sc.dst * D;
+                it.ovr_op = sc.ovr_op;
+                it.accumulate = sc.accumulate ? 1u : 0u;
+                if (sc.ovr_op >= 0) {
+                    const int sp = find_subpass(run, sc.ovr_op);
+                    if (sp < 0) return fail(QGT_B200_ERR_INTERNAL, "override op outside every sub-pass");
+                    it.ovr = bind_op(run, run.subs[sp], run.ops[sc.ovr_op], true);
+                }
+                items.push_back(it);
+            }
+        } else if (in.kind == INSTR_GRAM) {
+            GramRec& g = grec[i];
+            g.na = (int)in.a_slots.size(); g.nb = (int)in.b_slots.size();
+            g.a_off = ptrs.size();
+            for (int s : in.a_slots) ptrs.push_back(arena + (size_t)s * D);
+            g.b_off = ptrs.size();
+            for (int s : in.b_slots) ptrs.push_back(arena + (size_t)s * D);
+            g.aid_off = ids.size();
+            for (int v : in.a_ids) ids.push_back(v);
+            g.bid_off = ids.size();
+            for (int v : in.b_ids) ids.push_back(v);
+            g.symmetric = g.nb >= g.na && std::equal(in.a_slots.begin(), in.a_slots.end(), in.b_slots.begin());
+            const GramShape shp = gram_shape(g.na, g.nb);
+            const int mt = (g.na + shp.MT - 1) / shp.MT, nt = (g.nb + shp.NT - 1) / shp.NT;
+            const int ks = gram_ksplit(c, mt * nt, D);
+            partial_bytes = std::max(partial_bytes, (size_t)ks * mt * shp.MT * nt * shp.NT * sizeof(cplx));
+        }
+    }
+    int rc;
+    if ((rc = c->items.reserve(std::max<size_t>(1, items.size()) * sizeof(QgtSweepItem)))) return rc;
+    const size_t ptr_bytes = ptrs.size() * sizeof(cplx*), id_bytes = ids.size() * sizeof(int);
+    if ((rc = c->aux.reserve(std::max<size_t>(16, ptr_bytes + id_bytes)))) return rc;
+    if ((rc = c->partial.reserve(std::max<size_t>(16, partial_bytes)))) return rc;
+    cudaError_t e = cudaSuccess;
+    if (!items.empty()) e = cudaMemcpyAsync(c->items.ptr, items.data(), items.size() * sizeof(QgtSweepItem), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && ptr_bytes) e = cudaMemcpyAsync(c->aux.ptr, ptrs.data(), ptr_bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && id_bytes) e = cudaMemcpyAsync((char*)c->aux.ptr + ptr_bytes, ids.data(), id_bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // host vectors are locals
+    if (e != cudaSuccess) return cuda_fail(e, "program upload");
+    const cplx* const* d_ptrs = (const cplx* const*)c->aux.ptr;
+    const int* d_ids = (const int*)((char*)c->aux.ptr + ptr_bytes);
+
+    // ---- execute ----------------------------------------------------------------------------------
+    const double plus_amp = std::pow(2.0, -0.5 * plan.n);
+    for (size_t i = 0; i < prog.instrs.size(); i++) {
+        const Instr& in = prog.instrs[i];
+        switch (in.kind) {
+        case INSTR_INIT: {
+            c->timer.begin(c->stream, 2);
+            e = launch_init_state(arena + (size_t)in.dst * D, D, circ.initial_state, plus_amp, (uint64_t)c->rank * D, c->stream);
+            c->timer.end(c->stream);
+            if (e != cudaSuccess) return cuda_fail(e, "init launch");
+            c->stats.other_launches++;
+            break; }
+        case INSTR_COPY: {
+            c->timer.begin(c->stream, 2);
+            e = cudaMemcpyAsync(arena + (size_t)in.dst * D, arena + (size_t)in.src * D, D * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
+            c->timer.end(c->stream);
+            if (e != cudaSuccess) return cuda_fail(e, "column copy");
+            c->stats.other_launches++;
+            break; }
+        case INSTR_SWEEP: {
+            const uint64_t ntiles = D >> plan.runs[in.run].K;
+            if ((rc = do_sweep(c, plan, in.run, (const QgtSweepItem*)c->items.ptr + item_off[i], (int)in.cols.size(), ntiles))) return rc;
+            for (const SweepCol& sc : in.cols)
+                c->stats.sweep_bytes += (sc.accumulate ? 48.0 : 32.0) * (double)D;
+            break; }
+        case INSTR_GRAM: {
+            const GramRec& g = grec[i];
+            GramLaunch gl;
+            gl.a_ptrs = d_ptrs + g.a_off; gl.b_ptrs = d_ptrs + g.b_off;
+            gl.na = g.na; gl.nb = g.nb; gl.D = D;
+            const GramShape shp = gram_shape(g.na, g.nb);
+            gl.mtiles = (g.na + shp.MT - 1) / shp.MT; gl.ntiles = (g.nb + shp.NT - 1) / shp.NT;
+            gl.ksplit = gram_ksplit(c, gl.mtiles * gl.ntiles, D);
+            gl.symmetric = g.symmetric ? 1 : 0;
+            gl.partial = (cplx*)c->partial.ptr;
+            c->timer.begin(c->stream, 1);
+            e = launch_gram(gl, shp, c->stream);
+            if (e == cudaSuccess) e = launch_gram_reduce(gl, shp, d_ids + g.aid_off, d_ids + g.bid_off, cmat, P + 1, c->stream);
+            c->timer.end(c->stream);
+            if (e != cudaSuccess) return cuda_fail(e, "gram launch");
+            c->stats.gram_launches++;
+            const double pairs = g.symmetric ? 0.5 * g.na * (g.na + 1) + (g.nb - g.na) * (double)g.na : (double)g.na * g.nb;
+            c->stats.gram_flops += 8.0 * pairs * (double)D;
+            c->stats.gram_bytes += 16.0 * (double)D * (g.symmetric ? g.nb : g.na + g.nb);
+            break; }
+        }
+    }
+    return QGT_B200_OK;
+}
+
+size_t workspace_slots(qgt_b200_ctx* c, uint64_t D, size_t reserve_bytes) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    size_t avail = free_b + c->arena.bytes;          // the cached arena is ours to reuse
+    avail = avail > reserve_bytes ? avail - reserve_bytes : 0;
+    size_t limit = c->ws_limit ? std::min(c->ws_limit, avail) : (size_t)(0.90 * (double)avail);
+    size_t slots = limit / (D * sizeof(cplx));
+    if (c->max_slots && slots > c->max_slots) slots = c->max_slots;
+    return slots;
+}
+
+void stats_begin(qgt_b200_ctx* c) {
+    std::memset(&c->stats, 0, sizeof c->stats);
+    cudaEventRecord(c->ev0, c->stream);
+}
+
+int stats_end(qgt_b200_ctx* c) {
+    cudaEventRecord(c->ev1, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "stream sync");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    double cat[3];
+    c->timer.collect(cat);
+    c->stats.ms_total = ms;
+    c->stats.ms_sweep = cat[0]; c->stats.ms_gram = cat[1]; c->stats.ms_other = cat[2];
+    return QGT_B200_OK;
+}
+
+}  // namespace qgt
+
+extern "C" {
+
+int qgt_b200_apply_circuit(qgt_b200_state* s, const qgt_b200_circuit* circ, const double* theta) {
+    if (!s) return fail(QGT_B200_ERR_INVALID_ARG, "state is NULL");
+    int rc = check_circuit(circ, theta);
+    if (rc) return rc;
+    if (circ->num_qubits != s->n) return fail(QGT_B200_ERR_DIMENSION, "circuit and state qubit counts differ");
+    qgt_b200_ctx* c = s->ctx;
+    cudaSetDevice(c->device);
+    if (c->world > 1) return qgt::dist_apply_circuit(s, circ, theta);
+    CircuitPlan plan;
+    std::string err;
+    if ((rc = build_plan(*circ, theta, c->opt, plan, err))) return fail(rc, err);
+    PlanImage img;
+    stats_begin(c);
+    if ((rc = upload_plan(c, *circ, plan, img))) return rc;
+    if ((rc = apply_plan_inplace(c, plan, s->d, s->D))) return rc;
+    if ((rc = stats_end(c))) return rc;
+    c->stats.num_runs = (int)plan.runs.size();
+    c->stats.tile_qubits = plan.runs.empty() ? 0 : plan.runs[0].K;
+    return QGT_B200_OK;
+}
+
+int qgt_b200_simulate_host(qgt_b200_ctx* c, double* host, int n, const qgt_b200_circuit* circ, const double* theta) {
+    if (!c || !host) return fail(QGT_B200_ERR_INVALID_ARG, "ctx/host is NULL");
+    qgt_b200_state* s = nullptr;
+    int rc = qgt_b200_state_create(c, n, &s);
+    if (rc) return rc;
+    rc = qgt_b200_state_upload(s, host);
+    if (!rc) rc = qgt_b200_apply_circuit(s, circ, theta);
+    if (!rc) rc = qgt_b200_state_download(s, host);
+    qgt_b200_state_destroy(s);
+    return rc;
+}
+
+int qgt_b200_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
+                 double* metric, double* berry, double* q_full, qgt_b200_state* psi_out) {
+    if (!c) return fail(QGT_B200_ERR_INVALID_ARG, "ctx is NULL");
+    int rc = check_circuit(circ, theta);
+    if (rc) return rc;
+    cudaSetDevice(c->device);
+    if (psi_out && psi_out->n != circ->num_qubits) return fail(QGT_B200_ERR_DIMENSION, "psi_out has a different qubit count");
+    if (c->world > 1) return qgt::dist_qgt(c, circ, theta, metric, berry, q_full, psi_out);
+    const int n = circ->num_qubits, P = circ->num_params;
+    const uint64_t D = (uint64_t)1 << n;
+    CircuitPlan plan;
+    std::string err;
+    if ((rc = build_plan(*circ, theta, c->opt, plan, err))) return fail(rc, err);
+    Program prog;
+    const size_t slots = workspace_slots(c, D, (size_t)64 << 20);
+    if ((rc = build_qgt_program(plan, slots, psi_out != nullptr, prog, err))) return fail(rc, err);
+    if ((rc = c->arena.reserve((size_t)prog.num_slots * D * sizeof(cplx)))) return rc;
+    const size_t cm = (size_t)(P + 1) * (P + 1);
+    if ((rc = c->cmat.reserve(std::max<size_t>(16, cm * sizeof(cplx))))) return rc;
+    if ((rc = c->outbuf.reserve(std::max<size_t>(16, (size_t)P * P * 4 * sizeof(double))))) return rc;
+    PlanImage img;
+    stats_begin(c);
+    if ((rc = upload_plan(c, *circ, plan, img))) return rc;
+    cudaError_t e = cudaMemsetAsync(c->cmat.ptr, 0, cm * sizeof(cplx), c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "memset");
+    if ((rc = run_program(c, *circ, plan, prog, (cplx*)c->arena.ptr, D, (cplx*)c->cmat.ptr))) return rc;
+    double* d_metric = (double*)c->outbuf.ptr;
+    double* d_berry = d_metric + (size_t)P * P;
+    cplx* d_q = (cplx*)(d_berry + (size_t)P * P);
+    c->timer.begin(c->stream, 2);
+    e = launch_finalize((const cplx*)c->cmat.ptr, P, d_metric, d_berry, d_q, c->stream);
+    c->timer.end(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "finalize launch");
+    c->stats.other_launches++;
+    const size_t pp = (size_t)P * P;
+    if (P > 0) {
+        if (metric && e == cudaSuccess) e = cudaMemcpyAsync(metric, d_metric, pp * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (berry && e == cudaSuccess) e = cudaMemcpyAsync(berry, d_berry, pp * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (q_full && e == cudaSuccess) e = cudaMemcpyAsync(q_full, d_q, pp * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (psi_out && e == cudaSuccess)
+        e = cudaMemcpyAsync(psi_out->d, (cplx*)c->arena.ptr + (size_t)prog.psi_slot * D, D * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "result copy");
+    if ((rc = stats_end(c))) return rc;
+    c->stats.num_runs = (int)plan.runs.size();
+    c->stats.resident_columns = prog.resident;
+    c->stats.blocks = prog.blocks;
+    c->stats.tile_qubits = plan.runs.empty() ? 0 : plan.runs[0].K;
+    return QGT_B200_OK;
+}
+
+int qgt_b200_derivative(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta, int mu, qgt_b200_state* out) {
+    if (!c || !out) return fail(QGT_B200_ERR_INVALID_ARG, "ctx/out is NULL");
+    int rc = check_circuit(circ, theta);
+    if (rc) return rc;
+    if (mu < 0 || mu >= circ->num_params) return fail(QGT_B200_ERR_INVALID_ARG, "parameter index out of range");
+    if (out->n != circ->num_qubits) return fail(QGT_B200_ERR_DIMENSION, "out has a different qubit count");
+    if (c->world > 1) return fail(QGT_B200_ERR_UNSUPPORTED, "derivative columns are single-GPU only");
+    cudaSetDevice(c->device);
+    const uint64_t D = out->D;
+    CircuitPlan plan;
+    std::string err;
+    if ((rc = build_plan(*circ, theta, c->opt, plan, err))) return fail(rc, err);
+    // a two-slot program: slot 0 = phi, slot 1 = the column
+    Program prog;
+    prog.num_slots = 2;
+    { Instr in; in.kind = INSTR_INIT; in.dst = 0; prog.instrs.push_back(in); }
+    bool alive = false;
+    for (int r = 0; r < (int)plan.runs.size(); r++) {
+        if (alive) { Instr in; in.kind = INSTR_SWEEP; in.run = r; in.cols.push_back({1, 1, -1, false}); prog.instrs.push_back(in); }
+        for (const ParamOcc& oc : plan.runs[r].occ) {
+            if (oc.param != mu) continue;
+            Instr in; in.kind = INSTR_SWEEP; in.run = r; in.cols.push_back({0, 1, oc.op, alive});
+            prog.instrs.push_back(in);
+            alive = true;
+        }
+        Instr in; in.kind = INSTR_SWEEP; in.run = r; in.cols.push_back({0, 0, -1, false}); prog.instrs.push_back(in);
+    }
+    if ((rc = c->arena.reserve(2 * D * sizeof(cplx)))) return rc;
+    if ((rc = c->cmat.reserve(16 * sizeof(cplx)))) return rc;
+    PlanImage img;
+    stats_begin(c);
+    if ((rc = upload_plan(c, *circ, plan, img))) return rc;
+    cudaError_t e = cudaMemsetAsync((cplx*)c->arena.ptr + D, 0, D * sizeof(cplx), c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "memset");
+    if ((rc = run_program(c, *circ, plan, prog, (cplx*)c->arena.ptr, D, (cplx*)c->cmat.ptr))) return rc;
+    e = cudaMemcpyAsync(out->d, (cplx*)c->arena.ptr + D, D * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "column copy");
+    return stats_end(c);
+}
+
+int qgt_b200_gram(qgt_b200_ctx* c, const double* psi, const double* dpsi, size_t dim, size_t num_params,
+                  double* metric, double* berry, double* q_full) {
+    if (!c || !psi || !dpsi) return fail(QGT_B200_ERR_INVALID_ARG, "ctx/psi/dpsi is NULL");
+    if (dim == 0 || num_params == 0) return fail(QGT_B200_ERR_INVALID_ARG, "empty problem");
+    if (c->world > 1) return fail(QGT_B200_ERR_UNSUPPORTED, "qgt_b200_gram is single-GPU only");
+    cudaSetDevice(c->device);
+    const int P = (int)num_params;
+    const uint64_t D = dim;
+    auto is_device = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+    };
+    int rc;
+    stats_begin(c);
+    const cplx* d_psi = (const cplx*)psi;
+    const cplx* d_cols = (const cplx*)dpsi;
+    size_t need = 0;
+    const bool up_psi = !is_device(psi), up_cols = !is_device(dpsi);
+    if (up_psi) need += D;
+    if (up_cols) need += (size_t)P * D;
+    if (need) {
+        if ((rc = c->arena.reserve(need * sizeof(cplx)))) return rc;
+        cplx* a = (cplx*)c->arena.ptr;
+        cudaError_t e = cudaSuccess;
+        if (up_cols) { e = cudaMemcpyAsync(a, dpsi, (size_t)P * D * sizeof(cplx), cudaMemcpyHostToDevice, c->stream); d_cols = a; a += (size_t)P * D; }
+        if (up_psi && e == cudaSuccess) { e = cudaMemcpyAsync(a, psi, D * sizeof(cplx), cudaMemcpyHostToDevice, c->stream); d_psi = a; }
+        if (e != cudaSuccess) return cuda_fail(e, "column upload");
+    }
+    std::vector<const cplx*> ptrs;
+    std::vector<int> ids;
+    for (int i = 0; i < P; i++) ptrs.push_back(d_cols + (size_t)i * D);      // A list
+    for (int i = 0; i < P; i++) ptrs.push_back(d_cols + (size_t)i * D);      // B list = A list + psi
+    ptrs.push_back(d_psi);
+    for (int i = 0; i < P; i++) ids.push_back(i);
+    for (int i = 0; i <= P; i++) ids.push_back(i);
+    const size_t ptr_bytes = ptrs.size() * sizeof(cplx*), id_bytes = ids.size() * sizeof(int);
+    if ((rc = c->aux.reserve(ptr_bytes + id_bytes))) return rc;
+    const size_t cm = (size_t)(P + 1) * (P + 1);
+    if ((rc = c->cmat.reserve(cm * sizeof(cplx)))) return rc;
+    if ((rc = c->outbuf.reserve((size_t)P * P * 4 * sizeof(double)))) return rc;
+    GramLaunch gl;
+    const GramShape shp = gram_shape(P, P + 1);
+    gl.na = P; gl.nb = P + 1; gl.D = D;
+    gl.mtiles = (gl.na + shp.MT - 1) / shp.MT; gl.ntiles = (gl.nb + shp.NT - 1) / shp.NT;
+    gl.ksplit = gram_ksplit(c, gl.mtiles * gl.ntiles, D);
+    gl.symmetric = 1;
+    if ((rc = c->partial.reserve((size_t)gl.ksplit * gl.mtiles * shp.MT * gl.ntiles * shp.NT * sizeof(cplx)))) return rc;
+    gl.partial = (cplx*)c->partial.ptr;
+    cudaError_t e = cudaMemcpyAsync(c->aux.ptr, ptrs.data(), ptr_bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((char*)c->aux.ptr + ptr_bytes, ids.data(), id_bytes, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->cmat.ptr, 0, cm * sizeof(cplx), c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gram setup");
+    gl.a_ptrs = (const cplx* const*)c->aux.ptr;
+    gl.b_ptrs = gl.a_ptrs + P;
+    const int* d_ids = (const int*)((char*)c->aux.ptr + ptr_bytes);
+    c->timer.begin(c->stream, 1);
+    e = launch_gram(gl, shp, c->stream);
+    if (e == cudaSuccess) e = launch_gram_reduce(gl, shp, d_ids, d_ids + P, (cplx*)c->cmat.ptr, P + 1, c->stream);
+    c->timer.end(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gram launch");
+    c->stats.gram_launches = 1;
+    c->stats.gram_flops = 8.0 * (0.5 * P * (P + 1) + P) * (double)D;
+    c->stats.gram_bytes = 16.0 * (double)D * (P + 1);
+    double* d_metric = (double*)c->outbuf.ptr;
+    double* d_berry = d_metric + (size_t)P * P;
+    cplx* d_q = (cplx*)(d_berry + (size_t)P * P);
+    e = launch_finalize((const cplx*)c->cmat.ptr, P, d_metric, d_berry, d_q, c->stream);
+    const size_t pp = (size_t)P * P;
+    if (metric && e == cudaSuccess) e = cudaMemcpyAsync(metric, d_metric, pp * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (berry && e == cudaSuccess) e = cudaMemcpyAsync(berry, d_berry, pp * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (q_full && e == cudaSuccess) e = cudaMemcpyAsync(q_full, d_q, pp * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gram result copy");
+    return stats_end(c);
+}
+
+int qgt_b200_expectation_gradient(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
+                                  double* energy, double* grad) {
+    if (!c) return fail(QGT_B200_ERR_INVALID_ARG, "ctx is NULL");
+    int rc = check_circuit(circ, theta);
+    if (rc) return rc;
+    if (c->world > 1) return fail(QGT_B200_ERR_UNSUPPORTED, "expectation gradient is single-GPU only");
+    cudaSetDevice(c->device);
+    const int n = circ->num_qubits, P = circ->num_params;
+    qgt_b200_state *psi = nullptr, *col = nullptr;
+    if ((rc = qgt_b200_state_create(c, n, &psi))) return rc;
+    if ((rc = qgt_b200_state_create(c, n, &col))) { qgt_b200_state_destroy(psi); return rc; }
+    rc = qgt_b200_state_init(psi, circ->initial_state);
+    if (!rc) rc = qgt_b200_apply_circuit(psi, circ, theta);
+    if (!rc) rc = c->scratch.reserve(256);
+    double h[2];
+    auto dot = [&](const cplx* a, const cplx* b) -> int {
+        cudaError_t e = launch_cost_dot(a, b, psi->D, c->cost, 0, (double*)c->scratch.ptr, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h, c->scratch.ptr, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "cost dot");
+    };
+    if (!rc) rc = dot(psi->d, psi->d);
+    if (!rc && energy) *energy = h[0];
+    for (int mu = 0; mu < P && !rc && grad; mu++) {
+        rc = qgt_b200_derivative(c, circ, theta, mu, col);
+        if (!rc) rc = dot(col->d, psi->d);
+        if (!rc) grad[mu] = 2.0 * h[0];
+    }
+    qgt_b200_state_destroy(psi);
+    qgt_b200_state_destroy(col);
+    return rc;
+}
+
+long qgt_b200_plan_dump(const qgt_b200_circuit* circ, const double* theta, int tile_qubits, int reg_qubits,
+                        size_t column_slots, char* buf, size_t buflen) {
+    if (!circ) return fail(QGT_B200_ERR_INVALID_ARG, "circuit is NULL");
+    PlanOptions opt;
+    if (tile_qubits) opt.tile_qubits = tile_qubits;
+    if (reg_qubits) opt.reg_qubits = reg_qubits;
+    std::vector<double> zeros((size_t)std::max(1, circ->num_params), 0.0);
+    CircuitPlan plan;
+    std::string err;
+    int rc = build_plan(*circ, theta ? theta : zeros.data(), opt, plan, err);
+    if (rc) return fail(rc, err);
+    Program prog;
+    const Program* pp = nullptr;
+    if (column_slots) {
+        if ((rc = build_qgt_program(plan, column_slots, true, prog, err))) return fail(rc, err);
+        pp = &prog;
+    }
+    const std::string js = dump_json(*circ, plan, pp);
+    if (buf && buflen > js.size()) std::memcpy(buf, js.c_str(), js.size() + 1);
+    return (long)js.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// ctx.hpp — internal definitions behind the opaque handles of include/qgt_b200.h
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/qgt_b200.h"
+#include "kernels.cuh"
+#include "plan.hpp"
+
+namespace qgt {
+
+extern thread_local std::string g_last_error;
+int fail(int status, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+// grow-only device buffer cached in the context
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t n);
+    void release();
+};
+
+// CUDA-event stopwatch on the library's stream; categories 0 = sweep, 1 = gram, 2 = other
+struct Timer {
+    bool enabled = true;
+    std::vector<cudaEvent_t> events;
+    std::vector<int> cats;
+    size_t used = 0;
+    void begin(cudaStream_t st, int cat);
+    void end(cudaStream_t st);
+    void collect(double ms[3]);
+    ~Timer();
+};
+
+struct DistState;   // dist.cu
+
+}  // namespace qgt
+
+struct qgt_b200_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    size_t ws_limit = 0;
+    size_t max_slots = 0;
+    qgt::PlanOptions opt;
+    qgt::DevBuf arena, img_runs, img_ops, img_subs, items, aux, partial, cmat, outbuf, edges, vweights, scratch;
+    void* pinned = nullptr;
+    QgtCostTable cost = {nullptr, 0, nullptr, 0};
+    qgt::Timer timer;
+    qgt_b200_stats stats = {};
+    // multi-GPU
+    int rank = 0, world = 1;
+    qgt::DistState* dist = nullptr;
+};
+
+struct qgt_b200_state {
+    qgt_b200_ctx* ctx = nullptr;
+    int n = 0;          // global qubits
+    int nloc = 0;       // qubits held locally (n - log2 world)
+    uint64_t D = 0;     // local amplitudes
+    cplx* d = nullptr;
+    bool owns = false;
+};
+
+namespace qgt {
+
+// executor pieces shared with dist.cu
+int upload_plan(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan& plan, PlanImage& img);
+int apply_plan_inplace(qgt_b200_ctx* c, const CircuitPlan& plan, cplx* d, uint64_t D);
+int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan& plan, const Program& prog,
+                cplx* arena, uint64_t D, cplx* cmat);
+size_t workspace_slots(qgt_b200_ctx* c, uint64_t D, size_t reserve_bytes);
+void stats_begin(qgt_b200_ctx* c);
+int stats_end(qgt_b200_ctx* c);
+
+// dist.cu
+void dist_shutdown(qgt_b200_ctx* c);
+int dist_allreduce_host(qgt_b200_ctx* c, double* v, int n);   // sum over ranks, no-op for world == 1
+int dist_apply_circuit(qgt_b200_state* s, const qgt_b200_circuit* circ, const double* theta);
+int dist_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
+             double* metric, double* berry, double* q_full, qgt_b200_state* psi_out);
+
+}  // namespace qgt

@@ -1,0 +1,53 @@
+// kernels.cuh — launch wrappers of the sm_100a kernels (definitions in kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dev_structs.h"
+#include "sweep_core.cuh"
+
+namespace qgt {
+
+struct SweepLaunch {
+    const QgtDevRun* runs;
+    const QgtDevOp* ops;
+    const QgtDevSubPass* subs;
+    int run_idx;
+    const QgtSweepItem* items;
+    int nitems;
+    uint64_t ntiles;
+    QgtCostTable ct;
+};
+
+struct GramLaunch {
+    const cplx* const* a_ptrs;   // device array of na column pointers
+    const cplx* const* b_ptrs;   // device array of nb column pointers
+    int na, nb;
+    uint64_t D;                  // amplitudes per column (local shard length)
+    int ksplit;
+    int mtiles, ntiles;
+    int symmetric;               // b list starts with the a list: tiles strictly below the diagonal are skipped
+    cplx* partial;               // [ksplit][mtiles*MT][ntiles*NT]
+};
+
+struct GramShape { int MT, NT; };
+
+// K, R: tile / register qubits of the run; grid is chosen inside
+cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int num_sms, cudaStream_t st);
+
+GramShape gram_shape(int na, int nb);
+cudaError_t launch_gram(const GramLaunch& g, GramShape shp, cudaStream_t st);
+// C[(a_ids[i]), (b_ids[j])] = sum_ks partial ; mirrored conj ; ldc = leading dimension of C
+cudaError_t launch_gram_reduce(const GramLaunch& g, GramShape shp, const int* a_ids, const int* b_ids,
+                               cplx* C, int ldc, cudaStream_t st);
+// Q = C[0:P,0:P] - v v^H with v = C[:,P];  any output may be null
+cudaError_t launch_finalize(const cplx* C, int P, double* metric, double* berry, cplx* q_full, cudaStream_t st);
+
+cudaError_t launch_init_state(cplx* dst, uint64_t D, int initial_state, double plus_amp, uint64_t global_offset, cudaStream_t st);
+cudaError_t launch_norm2(const cplx* src, uint64_t D, double* out /*device, zeroed inside*/, cudaStream_t st);
+cudaError_t launch_axpy(cplx* dst, const cplx* src, uint64_t D, double ar, double ai, cudaStream_t st);   // dst += a*src
+// expectation of the diagonal cost:  out[0] = sum |psi|^2 E ;  out2 = sum conj(a) b E  (re, im)
+cudaError_t launch_cost_dot(const cplx* a, const cplx* b, uint64_t D, QgtCostTable ct, uint64_t global_offset,
+                            double* out2 /*device, 2 doubles, zeroed inside*/, cudaStream_t st);
+
+}  // namespace qgt

@@ -1,0 +1,654 @@
+// plan.cpp — circuit lowering, commutation-aware fusion into runs / sub-passes, QGT column schedule.
+//
+// Replaces, on the host side, the per-gate loop of sim_execute_circuit
+// (reference src/quantum_geometric/hardware/quantum_simulator.c:499-533), the gate tables of
+// apply_gate_by_type (:188-283) / generate_gate_matrix (hardware/quantum_simulator_cpu.c:659-746),
+// and the per-element derivative/overlap orchestration of compute_quantum_geometric_tensor
+// (core/quantum_geometric_tensor_network.c:1058-1181) with one static schedule per QGT evaluation.
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <sstream>
+
+namespace qgt {
+
+static const double kPi = 3.14159265358979323846;
+static const double kSqrt2 = 1.41421356237309504880;  // same literal as quantum_simulator.c:36
+
+static inline void setc(double* m, int k, double re, double im) { m[2 * k] = re; m[2 * k + 1] = im; }
+static inline uint64_t bit(int q) { return (uint64_t)1 << q; }
+
+static double gate_angle(const qgt_b200_gate& g, const double* theta) {
+    return g.param >= 0 ? g.scale * theta[g.param] + g.angle : g.angle;
+}
+
+static bool is_two_qubit(int kind) {
+    switch (kind) {
+    case QGT_B200_GATE_CNOT: case QGT_B200_GATE_CY: case QGT_B200_GATE_CZ: case QGT_B200_GATE_SWAP:
+    case QGT_B200_GATE_CRX: case QGT_B200_GATE_CRY: case QGT_B200_GATE_CRZ: case QGT_B200_GATE_CH:
+    case QGT_B200_GATE_ZZ: return true;
+    default: return false;
+    }
+}
+
+static bool is_parametric(int kind) {
+    switch (kind) {
+    case QGT_B200_GATE_RX: case QGT_B200_GATE_RY: case QGT_B200_GATE_RZ: case QGT_B200_GATE_U1:
+    case QGT_B200_GATE_PHASE: case QGT_B200_GATE_CRX: case QGT_B200_GATE_CRY: case QGT_B200_GATE_CRZ:
+    case QGT_B200_GATE_ZZ: case QGT_B200_GATE_COST: return true;
+    default: return false;
+    }
+}
+
+int lower_gate(const qgt_b200_circuit& c, const double* theta, int gi, std::vector<LoweredOp>& out, std::string& err) {
+    const qgt_b200_gate& g = c.gates[gi];
+    const int n = c.num_qubits;
+    char buf[160];
+    if (g.kind != QGT_B200_GATE_COST && (g.target < 0 || g.target >= n)) {
+        snprintf(buf, sizeof buf, "gate %d: target %d out of range for %d qubits", gi, g.target, n);
+        err = buf; return QGT_B200_ERR_CIRCUIT;
+    }
+    if (is_two_qubit(g.kind) && (g.control < 0 || g.control >= n || g.control == g.target)) {
+        snprintf(buf, sizeof buf, "gate %d: control %d invalid (target %d, %d qubits)", gi, g.control, g.target, n);
+        err = buf; return QGT_B200_ERR_CIRCUIT;
+    }
+    if (g.param >= c.num_params) {
+        snprintf(buf, sizeof buf, "gate %d: parameter %d out of range (%d parameters)", gi, g.param, c.num_params);
+        err = buf; return QGT_B200_ERR_CIRCUIT;
+    }
+    if (g.param >= 0 && !is_parametric(g.kind)) {
+        snprintf(buf, sizeof buf, "gate %d: kind %d takes no parameter", gi, g.kind);
+        err = buf; return QGT_B200_ERR_CIRCUIT;
+    }
+    const double a = (theta || g.param < 0) ? gate_angle(g, theta) : g.angle;
+    const double s = g.scale;
+    const double cs = std::cos(a / 2.0), sn = std::sin(a / 2.0);
+    LoweredOp op;
+    op.gate = gi;
+    op.param = g.param;
+    op.target = g.target;
+    const uint64_t cb = is_two_qubit(g.kind) ? bit(g.control) : 0;
+
+    auto diag = [&](double d0r, double d0i, double d1r, double d1i) {
+        op.type = QGT_OP_DIAG; op.target = -1; op.pmask = bit(g.target);
+        setc(op.m, 0, d0r, d0i); setc(op.m, 1, d1r, d1i);
+    };
+    auto rz_like = [&]() {   // d0 = e^{-ia/2}, d1 = e^{+ia/2}; derivative -i/2 d0, +i/2 d1 (times scale)
+        setc(op.m, 0, cs, -sn); setc(op.m, 1, cs, sn);
+        setc(op.dm, 0, -0.5 * s * sn, -0.5 * s * cs); setc(op.dm, 1, -0.5 * s * sn, 0.5 * s * cs);
+    };
+
+    switch (g.kind) {
+    case QGT_B200_GATE_I: return QGT_B200_OK;
+    case QGT_B200_GATE_X: op.type = QGT_OP_PERM; break;
+    case QGT_B200_GATE_CNOT: op.type = QGT_OP_PERM; op.cmask = cb; break;
+    case QGT_B200_GATE_Y:
+    case QGT_B200_GATE_CY:
+        op.type = QGT_OP_U; op.cmask = cb;
+        setc(op.m, 0, 0, 0); setc(op.m, 1, 0, -1); setc(op.m, 2, 0, 1); setc(op.m, 3, 0, 0); break;
+    case QGT_B200_GATE_Z: diag(1, 0, -1, 0); break;
+    case QGT_B200_GATE_CZ: diag(1, 0, -1, 0); op.cmask = cb; break;
+    case QGT_B200_GATE_H:
+    case QGT_B200_GATE_CH: {
+        const double h = 1.0 / kSqrt2;
+        op.type = QGT_OP_UREAL; op.cmask = cb;
+        setc(op.m, 0, h, 0); setc(op.m, 1, h, 0); setc(op.m, 2, h, 0); setc(op.m, 3, -1.0 / kSqrt2, 0); break; }
+    case QGT_B200_GATE_S: diag(1, 0, 0, 1); break;
+    case QGT_B200_GATE_SDG: diag(1, 0, 0, -1); break;
+    case QGT_B200_GATE_T: diag(1, 0, std::cos(kPi / 4.0), std::sin(kPi / 4.0)); break;
+    case QGT_B200_GATE_TDG: diag(1, 0, std::cos(kPi / 4.0), -std::sin(kPi / 4.0)); break;
+    case QGT_B200_GATE_SX:
+        op.type = QGT_OP_U;
+        setc(op.m, 0, 0.5, 0.5); setc(op.m, 1, 0.5, -0.5); setc(op.m, 2, 0.5, -0.5); setc(op.m, 3, 0.5, 0.5); break;
+    case QGT_B200_GATE_RX:
+    case QGT_B200_GATE_CRX:
+        op.type = QGT_OP_URX; op.cmask = cb;
+        setc(op.m, 0, cs, 0); setc(op.m, 1, 0, -sn); setc(op.m, 2, 0, -sn); setc(op.m, 3, cs, 0);
+        setc(op.dm, 0, -0.5 * s * sn, 0); setc(op.dm, 1, 0, -0.5 * s * cs);
+        setc(op.dm, 2, 0, -0.5 * s * cs); setc(op.dm, 3, -0.5 * s * sn, 0);
+        break;
+    case QGT_B200_GATE_RY:
+    case QGT_B200_GATE_CRY:
+        op.type = QGT_OP_UREAL; op.cmask = cb;
+        setc(op.m, 0, cs, 0); setc(op.m, 1, -sn, 0); setc(op.m, 2, sn, 0); setc(op.m, 3, cs, 0);
+        setc(op.dm, 0, -0.5 * s * sn, 0); setc(op.dm, 1, -0.5 * s * cs, 0);
+        setc(op.dm, 2, 0.5 * s * cs, 0); setc(op.dm, 3, -0.5 * s * sn, 0);
+        break;
+    case QGT_B200_GATE_RZ:
+    case QGT_B200_GATE_CRZ:
+        op.type = QGT_OP_DIAG; op.target = -1; op.pmask = bit(g.target); op.cmask = cb;
+        rz_like(); break;
+    case QGT_B200_GATE_ZZ:
+        op.type = QGT_OP_DIAG; op.target = -1; op.pmask = bit(g.target) | bit(g.control);
+        rz_like(); break;
+    case QGT_B200_GATE_U1:
+    case QGT_B200_GATE_PHASE:
+        diag(1, 0, std::cos(a), std::sin(a));
+        setc(op.dm, 0, 0, 0); setc(op.dm, 1, -s * std::sin(a), s * std::cos(a)); break;
+    case QGT_B200_GATE_SWAP: {   // three CNOTs, quantum_simulator.c:269-275
+        LoweredOp p1 = op; p1.type = QGT_OP_PERM; p1.target = g.target; p1.cmask = bit(g.control);
+        LoweredOp p2 = op; p2.type = QGT_OP_PERM; p2.target = g.control; p2.cmask = bit(g.target);
+        out.push_back(p1); out.push_back(p2); out.push_back(p1);
+        return QGT_B200_OK; }
+    case QGT_B200_GATE_COST:
+        op.type = QGT_OP_COST; op.target = -1;
+        op.m[0] = a; op.m[1] = 0; op.dm[0] = a; op.dm[1] = s; op.dflags = QGT_FLAG_COST_DERIV; break;
+    default:
+        snprintf(buf, sizeof buf, "gate %d: unsupported kind %d", gi, g.kind);
+        err = buf; return QGT_B200_ERR_UNSUPPORTED;
+    }
+    if (g.kind == QGT_B200_GATE_CRX || g.kind == QGT_B200_GATE_CRY || g.kind == QGT_B200_GATE_CRZ)
+        op.dflags |= QGT_FLAG_ZERO_CTRL_FAIL;
+    out.push_back(op);
+    return QGT_B200_OK;
+}
+
+// ---- fusion into runs ------------------------------------------------------------------------
+namespace {
+
+struct Dag {
+    std::vector<std::vector<int>> succ;
+    std::vector<int> indeg;
+};
+
+uint64_t diag_qubits(const LoweredOp& op, int n) {
+    if (op.type == QGT_OP_COST) return n >= 64 ? ~0ull : (bit(n) - 1);
+    return op.cmask | op.pmask;
+}
+
+Dag build_dag(const std::vector<LoweredOp>& ops, int n) {
+    Dag d;
+    const int N = (int)ops.size();
+    d.succ.assign(N, {});
+    d.indeg.assign(N, 0);
+    std::vector<int> last_nd(n, -1);
+    std::vector<std::vector<int>> diag_since(n);
+    std::vector<std::set<int>> preds(N);
+    for (int i = 0; i < N; i++) {
+        const uint64_t dq = diag_qubits(ops[i], n);
+        for (int q = 0; q < n; q++) {
+            if (!(dq >> q & 1)) continue;
+            if (last_nd[q] >= 0) preds[i].insert(last_nd[q]);
+            diag_since[q].push_back(i);
+        }
+        if (ops[i].target >= 0) {
+            const int q = ops[i].target;
+            if (last_nd[q] >= 0) preds[i].insert(last_nd[q]);
+            for (int j : diag_since[q]) if (j != i) preds[i].insert(j);
+            last_nd[q] = i;
+            diag_since[q].clear();
+        }
+    }
+    for (int i = 0; i < N; i++)
+        for (int p : preds[i]) { d.succ[p].push_back(i); d.indeg[i]++; }
+    return d;
+}
+
+void make_tperm(int K, const std::vector<int>& reg_local, std::vector<int>& tperm) {
+    std::vector<char> is_reg(K, 0);
+    for (int r : reg_local) is_reg[r] = 1;
+    std::vector<int> freep;
+    for (int p = 0; p < K; p++) if (!is_reg[p]) freep.push_back(p);
+    // the shared-memory swizzle XORs bit p of the index into bank-group bit (p mod 3): give the three
+    // lowest thread bits positions with distinct residues so a quarter-warp hits 8 distinct 16-byte groups
+    int pick[3] = {-1, -1, -1};
+    for (int p : freep) if (pick[p % 3] < 0) pick[p % 3] = p;
+    tperm.clear();
+    if (pick[0] >= 0 && pick[1] >= 0 && pick[2] >= 0) {
+        std::vector<int> first = {pick[0], pick[1], pick[2]};
+        std::sort(first.begin(), first.end());
+        for (int p : first) tperm.push_back(p);
+        for (int p : freep) if (p != pick[0] && p != pick[1] && p != pick[2]) tperm.push_back(p);
+    } else {
+        tperm = freep;
+    }
+}
+
+}  // namespace
+
+int find_subpass(const Run& run, int op_index) {
+    for (size_t s = 0; s < run.subs.size(); s++)
+        if (op_index >= run.subs[s].op_begin && op_index < run.subs[s].op_end) return (int)s;
+    return -1;
+}
+
+QgtDevOp bind_op(const Run& run, const SubPass& sp, const LoweredOp& op, bool derivative) {
+    QgtDevOp d;
+    std::memset(&d, 0, sizeof d);
+    d.type = op.type;
+    d.flags = derivative ? op.dflags : op.flags;
+    std::memcpy(d.m, derivative ? op.dm : op.m, sizeof d.m);
+    uint64_t regmask_global = 0;
+    for (size_t r = 0; r < sp.reg_local.size(); r++) regmask_global |= bit(run.tile_qubits[sp.reg_local[r]]);
+    d.tbit = -1;
+    for (size_t r = 0; r < sp.reg_local.size(); r++) {
+        const int gq = run.tile_qubits[sp.reg_local[r]];
+        if (op.target == gq) d.tbit = (int)r;
+        if (op.cmask >> gq & 1) d.creg |= 1u << r;
+        if (op.pmask >> gq & 1) d.preg |= 1u << r;
+    }
+    d.cmask = op.cmask & ~regmask_global;
+    d.pmask = op.pmask & ~regmask_global;
+    return d;
+}
+
+int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions& opt_in, CircuitPlan& plan, std::string& err) {
+    const int n = c.num_qubits;
+    if (n < 1 || n > QGT_MAX_QUBITS) { err = "num_qubits out of range"; return QGT_B200_ERR_INVALID_ARG; }
+    if (c.num_gates && !c.gates) { err = "gates is NULL"; return QGT_B200_ERR_INVALID_ARG; }
+    PlanOptions opt = opt_in;
+    opt.tile_qubits = std::max(opt.reg_qubits + 2, std::min(opt.tile_qubits, (int)QGT_MAX_TILE_QUBITS));
+    const int K = std::min(n, opt.tile_qubits);
+    const int R = std::min(opt.reg_qubits, K);
+    // the forced low qubits must leave room for at least R freely chosen tile qubits
+    const int L = (K == n) ? K : std::max(0, std::min(opt.low_qubits, K - R));
+    plan = CircuitPlan();
+    plan.n = n; plan.P = c.num_params; plan.opt = opt;
+    plan.first_run.assign(std::max(0, c.num_params), -1);
+    plan.last_run.assign(std::max(0, c.num_params), -1);
+
+    std::vector<LoweredOp> ops;
+    for (size_t g = 0; g < c.num_gates; g++) {
+        int rc = lower_gate(c, theta, (int)g, ops, err);
+        if (rc) return rc;
+    }
+    const int N = (int)ops.size();
+    Dag dag = build_dag(ops, n);
+    std::vector<char> done(N, 0);
+    std::vector<int> ready;
+    for (int i = 0; i < N; i++) if (dag.indeg[i] == 0) ready.push_back(i);
+    int scheduled = 0;
+
+    while (scheduled < N) {
+        Run run;
+        run.K = K;
+        std::vector<char> inS(n, 0);
+        int sizeS = 0;
+        for (int q = 0; q < L; q++) { inS[q] = 1; sizeS++; }
+        if (K == n) { for (int q = 0; q < n; q++) inS[q] = 1; sizeS = n; }
+        struct RawSub { std::vector<int> regq; int b, e; };
+        std::vector<RawSub> raw;
+        bool run_full = false;
+        while (!run_full) {
+            RawSub sp; sp.b = (int)run.ops.size();
+            std::vector<char> inR(n, 0);
+            int sizeR = 0;
+            for (;;) {
+                if ((int)run.ops.size() >= opt.max_ops_per_run) { run_full = true; break; }
+                int best = -1, best_pri = 99;
+                for (int i : ready) {
+                    const LoweredOp& o = ops[i];
+                    int pri;
+                    if (o.target < 0) pri = 0;
+                    else if (inR[o.target]) pri = 0;
+                    else if (sizeR < R && inS[o.target]) pri = 1;
+                    else if (sizeR < R && sizeS < K) pri = 2;
+                    else continue;
+                    if (pri < best_pri || (pri == best_pri && i < best)) { best = i; best_pri = pri; }
+                }
+                if (best < 0) break;
+                const LoweredOp& o = ops[best];
+                if (o.target >= 0) {
+                    if (!inS[o.target]) { inS[o.target] = 1; sizeS++; }
+                    if (!inR[o.target]) { inR[o.target] = 1; sizeR++; sp.regq.push_back(o.target); }
+                }
+                run.ops.push_back(o);
+                done[best] = 1; scheduled++;
+                ready.erase(std::find(ready.begin(), ready.end(), best));
+                for (int sidx : dag.succ[best]) if (--dag.indeg[sidx] == 0) ready.push_back(sidx);
+            }
+            sp.e = (int)run.ops.size();
+            if (sp.e == sp.b) break;          // nothing fits a fresh sub-pass: the run is complete
+            raw.push_back(sp);
+        }
+        if (run.ops.empty()) { err = "planner made no progress"; return QGT_B200_ERR_INTERNAL; }
+        // pad the tile to K qubits with the lowest unused ones
+        for (int q = 0; q < n && sizeS < K; q++) if (!inS[q]) { inS[q] = 1; sizeS++; }
+        for (int q = 0; q < n; q++) (inS[q] ? run.tile_qubits : run.other_qubits).push_back(q);
+        std::vector<int> local_of(n, -1);
+        for (int j = 0; j < K; j++) local_of[run.tile_qubits[j]] = j;
+        for (const RawSub& rs : raw) {
+            SubPass sp;
+            sp.op_begin = rs.b; sp.op_end = rs.e;
+            sp.nreg_used = (int)rs.regq.size();
+            std::vector<char> used(K, 0);
+            for (int q : rs.regq) { sp.reg_local.push_back(local_of[q]); used[local_of[q]] = 1; }
+            for (int p = K - 1; p >= 0 && (int)sp.reg_local.size() < R; p--)
+                if (!used[p]) { sp.reg_local.push_back(p); used[p] = 1; }
+            std::sort(sp.reg_local.begin(), sp.reg_local.end());
+            make_tperm(K, sp.reg_local, sp.tperm);
+            run.subs.push_back(sp);
+        }
+        const int ridx = (int)plan.runs.size();
+        for (int i = 0; i < (int)run.ops.size(); i++) {
+            const int p = run.ops[i].param;
+            if (p < 0) continue;
+            run.occ.push_back({p, i});
+            if (plan.first_run[p] < 0) plan.first_run[p] = ridx;
+            plan.last_run[p] = ridx;
+        }
+        plan.runs.push_back(std::move(run));
+    }
+    return QGT_B200_OK;
+}
+
+void build_image(const CircuitPlan& plan, PlanImage& img) {
+    img = PlanImage();
+    for (const Run& run : plan.runs) {
+        QgtDevRun dr;
+        std::memset(&dr, 0, sizeof dr);
+        dr.K = run.K; dr.n = plan.n;
+        dr.nsub = (int)run.subs.size();
+        dr.nops = (int)run.ops.size();
+        dr.ops_off = (int)img.ops.size();
+        dr.sub_off = (int)img.subs.size();
+        for (int j = 0; j < run.K; j++) dr.tq[j] = (int8_t)run.tile_qubits[j];
+        for (size_t j = 0; j < run.other_qubits.size(); j++) dr.ntq[j] = (int8_t)run.other_qubits[j];
+        for (const SubPass& sp : run.subs) {
+            QgtDevSubPass ds;
+            std::memset(&ds, 0, sizeof ds);
+            ds.nreg = (int)sp.reg_local.size();
+            ds.op_begin = sp.op_begin; ds.op_end = sp.op_end;
+            for (size_t r = 0; r < sp.reg_local.size(); r++) ds.regq[r] = (int8_t)sp.reg_local[r];
+            for (size_t t = 0; t < sp.tperm.size(); t++) ds.tperm[t] = (int8_t)sp.tperm[t];
+            img.subs.push_back(ds);
+            for (int i = sp.op_begin; i < sp.op_end; i++) img.ops.push_back(bind_op(run, sp, run.ops[i], false));
+        }
+        img.runs.push_back(dr);
+    }
+}
+
+// ---- QGT column schedule ---------------------------------------------------------------------
+namespace {
+
+struct Sched {
+    const CircuitPlan& plan;
+    Program& prog;
+    int psi;                         // slot of the marching state phi
+    int ckpt;                        // slot of the rolling checkpoint (blocked mode) or -1
+    int ckpt_time = 0;               // the checkpoint holds the state BEFORE run ckpt_time
+    std::vector<int> res_slots, str_slots;
+
+    Sched(const CircuitPlan& p, Program& g) : plan(p), prog(g), psi(0), ckpt(-1) {}
+
+    void sweep(int run, const std::vector<SweepCol>& cols) {
+        if (cols.empty()) return;
+        Instr in; in.kind = INSTR_SWEEP; in.run = run; in.cols = cols;
+        prog.instrs.push_back(std::move(in));
+    }
+    void gram(const std::vector<int>& as, const std::vector<int>& aid, const std::vector<int>& bs, const std::vector<int>& bid) {
+        if (as.empty() || bs.empty()) return;
+        Instr in; in.kind = INSTR_GRAM; in.a_slots = as; in.a_ids = aid; in.b_slots = bs; in.b_ids = bid;
+        prog.instrs.push_back(std::move(in));
+    }
+    void copy(int src, int dst) { Instr in; in.kind = INSTR_COPY; in.src = src; in.dst = dst; prog.instrs.push_back(in); }
+    void init(int dst) { Instr in; in.kind = INSTR_INIT; in.dst = dst; prog.instrs.push_back(in); }
+
+    // accumulate-spawn launches: occurrences beyond the first of a parameter in one run (and every
+    // occurrence of an already alive column) write dst += ..., so no two items of a launch may share dst
+    void emit_accumulates(int run, std::vector<SweepCol>& acc) {
+        while (!acc.empty()) {
+            std::vector<SweepCol> now, later;
+            std::set<int> dsts;
+            for (const SweepCol& c : acc) (dsts.insert(c.dst).second ? now : later).push_back(c);
+            sweep(run, now);
+            acc.swap(later);
+        }
+    }
+
+    // March phi from run r0 with `resident` columns (parameters) and, per run, the streaming
+    // parameters in `streaming` (all born at or after r0).  diag: also emit the resident x resident
+    // (+psi) Gram at T_res.
+    void march(int r0, const std::vector<int>& resident, const std::vector<int>& streaming, bool diag, bool to_end) {
+        const int R = (int)plan.runs.size();
+        const int P = plan.P;
+        std::vector<int> slot_of(P, -1);
+        std::vector<char> is_res(P, 0), is_str(P, 0), alive(P, 0);
+        int T_res = r0;
+        for (size_t i = 0; i < resident.size(); i++) {
+            slot_of[resident[i]] = res_slots[i]; is_res[resident[i]] = 1;
+            T_res = std::max(T_res, plan.last_run[resident[i]]);
+        }
+        for (int p : streaming) is_str[p] = 1;
+        std::vector<int> free_str(str_slots.rbegin(), str_slots.rend());
+        size_t str_left = streaming.size();
+        bool diag_done = !diag;
+        std::vector<int> res_ids(resident.begin(), resident.end());
+        std::vector<int> res_sl;
+        for (int p : resident) res_sl.push_back(slot_of[p]);
+
+        for (int r = r0; r < R; r++) {
+            const Run& run = plan.runs[r];
+            // 1. advance every alive column; first occurrences of resident parameters born here
+            std::vector<SweepCol> A, acc;
+            std::vector<int> alive_str_now;
+            for (int p = 0; p < P; p++) if (alive[p]) { A.push_back({slot_of[p], slot_of[p], -1, false}); if (is_str[p]) alive_str_now.push_back(p); }
+            std::vector<int> born_str;
+            std::vector<char> spawned_here(P, 0);
+            for (const ParamOcc& oc : run.occ) {
+                const int p = oc.param;
+                if (is_res[p]) {
+                    if (!alive[p] && !spawned_here[p]) { A.push_back({psi, slot_of[p], oc.op, false}); spawned_here[p] = 1; }
+                    else acc.push_back({psi, slot_of[p], oc.op, true});
+                } else if (is_str[p]) {
+                    if (alive[p]) acc.push_back({psi, slot_of[p], oc.op, true});
+                    else if (!spawned_here[p]) { born_str.push_back(p); spawned_here[p] = 1; }
+                }
+            }
+            sweep(r, A);
+            emit_accumulates(r, acc);
+            for (int p = 0; p < P; p++) if (spawned_here[p] && is_res[p]) alive[p] = 1;
+
+            const bool res_complete = (r >= T_res);
+            // 2. streaming columns that were alive and are ready now
+            if (res_complete) {
+                std::vector<int> bs, bid;
+                for (int p : alive_str_now)
+                    if (plan.last_run[p] <= r) { bs.push_back(slot_of[p]); bid.push_back(p); }
+                if (!bs.empty()) {
+                    gram(res_sl, res_ids, bs, bid);
+                    for (int p : bid) { alive[p] = 0; free_str.push_back(slot_of[p]); slot_of[p] = -1; str_left--; }
+                }
+            }
+            // 3. streaming parameters born in this run, in rounds of the free slots
+            size_t bi = 0;
+            // persistent ones first (they keep their slot beyond this run)
+            std::stable_sort(born_str.begin(), born_str.end(), [&](int x, int y) {
+                const bool px = !(res_complete && plan.last_run[x] <= r), py = !(res_complete && plan.last_run[y] <= r);
+                return px > py;
+            });
+            while (bi < born_str.size()) {
+                std::vector<SweepCol> S, sacc;
+                std::vector<int> round;
+                while (bi < born_str.size() && !free_str.empty()) {
+                    const int p = born_str[bi++];
+                    slot_of[p] = free_str.back(); free_str.pop_back();
+                    round.push_back(p);
+                    bool first = true;
+                    for (const ParamOcc& oc : run.occ) {
+                        if (oc.param != p) continue;
+                        if (first) { S.push_back({psi, slot_of[p], oc.op, false}); first = false; }
+                        else sacc.push_back({psi, slot_of[p], oc.op, true});
+                    }
+                }
+                sweep(r, S);
+                emit_accumulates(r, sacc);
+                std::vector<int> bs, bid;
+                for (int p : round) {
+                    if (res_complete && plan.last_run[p] <= r) { bs.push_back(slot_of[p]); bid.push_back(p); }
+                    else alive[p] = 1;
+                }
+                if (!bs.empty()) {
+                    gram(res_sl, res_ids, bs, bid);
+                    for (int p : bid) { free_str.push_back(slot_of[p]); slot_of[p] = -1; str_left--; }
+                }
+                if (round.empty()) break;   // no free slot at all: select_fit() prevents this
+            }
+            // 4. phi itself
+            sweep(r, {{psi, psi, -1, false}});
+            // 5. resident x (resident, psi) at the first time every resident column is complete
+            if (!diag_done && res_complete) {
+                std::vector<int> bs = res_sl, bid = res_ids;
+                bs.push_back(psi); bid.push_back(P);
+                gram(res_sl, res_ids, bs, bid);
+                diag_done = true;
+            }
+            if (diag_done && str_left == 0 && !to_end) return;
+        }
+    }
+};
+
+// choose the streaming parameters one march can serve with c slots; the rest waits for another pass
+void select_fit(const CircuitPlan& plan, const std::vector<int>& pending, int c, int T_res,
+                std::vector<int>& take, std::vector<int>& rest) {
+    const int R = (int)plan.runs.size();
+    std::vector<int> occ(R + 1, 0);
+    take.clear(); rest.clear();
+    for (int p : pending) {
+        const int f = plan.first_run[p];
+        const int ready = std::max(plan.last_run[p], T_res);
+        if (ready == f) { take.push_back(p); continue; }     // transient: uses the reserved slot
+        bool ok = true;
+        for (int r = f; r <= ready; r++) if (occ[r] >= c - 1) { ok = false; break; }
+        if (ok) { for (int r = f; r <= ready; r++) occ[r]++; take.push_back(p); }
+        else rest.push_back(p);
+    }
+    if (take.empty() && !rest.empty()) { take.push_back(rest.front()); rest.erase(rest.begin()); }
+}
+
+}  // namespace
+
+int build_qgt_program(const CircuitPlan& plan, size_t total_slots, bool want_psi, Program& prog, std::string& err) {
+    prog = Program();
+    const int P = plan.P;
+    const int R = (int)plan.runs.size();
+    std::vector<int> ord;
+    for (int p = 0; p < P; p++) if (plan.first_run[p] >= 0) ord.push_back(p);
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return plan.first_run[a] < plan.first_run[b]; });
+    const int Pa = (int)ord.size();
+
+    Sched s(plan, prog);
+    int b, c;
+    if ((size_t)Pa + 1 <= total_slots) { b = Pa; c = 0; }
+    else {
+        if (total_slots < 5) { err = "workspace too small: need at least 5 statevector-sized columns"; return QGT_B200_ERR_NO_MEMORY; }
+        const int avail = (int)total_slots - 2;             // phi + rolling checkpoint
+        c = std::max(2, std::min(avail / 3, 16));
+        b = avail - c;
+    }
+    const bool blocked = (c > 0);
+    int next = 0;
+    s.psi = next++;
+    if (blocked) s.ckpt = next++;
+    for (int i = 0; i < b; i++) s.res_slots.push_back(next++);
+    for (int i = 0; i < c; i++) s.str_slots.push_back(next++);
+    prog.num_slots = next; prog.psi_slot = s.psi; prog.resident = b; prog.streaming = c;
+
+    if (!blocked) {
+        s.init(s.psi);
+        prog.blocks = Pa ? 1 : 0;
+        s.march(0, ord, {}, true, want_psi);
+        if (Pa == 0 && want_psi) for (int r = 0; r < R; r++) s.sweep(r, {{s.psi, s.psi, -1, false}});
+        prog.psi_final = want_psi;
+        return QGT_B200_OK;
+    }
+    s.init(s.ckpt);
+    s.ckpt_time = 0;
+    for (int lo = 0; lo < Pa; lo += b) {
+        const int hi = std::min(Pa, lo + b);
+        std::vector<int> resident(ord.begin() + lo, ord.begin() + hi);
+        std::vector<int> pending(ord.begin() + hi, ord.end());
+        const int r0 = plan.first_run[resident.front()];
+        int T_res = r0;
+        for (int p : resident) T_res = std::max(T_res, plan.last_run[p]);
+        while (s.ckpt_time < r0) { s.sweep(s.ckpt_time, {{s.ckpt, s.ckpt, -1, false}}); s.ckpt_time++; }
+        bool first_pass = true;
+        do {
+            std::vector<int> take, rest;
+            select_fit(plan, pending, c, T_res, take, rest);
+            s.copy(s.ckpt, s.psi);
+            s.march(r0, resident, take, first_pass, false);
+            pending.swap(rest);
+            first_pass = false;
+        } while (!pending.empty());
+        prog.blocks++;
+    }
+    if (want_psi) {
+        while (s.ckpt_time < R) { s.sweep(s.ckpt_time, {{s.ckpt, s.ckpt, -1, false}}); s.ckpt_time++; }
+        s.copy(s.ckpt, s.psi);
+        prog.psi_final = true;
+    }
+    return QGT_B200_OK;
+}
+
+// ---- JSON dump (tests interpret this on the CPU) ------------------------------------------------
+static void jarr(std::ostringstream& o, const std::vector<int>& v) {
+    o << "[";
+    for (size_t i = 0; i < v.size(); i++) o << (i ? "," : "") << v[i];
+    o << "]";
+}
+
+static void jop(std::ostringstream& o, const LoweredOp& op, bool deriv) {
+    char b[64];
+    o << "{\"type\":" << op.type << ",\"target\":" << op.target << ",\"cmask\":" << op.cmask
+      << ",\"pmask\":" << op.pmask << ",\"flags\":" << (deriv ? op.dflags : op.flags) << ",\"gate\":" << op.gate
+      << ",\"param\":" << op.param << ",\"m\":[";
+    const double* m = deriv ? op.dm : op.m;
+    for (int i = 0; i < 8; i++) { snprintf(b, sizeof b, "%.17g", m[i]); o << (i ? "," : "") << b; }
+    o << "]}";
+}
+
+std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const Program* prog) {
+    std::ostringstream o;
+    o << "{\"n\":" << plan.n << ",\"P\":" << plan.P << ",\"K\":" << (plan.runs.empty() ? 0 : plan.runs[0].K)
+      << ",\"initial_state\":" << c.initial_state << ",\"runs\":[";
+    for (size_t r = 0; r < plan.runs.size(); r++) {
+        const Run& run = plan.runs[r];
+        o << (r ? "," : "") << "{\"tile\":"; jarr(o, run.tile_qubits);
+        o << ",\"subs\":[";
+        for (size_t s = 0; s < run.subs.size(); s++) {
+            const SubPass& sp = run.subs[s];
+            o << (s ? "," : "") << "{\"reg\":"; jarr(o, sp.reg_local);
+            o << ",\"tperm\":"; jarr(o, sp.tperm);
+            o << ",\"ops\":[" << sp.op_begin << "," << sp.op_end << "]}";
+        }
+        o << "],\"ops\":[";
+        for (size_t i = 0; i < run.ops.size(); i++) { o << (i ? "," : ""); jop(o, run.ops[i], false); }
+        o << "],\"dops\":{";
+        bool firstd = true;
+        for (const ParamOcc& oc : run.occ) { o << (firstd ? "" : ",") << "\"" << oc.op << "\":"; jop(o, run.ops[oc.op], true); firstd = false; }
+        o << "}}";
+    }
+    o << "]";
+    if (prog) {
+        o << ",\"program\":{\"slots\":" << prog->num_slots << ",\"psi\":" << prog->psi_slot << ",\"resident\":" << prog->resident
+          << ",\"streaming\":" << prog->streaming << ",\"blocks\":" << prog->blocks << ",\"psi_final\":" << (prog->psi_final ? 1 : 0)
+          << ",\"instrs\":[";
+        for (size_t i = 0; i < prog->instrs.size(); i++) {
+            const Instr& in = prog->instrs[i];
+            o << (i ? "," : "");
+            if (in.kind == INSTR_SWEEP) {
+                o << "{\"k\":\"sweep\",\"run\":" << in.run << ",\"cols\":[";
+                for (size_t j = 0; j < in.cols.size(); j++)
+                    o << (j ? "," : "") << "[" << in.cols[j].src << "," << in.cols[j].dst << "," << in.cols[j].ovr_op << "," << (in.cols[j].accumulate ? 1 : 0) << "]";
+                o << "]}";
+            } else if (in.kind == INSTR_GRAM) {
+                o << "{\"k\":\"gram\",\"a\":"; jarr(o, in.a_slots); o << ",\"aid\":"; jarr(o, in.a_ids);
+                o << ",\"b\":"; jarr(o, in.b_slots); o << ",\"bid\":"; jarr(o, in.b_ids); o << "}";
+            } else if (in.kind == INSTR_COPY) {
+                o << "{\"k\":\"copy\",\"src\":" << in.src << ",\"dst\":" << in.dst << "}";
+            } else {
+                o << "{\"k\":\"init\",\"dst\":" << in.dst << "}";
+            }
+        }
+        o << "]}";
+    }
+    o << "}";
+    return o.str();
+}
+
+}  // namespace qgt

@@ -1,0 +1,127 @@
+"""numpy interpreter of the planner's JSON dump (qgt_b200_plan_dump).   TEST INFRASTRUCTURE ONLY.
+
+Executes the fused-run plan and the column schedule exactly as the CUDA executor would (same op
+order, same derivative overrides, same Gram calls) so the host-side planning logic can be checked
+against the oracle without a GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _cost_energy(circ, idx):
+    e = np.zeros(idx.shape, dtype=np.float64)
+    for (i, j, w) in circ.edges:
+        e += w * (((idx >> i) ^ (idx >> j)) & 1)
+    if circ.vertex_weights is not None:
+        for q in range(circ.num_qubits):
+            e += circ.vertex_weights[q] * (1 - 2 * ((idx >> q) & 1))
+    return e
+
+
+def apply_op(state: np.ndarray, op: dict, circ) -> np.ndarray:
+    n = circ.num_qubits
+    idx = np.arange(1 << n, dtype=np.uint64)
+    cm = np.uint64(op["cmask"])
+    ctrl_ok = (idx & cm) == cm
+    m = np.array(op["m"], dtype=np.float64)
+    t = op["type"]
+    out = state.copy()
+    zero_fail = bool(op["flags"] & 1)
+    if t in (0, 1, 2, 3):
+        tb = np.uint64(1) << np.uint64(op["target"])
+        lo = (idx & tb) == 0
+        i0 = idx[lo & ctrl_ok]
+        i1 = i0 | tb
+        a0, a1 = state[i0], state[i1]
+        if t == 3:
+            out[i0], out[i1] = a1, a0
+        else:
+            M = (m[0::2] + 1j * m[1::2]).reshape(2, 2)
+            out[i0] = M[0, 0] * a0 + M[0, 1] * a1
+            out[i1] = M[1, 0] * a0 + M[1, 1] * a1
+        if zero_fail:
+            out[~ctrl_ok] = 0
+    elif t == 4:
+        pm = np.uint64(op["pmask"])
+        par = np.zeros(idx.shape, dtype=np.uint64)
+        v = idx & pm
+        for b in range(n):
+            par ^= (v >> np.uint64(b)) & np.uint64(1)
+        d = np.where(par == 1, m[2] + 1j * m[3], m[0] + 1j * m[1])
+        out = np.where(ctrl_ok, state * d, 0 if zero_fail else state)
+    elif t == 5:
+        e = _cost_energy(circ, idx.astype(np.int64))
+        out = state * np.exp(-1j * m[0] * e)
+        if op["flags"] & 2:
+            out = out * (-1j * m[1] * e)
+    else:
+        raise ValueError(t)
+    return out
+
+
+def run_sweep(plan: dict, run_idx: int, src: np.ndarray, ovr: int, circ) -> np.ndarray:
+    run = plan["runs"][run_idx]
+    v = src
+    for i, op in enumerate(run["ops"]):
+        v = apply_op(v, run["dops"][str(i)] if i == ovr else op, circ)
+    return v
+
+
+def initial_state(circ) -> np.ndarray:
+    dim = 1 << circ.num_qubits
+    if circ.initial_state == 1:
+        return np.full(dim, 1.0 / np.sqrt(dim), dtype=np.complex128)
+    v = np.zeros(dim, dtype=np.complex128)
+    v[0] = 1
+    return v
+
+
+def apply_plan(plan: dict, circ, state: np.ndarray) -> np.ndarray:
+    for r in range(len(plan["runs"])):
+        state = run_sweep(plan, r, state, -1, circ)
+    return state
+
+
+def run_program(plan: dict, circ):
+    """Returns (Q, psi or None, counters)."""
+    prog = plan["program"]
+    P = plan["P"]
+    dim = 1 << circ.num_qubits
+    slots = [np.zeros(dim, dtype=np.complex128) for _ in range(prog["slots"])]
+    Cm = np.zeros((P + 1, P + 1), dtype=np.complex128)
+    seen = np.zeros((P + 1, P + 1), dtype=np.int32)
+    counters = {"sweep_cols": 0, "gram_pairs": 0, "launches": 0}
+    for ins in prog["instrs"]:
+        k = ins["k"]
+        if k == "init":
+            slots[ins["dst"]] = initial_state(circ)
+        elif k == "copy":
+            slots[ins["dst"]] = slots[ins["src"]].copy()
+        elif k == "sweep":
+            counters["launches"] += 1
+            dsts = [c[1] for c in ins["cols"]]
+            assert len(set(dsts)) == len(dsts), "two items of one launch share a destination"
+            srcs_oop = {c[0] for c in ins["cols"] if c[0] != c[1]}
+            assert not (srcs_oop & set(dsts)), "a launch reads a column another item of it writes"
+            results = []
+            for (src, dst, ovr, acc) in ins["cols"]:
+                results.append((dst, acc, run_sweep(plan, ins["run"], slots[src], ovr, circ)))
+                counters["sweep_cols"] += 1
+            for dst, acc, v in results:
+                slots[dst] = slots[dst] + v if acc else v
+        elif k == "gram":
+            for sa, ia in zip(ins["a"], ins["aid"]):
+                for sb, ib in zip(ins["b"], ins["bid"]):
+                    val = np.vdot(slots[sa], slots[sb])
+                    Cm[ia, ib] = val
+                    Cm[ib, ia] = np.conj(val)
+                    seen[ia, ib] += 1
+                    seen[ib, ia] += 1
+                    counters["gram_pairs"] += 1
+        else:
+            raise ValueError(k)
+    v = Cm[:P, P]
+    Q = Cm[:P, :P] - np.outer(v, v.conj())
+    psi = slots[prog["psi"]] if prog["psi_final"] else None
+    return Q, psi, counters, seen

@@ -1,0 +1,164 @@
+"""CPU tests of the host-side planner (fusion into runs, derivative overrides, column schedule) and of
+the sweep kernel's index arithmetic through the host emulation.  No GPU needed."""
+import numpy as np
+import pytest
+
+from quantum_geometric_tensor_b200 import api, circuits as K
+
+import emul_lib
+import plan_interp as pi
+
+ALL_KINDS = [K.X, K.Y, K.Z, K.H, K.S, K.T, K.SDG, K.TDG, K.SX, K.RX, K.RY, K.RZ, K.PHASE, K.CNOT, K.CY, K.CZ,
+             K.CH, K.SWAP, K.CRX, K.CRY, K.CRZ, K.ZZ]
+
+
+def _run_program_emulated(plan, circ, theta, Kt, R):
+    """Same as plan_interp.run_program but every sweep item goes through the emulated CUDA kernel."""
+    prog = plan["program"]
+    P = plan["P"]
+    dim = 1 << circ.num_qubits
+    slots = [np.zeros(dim, dtype=np.complex128) for _ in range(prog["slots"])]
+    Cm = np.zeros((P + 1, P + 1), dtype=np.complex128)
+    for ins in prog["instrs"]:
+        k = ins["k"]
+        if k == "init":
+            slots[ins["dst"]] = pi.initial_state(circ)
+        elif k == "copy":
+            slots[ins["dst"]] = slots[ins["src"]].copy()
+        elif k == "sweep":
+            res = [(dst, emul_lib.sweep(circ, theta, Kt, R, ins["run"], slots[src], ovr, slots[dst], bool(acc)))
+                   for (src, dst, ovr, acc) in ins["cols"]]
+            for dst, v in res:
+                slots[dst] = v
+        else:
+            for sa, ia in zip(ins["a"], ins["aid"]):
+                for sb, ib in zip(ins["b"], ins["bid"]):
+                    val = np.vdot(slots[sa], slots[sb])
+                    Cm[ia, ib] = val
+                    Cm[ib, ia] = np.conj(val)
+    v = Cm[:P, P]
+    return Cm[:P, :P] - np.outer(v, v.conj()), slots[prog["psi"]]
+
+
+@pytest.mark.parametrize("n,layers,Kt,R", [(5, 2, 4, 2), (6, 1, 5, 3), (7, 2, 11, 3), (3, 2, 11, 3), (8, 1, 6, 3)])
+def test_plan_forward_matches_oracle(oracle, n, layers, Kt, R):
+    c = K.hea_layers(n, layers)
+    th = K.default_angles(c.num_params)
+    plan = api.plan_dump(c, th, tile_qubits=Kt, reg_qubits=R)
+    psi = pi.apply_plan(plan, c, pi.initial_state(c))
+    assert np.abs(psi - oracle.apply(c, th)).max() < 1e-14
+    # every gate is scheduled exactly once
+    gates = sorted(op["gate"] for r in plan["runs"] for op in r["ops"])
+    assert gates == list(range(len(c.gates)))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_plan_random_circuits_all_kinds(oracle, seed):
+    n = 2 + seed % 5
+    c = K.random_circuit(n, 30 + 5 * seed, seed, kinds=ALL_KINDS, share_params=True)
+    th = K.default_angles(max(1, c.num_params), seed + 1)
+    plan = api.plan_dump(c, th, tile_qubits=max(3, n - 1), reg_qubits=2, column_slots=256)
+    Q, psi, _, seen = pi.run_program(plan, c)
+    assert np.abs(psi - oracle.apply(c, th)).max() < 1e-13
+    assert np.abs(Q - oracle.qgt(c, th)).max() < 1e-12
+
+
+@pytest.mark.parametrize("slots", [5, 6, 7, 9, 13, 40])
+def test_blocked_schedule_covers_every_pair(oracle, slots):
+    c = K.hea_layers(5, 2)
+    th = K.default_angles(c.num_params)
+    plan = api.plan_dump(c, th, tile_qubits=4, reg_qubits=2, column_slots=slots)
+    Q, psi, cnt, seen = pi.run_program(plan, c)
+    P = c.num_params
+    assert seen[:P, :P].min() >= 1, "a (mu, nu) pair was never computed"
+    assert seen[:P, P].min() >= 1, "a projection <d_mu psi|psi> was never computed"
+    assert np.abs(Q - oracle.qgt(c, th)).max() < 1e-13
+    assert np.abs(psi - oracle.apply(c, th)).max() < 1e-14
+
+
+@pytest.mark.parametrize("slots", [5, 8, 64])
+def test_shared_parameters_and_qaoa_schedule(oracle, slots):
+    c = K.qaoa_maxcut(6, 3)
+    th = K.default_angles(c.num_params, 11)
+    plan = api.plan_dump(c, th, tile_qubits=4, reg_qubits=2, column_slots=slots)
+    Q, psi, cnt, seen = pi.run_program(plan, c)
+    assert np.abs(Q - oracle.qgt(c, th)).max() < 1e-12
+    assert np.abs(psi - oracle.apply(c, th)).max() < 1e-13
+
+
+@pytest.mark.parametrize("slots", [5, 7, 64])
+def test_long_lived_shared_parameters_multi_pass(oracle, slots):
+    # parameters reused far apart in the circuit: streaming columns stay alive across many runs
+    n = 5
+    c = K.Circuit(n)
+    for rep in range(3):
+        for q in range(n):
+            c.add(K.RY, q, -1, q, 0.1 * rep, 1.0 + 0.5 * rep)
+        for q in range(n - 1):
+            c.add(K.CNOT, q + 1, q)
+        for q in range(n):
+            c.add(K.RZ, q, -1, n + q, 0.0, 1.0)
+    th = K.default_angles(c.num_params, 5)
+    plan = api.plan_dump(c, th, tile_qubits=4, reg_qubits=2, column_slots=slots)
+    Q, psi, cnt, seen = pi.run_program(plan, c)
+    assert seen[:c.num_params, :c.num_params].min() >= 1
+    assert np.abs(Q - oracle.qgt(c, th)).max() < 1e-12
+
+
+@pytest.mark.parametrize("n,Kt,R", [(1, 11, 3), (2, 11, 3), (3, 11, 3), (4, 11, 3), (6, 5, 3), (7, 6, 2), (9, 8, 3), (10, 11, 3), (12, 11, 3), (12, 9, 3)])
+def test_emulated_kernel_forward(oracle, n, Kt, R):
+    c = K.random_circuit(n, 40, 100 + n, kinds=ALL_KINDS if n > 1 else [K.X, K.Y, K.H, K.RX, K.RZ, K.T, K.SX])
+    th = K.default_angles(max(1, c.num_params), 3)
+    nruns = emul_lib.load().emul_num_runs(c.to_c(), th.ctypes.data_as(emul_lib._DP), Kt, R)
+    assert nruns >= 1
+    v = pi.initial_state(c)
+    for r in range(nruns):
+        v = emul_lib.sweep(c, th, Kt, R, r, v)
+    assert np.abs(v - oracle.apply(c, th)).max() < 1e-13
+
+
+@pytest.mark.parametrize("seed,slots", [(0, 64), (1, 6), (2, 9), (3, 64)])
+def test_emulated_kernel_full_qgt(oracle, seed, slots):
+    n = 5 + seed % 3
+    kinds = ALL_KINDS
+    c = K.random_circuit(n, 36, 40 + seed, kinds=kinds, share_params=(seed % 2 == 1))
+    th = K.default_angles(max(1, c.num_params), seed)
+    Kt, R = 4 + seed % 2, 2 + seed % 2
+    plan = api.plan_dump(c, th, tile_qubits=Kt, reg_qubits=R, column_slots=slots)
+    Q, psi = _run_program_emulated(plan, c, th, Kt, R)
+    assert np.abs(psi - oracle.apply(c, th)).max() < 1e-13
+    assert np.abs(Q - oracle.qgt(c, th)).max() < 1e-12
+
+
+def test_emulated_kernel_qaoa_cost_and_derivative(oracle):
+    c = K.qaoa_maxcut(6, 2)
+    c.vertex_weights = [0.3, -0.2, 0.1, 0.0, 0.5, -0.4]
+    th = K.default_angles(c.num_params, 9)
+    plan = api.plan_dump(c, th, tile_qubits=5, reg_qubits=3, column_slots=32)
+    Q, psi = _run_program_emulated(plan, c, th, 5, 3)
+    assert np.abs(psi - oracle.apply(c, th)).max() < 1e-13
+    assert np.abs(Q - oracle.qgt(c, th)).max() < 1e-12
+
+
+def test_planner_rejects_bad_circuits():
+    c = K.Circuit(3)
+    c.add(K.CNOT, 1, 1)
+    with pytest.raises(api.QgtError):
+        api.plan_dump(c)
+    c = K.Circuit(3)
+    c.add(K.RX, 5, -1, 0)
+    with pytest.raises(api.QgtError):
+        api.plan_dump(c)
+    c = K.Circuit(3)
+    c.add(77, 0)
+    with pytest.raises(api.QgtError):
+        api.plan_dump(c)
+
+
+def test_fusion_depth_on_hea():
+    # the 28-qubit ansatz must fuse into a handful of sweeps per layer, not one per gate
+    c = K.hea(28, 256)
+    plan = api.plan_dump(c, K.default_angles(256))
+    assert len(plan["runs"]) <= 24, len(plan["runs"])
+    for r in plan["runs"]:
+        assert len(r["tile"]) == 11 and r["tile"][:4] == [0, 1, 2, 3]
