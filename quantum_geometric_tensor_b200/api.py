@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import weakref
 from typing import Optional, Tuple
 
 import numpy as np
@@ -126,6 +127,7 @@ class State:
         self.num_qubits = num_qubits
         self.h = C.c_void_p()
         _check(ctx.L.qgt_b200_state_create(ctx.h, num_qubits, C.byref(self.h)))
+        ctx._states.add(self)
 
     def init(self, initial_state: int = 0) -> "State":
         _check(self.ctx.L.qgt_b200_state_init(self.h, initial_state))
@@ -156,9 +158,9 @@ class State:
         return int(self.ctx.L.qgt_b200_state_device_ptr(self.h) or 0)
 
     def close(self) -> None:
-        if self.h:
+        if self.h and self.ctx.h:
             self.ctx.L.qgt_b200_state_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -175,6 +177,7 @@ class Context:
         self.h = C.c_void_p()
         self.world = 1
         self.rank = 0
+        self._states = weakref.WeakSet()     # states must be destroyed before their context
         _check(self.L.qgt_b200_create(C.byref(self.h), device))
 
     def set_option(self, key: str, value: float) -> None:
@@ -251,6 +254,8 @@ class Context:
 
     def close(self) -> None:
         if self.h:
+            for st in list(self._states):
+                st.close()
             self.L.qgt_b200_destroy(self.h)
             self.h = C.c_void_p()
 

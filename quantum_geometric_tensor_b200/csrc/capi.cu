@@ -154,7 +154,8 @@ void qgt_b200_destroy(qgt_b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     qgt::dist_shutdown(c);
-    c->arena.release(); c->img_runs.release(); c->img_ops.release(); c->img_subs.release();
+    c->arena.release(); c->img_runs.release(); c->img_subs.release(); c->img_stages.release();
+    c->img_tdiags.release(); c->img_costs.release(); c->img_pool.release(); c->ovr_pool.release();
     c->items.release(); c->aux.release(); c->partial.release(); c->cmat.release(); c->outbuf.release();
     c->edges.release(); c->vweights.release(); c->scratch.release();
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -175,6 +176,8 @@ int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
     if (k == "tile_qubits") { if (value) c->opt.tile_qubits = (int)value; }
     else if (k == "low_qubits") c->opt.low_qubits = (int)value;
     else if (k == "max_ops_per_run") c->opt.max_ops_per_run = (int)value;
+    else if (k == "reg_qubits") c->opt.reg_qubits = (int)value;
+    else if (k == "batch_qubits") c->opt.batch_qubits = (int)value;
     else if (k == "profile") c->timer.enabled = value != 0;
     else if (k == "max_slots") c->max_slots = (size_t)value;
     else return fail(QGT_B200_ERR_INVALID_ARG, "unknown option " + k);
@@ -283,13 +286,20 @@ static int check_circuit(const qgt_b200_circuit* circ, const double* theta) {
 int upload_plan(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan& plan, PlanImage& img) {
     build_image(plan, img);
     int rc;
-    if ((rc = c->img_runs.reserve(std::max<size_t>(1, img.runs.size()) * sizeof(QgtDevRun)))) return rc;
-    if ((rc = c->img_ops.reserve(std::max<size_t>(1, img.ops.size()) * sizeof(QgtDevOp)))) return rc;
-    if ((rc = c->img_subs.reserve(std::max<size_t>(1, img.subs.size()) * sizeof(QgtDevSubPass)))) return rc;
+    struct Up { DevBuf* buf; const void* src; size_t bytes; };
+    const Up ups[] = {
+        {&c->img_runs, img.runs.data(), img.runs.size() * sizeof(QgtDevRun)},
+        {&c->img_subs, img.subs.data(), img.subs.size() * sizeof(QgtDevSubPass)},
+        {&c->img_stages, img.stages.data(), img.stages.size() * sizeof(QgtDevStage)},
+        {&c->img_tdiags, img.tdiags.data(), img.tdiags.size() * sizeof(QgtDevThrDiag)},
+        {&c->img_costs, img.costs.data(), img.costs.size() * sizeof(QgtDevCost)},
+        {&c->img_pool, img.pool.data(), img.pool.size() * sizeof(double)},
+    };
     cudaError_t e = cudaSuccess;
-    if (!img.runs.empty()) e = cudaMemcpyAsync(c->img_runs.ptr, img.runs.data(), img.runs.size() * sizeof(QgtDevRun), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess && !img.ops.empty()) e = cudaMemcpyAsync(c->img_ops.ptr, img.ops.data(), img.ops.size() * sizeof(QgtDevOp), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess && !img.subs.empty()) e = cudaMemcpyAsync(c->img_subs.ptr, img.subs.data(), img.subs.size() * sizeof(QgtDevSubPass), cudaMemcpyHostToDevice, c->stream);
+    for (const Up& u : ups) {
+        if ((rc = u.buf->reserve(std::max<size_t>(16, u.bytes)))) return rc;
+        if (u.bytes && e == cudaSuccess) e = cudaMemcpyAsync(u.buf->ptr, u.src, u.bytes, cudaMemcpyHostToDevice, c->stream);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "plan upload");
     c->cost.edges = nullptr; c->cost.num_edges = 0; c->cost.vertex_weights = nullptr; c->cost.n = circ.num_qubits;
     if (circ.num_edges && circ.edges) {
@@ -322,17 +332,23 @@ static int do_sweep(qgt_b200_ctx* c, const CircuitPlan& plan, int run, const Qgt
                     uint64_t shard_tiles) {
     SweepLaunch a;
     a.runs = (const QgtDevRun*)c->img_runs.ptr;
-    a.ops = (const QgtDevOp*)c->img_ops.ptr;
     a.subs = (const QgtDevSubPass*)c->img_subs.ptr;
+    a.stages = (const QgtDevStage*)c->img_stages.ptr;
+    a.tdiags = (const QgtDevThrDiag*)c->img_tdiags.ptr;
+    a.costs = (const QgtDevCost*)c->img_costs.ptr;
+    a.pool = (const cplx*)c->img_pool.ptr;
     a.run_idx = run;
     a.items = d_items;
     a.nitems = nitems;
     a.ntiles = shard_tiles;
     a.ct = c->cost;
     const int K = plan.runs[run].K;
-    const int R = (int)plan.runs[run].subs.empty() ? std::min(plan.opt.reg_qubits, K) : (int)plan.runs[run].subs[0].reg_local.size();
+    const int R = plan.R;
+    int mat_count = 0;
+    for (const SubPass& sp : plan.runs[run].subs)
+        for (const Stage& stg : sp.stages) mat_count += QGT_VARIANT_STRIDE(1 << R) << stg.vqubits.size();
     c->timer.begin(c->stream, 0);
-    cudaError_t e = launch_sweep(a, K, R, c->num_sms, c->stream);
+    cudaError_t e = launch_sweep(a, K, R, plan.B, mat_count, c->num_sms, c->stream);
     c->timer.end(c->stream);
     if (e != cudaSuccess) return cuda_fail(e, "sweep launch");
     c->stats.sweep_launches++;
@@ -347,7 +363,7 @@ int apply_plan_inplace(qgt_b200_ctx* c, const CircuitPlan& plan, cplx* d, uint64
     if (rc) return rc;
     QgtSweepItem it;
     std::memset(&it, 0, sizeof it);
-    it.src = d; it.dst = d; it.ovr_op = -1; it.accumulate = 0;
+    it.src = d; it.dst = d; it.ovr_kind = 0; it.ovr_index = -1; it.accumulate = 0;
     cudaError_t e = cudaMemcpyAsync(c->items.ptr, &it, sizeof it, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return cuda_fail(e, "item upload");
@@ -372,6 +388,8 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
     const int P = plan.P;
     // ---- pack every launch's arguments and upload them once ------------------------------------
     std::vector<QgtSweepItem> items;
+    std::vector<double> ovr_pool, mats;          // derivative matrices of the spawn items
+    std::vector<size_t> ovr_off, ovr_item;
     std::vector<const cplx*> ptrs;
     std::vector<int> ids;
     struct GramRec { size_t a_off, b_off, aid_off, bid_off; int na, nb; bool symmetric; };
@@ -388,12 +406,26 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                 std::memset(&it, 0, sizeof it);
                 it.src = arena + (size_t)sc.src * D;
                 it.dst = arena + (size_t)sc.dst * D;
-                it.ovr_op = sc.ovr_op;
                 it.accumulate = sc.accumulate ? 1u : 0u;
+                it.ovr_kind = 0; it.ovr_index = -1;
                 if (sc.ovr_op >= 0) {
-                    const int sp = find_subpass(run, sc.ovr_op);
-                    if (sp < 0) return fail(QGT_B200_ERR_INTERNAL, "override op outside every sub-pass");
-                    it.ovr = bind_op(run, run.subs[sp], run.ops[sc.ovr_op], true);
+                    const OpLocation loc = locate_op(run, sc.ovr_op);
+                    if (loc.kind == 0) return fail(QGT_B200_ERR_INTERNAL, "override op outside every sub-pass");
+                    it.ovr_kind = loc.kind;
+                    it.ovr_index = loc.index;
+                    const SubPass& sp = run.subs[loc.sub];
+                    if (loc.kind == 1) {
+                        int first = 0;
+                        for (int s2 = 0; s2 < loc.sub; s2++) first += (int)run.subs[s2].stages.size();
+                        stage_matrices(run, sp, sp.stages[loc.index - first], sc.ovr_op, mats);
+                        ovr_off.push_back(ovr_pool.size());
+                        ovr_item.push_back(items.size());
+                        ovr_pool.insert(ovr_pool.end(), mats.begin(), mats.end());
+                    } else if (loc.kind == 2) {
+                        it.ovr_tdiag = make_tdiag(run.ops[sc.ovr_op], true);
+                    } else {
+                        it.ovr_cost = make_cost(run.ops[sc.ovr_op], true);
+                    }
                 }
                 items.push_back(it);
             }
@@ -416,12 +448,16 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
         }
     }
     int rc;
+    if ((rc = c->ovr_pool.reserve(std::max<size_t>(16, ovr_pool.size() * sizeof(double))))) return rc;
+    for (size_t k = 0; k < ovr_item.size(); k++)
+        items[ovr_item[k]].ovr_mat = (const char*)c->ovr_pool.ptr + ovr_off[k] * sizeof(double);
     if ((rc = c->items.reserve(std::max<size_t>(1, items.size()) * sizeof(QgtSweepItem)))) return rc;
     const size_t ptr_bytes = ptrs.size() * sizeof(cplx*), id_bytes = ids.size() * sizeof(int);
     if ((rc = c->aux.reserve(std::max<size_t>(16, ptr_bytes + id_bytes)))) return rc;
     if ((rc = c->partial.reserve(std::max<size_t>(16, partial_bytes)))) return rc;
     cudaError_t e = cudaSuccess;
     if (!items.empty()) e = cudaMemcpyAsync(c->items.ptr, items.data(), items.size() * sizeof(QgtSweepItem), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && !ovr_pool.empty()) e = cudaMemcpyAsync(c->ovr_pool.ptr, ovr_pool.data(), ovr_pool.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess && ptr_bytes) e = cudaMemcpyAsync(c->aux.ptr, ptrs.data(), ptr_bytes, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess && id_bytes) e = cudaMemcpyAsync((char*)c->aux.ptr + ptr_bytes, ids.data(), id_bytes, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // host vectors are locals

@@ -15,13 +15,14 @@
 #define QGT_MAX_QUBITS 40
 #define QGT_MAX_REG_QUBITS 4
 
+// lowered-op types (host side; the device only sees dense stages, thread diagonals and the cost pass)
 enum QgtOpType {
-    QGT_OP_U = 0,      // dense complex 2x2 on a register qubit
-    QGT_OP_UREAL = 1,  // 2x2 with real entries (RY, H and their derivatives)
-    QGT_OP_URX = 2,    // real diagonal, imaginary off-diagonal (RX and its derivative)
-    QGT_OP_PERM = 3,   // exchange the pair (X, CNOT)
-    QGT_OP_DIAG = 4,   // amp *= parity(g & pmask) ? d1 : d0   when (g & cmask) == cmask
-    QGT_OP_COST = 5    // amp *= exp(-i a E(g)),  E from the edge list (QAOA cost layer)
+    QGT_OP_U = 0,        // dense complex 2x2
+    QGT_OP_UREAL = 1,    // 2x2 with real entries (RY, H and their derivatives)
+    QGT_OP_URX = 2,      // real diagonal, imaginary off-diagonal (RX and its derivative)
+    QGT_OP_PERM = 3,     // exchange the pair (X, CNOT)
+    QGT_OP_DIAG = 4,     // amp *= parity(g & pmask) ? d1 : d0   when (g & cmask) == cmask
+    QGT_OP_COST = 5      // amp *= exp(-i a E(g)),  E from the edge list (QAOA cost layer); a tile-level pass
 };
 
 enum QgtOpFlags {
@@ -29,33 +30,57 @@ enum QgtOpFlags {
     QGT_FLAG_COST_DERIV = 2       // multiply additionally by (-i * m[1] * E(g))
 };
 
-typedef struct QgtDevOp {
-    int32_t  type;
-    int32_t  tbit;     // U-types: index (0..R-1) of the target inside the sub-pass's register qubits
-    uint32_t creg;     // controls that are register qubits of the sub-pass (mask over register index)
-    uint32_t preg;     // DIAG: parity bits that are register qubits (mask over register index)
-    uint64_t cmask;    // remaining controls, as a mask over GLOBAL amplitude-index bits
-    uint64_t pmask;    // DIAG: remaining parity bits, global mask
+#define QGT_MAX_VARIANT_BITS 2
+// matrix variants are laid out QGT_VARIANT_STRIDE(N) complex elements apart: the odd padding keeps two
+// variants read by lanes of one quarter-warp in different shared-memory bank groups
+#define QGT_VARIANT_STRIDE(N) ((N) * (N) + 1)
+
+// One dense stage of a sub-pass: all gates that touch the sub-pass's R register qubits, multiplied together
+// on the host into a 2^R x 2^R complex matrix.  Gates controlled by (or diagonal on) up to
+// QGT_MAX_VARIANT_BITS non-register qubits give 2^nvar matrix variants; a thread picks its variant from
+// the bits of its global index.
+typedef struct QgtDevStage {
+    int32_t  nvar;                           // number of selecting bits
+    int32_t  mat_off;                        // offset of variant 0 in the run's matrix pool, in complex elements
+    uint64_t vmask[QGT_MAX_VARIANT_BITS];    // global index bit selecting variant bit k
+} QgtDevStage;                               // 24 bytes
+
+// a diagonal gate (or the derivative of one) that touches no register qubit: one phase per thread
+typedef struct QgtDevThrDiag {
+    uint64_t cmask;                          // controls (global index bits), all must be 1
+    uint64_t pmask;                          // parity bits (global index bits)
+    double   d[4];                           // d0, d1 (re, im)
     uint32_t flags;
     uint32_t pad;
-    double   m[8];     // U: m00,m01,m10,m11 (re,im);  DIAG: d0,d1 (re,im);  COST: m[0]=angle, m[1]=derivative scale
-} QgtDevOp;            // 112 bytes
+} QgtDevThrDiag;                             // 56 bytes
+
+// the cost layer (tile-level pass)
+typedef struct QgtDevCost {
+    double   angle;
+    double   dscale;
+    uint32_t flags;
+    uint32_t pad;
+} QgtDevCost;
 
 typedef struct QgtDevSubPass {
-    int32_t nreg;                        // register qubits used (<= R); unused ones are padded with free tile positions
-    int32_t op_begin, op_end;            // range in the run's op array
-    int32_t pad;
+    int32_t nreg;                        // register qubits (R); 0 marks a tile-level pass holding one COST op
+    int32_t stage_begin, stage_end;      // dense stages (indices into the run's stage array)
+    int32_t tdiag_begin, tdiag_end;      // thread diagonals (indices into the run's thread-diagonal array)
+    int32_t cost;                        // index into the run's cost array when nreg == 0
     int8_t  regq[QGT_MAX_REG_QUBITS];    // LOCAL bit positions (0..K-1) held in registers, ascending
     int8_t  tperm[QGT_MAX_TILE_QUBITS];  // thread bit i -> LOCAL bit position
-} QgtDevSubPass;                         // 32 bytes
+} QgtDevSubPass;                         // 40 bytes
 
 typedef struct QgtDevRun {
     int32_t K;                           // tile qubits (== num_qubits when the state is smaller than a tile)
     int32_t n;                           // total qubits
     int32_t nsub;
-    int32_t nops;
-    int32_t ops_off;                     // offsets into the global op / sub-pass arrays
-    int32_t sub_off;
+    int32_t sub_off;                     // offsets into the plan-wide arrays
+    int32_t stage_off;
+    int32_t tdiag_off;
+    int32_t cost_off;
+    int32_t mat_off;                     // first matrix element of this run in the matrix pool
+    int32_t mat_count;                   // complex elements of this run in the pool
     int8_t  tq[QGT_MAX_TILE_QUBITS];     // tile qubits: local bit j <-> global bit tq[j], ascending
     int8_t  ntq[QGT_MAX_QUBITS];         // the n-K other qubits, ascending (tile id bits are deposited here)
     int32_t pad;
@@ -65,9 +90,13 @@ typedef struct QgtDevRun {
 typedef struct QgtSweepItem {
     const void* src;                     // complex double [2^n]
     void*       dst;                     // may equal src (in place)
-    int32_t     ovr_op;                  // index into the run's ops that is replaced by `ovr`, or -1
     uint32_t    accumulate;              // dst += result instead of dst = result
-    QgtDevOp    ovr;                     // the derivative op (generator folded into the gate)
+    int32_t     ovr_kind;                // 0 none, 1 dense stage, 2 thread diagonal, 3 cost
+    int32_t     ovr_index;               // which stage / thread diagonal / cost entry of the run is replaced
+    int32_t     pad;
+    const void* ovr_mat;                 // kind 1: the replacement matrices (all variants) in global memory
+    QgtDevThrDiag ovr_tdiag;             // kind 2
+    QgtDevCost    ovr_cost;              // kind 3
 } QgtSweepItem;
 
 typedef struct QgtDevEdge { int32_t i, j; double w; } QgtDevEdge;

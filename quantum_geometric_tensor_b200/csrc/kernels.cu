@@ -22,101 +22,103 @@ namespace qgt {
 // ------------------------------------------------------------------------------------------------
 // gate sweep
 // ------------------------------------------------------------------------------------------------
-template <int R>
-__global__ void __launch_bounds__(256, 2) qgt_sweep_kernel(SweepLaunch a) {
+// Shared memory: [tile: 2^K amplitudes][matrix pool of the run][override matrices of the current item].
+// The kernel is persistent over (tile, column) work items; the run header and its matrix pool are staged
+// once per CTA.  R = qubits of a stage matrix, B = batch qubits: a thread owns 2^(R+B) amplitudes.
+template <int R, int B, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
+    constexpr int N = 1 << R;
+    constexpr int OVR_ELEMS = QGT_VARIANT_STRIDE(N) << QGT_MAX_VARIANT_BITS;
     extern __shared__ __align__(16) unsigned char qgt_smem_raw[];
     cplx* tile = reinterpret_cast<cplx*>(qgt_smem_raw);
     __shared__ QgtDevRun run;
-    if (threadIdx.x < sizeof(QgtDevRun) / 4) {
-        reinterpret_cast<uint32_t*>(&run)[threadIdx.x] =
-            reinterpret_cast<const uint32_t*>(&a.runs[a.run_idx])[threadIdx.x];
-    }
-    __syncthreads();
-    const QgtDevOp* ops = a.ops + run.ops_off;
-    const QgtDevSubPass* subs = a.subs + run.sub_off;
     const int tid = threadIdx.x;
     const int T = blockDim.x;
-    const QgtIoMap<R> io = qgt_make_iomap<R>(run, tid);
-    const uint64_t total = a.ntiles * (uint64_t)a.nitems;
-    for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
-        const int item = (int)(w % (uint64_t)a.nitems);
-        const uint64_t tau = w / (uint64_t)a.nitems;
-        const QgtSweepItem& it = a.items[item];
-        const uint64_t tilebase = qgt_tile_base(run, tau);
-        qgt_phase_load<R>(io, tile, reinterpret_cast<const cplx*>(it.src), tilebase, tid, T);
-        __syncthreads();
-        const int ovr = it.ovr_op;
-        for (int s = 0; s < run.nsub; ++s) {
-            qgt_phase_subpass<R>(run, subs[s], ops, ovr, it.ovr, tile, tilebase, tid, a.ct);
-            __syncthreads();
-        }
-        qgt_phase_store<R>(io, tile, reinterpret_cast<cplx*>(it.dst), tilebase, tid, T, it.accumulate != 0);
-        __syncthreads();
-    }
-}
-
-// small states (fewer than 2^R * 32 amplitudes per tile) use the same code with one thread per 2^R
-// amplitudes; sizeof(QgtDevRun)/4 threads may not exist there, so the run header is copied in a loop.
-template <int R>
-__global__ void __launch_bounds__(256) qgt_sweep_small_kernel(SweepLaunch a) {
-    extern __shared__ __align__(16) unsigned char qgt_smem_raw[];
-    cplx* tile = reinterpret_cast<cplx*>(qgt_smem_raw);
-    __shared__ QgtDevRun run;
-    for (int i = threadIdx.x; i < (int)(sizeof(QgtDevRun) / 4); i += blockDim.x)
+    for (int i = tid; i < (int)(sizeof(QgtDevRun) / 4); i += T)
         reinterpret_cast<uint32_t*>(&run)[i] = reinterpret_cast<const uint32_t*>(&a.runs[a.run_idx])[i];
     __syncthreads();
-    const QgtDevOp* ops = a.ops + run.ops_off;
+    cplx* spool = tile + ((size_t)1 << run.K);
+    cplx* sovr = spool + run.mat_count;
+    {
+        const cplx* gpool = a.pool + run.mat_off;
+        for (int i = tid; i < run.mat_count; i += T) spool[i] = gpool[i];
+    }
     const QgtDevSubPass* subs = a.subs + run.sub_off;
-    const int tid = threadIdx.x;
-    const int T = blockDim.x;
-    const QgtIoMap<R> io = qgt_make_iomap<R>(run, tid);
+    QgtSubCtx cx;
+    cx.stages = a.stages + run.stage_off;
+    cx.tdiags = a.tdiags + run.tdiag_off;
+    cx.pool = spool;
+    cx.ovr_mat_off = run.mat_count;
+    const QgtIoMap<R + B> io = qgt_make_iomap<R + B>(run, tid);
     const uint64_t total = a.ntiles * (uint64_t)a.nitems;
     for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
         const int item = (int)(w % (uint64_t)a.nitems);
         const uint64_t tau = w / (uint64_t)a.nitems;
         const QgtSweepItem& it = a.items[item];
         const uint64_t tilebase = qgt_tile_base(run, tau);
-        qgt_phase_load<R>(io, tile, reinterpret_cast<const cplx*>(it.src), tilebase, tid, T);
+        cx.ovr_kind = it.ovr_kind;
+        cx.ovr_index = it.ovr_index;
+        cx.ovr_tdiag = &it.ovr_tdiag;
+        if (it.ovr_kind == 1) {
+            const cplx* g = reinterpret_cast<const cplx*>(it.ovr_mat);
+            const int cnt = QGT_VARIANT_STRIDE(N) << cx.stages[it.ovr_index].nvar;
+            for (int i = tid; i < cnt && i < OVR_ELEMS; i += T) sovr[i] = g[i];
+        }
+        qgt_phase_load<R + B>(io, tile, reinterpret_cast<const cplx*>(it.src), tilebase, tid, T);
         __syncthreads();
         for (int s = 0; s < run.nsub; ++s) {
-            qgt_phase_subpass<R>(run, subs[s], ops, it.ovr_op, it.ovr, tile, tilebase, tid, a.ct);
+            if (subs[s].nreg == 0) {
+                const QgtDevCost& co = (it.ovr_kind == 3 && subs[s].cost == it.ovr_index) ? it.ovr_cost : a.costs[run.cost_off + subs[s].cost];
+                qgt_phase_cost(run, co, tile, tilebase, tid, T, a.ct);
+            } else {
+                qgt_phase_subpass<R, B>(run, subs[s], cx, tile, tilebase, tid);
+            }
             __syncthreads();
         }
-        qgt_phase_store<R>(io, tile, reinterpret_cast<cplx*>(it.dst), tilebase, tid, T, it.accumulate != 0);
+        qgt_phase_store<R + B>(io, tile, reinterpret_cast<cplx*>(it.dst), tilebase, tid, T, it.accumulate != 0);
         __syncthreads();
     }
 }
 
-template <int R>
-static cudaError_t launch_sweep_r(const SweepLaunch& a, int K, int num_sms, cudaStream_t st) {
-    const int T = 1 << (K - R);
-    const size_t smem = sizeof(cplx) << K;
-    const uint64_t total = a.ntiles * (uint64_t)a.nitems;
-    if (total == 0) return cudaSuccess;
-    if (T >= 32) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(qgt_sweep_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
-        const uint64_t cap = (uint64_t)num_sms * 2 * 4;
-        const unsigned grid = (unsigned)(total < cap ? total : cap);
-        qgt_sweep_kernel<R><<<grid, T, smem, st>>>(a);
-    } else {
-        const uint64_t cap = (uint64_t)num_sms * 8;
-        const unsigned grid = (unsigned)(total < cap ? total : cap);
-        qgt_sweep_small_kernel<R><<<grid, T, smem, st>>>(a);
+template <int R, int B, int MAXT, int MINB>
+static cudaError_t launch_sweep_cfg(const SweepLaunch& a, int T, size_t smem, unsigned grid, cudaStream_t st) {
+    auto kern = qgt_sweep_kernel<R, B, MAXT, MINB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
     }
+    kern<<<grid, T, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int num_sms, cudaStream_t st) {
-    if (K - R > 8 || K > QGT_MAX_TILE_QUBITS) return cudaErrorInvalidValue;
-    switch (R) {
-    case 1: return launch_sweep_r<1>(a, K, num_sms, st);
-    case 2: return launch_sweep_r<2>(a, K, num_sms, st);
-    case 3: return launch_sweep_r<3>(a, K, num_sms, st);
+template <int R, int B>
+static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, int num_sms, cudaStream_t st) {
+    constexpr int N = 1 << R;
+    const int T = 1 << (K - R - B);
+    const size_t smem = (sizeof(cplx) << K) + sizeof(cplx) * (size_t)mat_count +
+                        sizeof(cplx) * (size_t)(QGT_VARIANT_STRIDE(N) << QGT_MAX_VARIANT_BITS);
+    const uint64_t total = a.ntiles * (uint64_t)a.nitems;
+    if (total == 0) return cudaSuccess;
+    if (smem > 200 * 1024 || T > 256) return cudaErrorInvalidValue;
+    const uint64_t cap = (uint64_t)num_sms * 8;
+    const unsigned grid = (unsigned)(total < cap ? total : cap);
+    // register budget follows the CTA size: 128-thread CTAs may use ~168 registers at 3 CTAs per SM
+    if (B > 0 && T <= 128) return launch_sweep_cfg<R, B, 128, 3>(a, T, smem, grid, st);
+    if (B > 0) return launch_sweep_cfg<R, B, 256, 1>(a, T, smem, grid, st);
+    return launch_sweep_cfg<R, B, 256, 2>(a, T, smem, grid, st);
+}
+
+cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int num_sms, cudaStream_t st) {
+    if (K > QGT_MAX_TILE_QUBITS) return cudaErrorInvalidValue;
+    switch (R * 2 + B) {
+    case 2: return launch_sweep_rb<1, 0>(a, K, mat_count, num_sms, st);
+    case 3: return launch_sweep_rb<1, 1>(a, K, mat_count, num_sms, st);
+    case 4: return launch_sweep_rb<2, 0>(a, K, mat_count, num_sms, st);
+    case 5: return launch_sweep_rb<2, 1>(a, K, mat_count, num_sms, st);
+    case 6: return launch_sweep_rb<3, 0>(a, K, mat_count, num_sms, st);
+    case 7: return launch_sweep_rb<3, 1>(a, K, mat_count, num_sms, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -125,20 +127,32 @@ cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int num_sms, cudaSt
 // Gram  C = A^H B  on the FP64 tensor pipe
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// CTA tile: MT = WM*BM*8 rows (columns of A) x NT = WN*BN*8 cols (columns of B); WM*WN warps, each
-// warp owns BM x BN blocks of 8x8.  K (the 2^n amplitude axis) is consumed in chunks of KC staged in
-// shared memory as split re / im planes with row stride KC+4 doubles (conflict-free fragment loads).
-template <int WM, int WN, int BM, int BN>
-__global__ void __launch_bounds__(WM * WN * 32) qgt_gram_kernel(GramLaunch g) {
-    constexpr int MT = WM * BM * 8, NT = WN * BN * 8, KC = 16, S = KC + 4, NTHR = WM * WN * 32;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// CTA tile: MT = WM*BM*8 rows (columns of A) x NT = WN*BN*8 cols (columns of B); WM*WN warps, each warp
+// owns BM x BN blocks of 8x8.  The 2^n-long amplitude axis is consumed in chunks of KC amplitudes moved
+// global -> shared with 16-byte cp.async through a STAGES-deep ring (no register staging).  Shared memory
+// keeps the complex numbers interleaved with a row stride of KC+4 elements: one 128-bit load then
+// delivers (re, im) of a fragment element and a quarter-warp touches 8 distinct 16-byte bank groups.
+template <int WM, int WN, int BM, int BN, int KC, int STAGES>
+__global__ void __launch_bounds__(WM * WN * 32, 2) qgt_gram_kernel(GramLaunch g) {
+    constexpr int MT = WM * BM * 8, NT = WN * BN * 8, S = KC + 4, NTHR = WM * WN * 32;
     constexpr int ELEMS = (MT + NT) * KC;
-    static_assert(ELEMS % NTHR == 0, "tile/threads mismatch");
+    static_assert(ELEMS % NTHR == 0 && NTHR % KC == 0, "tile/threads mismatch");
     constexpr int PER = ELEMS / NTHR;
-    __shared__ double sAr[MT * S], sAi[MT * S], sBr[NT * S], sBi[NT * S];
+    constexpr int STAGE_ELEMS = (MT + NT) * S;
+    extern __shared__ __align__(16) unsigned char qgt_gram_smem[];
+    cplx* sm = reinterpret_cast<cplx*>(qgt_gram_smem);
 
     const int tiles = g.mtiles * g.ntiles;
     const int ks = blockIdx.x / tiles;
@@ -156,85 +170,88 @@ __global__ void __launch_bounds__(WM * WN * 32) qgt_gram_kernel(GramLaunch g) {
     // this thread's share of a chunk: element e -> (column e / KC, offset e % KC)
     const cplx* colptr[PER];
     int soff[PER];
-    bool isA[PER];
+    const int koff = tid % KC;
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
-        const int e = tid + j * NTHR;
-        const int col = e / KC, k = e % KC;
-        if (col < MT) {
-            const int gc = mt * MT + col;
-            colptr[j] = gc < g.na ? g.a_ptrs[gc] + k : nullptr;
-            soff[j] = col * S + k; isA[j] = true;
-        } else {
-            const int gc = nt * NT + (col - MT);
-            colptr[j] = gc < g.nb ? g.b_ptrs[gc] + k : nullptr;
-            soff[j] = (col - MT) * S + k; isA[j] = false;
-        }
+        const int col = (tid + j * NTHR) / KC;
+        const int gc = col < MT ? mt * MT + col : nt * NT + (col - MT);
+        const bool ok = col < MT ? gc < g.na : gc < g.nb;
+        colptr[j] = ok ? (col < MT ? g.a_ptrs[gc] : g.b_ptrs[gc]) + koff : nullptr;
+        soff[j] = col * S + koff;
     }
-    const int koff = tid % KC;   // == e % KC for every j because NTHR % KC == 0
+    auto issue = [&](uint64_t kb, int stage) {
+        cplx* dst = sm + (size_t)stage * STAGE_ELEMS;
+        const bool in = kb + (uint64_t)koff < k1;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const bool ok = in && colptr[j] != nullptr;
+            cp_async16(dst + soff[j], ok ? (const void*)(colptr[j] + kb) : (const void*)g.a_ptrs, ok ? 16 : 0);
+        }
+    };
 
     double cre[BM][BN][2], cim[BM][BN][2];
 #pragma unroll
     for (int i = 0; i < BM; ++i)
 #pragma unroll
         for (int j = 0; j < BN; ++j) { cre[i][j][0] = cre[i][j][1] = cim[i][j][0] = cim[i][j][1] = 0.0; }
-
-    // blocks entirely in the padding do no tensor work
-    bool rowok[BM], colok[BN];
+    // blocks entirely in the padding, or (symmetric case) entirely below the diagonal, do no tensor work
+    bool blk[BM][BN];
 #pragma unroll
-    for (int i = 0; i < BM; ++i) rowok[i] = (mt * MT + (wm * BM + i) * 8) < g.na;
+    for (int i = 0; i < BM; ++i)
 #pragma unroll
-    for (int j = 0; j < BN; ++j) colok[j] = (nt * NT + (wn * BN + j) * 8) < g.nb;
-
-    cplx pre[PER];
-    auto fetch = [&](uint64_t kb) {
-#pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            cplx z; z.x = 0.0; z.y = 0.0;
-            if (colptr[j] != nullptr && kb + (uint64_t)koff < k1) z = colptr[j][kb];
-            pre[j] = z;
+        for (int j = 0; j < BN; ++j) {
+            const int r0 = mt * MT + (wm * BM + i) * 8, c0 = nt * NT + (wn * BN + j) * 8;
+            blk[i][j] = r0 < g.na && c0 < g.nb && !(g.symmetric && c0 + 8 <= r0);
         }
-    };
-    if (k0 < k1) fetch(k0);
-    for (uint64_t kb = k0; kb < k1; kb += KC) {
+
+    const uint64_t nchunks = k1 > k0 ? (k1 - k0 + KC - 1) / KC : 0;
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            if (isA[j]) { sAr[soff[j]] = pre[j].x; sAi[soff[j]] = pre[j].y; }
-            else        { sBr[soff[j]] = pre[j].x; sBi[soff[j]] = pre[j].y; }
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if ((uint64_t)s < nchunks) issue(k0 + (uint64_t)s * KC, s);
+        cp_async_commit();
+    }
+    const int fr = lane >> 2, fk = lane & 3;
+    for (uint64_t ch = 0; ch < nchunks; ++ch) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();            // chunk `ch` has landed for every thread; stage (ch-1)%STAGES is free again
+        {
+            const uint64_t nx = ch + STAGES - 1;
+            if (nx < nchunks) issue(k0 + nx * KC, (int)(nx % STAGES));
+            cp_async_commit();
         }
-        __syncthreads();
-        if (kb + KC < k1) fetch(kb + KC);
-        const int fr = lane >> 2, fk = lane & 3;
+        const cplx* sA = sm + (size_t)(ch % STAGES) * STAGE_ELEMS;
+        const cplx* sB = sA + MT * S;
 #pragma unroll
         for (int kk = 0; kk < KC; kk += 4) {
-            double ar[BM], ai[BM], br[BN], bi[BN];
+            cplx a[BM], b[BN];
+#pragma unroll
+            for (int i = 0; i < BM; ++i) a[i] = sA[((wm * BM + i) * 8 + fr) * S + kk + fk];
+#pragma unroll
+            for (int j = 0; j < BN; ++j) b[j] = sB[((wn * BN + j) * 8 + fr) * S + kk + fk];
+            // conj(a) * b = (ar*br + ai*bi) + i (ar*bi - ai*br); the two updates of one accumulator are issued
+            // a whole block sweep apart so that dependent DMMAs never sit back to back
 #pragma unroll
             for (int i = 0; i < BM; ++i) {
-                const int o = ((wm * BM + i) * 8 + fr) * S + kk + fk;
-                ar[i] = sAr[o]; ai[i] = sAi[o];
-            }
-#pragma unroll
-            for (int j = 0; j < BN; ++j) {
-                const int o = ((wn * BN + j) * 8 + fr) * S + kk + fk;
-                br[j] = sBr[o]; bi[j] = sBi[o];
-            }
-#pragma unroll
-            for (int i = 0; i < BM; ++i) {
-                if (!rowok[i]) continue;
-                const double nai = -ai[i];
 #pragma unroll
                 for (int j = 0; j < BN; ++j) {
-                    if (!colok[j]) continue;
-                    // conj(a) * b = (ar*br + ai*bi) + i (ar*bi - ai*br)
-                    dmma884(cre[i][j][0], cre[i][j][1], ar[i], br[j]);
-                    dmma884(cre[i][j][0], cre[i][j][1], ai[i], bi[j]);
-                    dmma884(cim[i][j][0], cim[i][j][1], ar[i], bi[j]);
-                    dmma884(cim[i][j][0], cim[i][j][1], nai, br[j]);
+                    if (!blk[i][j]) continue;
+                    dmma884(cre[i][j][0], cre[i][j][1], a[i].x, b[j].x);
+                    dmma884(cim[i][j][0], cim[i][j][1], a[i].x, b[j].y);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < BM; ++i) {
+                const double nai = -a[i].y;
+#pragma unroll
+                for (int j = 0; j < BN; ++j) {
+                    if (!blk[i][j]) continue;
+                    dmma884(cre[i][j][0], cre[i][j][1], a[i].y, b[j].y);
+                    dmma884(cim[i][j][0], cim[i][j][1], nai, b[j].x);
                 }
             }
         }
-        __syncthreads();
     }
+    cp_async_wait<0>();
     const int Npad = g.ntiles * NT;
     const int Mpad = g.mtiles * MT;
     cplx* out = g.partial + (size_t)ks * Mpad * Npad;
@@ -285,19 +302,41 @@ __global__ void qgt_finalize_kernel(const cplx* C, int P, double* metric, double
     if (q_full) { q_full[idx].x = qr; q_full[idx].y = qi; }
 }
 
+// tile shape with the least padded work: 64x64 for big blocks, 32x32 when that wastes less, 32x16 for the
+// few-column Grams of the blocked schedule
 GramShape gram_shape(int na, int nb) {
     GramShape s;
-    if (na > 32 || nb > 32) { s.MT = 64; s.NT = 64; }
-    else { s.MT = 32; s.NT = 16; }
+    if (na <= 32 && nb <= 16) { s.MT = 32; s.NT = 16; return s; }
+    auto padded = [&](int mt, int nt) {
+        const long m = (na + mt - 1) / mt, n = (nb + nt - 1) / nt;
+        return m * n * (long)mt * nt;
+    };
+    if (padded(64, 64) <= padded(32, 32) + padded(32, 32) / 8) { s.MT = 64; s.NT = 64; }
+    else { s.MT = 32; s.NT = 32; }
     return s;
 }
 
-cudaError_t launch_gram(const GramLaunch& g, GramShape shp, cudaStream_t st) {
+template <int WM, int WN, int BM, int BN, int KC, int STAGES>
+static cudaError_t launch_gram_t(const GramLaunch& g, cudaStream_t st) {
+    constexpr int MT = WM * BM * 8, NT = WN * BN * 8;
+    constexpr size_t smem = (size_t)STAGES * (MT + NT) * (KC + 4) * sizeof(cplx);
+    auto kern = qgt_gram_kernel<WM, WN, BM, BN, KC, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
     const unsigned grid = (unsigned)(g.mtiles * g.ntiles * g.ksplit);
-    if (grid == 0) return cudaSuccess;
-    if (shp.MT == 64) qgt_gram_kernel<2, 4, 4, 2><<<grid, 256, 0, st>>>(g);
-    else qgt_gram_kernel<4, 2, 1, 1><<<grid, 256, 0, st>>>(g);
+    kern<<<grid, WM * WN * 32, smem, st>>>(g);
     return cudaGetLastError();
+}
+
+cudaError_t launch_gram(const GramLaunch& g, GramShape shp, cudaStream_t st) {
+    if (g.mtiles * g.ntiles * g.ksplit == 0) return cudaSuccess;
+    if (shp.MT == 64) return launch_gram_t<2, 4, 4, 2, 8, 4>(g, st);
+    if (shp.NT == 32) return launch_gram_t<2, 4, 2, 1, 16, 4>(g, st);
+    return launch_gram_t<4, 2, 1, 1, 16, 4>(g, st);
 }
 
 cudaError_t launch_gram_reduce(const GramLaunch& g, GramShape shp, const int* a_ids, const int* b_ids,

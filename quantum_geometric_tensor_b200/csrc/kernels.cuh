@@ -10,8 +10,11 @@ namespace qgt {
 
 struct SweepLaunch {
     const QgtDevRun* runs;
-    const QgtDevOp* ops;
     const QgtDevSubPass* subs;
+    const QgtDevStage* stages;
+    const QgtDevThrDiag* tdiags;
+    const QgtDevCost* costs;
+    const cplx* pool;
     int run_idx;
     const QgtSweepItem* items;
     int nitems;
@@ -33,7 +36,7 @@ struct GramLaunch {
 struct GramShape { int MT, NT; };
 
 // K, R: tile / register qubits of the run; grid is chosen inside
-cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int num_sms, cudaStream_t st);
+cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int num_sms, cudaStream_t st);
 
 GramShape gram_shape(int na, int nb);
 cudaError_t launch_gram(const GramLaunch& g, GramShape shp, cudaStream_t st);

@@ -188,9 +188,10 @@ Dag build_dag(const std::vector<LoweredOp>& ops, int n) {
     return d;
 }
 
-void make_tperm(int K, const std::vector<int>& reg_local, std::vector<int>& tperm) {
+void make_tperm(int K, const std::vector<int>& reg_local, const std::vector<int>& batch_local, std::vector<int>& tperm) {
     std::vector<char> is_reg(K, 0);
     for (int r : reg_local) is_reg[r] = 1;
+    for (int r : batch_local) is_reg[r] = 1;
     std::vector<int> freep;
     for (int p = 0; p < K; p++) if (!is_reg[p]) freep.push_back(p);
     // the shared-memory swizzle XORs bit p of the index into bank-group bit (p mod 3): give the three
@@ -210,30 +211,117 @@ void make_tperm(int K, const std::vector<int>& reg_local, std::vector<int>& tper
 
 }  // namespace
 
-int find_subpass(const Run& run, int op_index) {
-    for (size_t s = 0; s < run.subs.size(); s++)
-        if (op_index >= run.subs[s].op_begin && op_index < run.subs[s].op_end) return (int)s;
-    return -1;
+OpLocation locate_op(const Run& run, int op_index) {
+    OpLocation loc;
+    int stage_base = 0, tdiag_base = 0, cost_base = 0;
+    for (size_t s = 0; s < run.subs.size(); s++) {
+        const SubPass& sp = run.subs[s];
+        if (op_index >= sp.op_begin && op_index < sp.op_end) {
+            loc.sub = (int)s;
+            if (sp.is_cost) { loc.kind = 3; loc.index = cost_base; return loc; }
+            for (size_t k = 0; k < sp.stages.size(); k++)
+                for (int o : sp.stages[k].ops) if (o == op_index) { loc.kind = 1; loc.index = stage_base + (int)k; return loc; }
+            for (size_t k = 0; k < sp.tdiags.size(); k++)
+                if (sp.tdiags[k] == op_index) { loc.kind = 2; loc.index = tdiag_base + (int)k; return loc; }
+            return loc;
+        }
+        stage_base += (int)sp.stages.size();
+        tdiag_base += (int)sp.tdiags.size();
+        cost_base += sp.is_cost ? 1 : 0;
+    }
+    return loc;
 }
 
-QgtDevOp bind_op(const Run& run, const SubPass& sp, const LoweredOp& op, bool derivative) {
-    QgtDevOp d;
-    std::memset(&d, 0, sizeof d);
-    d.type = op.type;
-    d.flags = derivative ? op.dflags : op.flags;
-    std::memcpy(d.m, derivative ? op.dm : op.m, sizeof d.m);
-    uint64_t regmask_global = 0;
-    for (size_t r = 0; r < sp.reg_local.size(); r++) regmask_global |= bit(run.tile_qubits[sp.reg_local[r]]);
-    d.tbit = -1;
-    for (size_t r = 0; r < sp.reg_local.size(); r++) {
-        const int gq = run.tile_qubits[sp.reg_local[r]];
-        if (op.target == gq) d.tbit = (int)r;
-        if (op.cmask >> gq & 1) d.creg |= 1u << r;
-        if (op.pmask >> gq & 1) d.preg |= 1u << r;
+QgtDevThrDiag make_tdiag(const LoweredOp& op, bool derivative) {
+    QgtDevThrDiag t;
+    std::memset(&t, 0, sizeof t);
+    t.cmask = op.cmask; t.pmask = op.pmask;
+    std::memcpy(t.d, derivative ? op.dm : op.m, 4 * sizeof(double));
+    t.flags = derivative ? op.dflags : op.flags;
+    return t;
+}
+
+QgtDevCost make_cost(const LoweredOp& op, bool derivative) {
+    QgtDevCost c;
+    std::memset(&c, 0, sizeof c);
+    c.angle = derivative ? op.dm[0] : op.m[0];
+    c.dscale = derivative ? op.dm[1] : op.m[1];
+    c.flags = derivative ? op.dflags : op.flags;
+    return c;
+}
+
+void stage_matrices(const Run& run, const SubPass& sp, const Stage& st, int deriv_op, std::vector<double>& out) {
+    const int R = (int)sp.reg_local.size();
+    const int N = 1 << R;
+    const int nvar = (int)st.vqubits.size();
+    const size_t vstride = (size_t)QGT_VARIANT_STRIDE(N) * 2;      // doubles per variant (one padding element)
+    out.assign((size_t)(1 << nvar) * vstride, 0.0);
+    // masks of each op over the register combo c and the variant pattern p
+    struct Bound { uint32_t creg, cvar, preg, pvar; int j; };
+    std::vector<Bound> bound(st.ops.size());
+    for (size_t k = 0; k < st.ops.size(); k++) {
+        const LoweredOp& op = run.ops[st.ops[k]];
+        Bound bd = {0, 0, 0, 0, -1};
+        for (int r = 0; r < R; r++) {
+            const int q = run.tile_qubits[sp.reg_local[r]];
+            if (op.cmask >> q & 1) bd.creg |= 1u << r;
+            if (op.pmask >> q & 1) bd.preg |= 1u << r;
+            if (op.target == q) bd.j = r;
+        }
+        for (int v = 0; v < nvar; v++) {
+            if (op.cmask >> st.vqubits[v] & 1) bd.cvar |= 1u << v;
+            if (op.pmask >> st.vqubits[v] & 1) bd.pvar |= 1u << v;
+        }
+        bound[k] = bd;
     }
-    d.cmask = op.cmask & ~regmask_global;
-    d.pmask = op.pmask & ~regmask_global;
-    return d;
+    std::vector<double> M((size_t)N * N * 2), T((size_t)N * N * 2);
+    for (int p = 0; p < (1 << nvar); p++) {
+        std::fill(M.begin(), M.end(), 0.0);
+        for (int i = 0; i < N; i++) M[2 * (i * N + i)] = 1.0;
+        for (size_t k = 0; k < st.ops.size(); k++) {
+            const int oi = st.ops[k];
+            const LoweredOp& op = run.ops[oi];
+            const Bound& bd = bound[k];
+            const bool der = (oi == deriv_op);
+            const double* m = der ? op.dm : op.m;
+            const bool zero_fail = ((der ? op.dflags : op.flags) & QGT_FLAG_ZERO_CTRL_FAIL) != 0;
+            const bool var_ok = ((uint32_t)p & bd.cvar) == bd.cvar;
+            double u[8];
+            if (op.type == QGT_OP_PERM) { const double x[8] = {0, 0, 1, 0, 1, 0, 0, 0}; std::memcpy(u, x, sizeof u); }
+            else if (op.type != QGT_OP_DIAG) std::memcpy(u, m, sizeof u);
+            const int pvar_par = __builtin_popcount((uint32_t)p & bd.pvar) & 1;
+            // T = A * M with A having at most two non-zeros per row
+            for (int c = 0; c < N; c++) {
+                double* trow = &T[2 * (size_t)c * N];
+                const double* mrow = &M[2 * (size_t)c * N];
+                const bool ok = var_ok && (((uint32_t)c & bd.creg) == bd.creg);
+                if (!ok) {
+                    if (zero_fail) std::fill(trow, trow + 2 * N, 0.0);
+                    else std::memcpy(trow, mrow, 2 * N * sizeof(double));
+                    continue;
+                }
+                if (op.type == QGT_OP_DIAG) {
+                    const int par = pvar_par ^ (__builtin_popcount((uint32_t)c & bd.preg) & 1);
+                    const double pr = m[2 * par], pi = m[2 * par + 1];
+                    for (int l = 0; l < N; l++) {
+                        trow[2 * l] = pr * mrow[2 * l] - pi * mrow[2 * l + 1];
+                        trow[2 * l + 1] = pr * mrow[2 * l + 1] + pi * mrow[2 * l];
+                    }
+                } else {
+                    const int bsel = (c >> bd.j) & 1;
+                    const double* r0 = &M[2 * (size_t)(c & ~(1 << bd.j)) * N];
+                    const double* r1 = &M[2 * (size_t)(c | (1 << bd.j)) * N];
+                    const double ar = u[4 * bsel], ai = u[4 * bsel + 1], br = u[4 * bsel + 2], bi = u[4 * bsel + 3];
+                    for (int l = 0; l < N; l++) {
+                        trow[2 * l] = ar * r0[2 * l] - ai * r0[2 * l + 1] + br * r1[2 * l] - bi * r1[2 * l + 1];
+                        trow[2 * l + 1] = ar * r0[2 * l + 1] + ai * r0[2 * l] + br * r1[2 * l + 1] + bi * r1[2 * l];
+                    }
+                }
+            }
+            M.swap(T);
+        }
+        std::memcpy(&out[(size_t)p * vstride], M.data(), M.size() * sizeof(double));
+    }
 }
 
 int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions& opt_in, CircuitPlan& plan, std::string& err) {
@@ -241,13 +329,17 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
     if (n < 1 || n > QGT_MAX_QUBITS) { err = "num_qubits out of range"; return QGT_B200_ERR_INVALID_ARG; }
     if (c.num_gates && !c.gates) { err = "gates is NULL"; return QGT_B200_ERR_INVALID_ARG; }
     PlanOptions opt = opt_in;
-    opt.tile_qubits = std::max(opt.reg_qubits + 2, std::min(opt.tile_qubits, (int)QGT_MAX_TILE_QUBITS));
+    opt.reg_qubits = std::max(1, std::min(opt.reg_qubits, 3));
+    opt.batch_qubits = std::max(0, std::min(opt.batch_qubits, (int)QGT_MAX_REG_QUBITS - opt.reg_qubits));
+    opt.tile_qubits = std::max(opt.reg_qubits + opt.batch_qubits + 2,
+                               std::min(opt.tile_qubits, std::min((int)QGT_MAX_TILE_QUBITS, opt.reg_qubits + opt.batch_qubits + 8)));
     const int K = std::min(n, opt.tile_qubits);
     const int R = std::min(opt.reg_qubits, K);
+    const int B = std::min(opt.batch_qubits, K - R);
     // the forced low qubits must leave room for at least R freely chosen tile qubits
     const int L = (K == n) ? K : std::max(0, std::min(opt.low_qubits, K - R));
     plan = CircuitPlan();
-    plan.n = n; plan.P = c.num_params; plan.opt = opt;
+    plan.n = n; plan.P = c.num_params; plan.opt = opt; plan.K = K; plan.R = R; plan.B = B;
     plan.first_run.assign(std::max(0, c.num_params), -1);
     plan.last_run.assign(std::max(0, c.num_params), -1);
 
@@ -270,11 +362,11 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
         int sizeS = 0;
         for (int q = 0; q < L; q++) { inS[q] = 1; sizeS++; }
         if (K == n) { for (int q = 0; q < n; q++) inS[q] = 1; sizeS = n; }
-        struct RawSub { std::vector<int> regq; int b, e; };
+        struct RawSub { std::vector<int> regq; int b, e; bool is_cost = false; };
         std::vector<RawSub> raw;
         bool run_full = false;
         while (!run_full) {
-            RawSub sp; sp.b = (int)run.ops.size();
+            RawSub sp; sp.b = (int)run.ops.size(); sp.is_cost = false;
             std::vector<char> inR(n, 0);
             int sizeR = 0;
             for (;;) {
@@ -283,15 +375,21 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
                 for (int i : ready) {
                     const LoweredOp& o = ops[i];
                     int pri;
-                    if (o.target < 0) pri = 0;
+                    // 2x2 ops first (on a held register qubit, then a new register qubit of the tile, then a
+                    // new tile qubit); diagonal ops last so that those on register qubits end up adjacent
+                    // and merge into one table; the cost layer gets a tile-level pass of its own
+                    if (o.type == QGT_OP_COST) pri = (sp.b == (int)run.ops.size()) ? 4 : 99;
+                    else if (o.target < 0) pri = 3;
                     else if (inR[o.target]) pri = 0;
                     else if (sizeR < R && inS[o.target]) pri = 1;
                     else if (sizeR < R && sizeS < K) pri = 2;
                     else continue;
+                    if (pri == 99) continue;
                     if (pri < best_pri || (pri == best_pri && i < best)) { best = i; best_pri = pri; }
                 }
                 if (best < 0) break;
                 const LoweredOp& o = ops[best];
+                if (o.type == QGT_OP_COST) sp.is_cost = true;
                 if (o.target >= 0) {
                     if (!inS[o.target]) { inS[o.target] = 1; sizeS++; }
                     if (!inR[o.target]) { inR[o.target] = 1; sizeR++; sp.regq.push_back(o.target); }
@@ -300,6 +398,7 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
                 done[best] = 1; scheduled++;
                 ready.erase(std::find(ready.begin(), ready.end(), best));
                 for (int sidx : dag.succ[best]) if (--dag.indeg[sidx] == 0) ready.push_back(sidx);
+                if (sp.is_cost) break;            // a cost pass holds exactly one op
             }
             sp.e = (int)run.ops.size();
             if (sp.e == sp.b) break;          // nothing fits a fresh sub-pass: the run is complete
@@ -314,13 +413,43 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
         for (const RawSub& rs : raw) {
             SubPass sp;
             sp.op_begin = rs.b; sp.op_end = rs.e;
+            sp.is_cost = rs.is_cost;
+            if (rs.is_cost) { run.subs.push_back(sp); continue; }
             sp.nreg_used = (int)rs.regq.size();
             std::vector<char> used(K, 0);
             for (int q : rs.regq) { sp.reg_local.push_back(local_of[q]); used[local_of[q]] = 1; }
             for (int p = K - 1; p >= 0 && (int)sp.reg_local.size() < R; p--)
                 if (!used[p]) { sp.reg_local.push_back(p); used[p] = 1; }
             std::sort(sp.reg_local.begin(), sp.reg_local.end());
-            make_tperm(K, sp.reg_local, sp.tperm);
+            uint64_t regmask = 0;
+            for (int p : sp.reg_local) regmask |= bit(run.tile_qubits[p]);
+            for (int i = rs.b; i < rs.e; i++) {
+                const LoweredOp& o = run.ops[i];
+                const uint64_t used_bits = o.cmask | o.pmask | (o.target >= 0 ? bit(o.target) : 0);
+                if (o.type == QGT_OP_DIAG && (used_bits & regmask) == 0) { sp.tdiags.push_back(i); continue; }
+                std::vector<int> need;               // non-register qubits this op depends on
+                for (int q = 0; q < n; q++) if ((used_bits & ~regmask) >> q & 1) need.push_back(q);
+                bool fits = !sp.stages.empty();
+                if (fits) {
+                    std::vector<int> merged = sp.stages.back().vqubits;
+                    for (int q : need) if (std::find(merged.begin(), merged.end(), q) == merged.end()) merged.push_back(q);
+                    if ((int)merged.size() > QGT_MAX_VARIANT_BITS) fits = false;
+                    else sp.stages.back().vqubits = merged;
+                }
+                if (!fits) { Stage st; st.vqubits = need; sp.stages.push_back(st); }
+                sp.stages.back().ops.push_back(i);
+            }
+            // batch positions: free tile positions, preferably not selecting a matrix variant of this
+            // sub-pass (then both halves of a thread always share their matrix), highest first
+            {
+                std::vector<char> is_var(K, 0);
+                for (const Stage& stg : sp.stages)
+                    for (int q : stg.vqubits) if (local_of[q] >= 0) is_var[local_of[q]] = 1;
+                for (int pass = 0; pass < 2 && (int)sp.batch_local.size() < B; pass++)
+                    for (int p = K - 1; p >= 0 && (int)sp.batch_local.size() < B; p--)
+                        if (!used[p] && (pass == 1 || !is_var[p])) { sp.batch_local.push_back(p); used[p] = 1; }
+            }
+            make_tperm(K, sp.reg_local, sp.batch_local, sp.tperm);
             run.subs.push_back(sp);
         }
         const int ridx = (int)plan.runs.size();
@@ -338,26 +467,46 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
 
 void build_image(const CircuitPlan& plan, PlanImage& img) {
     img = PlanImage();
+    std::vector<double> mats;
     for (const Run& run : plan.runs) {
         QgtDevRun dr;
         std::memset(&dr, 0, sizeof dr);
         dr.K = run.K; dr.n = plan.n;
         dr.nsub = (int)run.subs.size();
-        dr.nops = (int)run.ops.size();
-        dr.ops_off = (int)img.ops.size();
         dr.sub_off = (int)img.subs.size();
+        dr.stage_off = (int)img.stages.size();
+        dr.tdiag_off = (int)img.tdiags.size();
+        dr.cost_off = (int)img.costs.size();
+        dr.mat_off = (int)(img.pool.size() / 2);
         for (int j = 0; j < run.K; j++) dr.tq[j] = (int8_t)run.tile_qubits[j];
         for (size_t j = 0; j < run.other_qubits.size(); j++) dr.ntq[j] = (int8_t)run.other_qubits[j];
         for (const SubPass& sp : run.subs) {
             QgtDevSubPass ds;
             std::memset(&ds, 0, sizeof ds);
-            ds.nreg = (int)sp.reg_local.size();
-            ds.op_begin = sp.op_begin; ds.op_end = sp.op_end;
+            ds.nreg = sp.is_cost ? 0 : (int)sp.reg_local.size();
+            ds.stage_begin = (int)img.stages.size() - dr.stage_off;
+            ds.tdiag_begin = (int)img.tdiags.size() - dr.tdiag_off;
+            ds.cost = (int)img.costs.size() - dr.cost_off;
             for (size_t r = 0; r < sp.reg_local.size(); r++) ds.regq[r] = (int8_t)sp.reg_local[r];
+            for (size_t r = 0; r < sp.batch_local.size(); r++) ds.regq[sp.reg_local.size() + r] = (int8_t)sp.batch_local[r];
             for (size_t t = 0; t < sp.tperm.size(); t++) ds.tperm[t] = (int8_t)sp.tperm[t];
+            if (sp.is_cost) img.costs.push_back(make_cost(run.ops[sp.op_begin], false));
+            for (int o : sp.tdiags) img.tdiags.push_back(make_tdiag(run.ops[o], false));
+            for (const Stage& st : sp.stages) {
+                QgtDevStage d;
+                std::memset(&d, 0, sizeof d);
+                d.nvar = (int)st.vqubits.size();
+                for (int k = 0; k < d.nvar; k++) d.vmask[k] = bit(st.vqubits[k]);
+                d.mat_off = (int)(img.pool.size() / 2) - dr.mat_off;
+                stage_matrices(run, sp, st, -1, mats);
+                img.pool.insert(img.pool.end(), mats.begin(), mats.end());
+                img.stages.push_back(d);
+            }
+            ds.stage_end = (int)img.stages.size() - dr.stage_off;
+            ds.tdiag_end = (int)img.tdiags.size() - dr.tdiag_off;
             img.subs.push_back(ds);
-            for (int i = sp.op_begin; i < sp.op_end; i++) img.ops.push_back(bind_op(run, sp, run.ops[i], false));
         }
+        dr.mat_count = (int)(img.pool.size() / 2) - dr.mat_off;
         img.runs.push_back(dr);
     }
 }
@@ -613,6 +762,7 @@ std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const 
         for (size_t s = 0; s < run.subs.size(); s++) {
             const SubPass& sp = run.subs[s];
             o << (s ? "," : "") << "{\"reg\":"; jarr(o, sp.reg_local);
+            o << ",\"batch\":"; jarr(o, sp.batch_local);
             o << ",\"tperm\":"; jarr(o, sp.tperm);
             o << ",\"ops\":[" << sp.op_begin << "," << sp.op_end << "]}";
         }

@@ -13,7 +13,8 @@ namespace qgt {
 
 struct PlanOptions {
     int tile_qubits = 11;   // K
-    int reg_qubits = 3;     // R
+    int reg_qubits = 3;     // R: qubits of a dense stage matrix
+    int batch_qubits = 0;   // B: extra amplitudes per thread (2^B halves share every matrix element)
     int low_qubits = 4;     // L: lowest qubits always in the tile (contiguous 16*2^L bytes)
     int max_ops_per_run = 160;
 };
@@ -33,11 +34,22 @@ struct LoweredOp {
     uint32_t dflags = 0;
 };
 
+// a dense stage of a sub-pass: the lowered ops (in order) whose product forms the 2^R x 2^R matrix, and the
+// non-register qubits that select among its variants
+struct Stage {
+    std::vector<int> ops;
+    std::vector<int> vqubits;       // global qubit numbers, variant bit k <-> vqubits[k]
+};
+
 struct SubPass {
-    std::vector<int> reg_local;     // local bit positions in registers (ascending, padded to R)
+    std::vector<int> reg_local;     // local bit positions in registers (ascending, padded to R); empty for a cost pass
     int nreg_used = 0;
+    std::vector<int> batch_local;   // local bit positions of the batch qubits (B entries)
     std::vector<int> tperm;         // thread bit -> local position
-    int op_begin = 0, op_end = 0;
+    int op_begin = 0, op_end = 0;   // lowered ops
+    bool is_cost = false;           // tile-level pass holding exactly one COST op
+    std::vector<Stage> stages;
+    std::vector<int> tdiags;        // lowered diagonal ops that touch no register qubit
 };
 
 struct ParamOcc { int param; int op; };   // op = index into Run::ops
@@ -53,6 +65,7 @@ struct Run {
 
 struct CircuitPlan {
     int n = 0, P = 0;
+    int K = 0, R = 0, B = 0;        // tile / matrix / batch qubits actually used (clamped to n)
     PlanOptions opt;
     std::vector<Run> runs;
     std::vector<int> first_run, last_run;   // per parameter, -1 when the parameter has no gate
@@ -61,15 +74,29 @@ struct CircuitPlan {
 // device-format image of a plan (what gets uploaded)
 struct PlanImage {
     std::vector<QgtDevRun> runs;
-    std::vector<QgtDevOp> ops;
     std::vector<QgtDevSubPass> subs;
+    std::vector<QgtDevStage> stages;
+    std::vector<QgtDevThrDiag> tdiags;
+    std::vector<QgtDevCost> costs;
+    std::vector<double> pool;            // matrices, interleaved (re, im)
+};
+
+// where a lowered op of a run ended up on the device
+struct OpLocation {
+    int kind = 0;       // 1 dense stage, 2 thread diagonal, 3 cost   (QgtSweepItem::ovr_kind)
+    int sub = -1;
+    int index = -1;     // stage / tdiag / cost index relative to the run's first one
 };
 
 int lower_gate(const qgt_b200_circuit& c, const double* theta, int gate_index, std::vector<LoweredOp>& out, std::string& err);
 int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions& opt, CircuitPlan& plan, std::string& err);
 void build_image(const CircuitPlan& plan, PlanImage& img);
-QgtDevOp bind_op(const Run& run, const SubPass& sp, const LoweredOp& op, bool derivative);
-int find_subpass(const Run& run, int op_index);
+OpLocation locate_op(const Run& run, int op_index);
+// all variants of a stage's matrix, (re, im) interleaved, row-major 2^R x 2^R each; deriv_op >= 0 replaces
+// that lowered op by its derivative
+void stage_matrices(const Run& run, const SubPass& sp, const Stage& st, int deriv_op, std::vector<double>& out);
+QgtDevThrDiag make_tdiag(const LoweredOp& op, bool derivative);
+QgtDevCost make_cost(const LoweredOp& op, bool derivative);
 
 // ---- column schedule ---------------------------------------------------------------------------
 enum InstrKind { INSTR_SWEEP = 0, INSTR_GRAM = 1, INSTR_COPY = 2, INSTR_INIT = 3 };

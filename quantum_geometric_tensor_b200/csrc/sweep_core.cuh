@@ -29,6 +29,14 @@ QGT_HD uint32_t qgt_swz(uint32_t idx) {
     return idx ^ ((idx >> 3) & 7u) ^ ((idx >> 6) & 7u) ^ ((idx >> 9) & 7u);
 }
 
+QGT_HD double qgt_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return fma(a, b, c);
+#else
+    return std::fma(a, b, c);
+#endif
+}
+
 QGT_HD int qgt_popc64(uint64_t v) {
 #if defined(__CUDA_ARCH__)
     return __popcll(v);
@@ -71,96 +79,24 @@ QGT_HD double qgt_cost_energy(const QgtCostTable& ct, uint64_t g) {
     return e;
 }
 
-// ---- register-level op application -----------------------------------------------------------------
-template <int R, int J>
-QGT_HD void qgt_apply_u(cplx (&v)[1 << R], const QgtDevOp& op) {
-    const double* m = op.m;
-#pragma unroll
-    for (int c = 0; c < (1 << R); ++c) {
-        if (c & (1 << J)) continue;
-        const int c1 = c | (1 << J);
-        if (((uint32_t)c & op.creg) != op.creg) {
-            if (op.flags & QGT_FLAG_ZERO_CTRL_FAIL) { v[c].x = v[c].y = v[c1].x = v[c1].y = 0.0; }
-            continue;
-        }
-        const cplx a = v[c], b = v[c1];
-        if (op.type == QGT_OP_PERM) {
-            v[c] = b; v[c1] = a;
-        } else if (op.type == QGT_OP_UREAL) {
-            v[c].x = m[0] * a.x + m[2] * b.x;   v[c].y = m[0] * a.y + m[2] * b.y;
-            v[c1].x = m[4] * a.x + m[6] * b.x;  v[c1].y = m[4] * a.y + m[6] * b.y;
-        } else if (op.type == QGT_OP_URX) {      // real diagonal, imaginary off-diagonal
-            v[c].x = m[0] * a.x - m[3] * b.y;   v[c].y = m[0] * a.y + m[3] * b.x;
-            v[c1].x = m[6] * b.x - m[5] * a.y;  v[c1].y = m[6] * b.y + m[5] * a.x;
-        } else {
-            v[c].x = m[0] * a.x - m[1] * a.y + m[2] * b.x - m[3] * b.y;
-            v[c].y = m[0] * a.y + m[1] * a.x + m[2] * b.y + m[3] * b.x;
-            v[c1].x = m[4] * a.x - m[5] * a.y + m[6] * b.x - m[7] * b.y;
-            v[c1].y = m[4] * a.y + m[5] * a.x + m[6] * b.y + m[7] * b.x;
-        }
+// ---- register-level work ---------------------------------------------------------------------------
+// fold one thread-level diagonal gate into a pending scalar
+QGT_HD void qgt_thread_diag(cplx& pend, const QgtDevThrDiag& t, uint64_t g) {
+    if ((g & t.cmask) == t.cmask) {
+        const int par = qgt_popc64(g & t.pmask) & 1;
+        const double dr = par ? t.d[2] : t.d[0], di = par ? t.d[3] : t.d[1];
+        const cplx a = pend;
+        pend.x = dr * a.x - di * a.y;
+        pend.y = dr * a.y + di * a.x;
+    } else if (t.flags & QGT_FLAG_ZERO_CTRL_FAIL) {
+        pend.x = 0.0; pend.y = 0.0;
     }
 }
 
-template <int R>
-QGT_HD void qgt_zero_all(cplx (&v)[1 << R]) {
-#pragma unroll
-    for (int c = 0; c < (1 << R); ++c) v[c].x = v[c].y = 0.0;
-}
-
-// apply one op to the 2^R amplitudes of a thread.  gbase = global index of combo 0 (register bits clear),
-// regg[r] = global bit of register qubit r.
-template <int R>
-QGT_HD void qgt_apply_op(cplx (&v)[1 << R], const QgtDevOp& op, uint64_t gbase, const uint64_t* regg,
-                         const QgtCostTable& ct) {
-    const bool thread_ok = (gbase & op.cmask) == op.cmask;
-    if (op.type <= QGT_OP_PERM) {
-        if (!thread_ok) {
-            if (op.flags & QGT_FLAG_ZERO_CTRL_FAIL) qgt_zero_all<R>(v);
-            return;
-        }
-        switch (op.tbit) {
-        case 0: qgt_apply_u<R, 0>(v, op); break;
-        case 1: if (R > 1) qgt_apply_u<R, (R > 1 ? 1 : 0)>(v, op); break;
-        case 2: if (R > 2) qgt_apply_u<R, (R > 2 ? 2 : 0)>(v, op); break;
-        case 3: if (R > 3) qgt_apply_u<R, (R > 3 ? 3 : 0)>(v, op); break;
-        default: break;
-        }
-    } else if (op.type == QGT_OP_DIAG) {
-        const int par_t = qgt_popc64(gbase & op.pmask) & 1;
-#pragma unroll
-        for (int c = 0; c < (1 << R); ++c) {
-            if (thread_ok && ((uint32_t)c & op.creg) == op.creg) {
-                const int par = par_t ^ (qgt_popc64((uint64_t)((uint32_t)c & op.preg)) & 1);
-                const double dr = par ? op.m[2] : op.m[0], di = par ? op.m[3] : op.m[1];
-                const cplx a = v[c];
-                v[c].x = dr * a.x - di * a.y;
-                v[c].y = dr * a.y + di * a.x;
-            } else if (op.flags & QGT_FLAG_ZERO_CTRL_FAIL) {
-                v[c].x = v[c].y = 0.0;
-            }
-        }
-    } else {   // QGT_OP_COST
-#pragma unroll
-        for (int c = 0; c < (1 << R); ++c) {
-            uint64_t g = gbase;
-#pragma unroll
-            for (int r = 0; r < R; ++r) if (c & (1 << r)) g |= regg[r];
-            const double e = qgt_cost_energy(ct, g);
-            double sn, cs;
-#if defined(__CUDA_ARCH__)
-            sincos(-op.m[0] * e, &sn, &cs);
-#else
-            sn = std::sin(-op.m[0] * e); cs = std::cos(-op.m[0] * e);
-#endif
-            cplx a = v[c];
-            cplx b; b.x = cs * a.x - sn * a.y; b.y = cs * a.y + sn * a.x;
-            if (op.flags & QGT_FLAG_COST_DERIV) {   // times (-i * scale * E)
-                const double f = op.m[1] * e;
-                a.x = f * b.y; a.y = -f * b.x; b = a;
-            }
-            v[c] = b;
-        }
-    }
+QGT_HD int qgt_variant_index(const QgtDevStage& st, uint64_t g) {
+    int v = 0;
+    for (int k = 0; k < st.nvar; ++k) v |= ((g & st.vmask[k]) != 0) << k;
+    return v;
 }
 
 // ---- per-thread phases --------------------------------------------------------------------------------
@@ -212,13 +148,30 @@ QGT_HD void qgt_phase_store(const QgtIoMap<R>& io, const cplx* tile, cplx* dst, 
     }
 }
 
-// one sub-pass for one thread: shared -> registers, ops, registers -> shared
-template <int R>
-QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, const QgtDevOp* ops, int ovr_op,
-                              const QgtDevOp& ovr, cplx* tile, uint64_t tilebase, int tid, const QgtCostTable& ct) {
+// everything a sub-pass needs besides the tile: the run's stage / thread-diagonal tables, the matrix
+// pool (staged in shared memory) and the item's override
+struct QgtSubCtx {
+    const QgtDevStage* stages;
+    const QgtDevThrDiag* tdiags;
+    const cplx* pool;            // the run's matrices (element 0 = run.mat_off of the plan-wide pool) ...
+    int ovr_mat_off;             // ... followed, at this element offset, by the item's override matrices
+    int ovr_kind, ovr_index;
+    const QgtDevThrDiag* ovr_tdiag;
+};
+
+// One sub-pass for one thread.  The thread owns 2^(R+B) amplitudes: R "matrix" qubits and B "batch" qubits.
+// Every gate of the sub-pass acting on the R matrix qubits was multiplied on the host into one dense
+// 2^R x 2^R complex matrix per stage, so the device does no per-gate dispatch; the 2^B batch halves reuse
+// each matrix element loaded from shared memory (the LSU wavefront rate, not the FP64 pipe, is the first
+// limit otherwise).  Results go straight back to the thread's own tile slots, row by row.
+template <int R, int B>
+QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, const QgtSubCtx& cx, cplx* tile,
+                              uint64_t tilebase, int tid) {
+    constexpr int N = 1 << R;
+    constexpr int NB = 1 << B;
     uint32_t lbase = 0;
     uint64_t gbase = tilebase;
-    const int nthr_bits = run.K - R;
+    const int nthr_bits = run.K - R - B;
     for (int i = 0; i < nthr_bits; i++) {
         if ((tid >> i) & 1) {
             const int p = sp.tperm[i];
@@ -226,27 +179,131 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
             gbase |= 1ull << run.tq[p];
         }
     }
-    uint32_t regl[R];
-    uint64_t regg[R];
+    uint32_t regl[R + B];
 #pragma unroll
-    for (int r = 0; r < R; ++r) { regl[r] = 1u << sp.regq[r]; regg[r] = 1ull << run.tq[sp.regq[r]]; }
-    cplx v[1 << R];
+    for (int r = 0; r < R + B; ++r) regl[r] = 1u << sp.regq[r];
+    // swizzled tile slot of (batch half h, matrix combo c)
+    uint32_t slot[NB][N];
+    uint64_t gh[NB];
 #pragma unroll
-    for (int c = 0; c < (1 << R); ++c) {
-        uint32_t l = lbase;
+    for (int h = 0; h < NB; ++h) {
+        uint32_t lh = lbase;
+        gh[h] = gbase;
 #pragma unroll
-        for (int r = 0; r < R; ++r) if (c & (1 << r)) l |= regl[r];
-        v[c] = tile[qgt_swz(l)];
+        for (int r = 0; r < B; ++r) if (h & (1 << r)) { lh |= regl[R + r]; gh[h] |= 1ull << run.tq[sp.regq[R + r]]; }
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            uint32_t l = lh;
+#pragma unroll
+            for (int r = 0; r < R; ++r) if (c & (1 << r)) l |= regl[r];
+            slot[h][c] = qgt_swz(l);
+        }
     }
-    for (int o = sp.op_begin; o < sp.op_end; ++o) {
-        if (o == ovr_op) qgt_apply_op<R>(v, ovr, gbase, regg, ct);
-        else qgt_apply_op<R>(v, ops[o], gbase, regg, ct);
+    cplx pend[NB];
+#pragma unroll
+    for (int h = 0; h < NB; ++h) { pend[h].x = 1.0; pend[h].y = 0.0; }
+    for (int t = sp.tdiag_begin; t < sp.tdiag_end; ++t) {
+        const QgtDevThrDiag& td = (cx.ovr_kind == 2 && t == cx.ovr_index) ? *cx.ovr_tdiag : cx.tdiags[t];
+#pragma unroll
+        for (int h = 0; h < NB; ++h) qgt_thread_diag(pend[h], td, gh[h]);
     }
+    const int nstage = sp.stage_end - sp.stage_begin;
+    for (int s = sp.stage_begin; s < sp.stage_end; ++s) {
+        const QgtDevStage& st = cx.stages[s];
+        const int off = (cx.ovr_kind == 1 && s == cx.ovr_index) ? cx.ovr_mat_off : st.mat_off;
+        const bool last = (s == sp.stage_end - 1);
+        cplx v[NB][N];
 #pragma unroll
-    for (int c = 0; c < (1 << R); ++c) {
-        uint32_t l = lbase;
+        for (int h = 0; h < NB; ++h)
 #pragma unroll
-        for (int r = 0; r < R; ++r) if (c & (1 << r)) l |= regl[r];
-        tile[qgt_swz(l)] = v[c];
+            for (int c = 0; c < N; ++c) v[h][c] = tile[slot[h][c]];
+        const cplx* M[NB];
+        bool same = true;
+#pragma unroll
+        for (int h = 0; h < NB; ++h) {
+            M[h] = cx.pool + off + qgt_variant_index(st, gh[h]) * QGT_VARIANT_STRIDE(N);
+            same = same && (M[h] == M[0]);
+        }
+        if (same) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double xr[NB], xi[NB];
+#pragma unroll
+                for (int h = 0; h < NB; ++h) { xr[h] = 0.0; xi[h] = 0.0; }
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const cplx m = M[0][i * N + j];
+#pragma unroll
+                    for (int h = 0; h < NB; ++h) {
+                        xr[h] = qgt_fma(m.x, v[h][j].x, xr[h]); xr[h] = qgt_fma(-m.y, v[h][j].y, xr[h]);
+                        xi[h] = qgt_fma(m.x, v[h][j].y, xi[h]); xi[h] = qgt_fma(m.y, v[h][j].x, xi[h]);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < NB; ++h) {
+                    cplx o; o.x = xr[h]; o.y = xi[h];
+                    if (last) { const cplx q = o; o.x = pend[h].x * q.x - pend[h].y * q.y; o.y = pend[h].x * q.y + pend[h].y * q.x; }
+                    tile[slot[h][i]] = o;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < NB; ++h) {
+#pragma unroll 1
+                for (int i = 0; i < N; ++i) {
+                    double xr = 0.0, xi = 0.0;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const cplx m = M[h][i * N + j];
+                        xr = qgt_fma(m.x, v[h][j].x, xr); xr = qgt_fma(-m.y, v[h][j].y, xr);
+                        xi = qgt_fma(m.x, v[h][j].y, xi); xi = qgt_fma(m.y, v[h][j].x, xi);
+                    }
+                    cplx o; o.x = xr; o.y = xi;
+                    if (last) { const cplx q = o; o.x = pend[h].x * q.x - pend[h].y * q.y; o.y = pend[h].x * q.y + pend[h].y * q.x; }
+                    uint32_t l = 0;   // slot[h][i] with a run-time i: recompute instead of indexing registers
+#pragma unroll
+                    for (int r = 0; r < R; ++r) if (i & (1 << r)) l |= regl[r];
+#pragma unroll
+                    for (int r = 0; r < B; ++r) if (h & (1 << r)) l |= regl[R + r];
+                    tile[qgt_swz(lbase | l)] = o;
+                }
+            }
+        }
+    }
+    if (nstage == 0) {          // only thread diagonals: scale the thread's amplitudes in place
+#pragma unroll
+        for (int h = 0; h < NB; ++h) {
+            if (pend[h].x == 1.0 && pend[h].y == 0.0) continue;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                const cplx q = tile[slot[h][c]];
+                cplx o; o.x = pend[h].x * q.x - pend[h].y * q.y; o.y = pend[h].x * q.y + pend[h].y * q.x;
+                tile[slot[h][c]] = o;
+            }
+        }
+    }
+}
+
+// tile-level pass for the (rare, transcendental-heavy) cost layer: thread `tid` of T handles local
+// indices tid, tid+T, ... directly in shared memory; kept out of the register path to keep that code small.
+QGT_HD void qgt_phase_cost(const QgtDevRun& run, const QgtDevCost& op, cplx* tile, uint64_t tilebase, int tid, int T,
+                           const QgtCostTable& ct) {
+    const uint32_t count = 1u << run.K;
+    for (uint32_t idx = (uint32_t)tid; idx < count; idx += (uint32_t)T) {
+        const uint64_t g = tilebase | qgt_local_to_global(run, idx);
+        const double e = qgt_cost_energy(ct, g);
+        double sn, cs;
+#if defined(__CUDA_ARCH__)
+        sincos(-op.angle * e, &sn, &cs);
+#else
+        sn = std::sin(-op.angle * e); cs = std::cos(-op.angle * e);
+#endif
+        const cplx a = tile[qgt_swz(idx)];
+        cplx b; b.x = cs * a.x - sn * a.y; b.y = cs * a.y + sn * a.x;
+        if (op.flags & QGT_FLAG_COST_DERIV) {   // times (-i * scale * E)
+            const double f = op.dscale * e;
+            cplx d; d.x = f * b.y; d.y = -f * b.x; b = d;
+        }
+        tile[qgt_swz(idx)] = b;
     }
 }
