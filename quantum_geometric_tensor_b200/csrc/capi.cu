@@ -51,8 +51,9 @@ void DevBuf::release() {
     ptr = nullptr; bytes = 0;
 }
 
-void Timer::begin(cudaStream_t st, int cat) {
+void Timer::begin(cudaStream_t st, int cat, const char* label) {
     if (!enabled) return;
+    if (trace) labels.push_back(label ? label : "");
     if (used + 2 > events.size()) {
         const size_t old = events.size();
         events.resize(old + 64);
@@ -74,7 +75,9 @@ void Timer::collect(double ms[3]) {
         float t = 0.f;
         cudaEventElapsedTime(&t, events[2 * i], events[2 * i + 1]);
         ms[cats[i]] += t;
+        if (trace) fprintf(stderr, "[qgt_b200 trace] cat=%d ms=%.4f %s\n", cats[i], t, i < labels.size() ? labels[i].c_str() : "");
     }
+    labels.clear();
     cats.clear();
     used = 0;
 }
@@ -145,6 +148,7 @@ int qgt_b200_create(qgt_b200_ctx** out, int device) {
     if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    if (const char* tr = getenv("QGT_B200_TRACE")) c->timer.trace = (tr[0] == '1');
     *out = c;
     return QGT_B200_OK;
 }
@@ -178,6 +182,7 @@ int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
     else if (k == "max_ops_per_run") c->opt.max_ops_per_run = (int)value;
     else if (k == "reg_qubits") c->opt.reg_qubits = (int)value;
     else if (k == "batch_qubits") c->opt.batch_qubits = (int)value;
+    else if (k == "use_mma") c->use_mma = value != 0;
     else if (k == "profile") c->timer.enabled = value != 0;
     else if (k == "max_slots") c->max_slots = (size_t)value;
     else return fail(QGT_B200_ERR_INVALID_ARG, "unknown option " + k);
@@ -341,14 +346,22 @@ static int do_sweep(qgt_b200_ctx* c, const CircuitPlan& plan, int run, const Qgt
     a.items = d_items;
     a.nitems = nitems;
     a.ntiles = shard_tiles;
+    a.use_mma = c->use_mma;
     a.ct = c->cost;
     const int K = plan.runs[run].K;
     const int R = plan.R;
     int mat_count = 0;
     for (const SubPass& sp : plan.runs[run].subs)
         for (const Stage& stg : sp.stages) mat_count += QGT_VARIANT_STRIDE(1 << R) << stg.vqubits.size();
-    c->timer.begin(c->stream, 0);
-    cudaError_t e = launch_sweep(a, K, R, plan.B, mat_count, c->num_sms, c->stream);
+    char label[160];
+    if (c->timer.trace) {
+        int nst = 0;
+        for (const SubPass& sp : plan.runs[run].subs) nst += (int)sp.stages.size();
+        snprintf(label, sizeof label, "sweep run=%d items=%d subs=%d stages=%d ops=%d tiles=%llu mats=%d", run, nitems,
+                 (int)plan.runs[run].subs.size(), nst, (int)plan.runs[run].ops.size(), (unsigned long long)shard_tiles, mat_count);
+    }
+    c->timer.begin(c->stream, 0, label);
+    cudaError_t e = launch_sweep(a, K, R, plan.B, mat_count, (int)plan.runs[run].subs.size(), c->num_sms, c->stream);
     c->timer.end(c->stream);
     if (e != cudaSuccess) return cuda_fail(e, "sweep launch");
     c->stats.sweep_launches++;

@@ -28,8 +28,10 @@ struct Timer {
     bool enabled = true;
     std::vector<cudaEvent_t> events;
     std::vector<int> cats;
+    std::vector<std::string> labels;
+    bool trace = false;          // QGT_B200_TRACE=1: print every launch with its device time to stderr
     size_t used = 0;
-    void begin(cudaStream_t st, int cat);
+    void begin(cudaStream_t st, int cat, const char* label = nullptr);
     void end(cudaStream_t st);
     void collect(double ms[3]);
     ~Timer();
@@ -46,6 +48,7 @@ struct qgt_b200_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     size_t ws_limit = 0;
     size_t max_slots = 0;
+    int use_mma = 1;
     qgt::PlanOptions opt;
     qgt::DevBuf arena, img_runs, img_subs, img_stages, img_tdiags, img_costs, img_pool, ovr_pool, items, aux, partial, cmat, outbuf, edges, vweights, scratch;
     void* pinned = nullptr;

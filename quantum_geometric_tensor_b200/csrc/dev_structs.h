@@ -62,14 +62,22 @@ typedef struct QgtDevCost {
     uint32_t pad;
 } QgtDevCost;
 
+// A sub-pass, with everything index-related precomputed on the host.  The shared-memory swizzle is linear
+// over XOR, so the swizzled slot of an amplitude is the XOR of per-bit contributions: s_thr[i] for thread
+// bit i, s_reg[r] for register bit r (matrix qubits first, then batch qubits); g_* are the matching global
+// amplitude-index bits.
 typedef struct QgtDevSubPass {
-    int32_t nreg;                        // register qubits (R); 0 marks a tile-level pass holding one COST op
-    int32_t stage_begin, stage_end;      // dense stages (indices into the run's stage array)
-    int32_t tdiag_begin, tdiag_end;      // thread diagonals (indices into the run's thread-diagonal array)
-    int32_t cost;                        // index into the run's cost array when nreg == 0
-    int8_t  regq[QGT_MAX_REG_QUBITS];    // LOCAL bit positions (0..K-1) held in registers, ascending
-    int8_t  tperm[QGT_MAX_TILE_QUBITS];  // thread bit i -> LOCAL bit position
-} QgtDevSubPass;                         // 40 bytes
+    int32_t  nreg;                           // matrix qubits R; 0 marks a tile-level pass holding one COST op
+    int32_t  stage_begin, stage_end;         // dense stages (indices into the run's stage array)
+    int32_t  tdiag_begin, tdiag_end;         // thread diagonals (indices into the run's thread-diagonal array)
+    int32_t  cost;                           // index into the run's cost array when nreg == 0
+    int32_t  mma_ok;                         // every stage's variant is uniform over a warp: tensor-pipe path applies
+    int32_t  pad;
+    uint32_t s_thr[QGT_MAX_TILE_QUBITS];
+    uint32_t s_reg[QGT_MAX_REG_QUBITS];
+    uint64_t g_thr[QGT_MAX_TILE_QUBITS];
+    uint64_t g_reg[QGT_MAX_REG_QUBITS];
+} QgtDevSubPass;                             // 224 bytes
 
 typedef struct QgtDevRun {
     int32_t K;                           // tile qubits (== num_qubits when the state is smaller than a tile)

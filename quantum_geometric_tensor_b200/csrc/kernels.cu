@@ -22,6 +22,113 @@ namespace qgt {
 // ------------------------------------------------------------------------------------------------
 // gate sweep
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// Tensor-pipe version of a sub-pass with 3 matrix qubits (DMMA.8x8x4).  A "vector" is the 8 amplitudes one
+// thread of the register path would own; a warp owns 32 vectors = 4 groups of 8.  Per stage the 8x8 complex
+// matrix M sits in A fragments (lane (r, k) holds M[r][k] and M[r][4+k]), the 8 vectors of a group form the
+// B operand (lane (n, k) holds amplitudes k and 4+k of vector n) and
+//     out_re = Mre Vre - Mim Vim,   out_im = Mre Vim + Mim Vre
+// takes 8 DMMAs per group.  The C fragment (lane (r, k') holds row r of vectors 2k', 2k'+1) goes straight
+// back to the vectors' tile slots.  Needs every stage's variant to be uniform over the warp (sp.mma_ok).
+__device__ __forceinline__ void qgt_warp_subpass_mma(const QgtDevRun& run, const QgtDevSubPass& sp, const QgtSubCtx& cx,
+                                                     cplx* tile, uint64_t tilebase, int warp, int lane) {
+    constexpr int N = 8;
+    const int q = lane >> 2, k = lane & 3;
+    const int nthr_bits = run.K - 3;
+    // virtual thread (= vector) index t = warp*32 + g*8 + v: bits 0..2 <- v, bits 3..4 <- g, bits 5.. <- warp.
+    // Slots are XORs of the host-precomputed per-bit swizzled contributions.
+    uint32_t st5[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) st5[i] = sp.s_thr[i];
+    const uint32_t sr0 = sp.s_reg[0], sr1 = sp.s_reg[1], sr2 = sp.s_reg[2];
+    uint32_t swarp = 0;
+    uint64_t gwarp = tilebase;
+    for (int i = 5; i < nthr_bits; ++i)
+        if ((warp >> (i - 5)) & 1) { swarp ^= sp.s_thr[i]; gwarp |= sp.g_thr[i]; }
+    const uint32_t s_q = ((q & 1) ? st5[0] : 0u) ^ ((q & 2) ? st5[1] : 0u) ^ ((q & 4) ? st5[2] : 0u);    // vector q
+    const uint32_t s_k = ((k & 1) ? st5[1] : 0u) ^ ((k & 2) ? st5[2] : 0u);                               // vector 2k
+    const uint32_t c_k = ((k & 1) ? sr0 : 0u) ^ ((k & 2) ? sr1 : 0u);                                     // combo k
+    const uint32_t c_q = ((q & 1) ? sr0 : 0u) ^ ((q & 2) ? sr1 : 0u) ^ ((q & 4) ? sr2 : 0u);              // combo q
+    // slots of this lane: B layout (vector g*8+q, combos k and 4+k), C layout (vectors g*8+2k, +1, combo q)
+    uint32_t sB0[4], sC0[4];
+    const bool has_tdiag = sp.tdiag_end > sp.tdiag_begin;
+    cplx pend0[4], pend1[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t sg = swarp ^ ((g & 1) ? st5[3] : 0u) ^ ((g & 2) ? st5[4] : 0u);
+        sB0[g] = sg ^ s_q ^ c_k;          // combo 4+k: ^ sr2
+        sC0[g] = sg ^ s_k ^ c_q;          // vector 2k+1: ^ st5[0]
+        if (has_tdiag) {
+            pend0[g].x = 1.0; pend0[g].y = 0.0; pend1[g] = pend0[g];
+            uint64_t gc0 = gwarp;
+            const int t0 = g * 8 + 2 * k;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) if ((t0 >> i) & 1) gc0 |= sp.g_thr[i];
+            const uint64_t gc1 = gc0 | sp.g_thr[0];
+            for (int t = sp.tdiag_begin; t < sp.tdiag_end; ++t) {
+                const QgtDevThrDiag& td = (cx.ovr_kind == 2 && t == cx.ovr_index) ? *cx.ovr_tdiag : cx.tdiags[t];
+                qgt_thread_diag(pend0[g], td, gc0);
+                qgt_thread_diag(pend1[g], td, gc1);
+            }
+        }
+    }
+    const int nstage = sp.stage_end - sp.stage_begin;
+    for (int s = sp.stage_begin; s < sp.stage_end; ++s) {
+        const QgtDevStage& st = cx.stages[s];
+        const int off = (cx.ovr_kind == 1 && s == cx.ovr_index) ? cx.ovr_mat_off : st.mat_off;
+        const cplx* M = cx.pool + off + qgt_variant_index(st, gwarp) * QGT_VARIANT_STRIDE(N);
+        const cplx m0 = M[q * N + k], m1 = M[q * N + 4 + k];
+        const double nm0y = -m0.y, nm1y = -m1.y;
+        const bool last = (s == sp.stage_end - 1);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const cplx v0 = tile[sB0[g]], v1 = tile[sB0[g] ^ sr2];
+            double cr0 = 0.0, cr1 = 0.0, ci0 = 0.0, ci1 = 0.0;
+            dmma884(cr0, cr1, m0.x, v0.x);
+            dmma884(ci0, ci1, m0.x, v0.y);
+            dmma884(cr0, cr1, m1.x, v1.x);
+            dmma884(ci0, ci1, m1.x, v1.y);
+            dmma884(cr0, cr1, nm0y, v0.y);
+            dmma884(ci0, ci1, m0.y, v0.x);
+            dmma884(cr0, cr1, nm1y, v1.y);
+            dmma884(ci0, ci1, m1.y, v1.x);
+            cplx o0, o1;
+            o0.x = cr0; o0.y = ci0; o1.x = cr1; o1.y = ci1;
+            if (last && has_tdiag) {
+                cplx t0 = o0, t1 = o1;
+                o0.x = pend0[g].x * t0.x - pend0[g].y * t0.y; o0.y = pend0[g].x * t0.y + pend0[g].y * t0.x;
+                o1.x = pend1[g].x * t1.x - pend1[g].y * t1.y; o1.y = pend1[g].x * t1.y + pend1[g].y * t1.x;
+            }
+            __syncwarp();                 // every lane has read the group's slots before they are overwritten
+            tile[sC0[g]] = o0;
+            tile[sC0[g] ^ st5[0]] = o1;
+        }
+        __syncwarp();                     // the next stage reads slots other lanes just wrote
+    }
+    if (nstage == 0 && has_tdiag) {       // only thread diagonals
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const cplx a0 = tile[sC0[g]], a1 = tile[sC0[g] ^ st5[0]];
+            cplx o0, o1;
+            o0.x = pend0[g].x * a0.x - pend0[g].y * a0.y; o0.y = pend0[g].x * a0.y + pend0[g].y * a0.x;
+            o1.x = pend1[g].x * a1.x - pend1[g].y * a1.y; o1.y = pend1[g].x * a1.y + pend1[g].y * a1.x;
+            tile[sC0[g]] = o0; tile[sC0[g] ^ st5[0]] = o1;
+        }
+    }
+}
+
 // Shared memory: [tile: 2^K amplitudes][matrix pool of the run][override matrices of the current item].
 // The kernel is persistent over (tile, column) work items; the run header and its matrix pool are staged
 // once per CTA.  R = qubits of a stage matrix, B = batch qubits: a thread owns 2^(R+B) amplitudes.
@@ -37,13 +144,17 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
     for (int i = tid; i < (int)(sizeof(QgtDevRun) / 4); i += T)
         reinterpret_cast<uint32_t*>(&run)[i] = reinterpret_cast<const uint32_t*>(&a.runs[a.run_idx])[i];
     __syncthreads();
-    cplx* spool = tile + ((size_t)1 << run.K);
+    // two tile buffers: the next work item's tile streams in with cp.async while this one is processed
+    cplx* spool = tile + ((size_t)2 << run.K);
     cplx* sovr = spool + run.mat_count;
+    QgtDevSubPass* subs = reinterpret_cast<QgtDevSubPass*>(sovr + OVR_ELEMS);
     {
         const cplx* gpool = a.pool + run.mat_off;
         for (int i = tid; i < run.mat_count; i += T) spool[i] = gpool[i];
+        const uint32_t* gs = reinterpret_cast<const uint32_t*>(a.subs + run.sub_off);
+        uint32_t* ss = reinterpret_cast<uint32_t*>(subs);
+        for (int i = tid; i < run.nsub * (int)(sizeof(QgtDevSubPass) / 4); i += T) ss[i] = gs[i];
     }
-    const QgtDevSubPass* subs = a.subs + run.sub_off;
     QgtSubCtx cx;
     cx.stages = a.stages + run.stage_off;
     cx.tdiags = a.tdiags + run.tdiag_off;
@@ -51,7 +162,21 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
     cx.ovr_mat_off = run.mat_count;
     const QgtIoMap<R + B> io = qgt_make_iomap<R + B>(run, tid);
     const uint64_t total = a.ntiles * (uint64_t)a.nitems;
-    for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    auto prefetch = [&](uint64_t w, cplx* buf) {
+        const QgtSweepItem& it = a.items[(int)(w % (uint64_t)a.nitems)];
+        const uint64_t tb = qgt_tile_base(run, w / (uint64_t)a.nitems);
+        const cplx* src = reinterpret_cast<const cplx*>(it.src);
+#pragma unroll
+        for (int i = 0; i < (1 << (R + B)); ++i) {
+            const uint32_t idx = (uint32_t)tid + (uint32_t)i * (uint32_t)T;
+            cp_async16(buf + qgt_swz(idx), src + (tb | qgt_io_offset<R + B>(io, i)), 16);
+        }
+    };
+    uint64_t w = blockIdx.x;
+    if (w < total) prefetch(w, tile);
+    cp_async_commit();
+    for (int par = 0; w < total; w += gridDim.x, par ^= 1) {
+        cplx* cur = tile + ((size_t)par << run.K);
         const int item = (int)(w % (uint64_t)a.nitems);
         const uint64_t tau = w / (uint64_t)a.nitems;
         const QgtSweepItem& it = a.items[item];
@@ -64,20 +189,26 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
             const int cnt = QGT_VARIANT_STRIDE(N) << cx.stages[it.ovr_index].nvar;
             for (int i = tid; i < cnt && i < OVR_ELEMS; i += T) sovr[i] = g[i];
         }
-        qgt_phase_load<R + B>(io, tile, reinterpret_cast<const cplx*>(it.src), tilebase, tid, T);
+        // the other buffer was last read by the previous item's store phase, which ended at a barrier
+        if (w + gridDim.x < total) prefetch(w + gridDim.x, tile + ((size_t)(par ^ 1) << run.K));
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncthreads();
         for (int s = 0; s < run.nsub; ++s) {
             if (subs[s].nreg == 0) {
                 const QgtDevCost& co = (it.ovr_kind == 3 && subs[s].cost == it.ovr_index) ? it.ovr_cost : a.costs[run.cost_off + subs[s].cost];
-                qgt_phase_cost(run, co, tile, tilebase, tid, T, a.ct);
+                qgt_phase_cost(run, co, cur, tilebase, tid, T, a.ct);
+            } else if (R == 3 && B == 0 && a.use_mma && subs[s].mma_ok && T >= 32) {
+                qgt_warp_subpass_mma(run, subs[s], cx, cur, tilebase, tid >> 5, tid & 31);
             } else {
-                qgt_phase_subpass<R, B>(run, subs[s], cx, tile, tilebase, tid);
+                qgt_phase_subpass<R, B>(run, subs[s], cx, cur, tilebase, tid);
             }
             __syncthreads();
         }
-        qgt_phase_store<R + B>(io, tile, reinterpret_cast<cplx*>(it.dst), tilebase, tid, T, it.accumulate != 0);
+        qgt_phase_store<R + B>(io, cur, reinterpret_cast<cplx*>(it.dst), tilebase, tid, T, it.accumulate != 0);
         __syncthreads();
     }
+    cp_async_wait<0>();
 }
 
 template <int R, int B, int MAXT, int MINB>
@@ -94,11 +225,11 @@ static cudaError_t launch_sweep_cfg(const SweepLaunch& a, int T, size_t smem, un
 }
 
 template <int R, int B>
-static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, int num_sms, cudaStream_t st) {
+static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, int nsub, int num_sms, cudaStream_t st) {
     constexpr int N = 1 << R;
     const int T = 1 << (K - R - B);
-    const size_t smem = (sizeof(cplx) << K) + sizeof(cplx) * (size_t)mat_count +
-                        sizeof(cplx) * (size_t)(QGT_VARIANT_STRIDE(N) << QGT_MAX_VARIANT_BITS);
+    const size_t smem = 2 * (sizeof(cplx) << K) + sizeof(cplx) * (size_t)mat_count +
+                        sizeof(cplx) * (size_t)(QGT_VARIANT_STRIDE(N) << QGT_MAX_VARIANT_BITS) + (size_t)nsub * sizeof(QgtDevSubPass);
     const uint64_t total = a.ntiles * (uint64_t)a.nitems;
     if (total == 0) return cudaSuccess;
     if (smem > 200 * 1024 || T > 256) return cudaErrorInvalidValue;
@@ -110,15 +241,15 @@ static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, i
     return launch_sweep_cfg<R, B, 256, 2>(a, T, smem, grid, st);
 }
 
-cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int num_sms, cudaStream_t st) {
+cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int num_sms, cudaStream_t st) {
     if (K > QGT_MAX_TILE_QUBITS) return cudaErrorInvalidValue;
     switch (R * 2 + B) {
-    case 2: return launch_sweep_rb<1, 0>(a, K, mat_count, num_sms, st);
-    case 3: return launch_sweep_rb<1, 1>(a, K, mat_count, num_sms, st);
-    case 4: return launch_sweep_rb<2, 0>(a, K, mat_count, num_sms, st);
-    case 5: return launch_sweep_rb<2, 1>(a, K, mat_count, num_sms, st);
-    case 6: return launch_sweep_rb<3, 0>(a, K, mat_count, num_sms, st);
-    case 7: return launch_sweep_rb<3, 1>(a, K, mat_count, num_sms, st);
+    case 2: return launch_sweep_rb<1, 0>(a, K, mat_count, nsub, num_sms, st);
+    case 3: return launch_sweep_rb<1, 1>(a, K, mat_count, nsub, num_sms, st);
+    case 4: return launch_sweep_rb<2, 0>(a, K, mat_count, nsub, num_sms, st);
+    case 5: return launch_sweep_rb<2, 1>(a, K, mat_count, nsub, num_sms, st);
+    case 6: return launch_sweep_rb<3, 0>(a, K, mat_count, nsub, num_sms, st);
+    case 7: return launch_sweep_rb<3, 1>(a, K, mat_count, nsub, num_sms, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -126,18 +257,6 @@ cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_coun
 // ------------------------------------------------------------------------------------------------
 // Gram  C = A^H B  on the FP64 tensor pipe
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 // CTA tile: MT = WM*BM*8 rows (columns of A) x NT = WN*BN*8 cols (columns of B); WM*WN warps, each warp
 // owns BM x BN blocks of 8x8.  The 2^n-long amplitude axis is consumed in chunks of KC amplitudes moved

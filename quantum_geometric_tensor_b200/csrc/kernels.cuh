@@ -19,6 +19,7 @@ struct SweepLaunch {
     const QgtSweepItem* items;
     int nitems;
     uint64_t ntiles;
+    int use_mma;                 // dense stages on the FP64 tensor pipe (DMMA) where the sub-pass allows it
     QgtCostTable ct;
 };
 
@@ -36,7 +37,7 @@ struct GramLaunch {
 struct GramShape { int MT, NT; };
 
 // K, R: tile / register qubits of the run; grid is chosen inside
-cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int num_sms, cudaStream_t st);
+cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int num_sms, cudaStream_t st);
 
 GramShape gram_shape(int na, int nb);
 cudaError_t launch_gram(const GramLaunch& g, GramShape shp, cudaStream_t st);

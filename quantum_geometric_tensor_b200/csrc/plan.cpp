@@ -188,25 +188,43 @@ Dag build_dag(const std::vector<LoweredOp>& ops, int n) {
     return d;
 }
 
-void make_tperm(int K, const std::vector<int>& reg_local, const std::vector<int>& batch_local, std::vector<int>& tperm) {
-    std::vector<char> is_reg(K, 0);
-    for (int r : reg_local) is_reg[r] = 1;
-    for (int r : batch_local) is_reg[r] = 1;
-    std::vector<int> freep;
-    for (int p = 0; p < K; p++) if (!is_reg[p]) freep.push_back(p);
-    // the shared-memory swizzle XORs bit p of the index into bank-group bit (p mod 3): give the three
-    // lowest thread bits positions with distinct residues so a quarter-warp hits 8 distinct 16-byte groups
-    int pick[3] = {-1, -1, -1};
-    for (int p : freep) if (pick[p % 3] < 0) pick[p % 3] = p;
+// Thread-bit -> tile-position map of a sub-pass.
+//  * positions that select a matrix variant go last (they become warp-index bits, so a warp shares one
+//    matrix: required by the tensor-pipe path); returns false when they do not all fit above bit 4;
+//  * the shared-memory swizzle XORs bit p of the index into bank-group bit (p mod 3).  The tensor-pipe
+//    path loads with lanes spanning {thread bit 0, matrix bits 0,1} and stores with lanes spanning
+//    {matrix bit 0, thread bits 1,2}; the register path spans thread bits 0..2.  Pick thread bits 0..2
+//    so those triples have distinct residues where possible (conflict-free quarter-warps).
+bool make_tperm(int K, const std::vector<int>& reg_local, const std::vector<int>& batch_local,
+                const std::vector<int>& variant_local, std::vector<int>& tperm) {
+    std::vector<char> taken(K, 0), is_var(K, 0);
+    for (int r : reg_local) taken[r] = 1;
+    for (int r : batch_local) taken[r] = 1;
+    for (int v : variant_local) if (!taken[v]) is_var[v] = 1;
+    std::vector<int> freep, varp;
+    for (int p = 0; p < K; p++) if (!taken[p]) (is_var[p] ? varp : freep).push_back(p);
+    const int r0 = reg_local.size() > 0 ? reg_local[0] % 3 : -1, r1 = reg_local.size() > 1 ? reg_local[1] % 3 : -1;
+    int best[3] = {-1, -1, -1}, best_score = -1;
+    const int nf = (int)freep.size();
+    for (int a = 0; a < nf; a++) for (int b2 = 0; b2 < nf; b2++) for (int c = 0; c < nf; c++) {
+        if (a == b2 || a == c || b2 == c) continue;
+        const int pa = freep[a] % 3, pb = freep[b2] % 3, pc = freep[c] % 3;
+        int score = 0;
+        if (pa != r0 && pa != r1 && r0 != r1) score += 4;          // tensor-path loads
+        if (pb != r0 && pc != r0 && pb != pc) score += 4;          // tensor-path stores
+        if (pa != pb && pa != pc && pb != pc) score += 2;          // register path
+        if (score > best_score) { best_score = score; best[0] = a; best[1] = b2; best[2] = c; }
+    }
     tperm.clear();
-    if (pick[0] >= 0 && pick[1] >= 0 && pick[2] >= 0) {
-        std::vector<int> first = {pick[0], pick[1], pick[2]};
-        std::sort(first.begin(), first.end());
-        for (int p : first) tperm.push_back(p);
-        for (int p : freep) if (p != pick[0] && p != pick[1] && p != pick[2]) tperm.push_back(p);
+    if (best_score >= 0) {
+        for (int k = 0; k < 3; k++) tperm.push_back(freep[best[k]]);
+        for (int i = 0; i < nf; i++) if (i != best[0] && i != best[1] && i != best[2]) tperm.push_back(freep[i]);
     } else {
         tperm = freep;
     }
+    const bool warp_uniform = (int)tperm.size() >= 5;       // variant bits start at thread bit >= 5
+    for (int p : varp) tperm.push_back(p);
+    return warp_uniform || varp.empty();
 }
 
 }  // namespace
@@ -449,7 +467,12 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
                     for (int p = K - 1; p >= 0 && (int)sp.batch_local.size() < B; p--)
                         if (!used[p] && (pass == 1 || !is_var[p])) { sp.batch_local.push_back(p); used[p] = 1; }
             }
-            make_tperm(K, sp.reg_local, sp.batch_local, sp.tperm);
+            {
+                std::vector<int> variant_local;
+                for (const Stage& stg : sp.stages)
+                    for (int q : stg.vqubits) if (local_of[q] >= 0) variant_local.push_back(local_of[q]);
+                sp.mma_ok = make_tperm(K, sp.reg_local, sp.batch_local, variant_local, sp.tperm);
+            }
             run.subs.push_back(sp);
         }
         const int ridx = (int)plan.runs.size();
@@ -487,9 +510,17 @@ void build_image(const CircuitPlan& plan, PlanImage& img) {
             ds.stage_begin = (int)img.stages.size() - dr.stage_off;
             ds.tdiag_begin = (int)img.tdiags.size() - dr.tdiag_off;
             ds.cost = (int)img.costs.size() - dr.cost_off;
-            for (size_t r = 0; r < sp.reg_local.size(); r++) ds.regq[r] = (int8_t)sp.reg_local[r];
-            for (size_t r = 0; r < sp.batch_local.size(); r++) ds.regq[sp.reg_local.size() + r] = (int8_t)sp.batch_local[r];
-            for (size_t t = 0; t < sp.tperm.size(); t++) ds.tperm[t] = (int8_t)sp.tperm[t];
+            ds.mma_ok = sp.mma_ok ? 1 : 0;
+            auto swz = [](uint32_t idx) { return idx ^ ((idx >> 3) & 7u) ^ ((idx >> 6) & 7u) ^ ((idx >> 9) & 7u); };
+            for (size_t r = 0; r < sp.reg_local.size() + sp.batch_local.size(); r++) {
+                const int p = r < sp.reg_local.size() ? sp.reg_local[r] : sp.batch_local[r - sp.reg_local.size()];
+                ds.s_reg[r] = swz(1u << p);
+                ds.g_reg[r] = bit(run.tile_qubits[p]);
+            }
+            for (size_t t = 0; t < sp.tperm.size(); t++) {
+                ds.s_thr[t] = swz(1u << sp.tperm[t]);
+                ds.g_thr[t] = bit(run.tile_qubits[sp.tperm[t]]);
+            }
             if (sp.is_cost) img.costs.push_back(make_cost(run.ops[sp.op_begin], false));
             for (int o : sp.tdiags) img.tdiags.push_back(make_tdiag(run.ops[o], false));
             for (const Stage& st : sp.stages) {

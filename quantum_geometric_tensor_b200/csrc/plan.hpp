@@ -48,6 +48,7 @@ struct SubPass {
     std::vector<int> tperm;         // thread bit -> local position
     int op_begin = 0, op_end = 0;   // lowered ops
     bool is_cost = false;           // tile-level pass holding exactly one COST op
+    bool mma_ok = false;            // variant-selecting tile qubits all sit on warp-index thread bits
     std::vector<Stage> stages;
     std::vector<int> tdiags;        // lowered diagonal ops that touch no register qubit
 };

@@ -169,34 +169,29 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
                               uint64_t tilebase, int tid) {
     constexpr int N = 1 << R;
     constexpr int NB = 1 << B;
-    uint32_t lbase = 0;
+    uint32_t sbase = 0;                  // swizzled slot of the thread's combo 0
     uint64_t gbase = tilebase;
     const int nthr_bits = run.K - R - B;
-    for (int i = 0; i < nthr_bits; i++) {
-        if ((tid >> i) & 1) {
-            const int p = sp.tperm[i];
-            lbase |= 1u << p;
-            gbase |= 1ull << run.tq[p];
-        }
-    }
-    uint32_t regl[R + B];
+    for (int i = 0; i < nthr_bits; i++)
+        if ((tid >> i) & 1) { sbase ^= sp.s_thr[i]; gbase |= sp.g_thr[i]; }
+    uint32_t sreg[R + B];
 #pragma unroll
-    for (int r = 0; r < R + B; ++r) regl[r] = 1u << sp.regq[r];
+    for (int r = 0; r < R + B; ++r) sreg[r] = sp.s_reg[r];
     // swizzled tile slot of (batch half h, matrix combo c)
     uint32_t slot[NB][N];
     uint64_t gh[NB];
 #pragma unroll
     for (int h = 0; h < NB; ++h) {
-        uint32_t lh = lbase;
+        uint32_t sh = sbase;
         gh[h] = gbase;
 #pragma unroll
-        for (int r = 0; r < B; ++r) if (h & (1 << r)) { lh |= regl[R + r]; gh[h] |= 1ull << run.tq[sp.regq[R + r]]; }
+        for (int r = 0; r < B; ++r) if (h & (1 << r)) { sh ^= sreg[R + r]; gh[h] |= sp.g_reg[R + r]; }
 #pragma unroll
         for (int c = 0; c < N; ++c) {
-            uint32_t l = lh;
+            uint32_t l = sh;
 #pragma unroll
-            for (int r = 0; r < R; ++r) if (c & (1 << r)) l |= regl[r];
-            slot[h][c] = qgt_swz(l);
+            for (int r = 0; r < R; ++r) if (c & (1 << r)) l ^= sreg[r];
+            slot[h][c] = l;
         }
     }
     cplx pend[NB];
@@ -260,12 +255,12 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
                     }
                     cplx o; o.x = xr; o.y = xi;
                     if (last) { const cplx q = o; o.x = pend[h].x * q.x - pend[h].y * q.y; o.y = pend[h].x * q.y + pend[h].y * q.x; }
-                    uint32_t l = 0;   // slot[h][i] with a run-time i: recompute instead of indexing registers
+                    uint32_t l = sbase;   // slot[h][i] with a run-time i: recompute instead of indexing registers
 #pragma unroll
-                    for (int r = 0; r < R; ++r) if (i & (1 << r)) l |= regl[r];
+                    for (int r = 0; r < R; ++r) if (i & (1 << r)) l ^= sreg[r];
 #pragma unroll
-                    for (int r = 0; r < B; ++r) if (h & (1 << r)) l |= regl[R + r];
-                    tile[qgt_swz(lbase | l)] = o;
+                    for (int r = 0; r < B; ++r) if (h & (1 << r)) l ^= sreg[R + r];
+                    tile[l] = o;
                 }
             }
         }

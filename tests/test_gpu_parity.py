@@ -71,6 +71,29 @@ def test_tile_size_option(ctx, oracle, n, tile):
     assert np.abs(psi - oracle.apply(c, th)).max() < 1e-13
 
 
+@pytest.mark.parametrize("opts", [{"use_mma": 0}, {"use_mma": 0, "batch_qubits": 1}, {"use_mma": 1, "reg_qubits": 2},
+                                  {"use_mma": 1, "tile_qubits": 10, "max_ops_per_run": 12}])
+def test_kernel_path_options(ctx, oracle, opts):
+    # the register (DFMA) path, the batched variant and other tilings must agree with the tensor-pipe default
+    defaults = {"use_mma": 1, "batch_qubits": 0, "reg_qubits": 3, "tile_qubits": 11, "max_ops_per_run": 160}
+    c = K.random_circuit(12, 80, 4242, kinds=ALL_KINDS, share_params=True)
+    th = K.default_angles(max(1, c.num_params), 1)
+    c1 = K.config("c1")
+    th1 = K.default_angles(c1.num_params)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    try:
+        psi = _state(ctx, c, th)
+        q = ctx.qgt(c, th)
+        q1 = ctx.qgt(c1, th1)
+    finally:
+        for k, v in defaults.items():
+            ctx.set_option(k, v)
+    assert np.abs(psi - oracle.apply(c, th)).max() < 1e-13
+    assert rel_err(q, oracle.qgt(c, th)) < TOL
+    assert rel_err(q1, oracle.qgt(c1, th1)) < TOL
+
+
 def test_every_target_every_kind(ctx, oracle):
     # each gate kind on each target (and a control on every other position) of a 13-qubit register
     n = 13
