@@ -184,6 +184,7 @@ typedef struct qgt_b200_stats {
     double sweep_bytes;       /* algorithmic bytes moved by sweep launches (32*D or 16*D+16*D per column pass) */
     double gram_flops;        /* algorithmic real flops of Gram launches (8*na*nb*D) */
     double gram_bytes;
+    double exchange_bytes;    /* bytes this rank sent in qubit-swap exchanges (sharded states) */
     int64_t sweep_launches;
     int64_t gram_launches;
     int64_t other_launches;
@@ -200,16 +201,20 @@ int  qgt_b200_get_stats(qgt_b200_ctx* ctx, qgt_b200_stats* out);
 long qgt_b200_plan_dump(const qgt_b200_circuit* circuit, const double* theta, int tile_qubits, int reg_qubits,
                         size_t column_slots, char* buf, size_t buflen);
 
-/* ---- multi-GPU (one process per GPU; amplitudes sharded on the top log2(world) qubits) ------ */
-#define QGT_B200_IPC_HANDLE_BYTES 64
+/* ---- multi-GPU (one process per GPU; amplitudes sharded on the top log2(world) qubits) ------
+ * Rank 0 creates the NCCL id, the host program broadcasts it (MPI, torch.distributed, a file ...), every rank
+ * calls qgt_b200_dist_init once.  Afterwards qgt_b200_state_create allocates a SHARD (2^n / world amplitudes;
+ * upload/download move the shard of this rank), and apply_circuit / qgt / state_norm2 act on the sharded
+ * state collectively: every rank must make the same calls with the same circuit and theta. */
 #define QGT_B200_NCCL_ID_BYTES    128
-int  qgt_b200_dist_unique_id(uint8_t id[QGT_B200_NCCL_ID_BYTES]);          /* rank 0 creates, host broadcasts */
+int  qgt_b200_dist_unique_id(uint8_t id[QGT_B200_NCCL_ID_BYTES]);
 int  qgt_b200_dist_init(qgt_b200_ctx* ctx, int rank, int world, const uint8_t id[QGT_B200_NCCL_ID_BYTES]);
 int  qgt_b200_dist_world(const qgt_b200_ctx* ctx, int* rank, int* world);
-/* peer-memory exchange buffers: every rank exports its handle, the host all-gathers them */
-int  qgt_b200_dist_export_ipc(qgt_b200_ctx* ctx, size_t local_bytes, uint8_t handle[QGT_B200_IPC_HANDLE_BYTES]);
-int  qgt_b200_dist_import_ipc(qgt_b200_ctx* ctx, const uint8_t* handles /* world * 64 */);
 int  qgt_b200_dist_barrier(qgt_b200_ctx* ctx);
+/* plan_dump for a state sharded over `world` ranks (no device needed): runs, EXCHANGE pseudo-runs and the
+ * per-segment logical->physical qubit maps */
+long qgt_b200_plan_dump_sharded(const qgt_b200_circuit* circuit, const double* theta, int world, int restore_identity,
+                                int tile_qubits, int reg_qubits, size_t column_slots, char* buf, size_t buflen);
 
 #ifdef __cplusplus
 }

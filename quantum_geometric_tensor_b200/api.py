@@ -29,7 +29,7 @@ class QgtError(RuntimeError):
 
 class Stats(C.Structure):
     _fields_ = [("ms_total", C.c_double), ("ms_sweep", C.c_double), ("ms_gram", C.c_double), ("ms_other", C.c_double),
-                ("sweep_bytes", C.c_double), ("gram_flops", C.c_double), ("gram_bytes", C.c_double),
+                ("sweep_bytes", C.c_double), ("gram_flops", C.c_double), ("gram_bytes", C.c_double), ("exchange_bytes", C.c_double),
                 ("sweep_launches", C.c_int64), ("gram_launches", C.c_int64), ("other_launches", C.c_int64),
                 ("sweep_column_passes", C.c_int64),
                 ("num_runs", C.c_int32), ("resident_columns", C.c_int32), ("blocks", C.c_int32), ("tile_qubits", C.c_int32)]
@@ -85,8 +85,8 @@ def load() -> C.CDLL:
     L.qgt_b200_dist_unique_id.argtypes = [C.c_char_p]
     L.qgt_b200_dist_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     L.qgt_b200_dist_world.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    L.qgt_b200_dist_export_ipc.argtypes = [vp, C.c_size_t, C.c_char_p]
-    L.qgt_b200_dist_import_ipc.argtypes = [vp, C.c_char_p]
+    L.qgt_b200_plan_dump_sharded.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t]
+    L.qgt_b200_plan_dump_sharded.restype = C.c_long
     L.qgt_b200_dist_barrier.argtypes = [vp]
     _lib = L
     return L
@@ -116,6 +116,23 @@ def plan_dump(circ: Circuit, theta: Optional[np.ndarray] = None, tile_qubits: in
         _check(int(n))
     buf = C.create_string_buffer(n + 1)
     n2 = L.qgt_b200_plan_dump(C.byref(cc), _dp(th), tile_qubits, reg_qubits, column_slots, buf, n + 1)
+    if n2 < 0:
+        _check(int(n2))
+    return json.loads(buf.value.decode())
+
+
+def plan_dump_sharded(circ: Circuit, theta: Optional[np.ndarray], world: int, restore_identity: bool = True,
+                      tile_qubits: int = 0, reg_qubits: int = 0, column_slots: int = 0) -> dict:
+    """Plan of a state sharded over ``world`` ranks: runs, EXCHANGE pseudo-runs, qubit maps.  Needs no GPU."""
+    L = load()
+    cc = circ.to_c()
+    th = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
+    args = (C.byref(cc), _dp(th), world, 1 if restore_identity else 0, tile_qubits, reg_qubits, column_slots)
+    n = L.qgt_b200_plan_dump_sharded(*args, None, 0)
+    if n < 0:
+        _check(int(n))
+    buf = C.create_string_buffer(n + 1)
+    n2 = L.qgt_b200_plan_dump_sharded(*args, buf, n + 1)
     if n2 < 0:
         _check(int(n2))
     return json.loads(buf.value.decode())
@@ -179,6 +196,21 @@ class Context:
         self.rank = 0
         self._states = weakref.WeakSet()     # states must be destroyed before their context
         _check(self.L.qgt_b200_create(C.byref(self.h), device))
+
+    def dist_init(self, rank: int, world: int, unique_id: bytes) -> None:
+        """Join the NCCL communicator (collective); ``unique_id`` comes from rank 0's ``dist_unique_id()``."""
+        assert len(unique_id) == 128
+        _check(self.L.qgt_b200_dist_init(self.h, rank, world, unique_id))
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def dist_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(load().qgt_b200_dist_unique_id(buf))
+        return buf.raw
+
+    def barrier(self) -> None:
+        _check(self.L.qgt_b200_dist_barrier(self.h))
 
     def set_option(self, key: str, value: float) -> None:
         _check(self.L.qgt_b200_set_option(self.h, key.encode(), float(value)))

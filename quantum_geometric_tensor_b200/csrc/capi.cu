@@ -306,6 +306,7 @@ int upload_plan(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
         if (u.bytes && e == cudaSuccess) e = cudaMemcpyAsync(u.buf->ptr, u.src, u.bytes, cudaMemcpyHostToDevice, c->stream);
     }
     if (e != cudaSuccess) return cuda_fail(e, "plan upload");
+    c->seg_cost.clear();
     c->cost.edges = nullptr; c->cost.num_edges = 0; c->cost.vertex_weights = nullptr; c->cost.n = circ.num_qubits;
     if (circ.num_edges && circ.edges) {
         std::vector<QgtDevEdge> ed(circ.num_edges);
@@ -347,7 +348,8 @@ static int do_sweep(qgt_b200_ctx* c, const CircuitPlan& plan, int run, const Qgt
     a.nitems = nitems;
     a.ntiles = shard_tiles;
     a.use_mma = c->use_mma;
-    a.ct = c->cost;
+    a.gprefix = (uint64_t)c->rank << plan.nloc;
+    a.ct = c->seg_cost.empty() ? c->cost : c->seg_cost[plan.runs[run].segment];
     const int K = plan.runs[run].K;
     const int R = plan.R;
     int mat_count = 0;
@@ -381,6 +383,10 @@ int apply_plan_inplace(qgt_b200_ctx* c, const CircuitPlan& plan, cplx* d, uint64
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return cuda_fail(e, "item upload");
     for (size_t r = 0; r < plan.runs.size(); r++) {
+        if (plan.runs[r].exchange_gbit >= 0) {
+            if ((rc = dist_exchange(c, d, D, plan.runs[r].exchange_gbit))) return rc;
+            continue;
+        }
         const uint64_t ntiles = D >> plan.runs[r].K;
         if ((rc = do_sweep(c, plan, (int)r, (const QgtSweepItem*)c->items.ptr, 1, ntiles))) return rc;
         c->stats.sweep_bytes += 32.0 * (double)D;
@@ -498,6 +504,16 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             c->stats.other_launches++;
             break; }
         case INSTR_SWEEP: {
+            if (plan.runs[in.run].exchange_gbit >= 0) {      // sharded state: pairwise half-shard exchange per column
+                for (const SweepCol& sc : in.cols) {
+                    c->timer.begin(c->stream, 2, "exchange");
+                    rc = dist_exchange(c, arena + (size_t)sc.dst * D, D, plan.runs[in.run].exchange_gbit);
+                    c->timer.end(c->stream);
+                    if (rc) return rc;
+                    c->stats.other_launches++;
+                }
+                break;
+            }
             const uint64_t ntiles = D >> plan.runs[in.run].K;
             if ((rc = do_sweep(c, plan, in.run, (const QgtSweepItem*)c->items.ptr + item_off[i], (int)in.cols.size(), ntiles))) return rc;
             for (const SweepCol& sc : in.cols)
@@ -813,6 +829,32 @@ long qgt_b200_plan_dump(const qgt_b200_circuit* circ, const double* theta, int t
         pp = &prog;
     }
     const std::string js = dump_json(*circ, plan, pp);
+    if (buf && buflen > js.size()) std::memcpy(buf, js.c_str(), js.size() + 1);
+    return (long)js.size();
+}
+
+long qgt_b200_plan_dump_sharded(const qgt_b200_circuit* circ, const double* theta, int world, int restore_identity,
+                                int tile_qubits, int reg_qubits, size_t column_slots, char* buf, size_t buflen) {
+    if (!circ) return fail(QGT_B200_ERR_INVALID_ARG, "circuit is NULL");
+    if (world < 1 || (world & (world - 1))) return fail(QGT_B200_ERR_INVALID_ARG, "world must be a power of two");
+    int gbits = 0;
+    while ((1 << gbits) < world) gbits++;
+    PlanOptions opt;
+    if (tile_qubits) opt.tile_qubits = tile_qubits;
+    if (reg_qubits) opt.reg_qubits = reg_qubits;
+    std::vector<double> zeros((size_t)std::max(1, circ->num_params), 0.0);
+    CircuitPlan plan;
+    std::vector<MappedSegment> segs;
+    std::string err;
+    int rc = build_plan_sharded(*circ, theta ? theta : zeros.data(), opt, circ->num_qubits - gbits, restore_identity != 0, plan, segs, err);
+    if (rc) return fail(rc, err);
+    Program prog;
+    const Program* pp = nullptr;
+    if (column_slots) {
+        if ((rc = build_qgt_program(plan, column_slots, restore_identity != 0, prog, err))) return fail(rc, err);
+        pp = &prog;
+    }
+    const std::string js = dump_json(*circ, plan, pp, &segs);
     if (buf && buflen > js.size()) std::memcpy(buf, js.c_str(), js.size() + 1);
     return (long)js.size();
 }

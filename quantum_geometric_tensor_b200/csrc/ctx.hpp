@@ -53,6 +53,7 @@ struct qgt_b200_ctx {
     qgt::DevBuf arena, img_runs, img_subs, img_stages, img_tdiags, img_costs, img_pool, ovr_pool, items, aux, partial, cmat, outbuf, edges, vweights, scratch;
     void* pinned = nullptr;
     QgtCostTable cost = {nullptr, 0, nullptr, 0};
+    std::vector<QgtCostTable> seg_cost;      // sharded states: one cost table per mapped segment (remapped qubits)
     qgt::Timer timer;
     qgt_b200_stats stats = {};
     // multi-GPU
@@ -84,6 +85,8 @@ int stats_end(qgt_b200_ctx* c);
 void dist_shutdown(qgt_b200_ctx* c);
 int dist_allreduce_host(qgt_b200_ctx* c, double* v, int n);   // sum over ranks, no-op for world == 1
 int dist_apply_circuit(qgt_b200_state* s, const qgt_b200_circuit* circ, const double* theta);
+int dist_exchange(qgt_b200_ctx* c, cplx* col, uint64_t D, int gbit);   // swap rank bit `gbit` with the top local qubit
+int dist_allreduce_device(qgt_b200_ctx* c, double* d_buf, size_t count);   // in place, stream ordered
 int dist_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
              double* metric, double* berry, double* q_full, qgt_b200_state* psi_out);
 

@@ -1,39 +1,304 @@
-// dist.cu — multi-GPU path: one process per GPU, amplitudes sharded on the top log2(world) qubits.
-// (placeholder until the sharded executor lands: world == 1 everywhere)
+// dist.cu — multi-GPU path inside one box: one process per GPU, amplitudes sharded on the top
+// log2(world) qubits (rank r owns the amplitudes whose high index bits equal r), NCCL over NVLink.
+//
+// Replaces the reference's qubit-count "sharding" and root-gather sync
+// (src/quantum_geometric/distributed/quantum_distributed_operations.c:260-316, documented as defective in
+// BASELINE.md §4 #13) and the serial ncclCommInitRank loop of core/multi_gpu_operations.c:46-116 (#14).
+//
+//   * gates acting diagonally on rank qubits (RZ/CZ/phases/controls/cost layer) cost no traffic: the sweep
+//     kernel ORs the rank bits into the global index its masks are evaluated on;
+//   * a gate acting non-diagonally on a rank qubit first swaps that qubit with the top local one: each rank
+//     exchanges the contiguous half of its shard it does not keep with one peer (ncclSend/ncclRecv pair);
+//     plan.cpp's mapper chooses which local qubit to evict and inserts these EXCHANGE pseudo-runs;
+//   * the Gram rows are sharded like the amplitudes: per-rank partial (P+1)x(P+1) matrices are summed with a
+//     single ncclAllReduce before Q = C - v v^H is formed.
+#include <nccl.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 #include "ctx.hpp"
+
+#include <dlfcn.h>
 
 namespace qgt {
 
-struct DistState { int dummy; };
+// NCCL is bound at run time, not at link time: a host process that already carries its own libnccl.so.2
+// (PyTorch bundles a newer one than the system's) keeps using it, and merely loading this library never
+// drags a second NCCL into the process.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
 
-void dist_shutdown(qgt_b200_ctx* c) { delete c->dist; c->dist = nullptr; }
+static int nccl_load() {
+    if (g_nccl.handle) return QGT_B200_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);       // the copy the host process already uses
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return fail(QGT_B200_ERR_HARDWARE, std::string("cannot load libnccl.so.2: ") + dlerror());
+    NcclApi a;
+    a.handle = h;
+    bool ok = true;
+    auto sym = [&](const char* name) { void* p = dlsym(h, name); if (!p) ok = false; return p; };
+    a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+    a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+    a.Send = (decltype(a.Send))sym("ncclSend");
+    a.Recv = (decltype(a.Recv))sym("ncclRecv");
+    a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+    a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) return fail(QGT_B200_ERR_HARDWARE, "libnccl.so.2 lacks a required symbol");
+    g_nccl = a;
+    return QGT_B200_OK;
+}
+
+struct DistState {
+    ncclComm_t comm = nullptr;
+    DevBuf bounce;       // receive buffer of an exchange: half a column
+    DevBuf red;          // small reduction buffer
+    DevBuf seg_edges, seg_vw;
+};
+
+static int nccl_fail(ncclResult_t r, const char* what) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    return fail(QGT_B200_ERR_HARDWARE, buf);
+}
+
+void dist_shutdown(qgt_b200_ctx* c) {
+    if (!c->dist) return;
+    if (c->dist->comm) g_nccl.CommDestroy(c->dist->comm);
+    c->dist->bounce.release(); c->dist->red.release(); c->dist->seg_edges.release(); c->dist->seg_vw.release();
+    delete c->dist;
+    c->dist = nullptr;
+}
+
+int dist_allreduce_device(qgt_b200_ctx* c, double* d_buf, size_t count) {
+    if (c->world == 1) return QGT_B200_OK;
+    ncclResult_t r = g_nccl.AllReduce(d_buf, d_buf, count, ncclDouble, ncclSum, c->dist->comm, c->stream);
+    if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce");
+    return QGT_B200_OK;
+}
 
 int dist_allreduce_host(qgt_b200_ctx* c, double* v, int n) {
-    (void)v; (void)n;
     if (c->world == 1) return QGT_B200_OK;
-    return fail(QGT_B200_ERR_UNSUPPORTED, "multi-GPU reductions not built");
+    int rc = c->dist->red.reserve((size_t)n * sizeof(double));
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(c->dist->red.ptr, v, n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "allreduce staging");
+    if ((rc = dist_allreduce_device(c, (double*)c->dist->red.ptr, (size_t)n))) return rc;
+    e = cudaMemcpyAsync(v, c->dist->red.ptr, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "allreduce readback");
+    return QGT_B200_OK;
 }
 
-int dist_apply_circuit(qgt_b200_state*, const qgt_b200_circuit*, const double*) {
-    return fail(QGT_B200_ERR_UNSUPPORTED, "multi-GPU circuit application not built");
+// swap rank bit `gbit` with the top local qubit of the column at `col` (D local amplitudes)
+int dist_exchange(qgt_b200_ctx* c, cplx* col, uint64_t D, int gbit) {
+    if (c->world == 1 || !c->dist) return fail(QGT_B200_ERR_INTERNAL, "exchange on an unsharded state");
+    const int peer = c->rank ^ (1 << gbit);
+    const int mybit = (c->rank >> gbit) & 1;
+    const uint64_t half = D / 2;
+    int rc = c->dist->bounce.reserve(half * sizeof(cplx));
+    if (rc) return rc;
+    // keep the half whose top local bit equals my rank bit; trade the other one with the peer
+    cplx* moving = col + (mybit ? 0 : half);
+    ncclResult_t r = g_nccl.GroupStart();
+    if (r == ncclSuccess) r = g_nccl.Send(moving, half * 2, ncclDouble, peer, c->dist->comm, c->stream);
+    if (r == ncclSuccess) r = g_nccl.Recv(c->dist->bounce.ptr, half * 2, ncclDouble, peer, c->dist->comm, c->stream);
+    if (r == ncclSuccess) r = g_nccl.GroupEnd();
+    if (r != ncclSuccess) return nccl_fail(r, "exchange send/recv");
+    cudaError_t e = cudaMemcpyAsync(moving, c->dist->bounce.ptr, half * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "exchange copy");
+    c->stats.exchange_bytes += (double)(half * sizeof(cplx));
+    return QGT_B200_OK;
 }
 
-int dist_qgt(qgt_b200_ctx*, const qgt_b200_circuit*, const double*, double*, double*, double*, qgt_b200_state*) {
-    return fail(QGT_B200_ERR_UNSUPPORTED, "multi-GPU QGT not built");
+// cost tables with qubits renamed by each segment's logical -> physical map
+static int upload_segment_costs(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const std::vector<MappedSegment>& segs) {
+    c->seg_cost.clear();
+    if (!circ.num_edges && !circ.vertex_weights) return QGT_B200_OK;
+    const int n = circ.num_qubits;
+    std::vector<QgtDevEdge> ed;
+    std::vector<double> vw;
+    for (const MappedSegment& sg : segs) {
+        for (size_t k = 0; k < circ.num_edges; k++) {
+            QgtDevEdge e;
+            e.i = sg.phys_of_logical[circ.edges[k].i]; e.j = sg.phys_of_logical[circ.edges[k].j]; e.w = circ.edges[k].weight;
+            ed.push_back(e);
+        }
+        if (circ.vertex_weights) {
+            std::vector<double> w(n, 0.0);
+            for (int q = 0; q < n; q++) w[sg.phys_of_logical[q]] = circ.vertex_weights[q];
+            vw.insert(vw.end(), w.begin(), w.end());
+        }
+    }
+    int rc;
+    if ((rc = c->dist->seg_edges.reserve(std::max<size_t>(16, ed.size() * sizeof(QgtDevEdge))))) return rc;
+    if ((rc = c->dist->seg_vw.reserve(std::max<size_t>(16, vw.size() * sizeof(double))))) return rc;
+    cudaError_t e = cudaSuccess;
+    if (!ed.empty()) e = cudaMemcpyAsync(c->dist->seg_edges.ptr, ed.data(), ed.size() * sizeof(QgtDevEdge), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && !vw.empty()) e = cudaMemcpyAsync(c->dist->seg_vw.ptr, vw.data(), vw.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "segment cost upload");
+    for (size_t s = 0; s < segs.size(); s++) {
+        QgtCostTable t;
+        t.edges = circ.num_edges ? (const QgtDevEdge*)c->dist->seg_edges.ptr + s * circ.num_edges : nullptr;
+        t.num_edges = (int)circ.num_edges;
+        t.vertex_weights = circ.vertex_weights ? (const double*)c->dist->seg_vw.ptr + s * n : nullptr;
+        t.n = n;
+        c->seg_cost.push_back(t);
+    }
+    return QGT_B200_OK;
+}
+
+int dist_apply_circuit(qgt_b200_state* s, const qgt_b200_circuit* circ, const double* theta) {
+    qgt_b200_ctx* c = s->ctx;
+    CircuitPlan plan;
+    std::vector<MappedSegment> segs;
+    std::string err;
+    int rc = build_plan_sharded(*circ, theta, c->opt, s->nloc, true, plan, segs, err);
+    if (rc) return fail(rc, err);
+    PlanImage img;
+    stats_begin(c);
+    if ((rc = upload_plan(c, *circ, plan, img))) return rc;
+    if ((rc = upload_segment_costs(c, *circ, segs))) return rc;
+    if ((rc = apply_plan_inplace(c, plan, s->d, s->D))) return rc;
+    if ((rc = stats_end(c))) return rc;
+    c->stats.num_runs = (int)plan.runs.size();
+    c->stats.tile_qubits = plan.K;
+    return QGT_B200_OK;
+}
+
+int dist_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
+             double* metric, double* berry, double* q_full, qgt_b200_state* psi_out) {
+    const int n = circ->num_qubits, P = circ->num_params;
+    int gbits = 0;
+    while ((1 << gbits) < c->world) gbits++;
+    const int nloc = n - gbits;
+    if (nloc < 4) return fail(QGT_B200_ERR_INVALID_ARG, "state too small for this many ranks");
+    const uint64_t D = (uint64_t)1 << nloc;
+    CircuitPlan plan;
+    std::vector<MappedSegment> segs;
+    std::string err;
+    int rc = build_plan_sharded(*circ, theta, c->opt, nloc, psi_out != nullptr, plan, segs, err);
+    if (rc) return fail(rc, err);
+    Program prog;
+    // every rank must build the same program: agree on the smallest slot count
+    size_t slots = workspace_slots(c, D, ((size_t)64 << 20) + (D / 2) * sizeof(cplx));
+    {
+        int rc2 = c->dist->red.reserve(sizeof(double));
+        if (rc2) return rc2;
+        double v = (double)slots;
+        cudaError_t e0 = cudaMemcpyAsync(c->dist->red.ptr, &v, sizeof v, cudaMemcpyHostToDevice, c->stream);
+        if (e0 != cudaSuccess) return cuda_fail(e0, "slot staging");
+        ncclResult_t r = g_nccl.AllReduce(c->dist->red.ptr, c->dist->red.ptr, 1, ncclDouble, ncclMin, c->dist->comm, c->stream);
+        if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce(min)");
+        e0 = cudaMemcpyAsync(&v, c->dist->red.ptr, sizeof v, cudaMemcpyDeviceToHost, c->stream);
+        if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(c->stream);
+        if (e0 != cudaSuccess) return cuda_fail(e0, "slot readback");
+        slots = (size_t)v;
+    }
+    if ((rc = build_qgt_program(plan, slots, psi_out != nullptr, prog, err))) return fail(rc, err);
+    if ((rc = c->arena.reserve((size_t)prog.num_slots * D * sizeof(cplx)))) return rc;
+    const size_t cm = (size_t)(P + 1) * (P + 1);
+    if ((rc = c->cmat.reserve(std::max<size_t>(16, cm * sizeof(cplx))))) return rc;
+    if ((rc = c->outbuf.reserve(std::max<size_t>(16, (size_t)P * P * 4 * sizeof(double))))) return rc;
+    PlanImage img;
+    stats_begin(c);
+    if ((rc = upload_plan(c, *circ, plan, img))) return rc;
+    if ((rc = upload_segment_costs(c, *circ, segs))) return rc;
+    cudaError_t e = cudaMemsetAsync(c->cmat.ptr, 0, cm * sizeof(cplx), c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "memset");
+    if ((rc = run_program(c, *circ, plan, prog, (cplx*)c->arena.ptr, D, (cplx*)c->cmat.ptr))) return rc;
+    // partial Gram matrices of the shards -> one allreduce of (P+1)^2 complex numbers
+    c->timer.begin(c->stream, 2, "gram allreduce");
+    rc = dist_allreduce_device(c, (double*)c->cmat.ptr, cm * 2);
+    c->timer.end(c->stream);
+    if (rc) return rc;
+    double* d_metric = (double*)c->outbuf.ptr;
+    double* d_berry = d_metric + (size_t)P * P;
+    cplx* d_q = (cplx*)(d_berry + (size_t)P * P);
+    e = launch_finalize((const cplx*)c->cmat.ptr, P, d_metric, d_berry, d_q, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "finalize launch");
+    const size_t pp = (size_t)P * P;
+    if (P > 0) {
+        if (metric && e == cudaSuccess) e = cudaMemcpyAsync(metric, d_metric, pp * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (berry && e == cudaSuccess) e = cudaMemcpyAsync(berry, d_berry, pp * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (q_full && e == cudaSuccess) e = cudaMemcpyAsync(q_full, d_q, pp * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (psi_out && e == cudaSuccess)
+        e = cudaMemcpyAsync(psi_out->d, (cplx*)c->arena.ptr + (size_t)prog.psi_slot * D, D * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "result copy");
+    if ((rc = stats_end(c))) return rc;
+    c->stats.num_runs = (int)plan.runs.size();
+    c->stats.resident_columns = prog.resident;
+    c->stats.blocks = prog.blocks;
+    c->stats.tile_qubits = plan.K;
+    return QGT_B200_OK;
 }
 
 }  // namespace qgt
 
 extern "C" {
-int qgt_b200_dist_unique_id(uint8_t*) { return qgt::fail(QGT_B200_ERR_UNSUPPORTED, "multi-GPU not built"); }
-int qgt_b200_dist_init(qgt_b200_ctx*, int, int, const uint8_t*) { return qgt::fail(QGT_B200_ERR_UNSUPPORTED, "multi-GPU not built"); }
+
+int qgt_b200_dist_unique_id(uint8_t id[QGT_B200_NCCL_ID_BYTES]) {
+    if (!id) return qgt::fail(QGT_B200_ERR_INVALID_ARG, "id is NULL");
+    static_assert(sizeof(ncclUniqueId) <= QGT_B200_NCCL_ID_BYTES, "unique id does not fit");
+    int lrc = qgt::nccl_load();
+    if (lrc) return lrc;
+    ncclUniqueId uid;
+    ncclResult_t r = qgt::g_nccl.GetUniqueId(&uid);
+    if (r != ncclSuccess) return qgt::nccl_fail(r, "ncclGetUniqueId");
+    std::memset(id, 0, QGT_B200_NCCL_ID_BYTES);
+    std::memcpy(id, &uid, sizeof uid);
+    return QGT_B200_OK;
+}
+
+int qgt_b200_dist_init(qgt_b200_ctx* c, int rank, int world, const uint8_t id[QGT_B200_NCCL_ID_BYTES]) {
+    if (!c || !id) return qgt::fail(QGT_B200_ERR_INVALID_ARG, "ctx/id is NULL");
+    if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world)
+        return qgt::fail(QGT_B200_ERR_INVALID_ARG, "world must be a power of two and 0 <= rank < world");
+    if (c->dist) return qgt::fail(-17 /* QGT_ERROR_ALREADY_INITIALIZED */, "communicator already initialised");
+    cudaSetDevice(c->device);
+    if (world == 1) { c->rank = 0; c->world = 1; return QGT_B200_OK; }
+    int lrc = qgt::nccl_load();
+    if (lrc) return lrc;
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof uid);
+    qgt::DistState* d = new qgt::DistState();
+    ncclResult_t r = qgt::g_nccl.CommInitRank(&d->comm, world, uid, rank);
+    if (r != ncclSuccess) { delete d; return qgt::nccl_fail(r, "ncclCommInitRank"); }
+    c->dist = d;
+    c->rank = rank;
+    c->world = world;
+    return QGT_B200_OK;
+}
+
 int qgt_b200_dist_world(const qgt_b200_ctx* c, int* rank, int* world) {
     if (!c) return qgt::fail(QGT_B200_ERR_INVALID_ARG, "ctx is NULL");
     if (rank) *rank = c->rank;
     if (world) *world = c->world;
     return QGT_B200_OK;
 }
-int qgt_b200_dist_export_ipc(qgt_b200_ctx*, size_t, uint8_t*) { return qgt::fail(QGT_B200_ERR_UNSUPPORTED, "multi-GPU not built"); }
-int qgt_b200_dist_import_ipc(qgt_b200_ctx*, const uint8_t*) { return qgt::fail(QGT_B200_ERR_UNSUPPORTED, "multi-GPU not built"); }
-int qgt_b200_dist_barrier(qgt_b200_ctx*) { return QGT_B200_OK; }
+
+int qgt_b200_dist_barrier(qgt_b200_ctx* c) {
+    if (!c) return qgt::fail(QGT_B200_ERR_INVALID_ARG, "ctx is NULL");
+    double v = 0.0;
+    return qgt::dist_allreduce_host(c, &v, 1);
 }
+
+}  // extern "C"

@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
         const uint64_t tau = w / (uint64_t)a.nitems;
         const QgtSweepItem& it = a.items[item];
         const uint64_t tilebase = qgt_tile_base(run, tau);
+        const uint64_t tileg = tilebase | a.gprefix;      // global index bits incl. the rank's (sharded states)
         cx.ovr_kind = it.ovr_kind;
         cx.ovr_index = it.ovr_index;
         cx.ovr_tdiag = &it.ovr_tdiag;
@@ -197,11 +198,11 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
         for (int s = 0; s < run.nsub; ++s) {
             if (subs[s].nreg == 0) {
                 const QgtDevCost& co = (it.ovr_kind == 3 && subs[s].cost == it.ovr_index) ? it.ovr_cost : a.costs[run.cost_off + subs[s].cost];
-                qgt_phase_cost(run, co, cur, tilebase, tid, T, a.ct);
+                qgt_phase_cost(run, co, cur, tilebase, tileg, tid, T, a.ct);
             } else if (R == 3 && B == 0 && a.use_mma && subs[s].mma_ok && T >= 32) {
-                qgt_warp_subpass_mma(run, subs[s], cx, cur, tilebase, tid >> 5, tid & 31);
+                qgt_warp_subpass_mma(run, subs[s], cx, cur, tileg, tid >> 5, tid & 31);
             } else {
-                qgt_phase_subpass<R, B>(run, subs[s], cx, cur, tilebase, tid);
+                qgt_phase_subpass<R, B>(run, subs[s], cx, cur, tileg, tid);
             }
             __syncthreads();
         }

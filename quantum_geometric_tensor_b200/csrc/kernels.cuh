@@ -19,6 +19,7 @@ struct SweepLaunch {
     const QgtSweepItem* items;
     int nitems;
     uint64_t ntiles;
+    uint64_t gprefix;            // rank bits of a sharded state, OR-ed into every global index used by masks
     int use_mma;                 // dense stages on the FP64 tensor pipe (DMMA) where the sub-pass allows it
     QgtCostTable ct;
 };

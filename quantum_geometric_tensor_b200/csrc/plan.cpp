@@ -351,13 +351,14 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
     opt.batch_qubits = std::max(0, std::min(opt.batch_qubits, (int)QGT_MAX_REG_QUBITS - opt.reg_qubits));
     opt.tile_qubits = std::max(opt.reg_qubits + opt.batch_qubits + 2,
                                std::min(opt.tile_qubits, std::min((int)QGT_MAX_TILE_QUBITS, opt.reg_qubits + opt.batch_qubits + 8)));
-    const int K = std::min(n, opt.tile_qubits);
+    const int nl = (opt.local_qubits > 0 && opt.local_qubits < n) ? opt.local_qubits : n;   // qubits inside one shard
+    const int K = std::min(nl, opt.tile_qubits);
     const int R = std::min(opt.reg_qubits, K);
     const int B = std::min(opt.batch_qubits, K - R);
     // the forced low qubits must leave room for at least R freely chosen tile qubits
-    const int L = (K == n) ? K : std::max(0, std::min(opt.low_qubits, K - R));
+    const int L = (K == nl) ? K : std::max(0, std::min(opt.low_qubits, K - R));
     plan = CircuitPlan();
-    plan.n = n; plan.P = c.num_params; plan.opt = opt; plan.K = K; plan.R = R; plan.B = B;
+    plan.n = n; plan.nloc = nl; plan.P = c.num_params; plan.opt = opt; plan.K = K; plan.R = R; plan.B = B;
     plan.first_run.assign(std::max(0, c.num_params), -1);
     plan.last_run.assign(std::max(0, c.num_params), -1);
 
@@ -367,6 +368,11 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
         if (rc) return rc;
     }
     const int N = (int)ops.size();
+    for (const LoweredOp& o : ops)
+        if (o.target >= nl) {
+            err = "a non-diagonal gate targets a rank (global) qubit: the circuit must be mapped first";
+            return QGT_B200_ERR_CIRCUIT;
+        }
     Dag dag = build_dag(ops, n);
     std::vector<char> done(N, 0);
     std::vector<int> ready;
@@ -379,7 +385,7 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
         std::vector<char> inS(n, 0);
         int sizeS = 0;
         for (int q = 0; q < L; q++) { inS[q] = 1; sizeS++; }
-        if (K == n) { for (int q = 0; q < n; q++) inS[q] = 1; sizeS = n; }
+        if (K == nl) { for (int q = 0; q < nl; q++) inS[q] = 1; sizeS = nl; }
         struct RawSub { std::vector<int> regq; int b, e; bool is_cost = false; };
         std::vector<RawSub> raw;
         bool run_full = false;
@@ -424,8 +430,8 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
         }
         if (run.ops.empty()) { err = "planner made no progress"; return QGT_B200_ERR_INTERNAL; }
         // pad the tile to K qubits with the lowest unused ones
-        for (int q = 0; q < n && sizeS < K; q++) if (!inS[q]) { inS[q] = 1; sizeS++; }
-        for (int q = 0; q < n; q++) (inS[q] ? run.tile_qubits : run.other_qubits).push_back(q);
+        for (int q = 0; q < nl && sizeS < K; q++) if (!inS[q]) { inS[q] = 1; sizeS++; }
+        for (int q = 0; q < nl; q++) (inS[q] ? run.tile_qubits : run.other_qubits).push_back(q);
         std::vector<int> local_of(n, -1);
         for (int j = 0; j < K; j++) local_of[run.tile_qubits[j]] = j;
         for (const RawSub& rs : raw) {
@@ -494,14 +500,14 @@ void build_image(const CircuitPlan& plan, PlanImage& img) {
     for (const Run& run : plan.runs) {
         QgtDevRun dr;
         std::memset(&dr, 0, sizeof dr);
-        dr.K = run.K; dr.n = plan.n;
+        dr.K = run.K; dr.n = plan.nloc;
         dr.nsub = (int)run.subs.size();
         dr.sub_off = (int)img.subs.size();
         dr.stage_off = (int)img.stages.size();
         dr.tdiag_off = (int)img.tdiags.size();
         dr.cost_off = (int)img.costs.size();
         dr.mat_off = (int)(img.pool.size() / 2);
-        for (int j = 0; j < run.K; j++) dr.tq[j] = (int8_t)run.tile_qubits[j];
+        for (size_t j = 0; j < run.tile_qubits.size(); j++) dr.tq[j] = (int8_t)run.tile_qubits[j];   // empty for an exchange pseudo-run
         for (size_t j = 0; j < run.other_qubits.size(); j++) dr.ntq[j] = (int8_t)run.other_qubits[j];
         for (const SubPass& sp : run.subs) {
             QgtDevSubPass ds;
@@ -540,6 +546,160 @@ void build_image(const CircuitPlan& plan, PlanImage& img) {
         dr.mat_count = (int)(img.pool.size() / 2) - dr.mat_off;
         img.runs.push_back(dr);
     }
+}
+
+// ---- sharded states --------------------------------------------------------------------------------
+namespace {
+// qubits a gate acts on non-diagonally (they must be local when the gate runs)
+void nondiag_qubits(const qgt_b200_gate& g, int out[2], int& cnt) {
+    cnt = 0;
+    switch (g.kind) {
+    case QGT_B200_GATE_X: case QGT_B200_GATE_Y: case QGT_B200_GATE_H: case QGT_B200_GATE_SX:
+    case QGT_B200_GATE_RX: case QGT_B200_GATE_RY: case QGT_B200_GATE_CNOT: case QGT_B200_GATE_CY:
+    case QGT_B200_GATE_CH: case QGT_B200_GATE_CRX: case QGT_B200_GATE_CRY:
+        out[cnt++] = g.target; break;
+    case QGT_B200_GATE_SWAP: out[cnt++] = g.target; out[cnt++] = g.control; break;
+    default: break;
+    }
+}
+}  // namespace
+
+int map_circuit_sharded(const qgt_b200_circuit& c, int nloc, bool restore_identity,
+                        std::vector<MappedSegment>& segs, std::string& err) {
+    const int n = c.num_qubits;
+    segs.clear();
+    if (nloc < 2 || nloc > n) { err = "invalid shard size"; return QGT_B200_ERR_INVALID_ARG; }
+    std::vector<int> phys(n), logical(n);
+    for (int q = 0; q < n; q++) { phys[q] = q; logical[q] = q; }
+    MappedSegment cur;
+    cur.phys_of_logical = phys;
+    auto close_segment = [&](int gbit) {
+        cur.exchange_gbit = gbit;
+        segs.push_back(cur);
+        cur = MappedSegment();
+    };
+    // bring logical qubit q (currently on a rank bit) into physical position nloc-1, evicting `victim`
+    auto bring_in = [&](int q, int victim) {
+        const int top = nloc - 1;
+        if (phys[victim] != top) {             // local SWAP: victim <-> whoever sits at the top local position
+            const int w = logical[top], pv = phys[victim];
+            qgt_b200_gate sw = {QGT_B200_GATE_SWAP, pv, top, -1, 0.0, 1.0};
+            cur.gates.push_back(sw);
+            phys[w] = pv; logical[pv] = w;
+            phys[victim] = top; logical[top] = victim;
+        }
+        const int pg = phys[q];
+        close_segment(pg - nloc);
+        phys[q] = top; logical[top] = q;
+        phys[victim] = pg; logical[pg] = victim;
+        cur.phys_of_logical = phys;
+    };
+    for (size_t gi = 0; gi < c.num_gates; gi++) {
+        const qgt_b200_gate& g = c.gates[gi];
+        int nd[2], cnt;
+        nondiag_qubits(g, nd, cnt);
+        for (int k = 0; k < cnt; k++) {
+            const int q = nd[k];
+            if (q < 0 || q >= n) { err = "gate qubit out of range"; return QGT_B200_ERR_CIRCUIT; }
+            if (phys[q] < nloc) continue;
+            // victim: a local logical qubit this gate does not need, whose next non-diagonal use is farthest
+            int victim = -1; size_t best = 0;
+            for (int v = 0; v < n; v++) {
+                if (phys[v] >= nloc) continue;
+                bool needed = false;
+                for (int k2 = 0; k2 < cnt; k2++) if (nd[k2] == v) needed = true;
+                if (needed) continue;
+                size_t next = c.num_gates + 1;
+                for (size_t gj = gi + 1; gj < c.num_gates; gj++) {
+                    int nd2[2], c2;
+                    nondiag_qubits(c.gates[gj], nd2, c2);
+                    bool hit = false;
+                    for (int k2 = 0; k2 < c2; k2++) if (nd2[k2] == v) hit = true;
+                    if (hit) { next = gj; break; }
+                }
+                if (victim < 0 || next > best) { victim = v; best = next; }
+            }
+            if (victim < 0) { err = "no local qubit available to exchange"; return QGT_B200_ERR_INTERNAL; }
+            bring_in(q, victim);
+        }
+        qgt_b200_gate pg = g;
+        if (g.kind != QGT_B200_GATE_COST) {
+            pg.target = phys[g.target];
+            if (g.control >= 0 && g.control < n) pg.control = phys[g.control];
+        }
+        cur.gates.push_back(pg);
+    }
+    if (restore_identity) {
+        // undo the permutation: fix the rank bits first (each needs its own logical qubit local at the top)
+        for (int pq = n - 1; pq >= nloc; pq--) {
+            if (logical[pq] == pq) continue;
+            const int want = pq;                       // logical qubit that belongs on this rank bit
+            if (phys[want] >= nloc) {                  // it sits on another rank bit: bring it in first
+                int victim = -1;
+                for (int v = 0; v < n; v++) if (phys[v] < nloc && v < nloc) { victim = v; break; }
+                if (victim < 0) for (int v = 0; v < n; v++) if (phys[v] < nloc) { victim = v; break; }
+                bring_in(want, victim);
+            }
+            // now `want` is local: move it to the top and exchange it with rank bit pq
+            const int top = nloc - 1;
+            if (phys[want] != top) {
+                const int w = logical[top], pv = phys[want];
+                qgt_b200_gate sw = {QGT_B200_GATE_SWAP, pv, top, -1, 0.0, 1.0};
+                cur.gates.push_back(sw);
+                phys[w] = pv; logical[pv] = w;
+                phys[want] = top; logical[top] = want;
+            }
+            const int other = logical[pq];
+            close_segment(pq - nloc);
+            phys[want] = pq; logical[pq] = want;
+            phys[other] = top; logical[top] = other;
+            cur.phys_of_logical = phys;
+        }
+        // then sort the local qubits with local SWAPs
+        for (int pq = 0; pq < nloc; pq++) {
+            if (logical[pq] == pq) continue;
+            const int pv = phys[pq], w = logical[pq];
+            qgt_b200_gate sw = {QGT_B200_GATE_SWAP, pv, pq, -1, 0.0, 1.0};
+            cur.gates.push_back(sw);
+            phys[w] = pv; logical[pv] = w;
+            phys[pq] = pq; logical[pq] = pq;
+        }
+    }
+    close_segment(-1);
+    return QGT_B200_OK;
+}
+
+int build_plan_sharded(const qgt_b200_circuit& c, const double* theta, const PlanOptions& opt_in, int nloc, bool restore_identity,
+                       CircuitPlan& plan, std::vector<MappedSegment>& segs, std::string& err) {
+    int rc = map_circuit_sharded(c, nloc, restore_identity, segs, err);
+    if (rc) return rc;
+    PlanOptions opt = opt_in;
+    opt.local_qubits = nloc;
+    plan = CircuitPlan();
+    for (size_t si = 0; si < segs.size(); si++) {
+        qgt_b200_circuit sub = c;
+        sub.gates = segs[si].gates.data();
+        sub.num_gates = segs[si].gates.size();
+        CircuitPlan sp;
+        if ((rc = build_plan(sub, theta, opt, sp, err))) return rc;
+        if (si == 0) { plan = sp; plan.runs.clear(); }
+        for (Run& r : sp.runs) { r.segment = (int)si; plan.runs.push_back(std::move(r)); }
+        if (segs[si].exchange_gbit >= 0) {
+            Run ex;
+            ex.K = plan.K;
+            ex.exchange_gbit = segs[si].exchange_gbit;
+            ex.segment = (int)si;
+            plan.runs.push_back(ex);
+        }
+    }
+    plan.first_run.assign(std::max(0, c.num_params), -1);
+    plan.last_run.assign(std::max(0, c.num_params), -1);
+    for (size_t r = 0; r < plan.runs.size(); r++)
+        for (const ParamOcc& oc : plan.runs[r].occ) {
+            if (plan.first_run[oc.param] < 0) plan.first_run[oc.param] = (int)r;
+            plan.last_run[oc.param] = (int)r;
+        }
+    return QGT_B200_OK;
 }
 
 // ---- QGT column schedule ---------------------------------------------------------------------
@@ -782,13 +942,14 @@ static void jop(std::ostringstream& o, const LoweredOp& op, bool deriv) {
     o << "]}";
 }
 
-std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const Program* prog) {
+std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const Program* prog,
+                      const std::vector<MappedSegment>* segs) {
     std::ostringstream o;
-    o << "{\"n\":" << plan.n << ",\"P\":" << plan.P << ",\"K\":" << (plan.runs.empty() ? 0 : plan.runs[0].K)
+    o << "{\"n\":" << plan.n << ",\"nloc\":" << plan.nloc << ",\"P\":" << plan.P << ",\"K\":" << (plan.runs.empty() ? 0 : plan.runs[0].K)
       << ",\"initial_state\":" << c.initial_state << ",\"runs\":[";
     for (size_t r = 0; r < plan.runs.size(); r++) {
         const Run& run = plan.runs[r];
-        o << (r ? "," : "") << "{\"tile\":"; jarr(o, run.tile_qubits);
+        o << (r ? "," : "") << "{\"exchange\":" << run.exchange_gbit << ",\"segment\":" << run.segment << ",\"tile\":"; jarr(o, run.tile_qubits);
         o << ",\"subs\":[";
         for (size_t s = 0; s < run.subs.size(); s++) {
             const SubPass& sp = run.subs[s];
@@ -805,6 +966,14 @@ std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const 
         o << "}}";
     }
     o << "]";
+    if (segs) {
+        o << ",\"segments\":[";
+        for (size_t i = 0; i < segs->size(); i++) {
+            o << (i ? "," : "") << "{\"phys\":"; jarr(o, (*segs)[i].phys_of_logical);
+            o << ",\"exchange\":" << (*segs)[i].exchange_gbit << ",\"gates\":" << (*segs)[i].gates.size() << "}";
+        }
+        o << "]";
+    }
     if (prog) {
         o << ",\"program\":{\"slots\":" << prog->num_slots << ",\"psi\":" << prog->psi_slot << ",\"resident\":" << prog->resident
           << ",\"streaming\":" << prog->streaming << ",\"blocks\":" << prog->blocks << ",\"psi_final\":" << (prog->psi_final ? 1 : 0)

@@ -17,6 +17,7 @@ struct PlanOptions {
     int batch_qubits = 0;   // B: extra amplitudes per thread (2^B halves share every matrix element)
     int low_qubits = 4;     // L: lowest qubits always in the tile (contiguous 16*2^L bytes)
     int max_ops_per_run = 160;
+    int local_qubits = 0;   // sharded states: qubits >= local_qubits are rank bits (diagonal use / controls only); 0 = all local
 };
 
 // an op in global-qubit terms, before it is bound to a sub-pass
@@ -62,10 +63,13 @@ struct Run {
     std::vector<LoweredOp> ops;     // in execution order
     std::vector<SubPass> subs;
     std::vector<ParamOcc> occ;      // parameterised ops in this run
+    int exchange_gbit = -1;         // pseudo-run of a sharded state: swap rank bit `exchange_gbit` with the top local qubit
+    int segment = 0;                // index of the mapped segment the run belongs to (selects the cost table)
 };
 
 struct CircuitPlan {
     int n = 0, P = 0;
+    int nloc = 0;                   // qubits addressed inside one shard (== n on a single GPU)
     int K = 0, R = 0, B = 0;        // tile / matrix / batch qubits actually used (clamped to n)
     PlanOptions opt;
     std::vector<Run> runs;
@@ -130,6 +134,24 @@ struct Program {
 // total_slots = number of 2^n-amplitude columns that fit in the workspace
 int build_qgt_program(const CircuitPlan& plan, size_t total_slots, bool want_psi, Program& prog, std::string& err);
 
-std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const Program* prog);
+// ---- sharded states: logical -> physical qubit mapping ------------------------------------------------
+// A state of n qubits sharded over 2^g ranks keeps physical qubits nloc.. (nloc = n - g) in the rank index.
+// Gates that act non-diagonally on such a qubit need it local: the mapper walks the gate list, and when a
+// gate needs a currently-global logical qubit it evicts the local qubit whose next non-diagonal use is
+// farthest away (moved to physical position nloc-1 by a local SWAP first), emitting an EXCHANGE of that rank
+// bit with physical qubit nloc-1.  Gates are re-expressed on physical qubits; a segment ends at each exchange.
+struct MappedSegment {
+    std::vector<qgt_b200_gate> gates;    // physical qubit numbers; targets of non-diagonal gates are < nloc
+    std::vector<int> phys_of_logical;    // mapping in force for these gates (cost tables are remapped with it)
+    int exchange_gbit = -1;              // after the gates: swap rank bit with physical qubit nloc-1; -1 = none
+};
+int map_circuit_sharded(const qgt_b200_circuit& c, int nloc, bool restore_identity,
+                        std::vector<MappedSegment>& segs, std::string& err);
+// plan of a mapped circuit: runs of every segment in order, with exchange pseudo-runs in between
+int build_plan_sharded(const qgt_b200_circuit& c, const double* theta, const PlanOptions& opt, int nloc, bool restore_identity,
+                       CircuitPlan& plan, std::vector<MappedSegment>& segs, std::string& err);
+
+std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const Program* prog,
+                      const std::vector<MappedSegment>* segs = nullptr);
 
 }  // namespace qgt

@@ -281,11 +281,12 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
 
 // tile-level pass for the (rare, transcendental-heavy) cost layer: thread `tid` of T handles local
 // indices tid, tid+T, ... directly in shared memory; kept out of the register path to keep that code small.
-QGT_HD void qgt_phase_cost(const QgtDevRun& run, const QgtDevCost& op, cplx* tile, uint64_t tilebase, int tid, int T,
-                           const QgtCostTable& ct) {
+QGT_HD void qgt_phase_cost(const QgtDevRun& run, const QgtDevCost& op, cplx* tile, uint64_t tilebase, uint64_t tileg,
+                           int tid, int T, const QgtCostTable& ct) {
+    (void)tilebase;
     const uint32_t count = 1u << run.K;
     for (uint32_t idx = (uint32_t)tid; idx < count; idx += (uint32_t)T) {
-        const uint64_t g = tilebase | qgt_local_to_global(run, idx);
+        const uint64_t g = tileg | qgt_local_to_global(run, idx);
         const double e = qgt_cost_energy(ct, g);
         double sn, cs;
 #if defined(__CUDA_ARCH__)

@@ -45,7 +45,7 @@ static void emul_item(const QgtDevRun& run, const PlanImage& img, const QgtSweep
             for (int tid = 0; tid < T; tid++) {
                 if (subs[s].nreg == 0) {
                     const QgtDevCost& co = (it.ovr_kind == 3 && subs[s].cost == it.ovr_index) ? it.ovr_cost : img.costs[run.cost_off + subs[s].cost];
-                    qgt_phase_cost(run, co, tile.data(), tilebase, tid, T, ct);
+                    qgt_phase_cost(run, co, tile.data(), tilebase, tilebase, tid, T, ct);
                 } else {
                     qgt_phase_subpass<R, B>(run, subs[s], cx, tile.data(), tilebase, tid);
                 }

@@ -125,3 +125,139 @@ def run_program(plan: dict, circ):
     Q = Cm[:P, :P] - np.outer(v, v.conj())
     psi = slots[prog["psi"]] if prog["psi_final"] else None
     return Q, psi, counters, seen
+
+
+# ---- sharded states (one shard per rank) -----------------------------------------------------------------
+def _apply_op_shard(shard, op, circ, gidx, nloc, edges, vweights):
+    """apply_op on one shard: gidx = global amplitude indices of the shard's entries (rank bits included)."""
+    cm = np.uint64(op["cmask"])
+    ctrl_ok = (gidx & cm) == cm
+    m = np.array(op["m"], dtype=np.float64)
+    t = op["type"]
+    out = shard.copy()
+    zero_fail = bool(op["flags"] & 1)
+    lidx = np.arange(shard.size, dtype=np.uint64)
+    if t in (0, 1, 2, 3):
+        assert op["target"] < nloc, "non-diagonal op on a rank qubit"
+        tb = np.uint64(1) << np.uint64(op["target"])
+        lo = (lidx & tb) == 0
+        i0 = lidx[lo & ctrl_ok]
+        i1 = i0 | tb
+        a0, a1 = shard[i0], shard[i1]
+        if t == 3:
+            out[i0], out[i1] = a1, a0
+        else:
+            M = (m[0::2] + 1j * m[1::2]).reshape(2, 2)
+            out[i0] = M[0, 0] * a0 + M[0, 1] * a1
+            out[i1] = M[1, 0] * a0 + M[1, 1] * a1
+        if zero_fail:
+            out[~ctrl_ok] = 0
+    elif t == 4:
+        pm = np.uint64(op["pmask"])
+        par = np.zeros(gidx.shape, dtype=np.uint64)
+        v = gidx & pm
+        for b in range(circ.num_qubits):
+            par ^= (v >> np.uint64(b)) & np.uint64(1)
+        d = np.where(par == 1, m[2] + 1j * m[3], m[0] + 1j * m[1])
+        out = np.where(ctrl_ok, shard * d, 0 if zero_fail else shard)
+    elif t == 5:
+        g = gidx.astype(np.int64)
+        e = np.zeros(g.shape)
+        for (i, j, w) in edges:
+            e += w * (((g >> i) ^ (g >> j)) & 1)
+        if vweights is not None:
+            for q in range(circ.num_qubits):
+                e += vweights[q] * (1 - 2 * ((g >> q) & 1))
+        out = shard * np.exp(-1j * m[0] * e)
+        if op["flags"] & 2:
+            out = out * (-1j * m[1] * e)
+    return out
+
+
+def segment_cost_tables(plan, circ):
+    """edge lists / vertex weights renamed by each segment's logical -> physical qubit map"""
+    tabs = []
+    for seg in plan["segments"]:
+        phys = seg["phys"]
+        edges = [(phys[i], phys[j], w) for (i, j, w) in circ.edges]
+        vw = None
+        if circ.vertex_weights is not None:
+            vw = [0.0] * circ.num_qubits
+            for q in range(circ.num_qubits):
+                vw[phys[q]] = circ.vertex_weights[q]
+        tabs.append((edges, vw))
+    return tabs
+
+
+def sweep_shard(plan, circ, run_idx, shard, rank, ovr, tabs):
+    run = plan["runs"][run_idx]
+    nloc = plan["nloc"]
+    gidx = (np.uint64(rank) << np.uint64(nloc)) | np.arange(shard.size, dtype=np.uint64)
+    edges, vw = tabs[run["segment"]]
+    v = shard
+    for i, op in enumerate(run["ops"]):
+        v = _apply_op_shard(v, run["dops"][str(i)] if i == ovr else op, circ, gidx, nloc, edges, vw)
+    return v
+
+
+def exchange_all_ranks(cols, gbit):
+    """cols[rank] = shard; swap rank bit `gbit` with the top local qubit"""
+    world = len(cols)
+    half = cols[0].size // 2
+    for r in range(world):
+        if (r >> gbit) & 1:
+            continue
+        p = r | (1 << gbit)
+        # rank r (bit 0) keeps its lower half, trades its upper half for the peer's lower half
+        tmp = cols[r][half:].copy()
+        cols[r][half:] = cols[p][:half]
+        cols[p][:half] = tmp
+
+
+def initial_shard(circ, rank, nloc):
+    dim = 1 << nloc
+    if circ.initial_state == 1:
+        return np.full(dim, 2.0 ** (-0.5 * circ.num_qubits), dtype=np.complex128)
+    v = np.zeros(dim, dtype=np.complex128)
+    if rank == 0:
+        v[0] = 1
+    return v
+
+
+def run_program_sharded(plan, circ, world):
+    """all ranks simulated in one process; returns (Q, full psi or None)"""
+    prog = plan["program"]
+    P, nloc = plan["P"], plan["nloc"]
+    tabs = segment_cost_tables(plan, circ)
+    slots = [[np.zeros(1 << nloc, dtype=np.complex128) for _ in range(prog["slots"])] for _ in range(world)]
+    Cm = np.zeros((P + 1, P + 1), dtype=np.complex128)
+    for ins in prog["instrs"]:
+        k = ins["k"]
+        if k == "init":
+            for r in range(world):
+                slots[r][ins["dst"]] = initial_shard(circ, r, nloc)
+        elif k == "copy":
+            for r in range(world):
+                slots[r][ins["dst"]] = slots[r][ins["src"]].copy()
+        elif k == "sweep":
+            run = plan["runs"][ins["run"]]
+            if run["exchange"] >= 0:
+                for (src, dst, ovr, acc) in ins["cols"]:
+                    assert src == dst and ovr < 0 and not acc
+                    cols = [slots[r][dst] for r in range(world)]
+                    exchange_all_ranks(cols, run["exchange"])
+                continue
+            for r in range(world):
+                res = [(dst, acc, sweep_shard(plan, circ, ins["run"], slots[r][src], r, ovr, tabs)) for (src, dst, ovr, acc) in ins["cols"]]
+                for dst, acc, v in res:
+                    slots[r][dst] = slots[r][dst] + v if acc else v
+        elif k == "gram":
+            for sa, ia in zip(ins["a"], ins["aid"]):
+                for sb, ib in zip(ins["b"], ins["bid"]):
+                    val = sum(np.vdot(slots[r][sa], slots[r][sb]) for r in range(world))   # the allreduce
+                    Cm[ia, ib] = val
+                    Cm[ib, ia] = np.conj(val)
+    v = Cm[:P, P]
+    Q = Cm[:P, :P] - np.outer(v, v.conj())
+    psi = np.concatenate([slots[r][prog["psi"]] for r in range(world)]) if prog["psi_final"] else None
+    return Q, psi
