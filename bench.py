@@ -170,6 +170,8 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded", action="store_true", help="N > 1: shard ONE state over the ranks (NCCL exchanges + Gram allreduce) "
+                                                           "instead of running N independent replicas")
     ap.add_argument("--explore", action="store_true", help="allow fewer than 3 warm-up steps (exploration only, never a reported number)")
     ap.add_argument("--opt", action="append", default=[], help="library tuning option key=value (qgt_b200_set_option)")
     args = ap.parse_args()
@@ -180,7 +182,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    theta = circuits.default_angles(circ.num_params, circuits.SEED_ANGLES + rank)
+    sharded = world > 1 and (args.sharded or args.workload == "c5")
+    theta = circuits.default_angles(circ.num_params, circuits.SEED_ANGLES + (0 if sharded else rank))
 
     if args.impl == "reference":
         run_reference(args, circ, theta)
@@ -198,6 +201,10 @@ def main():
     for kv in args.opt:
         k, v = kv.split("=")
         ctx.set_option(k, float(v))
+    if sharded:                            # one state over all ranks: rank 0's NCCL id goes round over torch.distributed
+        uid = [api.Context.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.dist_init(rank, world, uid[0])
     P = circ.num_params
     flush = None
     if "flushed" in workload_config(args, circ)["l2"]:
@@ -252,7 +259,7 @@ def main():
     dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
     if rank == 0:
         peaks = load_peaks()
-        evals = args.steps * world
+        evals = args.steps * (1 if sharded else world)
         value = evals / (dev_ms_max * 1e-3)
         e2e = evals / (wall_ms_max * 1e-3)
         sweep_gbs = agg["sweep_bytes"] / (agg["ms_sweep"] * 1e-3) * 1e-9 if agg["ms_sweep"] > 0 else 0.0
@@ -277,8 +284,10 @@ def main():
         dominant, other = (sweep_roof, gram_roof) if agg["ms_sweep"] >= agg["ms_gram"] else (gram_roof, sweep_roof)
         line = {"metric": "QGT evals/sec", "value": value, "unit": "QGT evals/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex double)", "data": "synthetic",
-                "config": dict(workload_config(args, circ), parallelism=f"replicas x{world}" if world > 1 else "single GPU",
+                "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64 (complex double)", "data": "synthetic",
+                "config": dict(workload_config(args, circ),
+                               parallelism=(f"state sharded over {world} GPUs (top qubits), NCCL exchange + allreduce" if sharded
+                                            else f"replicas x{world} (independent parameter points)" if world > 1 else "single GPU"),
                                runs=st["num_runs"], resident_columns=st["resident_columns"], blocks=st["blocks"],
                                tile_qubits=st["tile_qubits"]),
                 "e2e": {"value": e2e, "unit": "QGT evals/s", "h2d_bytes_per_step": 8 * P + 32 * len(circ.gates),

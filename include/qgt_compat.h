@@ -1,0 +1,267 @@
+/*
+ * qgt_compat.h — the reference's C API for the QGT hot path, served by the sm_100a library.
+ *
+ * One consolidated header; the files under include/quantum_geometric/ only forward to it so that
+ * reference callers keep their #include lines.  Type layouts follow the reference headers they replace
+ * (cited per block) so objects can cross the boundary unchanged; every function below is a thin host-C
+ * wrapper (quantum_geometric_tensor_b200/csrc/compat/) over include/qgt_b200.h.  There is no CPU
+ * fallback: without an sm_100 device the compute entry points report an error (and, where the reference
+ * signature is `void`, print it to stderr and leave their outputs untouched).
+ */
+#ifndef QGT_COMPAT_H
+#define QGT_COMPAT_H
+
+#include <complex.h>
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- core/quantum_base_types.h:32-72, 118-141, 187-198 ---------------------------------------- */
+typedef enum {
+    GATE_TYPE_I = 0, GATE_TYPE_X = 1, GATE_TYPE_Y = 2, GATE_TYPE_Z = 3, GATE_TYPE_H = 4, GATE_TYPE_S = 5,
+    GATE_TYPE_T = 6, GATE_TYPE_RX = 7, GATE_TYPE_RY = 8, GATE_TYPE_RZ = 9, GATE_TYPE_CNOT = 10,
+    GATE_TYPE_CY = 11, GATE_TYPE_CZ = 12, GATE_TYPE_SWAP = 13, GATE_TYPE_CUSTOM = 14, GATE_TYPE_U1 = 15,
+    GATE_TYPE_U2 = 16, GATE_TYPE_U3 = 17, GATE_TYPE_CCX = 18, GATE_TYPE_PHASE = 19, GATE_TYPE_CSWAP = 20,
+    GATE_TYPE_ISWAP = 21, GATE_TYPE_CRX = 22, GATE_TYPE_CRY = 23, GATE_TYPE_CRZ = 24, GATE_TYPE_CH = 25,
+    GATE_TYPE_SDG = 26, GATE_TYPE_TDG = 27, GATE_TYPE_ECR = 28, GATE_TYPE_SX = 29, GATE_TYPE_MEASURE = 30,
+    GATE_TYPE_RESET = 31, GATE_TYPE_BARRIER = 32, GATE_TYPE_XX = 33, GATE_TYPE_YY = 34, GATE_TYPE_ZZ = 35
+} gate_type_t;
+#define GATE_I GATE_TYPE_I
+#define GATE_X GATE_TYPE_X
+#define GATE_Y GATE_TYPE_Y
+#define GATE_Z GATE_TYPE_Z
+#define GATE_H GATE_TYPE_H
+#define GATE_S GATE_TYPE_S
+#define GATE_T GATE_TYPE_T
+#define GATE_RX GATE_TYPE_RX
+#define GATE_RY GATE_TYPE_RY
+#define GATE_RZ GATE_TYPE_RZ
+#define GATE_CNOT GATE_TYPE_CNOT
+#define GATE_CY GATE_TYPE_CY
+#define GATE_CZ GATE_TYPE_CZ
+#define GATE_SWAP GATE_TYPE_SWAP
+#define GATE_PHASE GATE_TYPE_PHASE
+#define GATE_CRX GATE_TYPE_CRX
+#define GATE_CRY GATE_TYPE_CRY
+#define GATE_CRZ GATE_TYPE_CRZ
+#define GATE_MEASURE GATE_TYPE_MEASURE
+
+typedef struct { float real, imag; } ComplexFloat;
+typedef struct { double real, imag; } ComplexDouble;
+
+typedef enum {
+    HARDWARE_TYPE_CPU, HARDWARE_TYPE_GPU, HARDWARE_TYPE_QPU, HARDWARE_TYPE_SIMULATOR, HARDWARE_TYPE_METAL,
+    HARDWARE_TYPE_CUDA, HARDWARE_TYPE_FPGA, HARDWARE_TYPE_IBM, HARDWARE_TYPE_RIGETTI, HARDWARE_TYPE_DWAVE,
+    HARDWARE_TYPE_CUSTOM
+} HardwareType;
+
+/* core/error_codes.h:17-110 (the values this layer returns) */
+typedef int qgt_error_t;
+#define QGT_SUCCESS 0
+#define QGT_ERROR_INVALID_PARAMETER (-1)
+#define QGT_ERROR_INVALID_ARGUMENT (-1)
+#define QGT_ERROR_MEMORY_ALLOCATION (-2)
+#define QGT_ERROR_DIMENSION_MISMATCH (-3)
+#define QGT_ERROR_INVALID_STATE (-4)
+#define QGT_ERROR_INVALID_DIMENSION (-22)
+
+/* ---- hardware/quantum_hardware_types.h:254-262, hardware/quantum_hardware_abstraction.h:51-82 ---- */
+typedef struct {
+    gate_type_t type;
+    uint32_t qubit;
+    uint32_t control_qubit;
+    uint32_t target_qubit;
+    double parameter;
+    double* parameters;
+    size_t num_parameters;
+} QuantumGate;
+
+typedef struct HardwareGate {
+    gate_type_t type;
+    uint32_t target, control, target1, target2;
+    double parameter;
+    double* parameters;
+    size_t num_params;
+} HardwareGate;
+
+typedef struct QuantumCircuit {
+    HardwareGate* gates;
+    size_t num_gates, capacity, num_qubits, num_classical_bits, depth;
+    bool* measured;
+    double max_circuit_depth;
+    void* optimization_data;
+    void* metadata;
+} QuantumCircuit;
+typedef struct QuantumCircuit CPUSimCircuit;
+
+/* ---- hardware/quantum_simulator_cpu.h:29-63 ---------------------------------------------------- */
+void init_simulator_state(double complex* state, size_t n);
+CPUSimCircuit* cpu_sim_create_circuit(size_t max_gates);
+void cpu_sim_add_gate(CPUSimCircuit* circuit, const QuantumGate* gate);
+void simulate_circuit_cpu(double complex* state, const CPUSimCircuit* circuit, size_t n_qubits);
+void cpu_sim_cleanup_circuit(CPUSimCircuit* circuit);
+void cpu_sim_get_error_statistics(const CPUSimCircuit* circuit, double* avg_error_rate, double* max_error_rate);
+void configure_circuit_optimization(CPUSimCircuit* circuit, bool use_error_correction, bool use_tensor_networks,
+                                    size_t cache_line_size);
+#define init_cpu_circuit cpu_sim_create_circuit
+#define add_gate_to_circuit cpu_sim_add_gate
+#define get_error_statistics cpu_sim_get_error_statistics
+
+/* ---- hardware/quantum_simulator.h:33-140 (the statevector subset) -------------------------------- */
+typedef enum noise_type_t { NOISE_NONE, NOISE_DEPOLARIZING, NOISE_AMPLITUDE_DAMPING, NOISE_PHASE_DAMPING, NOISE_THERMAL, NOISE_CUSTOM } NoiseType;
+typedef enum { MITIGATION_NONE, MITIGATION_RICHARDSON, MITIGATION_ZNE, MITIGATION_PROBABILISTIC, MITIGATION_CUSTOM } MitigationType;
+struct HierarchicalMatrix;
+typedef struct noise_model_t {
+    NoiseType type;
+    double gate_error_rate, measurement_error_rate, decoherence_rate;
+    double* custom_parameters;
+    size_t num_custom_parameters;
+    size_t size;
+    struct HierarchicalMatrix* h_matrix;
+} NoiseModel;
+typedef struct { MitigationType type; uint32_t num_samples; double scale_factors[4]; void* custom_parameters; } MitigationParams;
+typedef struct {
+    double complex* amplitudes;
+    uint32_t num_qubits;
+    uint32_t num_classical_bits;
+    bool* classical_bits;
+    double fidelity;
+    double error_rate;
+    NoiseModel active_noise;
+    MitigationParams active_mitigation;
+    void* device_ptr;      /* qgt_b200_state* once the state lives on the GPU */
+    void* custom_state;
+} SimulatorState;
+struct SimulatorConfig;
+typedef struct qgt_sim_circuit SimulatorCircuit;   /* opaque; the reference aliases struct quantum_circuit_t */
+
+SimulatorState* sim_init(uint32_t num_qubits, uint32_t num_classical_bits, const struct SimulatorConfig* config);
+void sim_reset_state(SimulatorState* state);
+void sim_cleanup(SimulatorState* state);
+SimulatorCircuit* sim_create_circuit(uint32_t num_qubits, uint32_t num_classical_bits);
+bool sim_add_gate(SimulatorCircuit* circuit, gate_type_t type, uint32_t target, uint32_t control, double* parameters);
+bool sim_add_controlled_gate(SimulatorCircuit* circuit, gate_type_t type, uint32_t target, uint32_t control,
+                             uint32_t control2, double* parameters);
+bool sim_execute_circuit(SimulatorState* state, const SimulatorCircuit* circuit);
+double complex* sim_get_statevector(const SimulatorState* state);
+void sim_cleanup_circuit(SimulatorCircuit* circuit);
+
+/* ---- distributed/differential_geometry.h:237-262, 573-595 ------------------------------------------ */
+typedef struct diffgeo_engine diffgeo_engine_t;
+diffgeo_engine_t* diffgeo_engine_create(void);
+void diffgeo_engine_destroy(diffgeo_engine_t* engine);
+/* g = Re Q */
+bool diffgeo_compute_fubini_study(diffgeo_engine_t* engine, const ComplexDouble* state, size_t dim,
+                                  const ComplexDouble* param_derivatives, size_t num_params, double* metric_out);
+/* F = -2 Im Q (the diffgeo convention, differential_geometry.c:2899-2900) */
+bool diffgeo_compute_berry_curvature(diffgeo_engine_t* engine, const ComplexDouble* state, size_t dim,
+                                     const ComplexDouble* param_derivatives, size_t num_params, double* curvature_out);
+
+/* ---- core/quantum_types.h:170-192, core/quantum_geometric_tensor_network.h ---------------------------- */
+typedef struct quantum_gate_t {
+    gate_type_t type;
+    size_t num_qubits;
+    bool is_controlled;
+    bool is_parameterized;
+    size_t* target_qubits;
+    size_t* control_qubits;
+    size_t num_controls;
+    size_t* qubits;
+    double* parameters;
+    size_t num_parameters;
+    ComplexFloat* matrix;
+    void* custom_data;
+} quantum_gate_t;
+
+typedef enum { QGTN_BACKEND_SIMULATOR, QGTN_BACKEND_IBM, QGTN_BACKEND_RIGETTI, QGTN_BACKEND_DWAVE, QGTN_BACKEND_IONQ,
+               QGTN_BACKEND_XANADU, QGTN_BACKEND_CUSTOM } qgtn_backend_type_t;
+typedef struct { qgtn_backend_type_t type; void* backend_specific; bool supports_gradients; bool supports_hybrid; } qgtn_hardware_config_t;
+struct tensor_network_t;
+struct quantum_circuit_t;
+typedef struct quantum_geometric_tensor_network {
+    struct tensor_network_t* network;      /* unused: the exact statevector path needs no tensor network */
+    struct quantum_circuit_t* circuit;     /* unused */
+    size_t num_qubits;
+    size_t num_layers;
+    bool is_distributed;
+    bool use_hardware_acceleration;
+    qgtn_hardware_config_t hardware_config;
+    void* backend_state;                   /* the gate list and the cached Q of this layer */
+} quantum_geometric_tensor_network_t;
+
+quantum_geometric_tensor_network_t* create_quantum_geometric_tensor_network(size_t num_qubits, size_t num_layers,
+                                                                             bool is_distributed, bool use_hardware_acceleration);
+void destroy_quantum_geometric_tensor_network(quantum_geometric_tensor_network_t* qgtn);
+/* appends the gate; a parameterised gate takes the next parameter index (order of is_parameterized gates,
+ * core/quantum_parameter_shift.c:278-337) with value gate->parameters[0] */
+bool apply_quantum_gate(quantum_geometric_tensor_network_t* qgtn, const quantum_gate_t* gate, const size_t* qubits, size_t num_qubits);
+bool get_quantum_state(const quantum_geometric_tensor_network_t* qgtn, ComplexFloat** state_vector, size_t* dimension);
+bool compute_quantum_geometric_tensor(const quantum_geometric_tensor_network_t* qgtn, size_t param_i, size_t param_j, ComplexFloat* result);
+bool compute_quantum_metric(const quantum_geometric_tensor_network_t* qgtn, size_t param_i, size_t param_j, double* result);
+bool compute_berry_curvature(const quantum_geometric_tensor_network_t* qgtn, size_t param_i, size_t param_j, double* result);
+const char* get_quantum_geometric_tensor_network_error(void);
+
+/* ---- core/quantum_geometric_types.h:365-459, core/quantum_geometric_metric.h, _curvature.h -------------- */
+#define QGT_MAX_DIMENSIONS 16
+typedef enum { GEOMETRIC_METRIC_EUCLIDEAN, GEOMETRIC_METRIC_MINKOWSKI, GEOMETRIC_METRIC_FUBINI_STUDY, GEOMETRIC_METRIC_KAHLER,
+               GEOMETRIC_METRIC_CUSTOM } geometric_metric_type_t;
+typedef enum { GEOMETRIC_CURVATURE_RIEMANN, GEOMETRIC_CURVATURE_RICCI, GEOMETRIC_CURVATURE_SCALAR, GEOMETRIC_CURVATURE_WEYL,
+               GEOMETRIC_CURVATURE_BERRY, GEOMETRIC_CURVATURE_CUSTOM } geometric_curvature_type_t;
+typedef struct quantum_geometric_metric_t {
+    geometric_metric_type_t type;
+    size_t dimension;
+    ComplexFloat* components;
+    bool is_symmetric;
+    void* auxiliary_data;
+    HardwareType hardware;
+} quantum_geometric_metric_t;
+typedef struct quantum_geometric_curvature_t {
+    geometric_curvature_type_t type;
+    size_t dimension;
+    ComplexFloat* components;
+    void* auxiliary_data;
+    bool is_flat;
+    HardwareType hardware;
+} quantum_geometric_curvature_t;
+
+/* legacy constructors keep the reference's dimension <= QGT_MAX_DIMENSIONS check (metric.c:14, curvature.c:14);
+ * qgt_b200_alloc_* lift it for the P x P outputs of real circuits */
+qgt_error_t geometric_create_metric(quantum_geometric_metric_t** metric, geometric_metric_type_t type, size_t dimension, HardwareType hardware);
+void geometric_destroy_metric(quantum_geometric_metric_t* metric);
+qgt_error_t geometric_create_curvature(quantum_geometric_curvature_t** curvature, geometric_curvature_type_t type, size_t dimension, HardwareType hardware);
+void geometric_destroy_curvature(quantum_geometric_curvature_t* curvature);
+qgt_error_t qgt_b200_alloc_metric(quantum_geometric_metric_t** metric, size_t dimension);
+qgt_error_t qgt_b200_alloc_curvature(quantum_geometric_curvature_t** curvature, size_t dimension);
+
+/* g in .real (symmetric), Omega = Im Q in .real (antisymmetric), full Hermitian Q */
+qgt_error_t geometric_compute_fubini_study_metric(quantum_geometric_metric_t* metric, const quantum_geometric_tensor_network_t* qgtn, size_t num_params);
+qgt_error_t geometric_compute_berry_curvature(quantum_geometric_curvature_t* curvature, const quantum_geometric_tensor_network_t* qgtn, size_t num_params);
+qgt_error_t geometric_compute_berry_curvature_element(const quantum_geometric_tensor_network_t* qgtn, size_t param_mu, size_t param_nu, float* result);
+qgt_error_t geometric_compose_qgt(ComplexFloat* qgt, const quantum_geometric_metric_t* metric, const quantum_geometric_curvature_t* curvature, size_t dimension);
+qgt_error_t geometric_compute_full_qgt(ComplexFloat* qgt, const quantum_geometric_tensor_network_t* qgtn, size_t num_params);
+
+/* ---- core/quantum_geometric_gradient.h:188-215 ------------------------------------------------------------ */
+typedef struct {
+    float regularization_param;
+    float condition_threshold;
+    bool use_adaptive_regularization;
+    bool use_pseudoinverse_fallback;
+    float singular_value_cutoff;
+} natural_gradient_config_t;
+natural_gradient_config_t get_default_natural_gradient_config(void);
+bool compute_regularized_natural_gradient(const ComplexFloat* gradient, const ComplexFloat* metric, ComplexFloat* natural_gradient,
+                                          size_t dimension, const natural_gradient_config_t* config);
+
+/* ---- this layer -------------------------------------------------------------------------------------------- */
+/* CUDA ordinal used by the wrappers (default: $QGT_B200_DEVICE or 0); call before the first compute call */
+int qgt_compat_set_device(int device);
+const char* qgt_compat_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QGT_COMPAT_H */

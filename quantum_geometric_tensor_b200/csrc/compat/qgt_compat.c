@@ -1,0 +1,330 @@
+/*
+ * qgt_compat.c — the reference's QGT entry points served by the CUDA library.
+ *
+ *   diffgeo_compute_fubini_study / _berry_curvature        distributed/differential_geometry.c:2819-2906
+ *   create_quantum_geometric_tensor_network, apply_quantum_gate, get_quantum_state,
+ *   compute_quantum_geometric_tensor / _metric / _berry_curvature
+ *                                                          core/quantum_geometric_tensor_network.c:27-209,585-880,1034-1227
+ *   geometric_compute_fubini_study_metric                  core/quantum_geometric_metric.c:353-396
+ *   geometric_compute_berry_curvature / compose / full_qgt core/quantum_geometric_curvature.c:201-320
+ *   compute_regularized_natural_gradient                   core/quantum_geometric_gradient.c:2721-2964
+ *
+ * The reference's per-element routine re-simulates the circuit for every (mu, nu) (6 P^2 circuit runs for a
+ * full tensor) on an engine that does not apply gates.  Here the
+ * network object just records the gate list; the first query evaluates the whole Q on the GPU in one
+ * qgt_b200_qgt call (complex double), caches it, and every element / matrix query reads the cache, narrowed
+ * to the ComplexFloat of the legacy API.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "compat_common.h"
+
+/* ---- diffgeo ------------------------------------------------------------------------------------------------ */
+struct diffgeo_engine { unsigned long metric_evaluations, curvature_evaluations; };
+
+diffgeo_engine_t* diffgeo_engine_create(void) { return (diffgeo_engine_t*)calloc(1, sizeof(diffgeo_engine_t)); }
+void diffgeo_engine_destroy(diffgeo_engine_t* e) { free(e); }
+
+static bool diffgeo_run(const ComplexDouble* state, size_t dim, const ComplexDouble* d, size_t P, double* metric, double* berry) {
+    qgt_b200_ctx* ctx = qgt_compat_ctx();
+    if (!ctx) return false;
+    int rc = qgt_b200_gram(ctx, (const double*)state, (const double*)d, dim, P, metric, berry, NULL);
+    if (rc) { qgt_compat_set_error("qgt_b200_gram", rc); return false; }
+    return true;
+}
+
+bool diffgeo_compute_fubini_study(diffgeo_engine_t* e, const ComplexDouble* state, size_t dim,
+                                  const ComplexDouble* d, size_t P, double* metric_out) {
+    if (!e || !state || !d || !metric_out || dim == 0 || P == 0) return false;
+    if (!diffgeo_run(state, dim, d, P, metric_out, NULL)) return false;
+    e->metric_evaluations++;
+    return true;
+}
+
+bool diffgeo_compute_berry_curvature(diffgeo_engine_t* e, const ComplexDouble* state, size_t dim,
+                                     const ComplexDouble* d, size_t P, double* curvature_out) {
+    if (!e || !state || !d || !curvature_out || dim == 0 || P == 0) return false;
+    if (!diffgeo_run(state, dim, d, P, NULL, curvature_out)) return false;
+    for (size_t i = 0; i < P * P; i++) curvature_out[i] *= -2.0;       /* F = -2 Im Q (:2899-2900) */
+    e->curvature_evaluations++;
+    return true;
+}
+
+/* ---- the "tensor network" object: a recorded gate list + cached Q --------------------------------------------- */
+typedef struct {
+    qgt_b200_gate* gates;
+    size_t num_gates, capacity;
+    double* theta;
+    size_t num_params, theta_cap;
+    double* q;              /* cached P x P complex (re, im), NULL when stale */
+    size_t q_params;
+} qgtn_state;
+
+static __thread char g_qgtn_err[256];
+const char* get_quantum_geometric_tensor_network_error(void) { return g_qgtn_err; }
+static void qgtn_err(const char* m) { snprintf(g_qgtn_err, sizeof g_qgtn_err, "%s", m); }
+
+quantum_geometric_tensor_network_t* create_quantum_geometric_tensor_network(size_t num_qubits, size_t num_layers,
+                                                                             bool is_distributed, bool use_hardware_acceleration) {
+    if (num_qubits == 0 || num_qubits > 40) { qgtn_err("invalid number of qubits"); return NULL; }
+    quantum_geometric_tensor_network_t* n = (quantum_geometric_tensor_network_t*)calloc(1, sizeof *n);
+    qgtn_state* st = (qgtn_state*)calloc(1, sizeof *st);
+    if (!n || !st) { free(n); free(st); qgtn_err("out of memory"); return NULL; }
+    n->num_qubits = num_qubits; n->num_layers = num_layers; n->is_distributed = is_distributed;
+    n->use_hardware_acceleration = use_hardware_acceleration;
+    n->hardware_config.type = QGTN_BACKEND_SIMULATOR; n->hardware_config.supports_gradients = true;
+    n->backend_state = st;
+    return n;
+}
+
+void destroy_quantum_geometric_tensor_network(quantum_geometric_tensor_network_t* n) {
+    if (!n) return;
+    qgtn_state* st = (qgtn_state*)n->backend_state;
+    if (st) { free(st->gates); free(st->theta); free(st->q); free(st); }
+    free(n);
+}
+
+bool apply_quantum_gate(quantum_geometric_tensor_network_t* n, const quantum_gate_t* gate, const size_t* qubits, size_t num_qubits) {
+    if (!n || !gate || !n->backend_state) { qgtn_err("invalid arguments"); return false; }
+    qgtn_state* st = (qgtn_state*)n->backend_state;
+    /* qubits[] (when given) overrides the gate's own targets: last entry = target, first = control for 2-qubit gates */
+    uint32_t target = 0, control = 0;
+    if (qubits && num_qubits >= 1) { target = (uint32_t)qubits[num_qubits - 1]; if (num_qubits >= 2) control = (uint32_t)qubits[0]; }
+    else {
+        if (gate->target_qubits) target = (uint32_t)gate->target_qubits[0];
+        else if (gate->qubits && gate->num_qubits) target = (uint32_t)gate->qubits[gate->num_qubits - 1];
+        if (gate->control_qubits && gate->num_controls) control = (uint32_t)gate->control_qubits[0];
+        else if (gate->qubits && gate->num_qubits >= 2) control = (uint32_t)gate->qubits[0];
+    }
+    if (target >= n->num_qubits || control >= n->num_qubits) { qgtn_err("qubit index out of range"); return false; }
+    const bool param = gate->is_parameterized && gate->parameters && gate->num_parameters > 0;
+    qgt_b200_gate g;
+    if (!qgt_compat_convert_gate(gate->type, target, control, gate->parameters ? gate->parameters[0] : 0.0,
+                                 param ? (int)st->num_params : -1, &g)) { qgtn_err("unsupported gate type"); return false; }
+    if (st->num_gates == st->capacity) {
+        size_t nc = st->capacity ? 2 * st->capacity : 64;
+        qgt_b200_gate* ng = (qgt_b200_gate*)realloc(st->gates, nc * sizeof *ng);
+        if (!ng) { qgtn_err("out of memory"); return false; }
+        st->gates = ng; st->capacity = nc;
+    }
+    if (g.param >= 0) {
+        if (st->num_params == st->theta_cap) {
+            size_t nc = st->theta_cap ? 2 * st->theta_cap : 64;
+            double* nt = (double*)realloc(st->theta, nc * sizeof *nt);
+            if (!nt) { qgtn_err("out of memory"); return false; }
+            st->theta = nt; st->theta_cap = nc;
+        }
+        st->theta[st->num_params++] = gate->parameters[0];
+    }
+    st->gates[st->num_gates++] = g;
+    free(st->q); st->q = NULL;                       /* cached tensor is stale */
+    return true;
+}
+
+static void qgtn_circuit(const quantum_geometric_tensor_network_t* n, qgt_b200_circuit* c) {
+    const qgtn_state* st = (const qgtn_state*)n->backend_state;
+    memset(c, 0, sizeof *c);
+    c->num_qubits = (int32_t)n->num_qubits; c->num_params = (int32_t)st->num_params;
+    c->gates = st->gates; c->num_gates = st->num_gates;
+}
+
+bool get_quantum_state(const quantum_geometric_tensor_network_t* n, ComplexFloat** state_vector, size_t* dimension) {
+    if (!n || !state_vector || !dimension || !n->backend_state) { qgtn_err("invalid arguments"); return false; }
+    qgt_b200_ctx* ctx = qgt_compat_ctx();
+    if (!ctx) { qgtn_err(qgt_compat_last_error()); return false; }
+    const qgtn_state* st = (const qgtn_state*)n->backend_state;
+    const size_t dim = (size_t)1 << n->num_qubits;
+    double* amps = (double*)calloc(dim, 2 * sizeof(double));
+    ComplexFloat* out = (ComplexFloat*)malloc(dim * sizeof *out);
+    if (!amps || !out) { free(amps); free(out); qgtn_err("out of memory"); return false; }
+    amps[0] = 1.0;
+    qgt_b200_circuit c;
+    qgtn_circuit(n, &c);
+    int rc = qgt_b200_simulate_host(ctx, amps, (int)n->num_qubits, &c, st->theta);
+    if (rc) { qgt_compat_set_error("get_quantum_state", rc); qgtn_err(qgt_compat_last_error()); free(amps); free(out); return false; }
+    for (size_t i = 0; i < dim; i++) { out[i].real = (float)amps[2 * i]; out[i].imag = (float)amps[2 * i + 1]; }
+    free(amps);
+    *state_vector = out;                             /* caller frees, as in the reference */
+    *dimension = dim;
+    return true;
+}
+
+/* full Q of the recorded circuit, evaluated once and cached */
+static const double* qgtn_full(const quantum_geometric_tensor_network_t* n) {
+    qgtn_state* st = (qgtn_state*)n->backend_state;
+    if (st->q && st->q_params == st->num_params) return st->q;
+    qgt_b200_ctx* ctx = qgt_compat_ctx();
+    if (!ctx) { qgtn_err(qgt_compat_last_error()); return NULL; }
+    const size_t P = st->num_params;
+    double* q = (double*)calloc(P * P ? P * P : 1, 2 * sizeof(double));
+    if (!q) { qgtn_err("out of memory"); return NULL; }
+    qgt_b200_circuit c;
+    qgtn_circuit(n, &c);
+    int rc = qgt_b200_qgt(ctx, &c, st->theta, NULL, NULL, q, NULL);
+    if (rc) { qgt_compat_set_error("qgt_b200_qgt", rc); qgtn_err(qgt_compat_last_error()); free(q); return NULL; }
+    free(st->q);
+    st->q = q; st->q_params = P;
+    return q;
+}
+
+bool compute_quantum_geometric_tensor(const quantum_geometric_tensor_network_t* n, size_t i, size_t j, ComplexFloat* result) {
+    if (!n || !result || !n->backend_state) { qgtn_err("invalid arguments"); return false; }
+    const size_t P = ((const qgtn_state*)n->backend_state)->num_params;
+    if (i >= P || j >= P) { qgtn_err("parameter index out of range"); return false; }
+    const double* q = qgtn_full(n);
+    if (!q) return false;
+    result->real = (float)q[2 * (i * P + j)]; result->imag = (float)q[2 * (i * P + j) + 1];
+    return true;
+}
+
+bool compute_quantum_metric(const quantum_geometric_tensor_network_t* n, size_t i, size_t j, double* result) {
+    if (!n || !result || !n->backend_state) { qgtn_err("invalid arguments"); return false; }
+    const size_t P = ((const qgtn_state*)n->backend_state)->num_params;
+    if (i >= P || j >= P) { qgtn_err("parameter index out of range"); return false; }
+    const double* q = qgtn_full(n);
+    if (!q) return false;
+    *result = q[2 * (i * P + j)];                    /* Re Q (:1183-1203) */
+    return true;
+}
+
+bool compute_berry_curvature(const quantum_geometric_tensor_network_t* n, size_t i, size_t j, double* result) {
+    if (!n || !result || !n->backend_state) { qgtn_err("invalid arguments"); return false; }
+    const size_t P = ((const qgtn_state*)n->backend_state)->num_params;
+    if (i >= P || j >= P) { qgtn_err("parameter index out of range"); return false; }
+    const double* q = qgtn_full(n);
+    if (!q) return false;
+    *result = q[2 * (i * P + j) + 1];                /* Im Q (:1205-1226) */
+    return true;
+}
+
+/* ---- metric / curvature objects --------------------------------------------------------------------------------- */
+static qgt_error_t alloc_metric(quantum_geometric_metric_t** m, geometric_metric_type_t type, size_t dim, HardwareType hw) {
+    quantum_geometric_metric_t* x = (quantum_geometric_metric_t*)calloc(1, sizeof *x);
+    if (!x) return QGT_ERROR_MEMORY_ALLOCATION;
+    x->components = (ComplexFloat*)calloc(dim * dim, sizeof(ComplexFloat));
+    if (!x->components) { free(x); return QGT_ERROR_MEMORY_ALLOCATION; }
+    x->type = type; x->dimension = dim; x->is_symmetric = true; x->hardware = hw;
+    *m = x;
+    return QGT_SUCCESS;
+}
+
+qgt_error_t geometric_create_metric(quantum_geometric_metric_t** m, geometric_metric_type_t type, size_t dim, HardwareType hw) {
+    if (!m || dim == 0 || dim > QGT_MAX_DIMENSIONS) return QGT_ERROR_INVALID_PARAMETER;     /* metric.c:14 */
+    return alloc_metric(m, type, dim, hw);
+}
+
+qgt_error_t qgt_b200_alloc_metric(quantum_geometric_metric_t** m, size_t dim) {
+    if (!m || dim == 0) return QGT_ERROR_INVALID_PARAMETER;
+    return alloc_metric(m, GEOMETRIC_METRIC_FUBINI_STUDY, dim, HARDWARE_TYPE_CUDA);
+}
+
+void geometric_destroy_metric(quantum_geometric_metric_t* m) { if (m) { free(m->components); free(m); } }
+
+static qgt_error_t alloc_curvature(quantum_geometric_curvature_t** c, geometric_curvature_type_t type, size_t dim, HardwareType hw) {
+    quantum_geometric_curvature_t* x = (quantum_geometric_curvature_t*)calloc(1, sizeof *x);
+    if (!x) return QGT_ERROR_MEMORY_ALLOCATION;
+    x->components = (ComplexFloat*)calloc(dim * dim, sizeof(ComplexFloat));
+    if (!x->components) { free(x); return QGT_ERROR_MEMORY_ALLOCATION; }
+    x->type = type; x->dimension = dim; x->hardware = hw;
+    *c = x;
+    return QGT_SUCCESS;
+}
+
+qgt_error_t geometric_create_curvature(quantum_geometric_curvature_t** c, geometric_curvature_type_t type, size_t dim, HardwareType hw) {
+    if (!c || dim == 0 || dim > QGT_MAX_DIMENSIONS) return QGT_ERROR_INVALID_PARAMETER;     /* curvature.c:14 */
+    return alloc_curvature(c, type, dim, hw);
+}
+
+qgt_error_t qgt_b200_alloc_curvature(quantum_geometric_curvature_t** c, size_t dim) {
+    if (!c || dim == 0) return QGT_ERROR_INVALID_PARAMETER;
+    return alloc_curvature(c, GEOMETRIC_CURVATURE_BERRY, dim, HARDWARE_TYPE_CUDA);
+}
+
+void geometric_destroy_curvature(quantum_geometric_curvature_t* c) { if (c) { free(c->components); free(c); } }
+
+static qgt_error_t check_params(const quantum_geometric_tensor_network_t* n, size_t num_params) {
+    if (!n || !n->backend_state || num_params == 0) return QGT_ERROR_INVALID_PARAMETER;
+    if (num_params != ((const qgtn_state*)n->backend_state)->num_params) return QGT_ERROR_DIMENSION_MISMATCH;
+    return QGT_SUCCESS;
+}
+
+qgt_error_t geometric_compute_fubini_study_metric(quantum_geometric_metric_t* m, const quantum_geometric_tensor_network_t* n, size_t P) {
+    if (!m || !m->components) return QGT_ERROR_INVALID_PARAMETER;
+    qgt_error_t rc = check_params(n, P);
+    if (rc) return rc;
+    if (m->dimension != P) return QGT_ERROR_DIMENSION_MISMATCH;
+    const double* q = qgtn_full(n);
+    if (!q) return QGT_ERROR_INVALID_STATE;
+    for (size_t i = 0; i < P * P; i++) { m->components[i].real = (float)q[2 * i]; m->components[i].imag = 0.0f; }
+    m->type = GEOMETRIC_METRIC_FUBINI_STUDY; m->is_symmetric = true;
+    return QGT_SUCCESS;
+}
+
+qgt_error_t geometric_compute_berry_curvature(quantum_geometric_curvature_t* c, const quantum_geometric_tensor_network_t* n, size_t P) {
+    if (!c || !c->components) return QGT_ERROR_INVALID_PARAMETER;
+    qgt_error_t rc = check_params(n, P);
+    if (rc) return rc;
+    if (c->dimension != P) return QGT_ERROR_DIMENSION_MISMATCH;
+    const double* q = qgtn_full(n);
+    if (!q) return QGT_ERROR_INVALID_STATE;
+    bool flat = true;
+    for (size_t i = 0; i < P * P; i++) {               /* Omega = Im Q, antisymmetric, stored in .real (curvature.c:201-247) */
+        c->components[i].real = (float)q[2 * i + 1]; c->components[i].imag = 0.0f;
+        if (fabs(q[2 * i + 1]) > 1e-12) flat = false;
+    }
+    c->type = GEOMETRIC_CURVATURE_BERRY; c->is_flat = flat;
+    return QGT_SUCCESS;
+}
+
+qgt_error_t geometric_compute_berry_curvature_element(const quantum_geometric_tensor_network_t* n, size_t mu, size_t nu, float* result) {
+    double v;
+    if (!result) return QGT_ERROR_INVALID_PARAMETER;
+    if (!compute_berry_curvature(n, mu, nu, &v)) return QGT_ERROR_INVALID_PARAMETER;
+    *result = (float)v;
+    return QGT_SUCCESS;
+}
+
+qgt_error_t geometric_compose_qgt(ComplexFloat* qgt, const quantum_geometric_metric_t* m, const quantum_geometric_curvature_t* c, size_t dim) {
+    if (!qgt || !m || !c || !m->components || !c->components) return QGT_ERROR_INVALID_PARAMETER;
+    if (m->dimension != dim || c->dimension != dim) return QGT_ERROR_DIMENSION_MISMATCH;
+    for (size_t i = 0; i < dim * dim; i++) { qgt[i].real = m->components[i].real; qgt[i].imag = c->components[i].real; }   /* Q = g + i Omega */
+    return QGT_SUCCESS;
+}
+
+qgt_error_t geometric_compute_full_qgt(ComplexFloat* qgt, const quantum_geometric_tensor_network_t* n, size_t P) {
+    if (!qgt) return QGT_ERROR_INVALID_PARAMETER;
+    qgt_error_t rc = check_params(n, P);
+    if (rc) return rc;
+    const double* q = qgtn_full(n);
+    if (!q) return QGT_ERROR_INVALID_STATE;
+    for (size_t i = 0; i < P * P; i++) { qgt[i].real = (float)q[2 * i]; qgt[i].imag = (float)q[2 * i + 1]; }
+    return QGT_SUCCESS;
+}
+
+/* ---- natural gradient ----------------------------------------------------------------------------------------------- */
+natural_gradient_config_t get_default_natural_gradient_config(void) {
+    natural_gradient_config_t c = {1e-4f, 1e8f, true, true, 1e-10f};
+    return c;
+}
+
+bool compute_regularized_natural_gradient(const ComplexFloat* gradient, const ComplexFloat* metric, ComplexFloat* natural_gradient,
+                                          size_t dimension, const natural_gradient_config_t* config) {
+    if (!gradient || !metric || !natural_gradient || !config || dimension == 0) return false;
+    const size_t P = dimension;
+    double* G = (double*)malloc(P * P * sizeof(double));
+    double* g = (double*)malloc(2 * P * sizeof(double));
+    double* x = (double*)malloc(2 * P * sizeof(double));
+    if (!G || !g || !x) { free(G); free(g); free(x); return false; }
+    for (size_t i = 0; i < P * P; i++) G[i] = metric[i].real;          /* the Fubini-Study metric is real symmetric */
+    for (size_t i = 0; i < P; i++) { g[i] = gradient[i].real; g[P + i] = gradient[i].imag; }
+    qgt_b200_natgrad_config cfg = {config->regularization_param, config->condition_threshold, config->use_adaptive_regularization,
+                                   config->use_pseudoinverse_fallback, config->singular_value_cutoff};
+    int rc = qgt_b200_natural_gradient(NULL, G, g, P, &cfg, x, NULL);            /* real and imaginary parts: the solve is linear */
+    if (!rc) rc = qgt_b200_natural_gradient(NULL, G, g + P, P, &cfg, x + P, NULL);
+    if (!rc) for (size_t i = 0; i < P; i++) { natural_gradient[i].real = (float)x[i]; natural_gradient[i].imag = (float)x[P + i]; }
+    free(G); free(g); free(x);
+    return rc == 0;
+}

@@ -1,0 +1,234 @@
+/*
+ * sim_compat.c — the reference's simulator entry points served by the CUDA library.
+ *
+ *   init_simulator_state / cpu_sim_* / simulate_circuit_cpu   hardware/quantum_simulator_cpu.c:98,761-926
+ *   sim_init / sim_add_gate / sim_execute_circuit / ...        hardware/quantum_simulator.c:57-112,418-560,677
+ *
+ * Host buffers in and out exactly like the reference (double complex[2^n]); the wrappers stage them through
+ * qgt_b200_simulate_host.  Known reference defects are NOT reproduced: 1-qubit
+ * gates act correctly on every target, CRX/CRY/CRZ are real gates, SWAP uses both of its qubits.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "compat_common.h"
+
+static qgt_b200_ctx* g_ctx = NULL;
+static int g_device = -1;
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static __thread char g_err[512];
+
+void qgt_compat_set_error(const char* where, int status) {
+    snprintf(g_err, sizeof g_err, "%s: %s (%s)", where, qgt_b200_error_string(status), qgt_b200_last_error());
+}
+
+const char* qgt_compat_last_error(void) { return g_err; }
+
+int qgt_compat_set_device(int device) {
+    pthread_mutex_lock(&g_lock);
+    int rc = 0;
+    if (g_ctx) rc = -17;            /* QGT_ERROR_ALREADY_INITIALIZED */
+    else g_device = device;
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+qgt_b200_ctx* qgt_compat_ctx(void) {
+    pthread_mutex_lock(&g_lock);
+    if (!g_ctx) {
+        int dev = g_device;
+        if (dev < 0) { const char* e = getenv("QGT_B200_DEVICE"); dev = e ? atoi(e) : 0; }
+        int rc = qgt_b200_create(&g_ctx, dev);
+        if (rc) { g_ctx = NULL; qgt_compat_set_error("qgt_b200_create", rc); }
+    }
+    qgt_b200_ctx* c = g_ctx;
+    pthread_mutex_unlock(&g_lock);
+    return c;
+}
+
+int qgt_compat_convert_gate(gate_type_t type, uint32_t target, uint32_t control, double angle, int param, qgt_b200_gate* out) {
+    out->kind = (int32_t)type; out->target = (int32_t)target; out->control = -1; out->param = param;
+    out->angle = param >= 0 ? 0.0 : angle; out->scale = 1.0;
+    switch (type) {
+    case GATE_TYPE_I: case GATE_TYPE_X: case GATE_TYPE_Y: case GATE_TYPE_Z: case GATE_TYPE_H: case GATE_TYPE_S:
+    case GATE_TYPE_T: case GATE_TYPE_SDG: case GATE_TYPE_TDG: case GATE_TYPE_SX:
+        out->param = -1; out->angle = 0.0; return 1;
+    case GATE_TYPE_RX: case GATE_TYPE_RY: case GATE_TYPE_RZ: case GATE_TYPE_U1: case GATE_TYPE_PHASE:
+        return 1;
+    case GATE_TYPE_CNOT: case GATE_TYPE_CY: case GATE_TYPE_CZ: case GATE_TYPE_CH: case GATE_TYPE_SWAP:
+        out->control = (int32_t)control; out->param = -1; out->angle = 0.0; return 1;
+    case GATE_TYPE_CRX: case GATE_TYPE_CRY: case GATE_TYPE_CRZ: case GATE_TYPE_ZZ:
+        out->control = (int32_t)control; return 1;
+    default:
+        return 0;       /* MEASURE, BARRIER, RESET, multi-qubit kinds outside the statevector hot path */
+    }
+}
+
+/* ---- hardware/quantum_simulator_cpu.h ------------------------------------------------------------------ */
+void init_simulator_state(double complex* state, size_t n) {        /* n = number of amplitudes (…_cpu.c:98-101) */
+    if (!state || n == 0) return;
+    memset(state, 0, n * sizeof(double complex));
+    state[0] = 1.0;
+}
+
+CPUSimCircuit* cpu_sim_create_circuit(size_t max_gates) {
+    QuantumCircuit* c = (QuantumCircuit*)calloc(1, sizeof *c);
+    if (!c) return NULL;
+    c->gates = (HardwareGate*)calloc(max_gates ? max_gates : 1, sizeof(HardwareGate));
+    if (!c->gates) { free(c); return NULL; }
+    c->capacity = max_gates;
+    return c;
+}
+
+static int two_qubit_kind(gate_type_t t) {
+    return t == GATE_TYPE_CNOT || t == GATE_TYPE_CZ || t == GATE_TYPE_SWAP || t == GATE_TYPE_ISWAP || t == GATE_TYPE_CRZ ||
+           t == GATE_TYPE_CRX || t == GATE_TYPE_CRY || t == GATE_TYPE_CY || t == GATE_TYPE_CH || t == GATE_TYPE_ZZ;
+}
+
+void cpu_sim_add_gate(CPUSimCircuit* circuit, const QuantumGate* gate) {
+    if (!circuit || !gate || circuit->num_gates >= circuit->capacity) return;     /* silent, like the reference */
+    HardwareGate* g = &circuit->gates[circuit->num_gates++];
+    memset(g, 0, sizeof *g);
+    g->type = gate->type; g->target = gate->target_qubit; g->control = gate->control_qubit; g->parameter = gate->parameter;
+    size_t top = gate->target_qubit;
+    if (two_qubit_kind(gate->type) && gate->control_qubit > top) top = gate->control_qubit;
+    if (top + 1 > circuit->num_qubits) circuit->num_qubits = top + 1;
+}
+
+void cpu_sim_cleanup_circuit(CPUSimCircuit* circuit) {
+    if (!circuit) return;
+    free(circuit->gates);
+    free(circuit);
+}
+
+void cpu_sim_get_error_statistics(const CPUSimCircuit* circuit, double* avg_error_rate, double* max_error_rate) {
+    if (!circuit || !avg_error_rate || !max_error_rate) return;
+    /* the reference's fixed per-kind estimates (…_cpu.c:872-908): 0.5 % two-qubit, 1 % measurement, 0.1 % otherwise */
+    double total = 0.0, mx = 0.0;
+    for (size_t i = 0; i < circuit->num_gates; i++) {
+        const gate_type_t t = circuit->gates[i].type;
+        const double e = two_qubit_kind(t) ? 0.005 : (t == GATE_TYPE_MEASURE ? 0.01 : 0.001);
+        total += e;
+        if (e > mx) mx = e;
+    }
+    *max_error_rate = mx;
+    *avg_error_rate = circuit->num_gates ? total / (double)circuit->num_gates : 0.0;
+}
+
+void configure_circuit_optimization(CPUSimCircuit* circuit, bool use_error_correction, bool use_tensor_networks, size_t cache_line_size) {
+    (void)circuit; (void)use_error_correction; (void)use_tensor_networks; (void)cache_line_size;   /* no-op there too (:913-926) */
+}
+
+void simulate_circuit_cpu(double complex* state, const CPUSimCircuit* circuit, size_t n_qubits) {
+    if (!state || !circuit || n_qubits == 0) return;
+    qgt_b200_ctx* ctx = qgt_compat_ctx();
+    if (!ctx) { fprintf(stderr, "simulate_circuit_cpu: %s\n", qgt_compat_last_error()); return; }
+    qgt_b200_gate* gates = (qgt_b200_gate*)malloc((circuit->num_gates ? circuit->num_gates : 1) * sizeof *gates);
+    if (!gates) return;
+    size_t ng = 0;
+    for (size_t i = 0; i < circuit->num_gates; i++) {
+        const HardwareGate* h = &circuit->gates[i];
+        if (qgt_compat_convert_gate(h->type, h->target, h->control, h->parameter, -1, &gates[ng])) ng++;
+    }
+    qgt_b200_circuit c;
+    memset(&c, 0, sizeof c);
+    c.num_qubits = (int32_t)n_qubits; c.gates = gates; c.num_gates = ng;
+    int rc = qgt_b200_simulate_host(ctx, (double*)state, (int)n_qubits, &c, NULL);
+    if (rc) { qgt_compat_set_error("simulate_circuit_cpu", rc); fprintf(stderr, "%s\n", qgt_compat_last_error()); }
+    free(gates);
+}
+
+/* ---- hardware/quantum_simulator.h ------------------------------------------------------------------------- */
+struct qgt_sim_circuit {
+    uint32_t num_qubits, num_classical_bits;
+    qgt_b200_gate* gates;
+    size_t num_gates, capacity;
+};
+
+SimulatorState* sim_init(uint32_t num_qubits, uint32_t num_classical_bits, const struct SimulatorConfig* config) {
+    (void)config;                                   /* noise models are outside the hot path */
+    if (num_qubits == 0 || num_qubits > 32) return NULL;      /* MAX_QUBITS, quantum_simulator.h:16 */
+    SimulatorState* s = (SimulatorState*)calloc(1, sizeof *s);
+    if (!s) return NULL;
+    s->num_qubits = num_qubits; s->num_classical_bits = num_classical_bits;
+    s->amplitudes = (double complex*)calloc((size_t)1 << num_qubits, sizeof(double complex));
+    if (!s->amplitudes) { free(s); return NULL; }
+    s->amplitudes[0] = 1.0;
+    if (num_classical_bits) s->classical_bits = (bool*)calloc(num_classical_bits, sizeof(bool));
+    s->fidelity = 1.0;
+    s->active_noise.type = NOISE_NONE;
+    return s;
+}
+
+void sim_reset_state(SimulatorState* s) {
+    if (!s || !s->amplitudes) return;
+    memset(s->amplitudes, 0, ((size_t)1 << s->num_qubits) * sizeof(double complex));
+    s->amplitudes[0] = 1.0;
+    if (s->classical_bits) memset(s->classical_bits, 0, s->num_classical_bits * sizeof(bool));
+    s->fidelity = 1.0; s->error_rate = 0.0;
+}
+
+void sim_cleanup(SimulatorState* s) {
+    if (!s) return;
+    free(s->amplitudes); free(s->classical_bits); free(s->active_noise.custom_parameters); free(s->custom_state);
+    free(s);
+}
+
+SimulatorCircuit* sim_create_circuit(uint32_t num_qubits, uint32_t num_classical_bits) {
+    SimulatorCircuit* c = (SimulatorCircuit*)calloc(1, sizeof *c);
+    if (!c) return NULL;
+    c->num_qubits = num_qubits; c->num_classical_bits = num_classical_bits; c->capacity = 64;
+    c->gates = (qgt_b200_gate*)calloc(c->capacity, sizeof *c->gates);
+    if (!c->gates) { free(c); return NULL; }
+    return c;
+}
+
+bool sim_add_gate(SimulatorCircuit* c, gate_type_t type, uint32_t target, uint32_t control, double* parameters) {
+    if (!c) return false;
+    if (c->num_gates >= c->capacity) {
+        qgt_b200_gate* ng = (qgt_b200_gate*)realloc(c->gates, 2 * c->capacity * sizeof *ng);
+        if (!ng) return false;
+        c->gates = ng; c->capacity *= 2;
+    }
+    qgt_b200_gate g;
+    const bool rot = type == GATE_TYPE_RX || type == GATE_TYPE_RY || type == GATE_TYPE_RZ || type == GATE_TYPE_U1 ||
+                     type == GATE_TYPE_PHASE || type == GATE_TYPE_CRX || type == GATE_TYPE_CRY || type == GATE_TYPE_CRZ;
+    if (rot && !parameters) return false;            /* apply_gate_by_type returns false there (:231,:241,:251) */
+    if (!qgt_compat_convert_gate(type, target, control, parameters ? parameters[0] : 0.0, -1, &g)) return false;
+    c->gates[c->num_gates++] = g;
+    return true;
+}
+
+bool sim_add_controlled_gate(SimulatorCircuit* c, gate_type_t type, uint32_t target, uint32_t control, uint32_t control2, double* parameters) {
+    (void)control2;
+    return sim_add_gate(c, type, target, control, parameters);
+}
+
+bool sim_execute_circuit(SimulatorState* s, const SimulatorCircuit* c) {
+    if (!s || !c) return false;
+    qgt_b200_ctx* ctx = qgt_compat_ctx();
+    if (!ctx) return false;
+    qgt_b200_circuit qc;
+    memset(&qc, 0, sizeof qc);
+    qc.num_qubits = (int32_t)s->num_qubits; qc.gates = c->gates; qc.num_gates = c->num_gates;
+    int rc = qgt_b200_simulate_host(ctx, (double*)s->amplitudes, (int)s->num_qubits, &qc, NULL);
+    if (rc) { qgt_compat_set_error("sim_execute_circuit", rc); return false; }
+    return true;
+}
+
+double complex* sim_get_statevector(const SimulatorState* s) {
+    if (!s) return NULL;
+    const size_t dim = (size_t)1 << s->num_qubits;
+    double complex* sv = (double complex*)malloc(dim * sizeof *sv);
+    if (sv) memcpy(sv, s->amplitudes, dim * sizeof *sv);
+    return sv;                                      /* caller frees, as in the reference */
+}
+
+void sim_cleanup_circuit(SimulatorCircuit* c) {
+    if (!c) return;
+    free(c->gates);
+    free(c);
+}
