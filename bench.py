@@ -165,7 +165,7 @@ def workload_config(args, circ):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

@@ -183,6 +183,8 @@ int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
     else if (k == "reg_qubits") c->opt.reg_qubits = (int)value;
     else if (k == "batch_qubits") c->opt.batch_qubits = (int)value;
     else if (k == "use_mma") c->use_mma = value != 0;
+    else if (k == "double_buffer") c->double_buffer = value != 0;
+    else if (k == "gram_tile") set_gram_tile_override((int)value);
     else if (k == "profile") c->timer.enabled = value != 0;
     else if (k == "max_slots") c->max_slots = (size_t)value;
     else return fail(QGT_B200_ERR_INVALID_ARG, "unknown option " + k);
@@ -348,6 +350,10 @@ static int do_sweep(qgt_b200_ctx* c, const CircuitPlan& plan, int run, const Qgt
     a.nitems = nitems;
     a.ntiles = shard_tiles;
     a.use_mma = c->use_mma;
+    a.double_buffer = c->double_buffer;
+    a.mma_only = c->use_mma && plan.R == 3 && plan.B == 0;
+    for (const SubPass& sp : plan.runs[run].subs)
+        if (sp.is_cost || !sp.mma_ok) a.mma_only = 0;
     a.gprefix = (uint64_t)c->rank << plan.nloc;
     a.ct = c->seg_cost.empty() ? c->cost : c->seg_cost[plan.runs[run].segment];
     const int K = plan.runs[run].K;
@@ -394,11 +400,13 @@ int apply_plan_inplace(qgt_b200_ctx* c, const CircuitPlan& plan, cplx* d, uint64
     return QGT_B200_OK;
 }
 
+// split-K factor: enough CTAs for ~6 waves at 3 CTAs per SM (fine-grained work keeps the tail short and
+// evens out diagonal / padded tiles that carry fewer blocks), at least 256 amplitudes per CTA
 static int gram_ksplit(const qgt_b200_ctx* c, int tiles, uint64_t D) {
     const uint64_t by_len = std::max<uint64_t>(1, D / 256);
-    uint64_t want = (uint64_t)std::max(1, (c->num_sms * 3 + tiles - 1) / tiles);
+    uint64_t want = (uint64_t)std::max(1, (c->num_sms * 18 + tiles - 1) / tiles);
     want = std::min<uint64_t>(want, by_len);
-    return (int)std::min<uint64_t>(want, 1024);
+    return (int)std::min<uint64_t>(want, 512);
 }
 
 // executes a Program on `nslots` columns of D amplitudes each living at arena + slot*D

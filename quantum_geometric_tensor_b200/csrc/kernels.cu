@@ -132,7 +132,10 @@ __device__ __forceinline__ void qgt_warp_subpass_mma(const QgtDevRun& run, const
 // Shared memory: [tile: 2^K amplitudes][matrix pool of the run][override matrices of the current item].
 // The kernel is persistent over (tile, column) work items; the run header and its matrix pool are staged
 // once per CTA.  R = qubits of a stage matrix, B = batch qubits: a thread owns 2^(R+B) amplitudes.
-template <int R, int B, int MAXT, int MINB>
+// MMA_ONLY: every sub-pass of the run takes the tensor-pipe path (no cost pass, warp-uniform variants): the
+// register-FMA code is not instantiated, which halves the register count and doubles the resident warps.
+// DB: two tile buffers with cp.async prefetch of the next work item.
+template <int R, int B, bool MMA_ONLY, bool DB, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
     constexpr int N = 1 << R;
     constexpr int OVR_ELEMS = QGT_VARIANT_STRIDE(N) << QGT_MAX_VARIANT_BITS;
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
         reinterpret_cast<uint32_t*>(&run)[i] = reinterpret_cast<const uint32_t*>(&a.runs[a.run_idx])[i];
     __syncthreads();
     // two tile buffers: the next work item's tile streams in with cp.async while this one is processed
-    cplx* spool = tile + ((size_t)2 << run.K);
+    cplx* spool = tile + ((size_t)(DB ? 2 : 1) << run.K);
     cplx* sovr = spool + run.mat_count;
     QgtDevSubPass* subs = reinterpret_cast<QgtDevSubPass*>(sovr + OVR_ELEMS);
     {
@@ -173,10 +176,12 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
         }
     };
     uint64_t w = blockIdx.x;
-    if (w < total) prefetch(w, tile);
-    cp_async_commit();
+    if (DB) {
+        if (w < total) prefetch(w, tile);
+        cp_async_commit();
+    }
     for (int par = 0; w < total; w += gridDim.x, par ^= 1) {
-        cplx* cur = tile + ((size_t)par << run.K);
+        cplx* cur = DB ? tile + ((size_t)par << run.K) : tile;
         const int item = (int)(w % (uint64_t)a.nitems);
         const uint64_t tau = w / (uint64_t)a.nitems;
         const QgtSweepItem& it = a.items[item];
@@ -190,13 +195,21 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
             const int cnt = QGT_VARIANT_STRIDE(N) << cx.stages[it.ovr_index].nvar;
             for (int i = tid; i < cnt && i < OVR_ELEMS; i += T) sovr[i] = g[i];
         }
-        // the other buffer was last read by the previous item's store phase, which ended at a barrier
-        if (w + gridDim.x < total) prefetch(w + gridDim.x, tile + ((size_t)(par ^ 1) << run.K));
-        cp_async_commit();
-        cp_async_wait<1>();
+        if (DB) {
+            // the other buffer was last read by the previous item's store phase, which ended at a barrier
+            if (w + gridDim.x < total) prefetch(w + gridDim.x, tile + ((size_t)(par ^ 1) << run.K));
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            prefetch(w, cur);
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
         __syncthreads();
         for (int s = 0; s < run.nsub; ++s) {
-            if (subs[s].nreg == 0) {
+            if (MMA_ONLY) {
+                qgt_warp_subpass_mma(run, subs[s], cx, cur, tileg, tid >> 5, tid & 31);
+            } else if (subs[s].nreg == 0) {
                 const QgtDevCost& co = (it.ovr_kind == 3 && subs[s].cost == it.ovr_index) ? it.ovr_cost : a.costs[run.cost_off + subs[s].cost];
                 qgt_phase_cost(run, co, cur, tilebase, tileg, tid, T, a.ct);
             } else if (R == 3 && B == 0 && a.use_mma && subs[s].mma_ok && T >= 32) {
@@ -212,15 +225,22 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
     cp_async_wait<0>();
 }
 
-template <int R, int B, int MAXT, int MINB>
-static cudaError_t launch_sweep_cfg(const SweepLaunch& a, int T, size_t smem, unsigned grid, cudaStream_t st) {
-    auto kern = qgt_sweep_kernel<R, B, MAXT, MINB>;
-    static bool attr_set = false;
-    if (!attr_set) {
+template <int R, int B, bool MMA_ONLY, bool DB, int MAXT, int MINB>
+static cudaError_t launch_sweep_cfg(const SweepLaunch& a, int T, size_t smem, uint64_t total, int num_sms, cudaStream_t st) {
+    auto kern = qgt_sweep_kernel<R, B, MMA_ONLY, DB, MAXT, MINB>;
+    static int ctas_per_sm = 0;
+    static size_t smem_seen = 0;
+    if (!ctas_per_sm || smem != smem_seen) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = occ > 0 ? occ : 1;
+        smem_seen = smem;
     }
+    const uint64_t cap = (uint64_t)num_sms * ctas_per_sm * 2;
+    const unsigned grid = (unsigned)(total < cap ? total : cap);
     kern<<<grid, T, smem, st>>>(a);
     return cudaGetLastError();
 }
@@ -229,17 +249,20 @@ template <int R, int B>
 static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, int nsub, int num_sms, cudaStream_t st) {
     constexpr int N = 1 << R;
     const int T = 1 << (K - R - B);
-    const size_t smem = 2 * (sizeof(cplx) << K) + sizeof(cplx) * (size_t)mat_count +
-                        sizeof(cplx) * (size_t)(QGT_VARIANT_STRIDE(N) << QGT_MAX_VARIANT_BITS) + (size_t)nsub * sizeof(QgtDevSubPass);
     const uint64_t total = a.ntiles * (uint64_t)a.nitems;
     if (total == 0) return cudaSuccess;
-    if (smem > 200 * 1024 || T > 256) return cudaErrorInvalidValue;
-    const uint64_t cap = (uint64_t)num_sms * 8;
-    const unsigned grid = (unsigned)(total < cap ? total : cap);
-    // register budget follows the CTA size: 128-thread CTAs may use ~168 registers at 3 CTAs per SM
-    if (B > 0 && T <= 128) return launch_sweep_cfg<R, B, 128, 3>(a, T, smem, grid, st);
-    if (B > 0) return launch_sweep_cfg<R, B, 256, 1>(a, T, smem, grid, st);
-    return launch_sweep_cfg<R, B, 256, 2>(a, T, smem, grid, st);
+    const size_t fixed = sizeof(cplx) * (size_t)mat_count + sizeof(cplx) * (size_t)(QGT_VARIANT_STRIDE(N) << QGT_MAX_VARIANT_BITS) +
+                         (size_t)nsub * sizeof(QgtDevSubPass);
+    const size_t tile_bytes = sizeof(cplx) << K;
+    if (fixed + 2 * tile_bytes > 200 * 1024 || T > 256) return cudaErrorInvalidValue;
+    if (R == 3 && B == 0 && a.mma_only && T >= 32) {
+        // single tile buffer: more resident CTAs hide the load latency instead of a second buffer
+        if (a.double_buffer) return launch_sweep_cfg<3, 0, true, true, 256, 3>(a, T, fixed + 2 * tile_bytes, total, num_sms, st);
+        return launch_sweep_cfg<3, 0, true, false, 256, 4>(a, T, fixed + tile_bytes, total, num_sms, st);
+    }
+    if (B > 0 && T <= 128) return launch_sweep_cfg<R, B, false, true, 128, 3>(a, T, fixed + 2 * tile_bytes, total, num_sms, st);
+    if (B > 0) return launch_sweep_cfg<R, B, false, true, 256, 1>(a, T, fixed + 2 * tile_bytes, total, num_sms, st);
+    return launch_sweep_cfg<R, B, false, true, 256, 2>(a, T, fixed + 2 * tile_bytes, total, num_sms, st);
 }
 
 cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int num_sms, cudaStream_t st) {
@@ -258,6 +281,42 @@ cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_coun
 // ------------------------------------------------------------------------------------------------
 // Gram  C = A^H B  on the FP64 tensor pipe
 // ------------------------------------------------------------------------------------------------
+
+// one staged chunk of KC amplitudes: fragments from shared memory, 4 DMMAs per 8x8 block and k-step.
+// conj(a) * b = (ar*br + ai*bi) + i (ar*bi - ai*br); the two updates of one accumulator are issued a whole
+// block sweep apart so that dependent DMMAs never sit back to back.
+template <int WM, int WN, int BM, int BN, int KC, bool ALL>
+__device__ __forceinline__ void gram_chunk(const cplx* __restrict__ sA, const cplx* __restrict__ sB, int wm, int wn, int fr, int fk,
+                                           const bool (&blk)[BM][BN], double (&cre)[BM][BN][2], double (&cim)[BM][BN][2]) {
+    constexpr int S = KC + 4;
+#pragma unroll
+    for (int kk = 0; kk < KC; kk += 4) {
+        cplx a[BM], b[BN];
+#pragma unroll
+        for (int i = 0; i < BM; ++i) a[i] = sA[((wm * BM + i) * 8 + fr) * S + kk + fk];
+#pragma unroll
+        for (int j = 0; j < BN; ++j) b[j] = sB[((wn * BN + j) * 8 + fr) * S + kk + fk];
+#pragma unroll
+        for (int i = 0; i < BM; ++i) {
+#pragma unroll
+            for (int j = 0; j < BN; ++j) {
+                if (!ALL && !blk[i][j]) continue;
+                dmma884(cre[i][j][0], cre[i][j][1], a[i].x, b[j].x);
+                dmma884(cim[i][j][0], cim[i][j][1], a[i].x, b[j].y);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < BM; ++i) {
+            const double nai = -a[i].y;
+#pragma unroll
+            for (int j = 0; j < BN; ++j) {
+                if (!ALL && !blk[i][j]) continue;
+                dmma884(cre[i][j][0], cre[i][j][1], a[i].y, b[j].y);
+                dmma884(cim[i][j][0], cim[i][j][1], nai, b[j].x);
+            }
+        }
+    }
+}
 
 // CTA tile: MT = WM*BM*8 rows (columns of A) x NT = WN*BN*8 cols (columns of B); WM*WN warps, each warp
 // owns BM x BN blocks of 8x8.  The 2^n-long amplitude axis is consumed in chunks of KC amplitudes moved
@@ -323,6 +382,11 @@ __global__ void __launch_bounds__(WM * WN * 32, 2) qgt_gram_kernel(GramLaunch g)
             const int r0 = mt * MT + (wm * BM + i) * 8, c0 = nt * NT + (wn * BN + j) * 8;
             blk[i][j] = r0 < g.na && c0 < g.nb && !(g.symmetric && c0 + 8 <= r0);
         }
+    bool all_valid = true;      // warp-uniform: the common case runs without a predicate on every mma.sync
+#pragma unroll
+    for (int i = 0; i < BM; ++i)
+#pragma unroll
+        for (int j = 0; j < BN; ++j) all_valid = all_valid && blk[i][j];
 
     const uint64_t nchunks = k1 > k0 ? (k1 - k0 + KC - 1) / KC : 0;
 #pragma unroll
@@ -341,35 +405,8 @@ __global__ void __launch_bounds__(WM * WN * 32, 2) qgt_gram_kernel(GramLaunch g)
         }
         const cplx* sA = sm + (size_t)(ch % STAGES) * STAGE_ELEMS;
         const cplx* sB = sA + MT * S;
-#pragma unroll
-        for (int kk = 0; kk < KC; kk += 4) {
-            cplx a[BM], b[BN];
-#pragma unroll
-            for (int i = 0; i < BM; ++i) a[i] = sA[((wm * BM + i) * 8 + fr) * S + kk + fk];
-#pragma unroll
-            for (int j = 0; j < BN; ++j) b[j] = sB[((wn * BN + j) * 8 + fr) * S + kk + fk];
-            // conj(a) * b = (ar*br + ai*bi) + i (ar*bi - ai*br); the two updates of one accumulator are issued
-            // a whole block sweep apart so that dependent DMMAs never sit back to back
-#pragma unroll
-            for (int i = 0; i < BM; ++i) {
-#pragma unroll
-                for (int j = 0; j < BN; ++j) {
-                    if (!blk[i][j]) continue;
-                    dmma884(cre[i][j][0], cre[i][j][1], a[i].x, b[j].x);
-                    dmma884(cim[i][j][0], cim[i][j][1], a[i].x, b[j].y);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < BM; ++i) {
-                const double nai = -a[i].y;
-#pragma unroll
-                for (int j = 0; j < BN; ++j) {
-                    if (!blk[i][j]) continue;
-                    dmma884(cre[i][j][0], cre[i][j][1], a[i].y, b[j].y);
-                    dmma884(cim[i][j][0], cim[i][j][1], nai, b[j].x);
-                }
-            }
-        }
+        if (all_valid) gram_chunk<WM, WN, BM, BN, KC, true>(sA, sB, wm, wn, fr, fk, blk, cre, cim);
+        else gram_chunk<WM, WN, BM, BN, KC, false>(sA, sB, wm, wn, fr, fk, blk, cre, cim);
     }
     cp_async_wait<0>();
     const int Npad = g.ntiles * NT;
@@ -424,15 +461,16 @@ __global__ void qgt_finalize_kernel(const cplx* C, int P, double* metric, double
 
 // tile shape with the least padded work: 64x64 for big blocks, 32x32 when that wastes less, 32x16 for the
 // few-column Grams of the blocked schedule
+static int g_gram_tile_override = 0;
+void set_gram_tile_override(int t) { g_gram_tile_override = t; }
+
 GramShape gram_shape(int na, int nb) {
     GramShape s;
+    if (g_gram_tile_override == 64) { s.MT = 64; s.NT = 64; return s; }
+    if (g_gram_tile_override == 32) { s.MT = 32; s.NT = 32; return s; }
     if (na <= 32 && nb <= 16) { s.MT = 32; s.NT = 16; return s; }
-    auto padded = [&](int mt, int nt) {
-        const long m = (na + mt - 1) / mt, n = (nb + nt - 1) / nt;
-        return m * n * (long)mt * nt;
-    };
-    if (padded(64, 64) <= padded(32, 32) + padded(32, 32) / 8) { s.MT = 64; s.NT = 64; }
-    else { s.MT = 32; s.NT = 32; }
+    // 32x32 tiles measured faster than 64x64 on B200 at every size tried (less padding, more CTAs per SM)
+    s.MT = 32; s.NT = 32;
     return s;
 }
 
@@ -455,7 +493,7 @@ static cudaError_t launch_gram_t(const GramLaunch& g, cudaStream_t st) {
 cudaError_t launch_gram(const GramLaunch& g, GramShape shp, cudaStream_t st) {
     if (g.mtiles * g.ntiles * g.ksplit == 0) return cudaSuccess;
     if (shp.MT == 64) return launch_gram_t<2, 4, 4, 2, 8, 4>(g, st);
-    if (shp.NT == 32) return launch_gram_t<2, 4, 2, 1, 16, 4>(g, st);
+    if (shp.NT == 32) return launch_gram_t<2, 4, 2, 1, 16, 3>(g, st);
     return launch_gram_t<4, 2, 1, 1, 16, 4>(g, st);
 }
 

@@ -20,6 +20,8 @@ struct SweepLaunch {
     int nitems;
     uint64_t ntiles;
     uint64_t gprefix;            // rank bits of a sharded state, OR-ed into every global index used by masks
+    int mma_only;                // every sub-pass of the run qualifies for the tensor-pipe path (host-checked)
+    int double_buffer;           // tensor-only kernel: two tile buffers (3 CTAs/SM) instead of one (4 CTAs/SM)
     int use_mma;                 // dense stages on the FP64 tensor pipe (DMMA) where the sub-pass allows it
     QgtCostTable ct;
 };
@@ -41,6 +43,7 @@ struct GramShape { int MT, NT; };
 cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int num_sms, cudaStream_t st);
 
 GramShape gram_shape(int na, int nb);
+void set_gram_tile_override(int t);   // tuning: 0 = automatic, 32 or 64 = force that square tile
 cudaError_t launch_gram(const GramLaunch& g, GramShape shp, cudaStream_t st);
 // C[(a_ids[i]), (b_ids[j])] = sum_ks partial ; mirrored conj ; ldc = leading dimension of C
 cudaError_t launch_gram_reduce(const GramLaunch& g, GramShape shp, const int* a_ids, const int* b_ids,
