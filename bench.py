@@ -218,10 +218,11 @@ def main():
     g_host = np.zeros((P, P))
     b_host = np.zeros((P, P))
 
+    import ctypes as C
+    cc = circ.to_c()                      # the host-side gate table (POD structs of include/qgt_b200.h)
+
     def step():
         # the public call: host theta + gate table in, host metric + Berry curvature out
-        cc = circ.to_c()
-        import ctypes as C
         rc = ctx.L.qgt_b200_qgt(ctx.h, C.byref(cc), theta.ctypes.data_as(api._DP), g_host.ctypes.data_as(api._DP),
                                 b_host.ctypes.data_as(api._DP), None, None)
         if rc:

@@ -193,6 +193,8 @@ typedef struct qgt_b200_stats {
     int32_t resident_columns; /* b */
     int32_t blocks;           /* number of resident blocks */
     int32_t tile_qubits;
+    double ms_wall;           /* host wall-clock time of the whole call */
+    double ms_host_plan;      /* of which: planning (fusion, stage matrices, schedule, derivative matrices) */
 } qgt_b200_stats;
 int  qgt_b200_get_stats(qgt_b200_ctx* ctx, qgt_b200_stats* out);
 

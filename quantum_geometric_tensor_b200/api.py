@@ -32,7 +32,8 @@ class Stats(C.Structure):
                 ("sweep_bytes", C.c_double), ("gram_flops", C.c_double), ("gram_bytes", C.c_double), ("exchange_bytes", C.c_double),
                 ("sweep_launches", C.c_int64), ("gram_launches", C.c_int64), ("other_launches", C.c_int64),
                 ("sweep_column_passes", C.c_int64),
-                ("num_runs", C.c_int32), ("resident_columns", C.c_int32), ("blocks", C.c_int32), ("tile_qubits", C.c_int32)]
+                ("num_runs", C.c_int32), ("resident_columns", C.c_int32), ("blocks", C.c_int32), ("tile_qubits", C.c_int32),
+                ("ms_wall", C.c_double), ("ms_host_plan", C.c_double)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -310,6 +311,7 @@ int upload_plan(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
     if (e != cudaSuccess) return cuda_fail(e, "plan upload");
     c->seg_cost.clear();
     c->cost.edges = nullptr; c->cost.num_edges = 0; c->cost.vertex_weights = nullptr; c->cost.n = circ.num_qubits;
+    if (circ.num_edges > QGT_COST_MAX_EDGES) return fail(QGT_B200_ERR_UNSUPPORTED, "more than 1024 cost-layer edges");
     if (circ.num_edges && circ.edges) {
         std::vector<QgtDevEdge> ed(circ.num_edges);
         for (size_t k = 0; k < circ.num_edges; k++) {
@@ -352,8 +354,11 @@ static int do_sweep(qgt_b200_ctx* c, const CircuitPlan& plan, int run, const Qgt
     a.use_mma = c->use_mma;
     a.double_buffer = c->double_buffer;
     a.mma_only = c->use_mma && plan.R == 3 && plan.B == 0;
-    for (const SubPass& sp : plan.runs[run].subs)
+    int has_cost = 0;
+    for (const SubPass& sp : plan.runs[run].subs) {
+        if (sp.is_cost) has_cost = 1;
         if (sp.is_cost || !sp.mma_ok) a.mma_only = 0;
+    }
     a.gprefix = (uint64_t)c->rank << plan.nloc;
     a.ct = c->seg_cost.empty() ? c->cost : c->seg_cost[plan.runs[run].segment];
     const int K = plan.runs[run].K;
@@ -369,7 +374,7 @@ static int do_sweep(qgt_b200_ctx* c, const CircuitPlan& plan, int run, const Qgt
                  (int)plan.runs[run].subs.size(), nst, (int)plan.runs[run].ops.size(), (unsigned long long)shard_tiles, mat_count);
     }
     c->timer.begin(c->stream, 0, label);
-    cudaError_t e = launch_sweep(a, K, R, plan.B, mat_count, (int)plan.runs[run].subs.size(), c->num_sms, c->stream);
+    cudaError_t e = launch_sweep(a, K, R, plan.B, mat_count, (int)plan.runs[run].subs.size(), a.mma_only ? 0 : has_cost, c->num_sms, c->stream);
     c->timer.end(c->stream);
     if (e != cudaSuccess) return cuda_fail(e, "sweep launch");
     c->stats.sweep_launches++;
@@ -413,6 +418,7 @@ static int gram_ksplit(const qgt_b200_ctx* c, int tiles, uint64_t D) {
 int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan& plan, const Program& prog,
                 cplx* arena, uint64_t D, cplx* cmat /* (P+1)^2 device */) {
     const int P = plan.P;
+    const auto t_pack0 = std::chrono::steady_clock::now();
     // ---- pack every launch's arguments and upload them once ------------------------------------
     std::vector<QgtSweepItem> items;
     std::vector<double> ovr_pool, mats;          // derivative matrices of the spawn items
@@ -444,7 +450,9 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                     if (loc.kind == 1) {
                         int first = 0;
                         for (int s2 = 0; s2 < loc.sub; s2++) first += (int)run.subs[s2].stages.size();
-                        stage_matrices(run, sp, sp.stages[loc.index - first], sc.ovr_op, mats);
+                        std::vector<int> dops(1, sc.ovr_op);
+                        dops.insert(dops.end(), sc.ovr_extra.begin(), sc.ovr_extra.end());
+                        stage_matrices_sum(run, sp, sp.stages[loc.index - first], dops, mats);
                         ovr_off.push_back(ovr_pool.size());
                         ovr_item.push_back(items.size());
                         ovr_pool.insert(ovr_pool.end(), mats.begin(), mats.end());
@@ -474,6 +482,7 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             partial_bytes = std::max(partial_bytes, (size_t)ks * mt * shp.MT * nt * shp.NT * sizeof(cplx));
         }
     }
+    c->ms_prog_pack = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pack0).count();
     int rc;
     if ((rc = c->ovr_pool.reserve(std::max<size_t>(16, ovr_pool.size() * sizeof(double))))) return rc;
     for (size_t k = 0; k < ovr_item.size(); k++)
@@ -626,6 +635,7 @@ int qgt_b200_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* th
     cudaSetDevice(c->device);
     if (psi_out && psi_out->n != circ->num_qubits) return fail(QGT_B200_ERR_DIMENSION, "psi_out has a different qubit count");
     if (c->world > 1) return qgt::dist_qgt(c, circ, theta, metric, berry, q_full, psi_out);
+    const auto t_wall0 = std::chrono::steady_clock::now();
     const int n = circ->num_qubits, P = circ->num_params;
     const uint64_t D = (uint64_t)1 << n;
     CircuitPlan plan;
@@ -634,6 +644,7 @@ int qgt_b200_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* th
     Program prog;
     const size_t slots = workspace_slots(c, D, (size_t)64 << 20);
     if ((rc = build_qgt_program(plan, slots, psi_out != nullptr, prog, err))) return fail(rc, err);
+    const double ms_plan0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wall0).count();
     if ((rc = c->arena.reserve((size_t)prog.num_slots * D * sizeof(cplx)))) return rc;
     const size_t cm = (size_t)(P + 1) * (P + 1);
     if ((rc = c->cmat.reserve(std::max<size_t>(16, cm * sizeof(cplx))))) return rc;
@@ -666,6 +677,8 @@ int qgt_b200_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* th
     c->stats.resident_columns = prog.resident;
     c->stats.blocks = prog.blocks;
     c->stats.tile_qubits = plan.runs.empty() ? 0 : plan.runs[0].K;
+    c->stats.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wall0).count();
+    c->stats.ms_host_plan = ms_plan0 + c->ms_prog_pack;
     return QGT_B200_OK;
 }
 

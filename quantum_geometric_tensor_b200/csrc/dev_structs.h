@@ -91,7 +91,7 @@ typedef struct QgtDevRun {
     int32_t mat_count;                   // complex elements of this run in the pool
     int8_t  tq[QGT_MAX_TILE_QUBITS];     // tile qubits: local bit j <-> global bit tq[j], ascending
     int8_t  ntq[QGT_MAX_QUBITS];         // the n-K other qubits, ascending (tile id bits are deposited here)
-    int32_t pad;
+    int32_t has_cost;                    // the run contains a cost-layer pass (energy tables are staged in shared memory)
 } QgtDevRun;
 
 // one column of a batched sweep launch

@@ -35,6 +35,51 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
+// Streamlined tensor-pipe sub-pass for the common shape: exactly one dense stage, no thread diagonals.
+// Same fragment layout as qgt_warp_subpass_mma below, with every slot an XOR of host-precomputed terms.
+__device__ __forceinline__ void qgt_warp_subpass_mma_simple(const QgtDevRun& run, const QgtDevSubPass& sp, const QgtSubCtx& cx,
+                                                            cplx* tile, uint64_t tileg, int warp, int lane) {
+    constexpr int N = 8;
+    const int q = lane >> 2, k = lane & 3;
+    const int nthr_bits = run.K - 3;
+    const uint32_t st0 = sp.s_thr[0], st1 = sp.s_thr[1], st2 = sp.s_thr[2], st3 = sp.s_thr[3], st4 = sp.s_thr[4];
+    const uint32_t sr0 = sp.s_reg[0], sr1 = sp.s_reg[1], sr2 = sp.s_reg[2];
+    uint32_t swarp = 0;
+    uint64_t gwarp = tileg;
+    for (int i = 5; i < nthr_bits; ++i)
+        if ((warp >> (i - 5)) & 1) { swarp ^= sp.s_thr[i]; gwarp |= sp.g_thr[i]; }
+    const uint32_t baseB = swarp ^ ((q & 1) ? st0 : 0u) ^ ((q & 2) ? st1 : 0u) ^ ((q & 4) ? st2 : 0u) ^ ((k & 1) ? sr0 : 0u) ^ ((k & 2) ? sr1 : 0u);
+    const uint32_t baseC = swarp ^ ((k & 1) ? st1 : 0u) ^ ((k & 2) ? st2 : 0u) ^ ((q & 1) ? sr0 : 0u) ^ ((q & 2) ? sr1 : 0u) ^ ((q & 4) ? sr2 : 0u);
+    const int s = sp.stage_begin;
+    const QgtDevStage& st = cx.stages[s];
+    const int off = (cx.ovr_kind == 1 && s == cx.ovr_index) ? cx.ovr_mat_off : st.mat_off;
+    int var = 0;
+    if (st.nvar > 0) var |= (gwarp & st.vmask[0]) != 0;
+    if (st.nvar > 1) var |= ((gwarp & st.vmask[1]) != 0) << 1;
+    const cplx* M = cx.pool + off + var * QGT_VARIANT_STRIDE(N);
+    const cplx m0 = M[q * N + k], m1 = M[q * N + 4 + k];
+    const double nm0y = -m0.y, nm1y = -m1.y;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t gx = ((g & 1) ? st3 : 0u) ^ ((g & 2) ? st4 : 0u);
+        const cplx v0 = tile[baseB ^ gx], v1 = tile[baseB ^ gx ^ sr2];
+        double cr0 = 0.0, cr1 = 0.0, ci0 = 0.0, ci1 = 0.0;
+        dmma884(cr0, cr1, m0.x, v0.x);
+        dmma884(ci0, ci1, m0.x, v0.y);
+        dmma884(cr0, cr1, m1.x, v1.x);
+        dmma884(ci0, ci1, m1.x, v1.y);
+        dmma884(cr0, cr1, nm0y, v0.y);
+        dmma884(ci0, ci1, m0.y, v0.x);
+        dmma884(cr0, cr1, nm1y, v1.y);
+        dmma884(ci0, ci1, m1.y, v1.x);
+        cplx o0, o1;
+        o0.x = cr0; o0.y = ci0; o1.x = cr1; o1.y = ci1;
+        __syncwarp();                 // every lane has read the group's slots before they are overwritten
+        tile[baseC ^ gx] = o0;
+        tile[baseC ^ gx ^ st0] = o1;
+    }
+}
+
 // Tensor-pipe version of a sub-pass with 3 matrix qubits (DMMA.8x8x4).  A "vector" is the 8 amplitudes one
 // thread of the register path would own; a warp owns 32 vectors = 4 groups of 8.  Per stage the 8x8 complex
 // matrix M sits in A fragments (lane (r, k) holds M[r][k] and M[r][4+k]), the 8 vectors of a group form the
@@ -151,12 +196,14 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
     cplx* spool = tile + ((size_t)(DB ? 2 : 1) << run.K);
     cplx* sovr = spool + run.mat_count;
     QgtDevSubPass* subs = reinterpret_cast<QgtDevSubPass*>(sovr + OVR_ELEMS);
+    QgtCostSmem cost_sm = qgt_cost_smem_carve(reinterpret_cast<double*>(subs + run.nsub), run.K, a.ct.num_edges);
     {
         const cplx* gpool = a.pool + run.mat_off;
         for (int i = tid; i < run.mat_count; i += T) spool[i] = gpool[i];
         const uint32_t* gs = reinterpret_cast<const uint32_t*>(a.subs + run.sub_off);
         uint32_t* ss = reinterpret_cast<uint32_t*>(subs);
         for (int i = tid; i < run.nsub * (int)(sizeof(QgtDevSubPass) / 4); i += T) ss[i] = gs[i];
+        if (!MMA_ONLY && run.has_cost) qgt_cost_build_ein(run, a.ct, cost_sm, tid, T);
     }
     QgtSubCtx cx;
     cx.stages = a.stages + run.stage_off;
@@ -208,10 +255,17 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
         __syncthreads();
         for (int s = 0; s < run.nsub; ++s) {
             if (MMA_ONLY) {
-                qgt_warp_subpass_mma(run, subs[s], cx, cur, tileg, tid >> 5, tid & 31);
+                if (subs[s].stage_end - subs[s].stage_begin == 1 && subs[s].tdiag_end == subs[s].tdiag_begin)
+                    qgt_warp_subpass_mma_simple(run, subs[s], cx, cur, tileg, tid >> 5, tid & 31);
+                else
+                    qgt_warp_subpass_mma(run, subs[s], cx, cur, tileg, tid >> 5, tid & 31);
             } else if (subs[s].nreg == 0) {
                 const QgtDevCost& co = (it.ovr_kind == 3 && subs[s].cost == it.ovr_index) ? it.ovr_cost : a.costs[run.cost_off + subs[s].cost];
-                qgt_phase_cost(run, co, cur, tilebase, tileg, tid, T, a.ct);
+                for (int t2 = tid; t2 <= run.K; t2 += T) qgt_cost_tile_lin(run, a.ct, cost_sm, tileg, t2);
+                __syncthreads();
+                qgt_cost_tile_tables(run, cost_sm, tid, T);
+                __syncthreads();
+                qgt_phase_cost(run, co, cur, cost_sm, tid, T);
             } else if (R == 3 && B == 0 && a.use_mma && subs[s].mma_ok && T >= 32) {
                 qgt_warp_subpass_mma(run, subs[s], cx, cur, tileg, tid >> 5, tid & 31);
             } else {
@@ -246,13 +300,13 @@ static cudaError_t launch_sweep_cfg(const SweepLaunch& a, int T, size_t smem, ui
 }
 
 template <int R, int B>
-static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, int nsub, int num_sms, cudaStream_t st) {
+static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, int nsub, int has_cost, int num_sms, cudaStream_t st) {
     constexpr int N = 1 << R;
     const int T = 1 << (K - R - B);
     const uint64_t total = a.ntiles * (uint64_t)a.nitems;
     if (total == 0) return cudaSuccess;
     const size_t fixed = sizeof(cplx) * (size_t)mat_count + sizeof(cplx) * (size_t)(QGT_VARIANT_STRIDE(N) << QGT_MAX_VARIANT_BITS) +
-                         (size_t)nsub * sizeof(QgtDevSubPass);
+                         (size_t)nsub * sizeof(QgtDevSubPass) + (has_cost ? qgt_cost_smem_doubles(K, a.ct.num_edges) * sizeof(double) : 0);
     const size_t tile_bytes = sizeof(cplx) << K;
     if (fixed + 2 * tile_bytes > 200 * 1024 || T > 256) return cudaErrorInvalidValue;
     if (R == 3 && B == 0 && a.mma_only && T >= 32) {
@@ -265,15 +319,15 @@ static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, i
     return launch_sweep_cfg<R, B, false, true, 256, 2>(a, T, fixed + 2 * tile_bytes, total, num_sms, st);
 }
 
-cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int num_sms, cudaStream_t st) {
+cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int has_cost, int num_sms, cudaStream_t st) {
     if (K > QGT_MAX_TILE_QUBITS) return cudaErrorInvalidValue;
     switch (R * 2 + B) {
-    case 2: return launch_sweep_rb<1, 0>(a, K, mat_count, nsub, num_sms, st);
-    case 3: return launch_sweep_rb<1, 1>(a, K, mat_count, nsub, num_sms, st);
-    case 4: return launch_sweep_rb<2, 0>(a, K, mat_count, nsub, num_sms, st);
-    case 5: return launch_sweep_rb<2, 1>(a, K, mat_count, nsub, num_sms, st);
-    case 6: return launch_sweep_rb<3, 0>(a, K, mat_count, nsub, num_sms, st);
-    case 7: return launch_sweep_rb<3, 1>(a, K, mat_count, nsub, num_sms, st);
+    case 2: return launch_sweep_rb<1, 0>(a, K, mat_count, nsub, has_cost, num_sms, st);
+    case 3: return launch_sweep_rb<1, 1>(a, K, mat_count, nsub, has_cost, num_sms, st);
+    case 4: return launch_sweep_rb<2, 0>(a, K, mat_count, nsub, has_cost, num_sms, st);
+    case 5: return launch_sweep_rb<2, 1>(a, K, mat_count, nsub, has_cost, num_sms, st);
+    case 6: return launch_sweep_rb<3, 0>(a, K, mat_count, nsub, has_cost, num_sms, st);
+    case 7: return launch_sweep_rb<3, 1>(a, K, mat_count, nsub, has_cost, num_sms, st);
     default: return cudaErrorInvalidValue;
     }
 }

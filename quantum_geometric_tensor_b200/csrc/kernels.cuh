@@ -40,7 +40,7 @@ struct GramLaunch {
 struct GramShape { int MT, NT; };
 
 // K, R: tile / register qubits of the run; grid is chosen inside
-cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int num_sms, cudaStream_t st);
+cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int has_cost, int num_sms, cudaStream_t st);
 
 GramShape gram_shape(int na, int nb);
 void set_gram_tile_override(int t);   // tuning: 0 = automatic, 32 or 64 = force that square tile

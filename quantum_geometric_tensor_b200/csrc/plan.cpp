@@ -342,6 +342,16 @@ void stage_matrices(const Run& run, const SubPass& sp, const Stage& st, int deri
     }
 }
 
+void stage_matrices_sum(const Run& run, const SubPass& sp, const Stage& st, const std::vector<int>& deriv_ops, std::vector<double>& out) {
+    std::vector<double> one;
+    out.clear();
+    for (int op : deriv_ops) {
+        stage_matrices(run, sp, st, op, one);
+        if (out.empty()) out = one;
+        else for (size_t i = 0; i < out.size(); i++) out[i] += one[i];
+    }
+}
+
 int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions& opt_in, CircuitPlan& plan, std::string& err) {
     const int n = c.num_qubits;
     if (n < 1 || n > QGT_MAX_QUBITS) { err = "num_qubits out of range"; return QGT_B200_ERR_INVALID_ARG; }
@@ -544,6 +554,7 @@ void build_image(const CircuitPlan& plan, PlanImage& img) {
             img.subs.push_back(ds);
         }
         dr.mat_count = (int)(img.pool.size() / 2) - dr.mat_off;
+        for (const SubPass& sp : run.subs) if (sp.is_cost) dr.has_cost = 1;
         img.runs.push_back(dr);
     }
 }
@@ -740,6 +751,25 @@ struct Sched {
         }
     }
 
+    // occurrences of parameter p in run r, grouped by dense stage (product rule inside a stage = one item)
+    std::vector<SweepCol> occurrence_items(int r, int p, int src, int dst) {
+        const Run& run = plan.runs[r];
+        std::vector<SweepCol> items;
+        std::vector<int> stage_of_item;
+        for (const ParamOcc& oc : run.occ) {
+            if (oc.param != p) continue;
+            const OpLocation loc = locate_op(run, oc.op);
+            int found = -1;
+            if (loc.kind == 1)
+                for (size_t k = 0; k < items.size(); k++) if (stage_of_item[k] == loc.index) found = (int)k;
+            if (found >= 0) { items[found].ovr_extra.push_back(oc.op); continue; }
+            SweepCol sc; sc.src = src; sc.dst = dst; sc.ovr_op = oc.op; sc.accumulate = true;
+            items.push_back(sc);
+            stage_of_item.push_back(loc.kind == 1 ? loc.index : -1 - (int)items.size());
+        }
+        return items;
+    }
+
     // March phi from run r0 with `resident` columns (parameters) and, per run, the streaming
     // parameters in `streaming` (all born at or after r0).  diag: also emit the resident x resident
     // (+psi) Gram at T_res.
@@ -769,14 +799,19 @@ struct Sched {
             for (int p = 0; p < P; p++) if (alive[p]) { A.push_back({slot_of[p], slot_of[p], -1, false}); if (is_str[p]) alive_str_now.push_back(p); }
             std::vector<int> born_str;
             std::vector<char> spawned_here(P, 0);
+            std::vector<char> seen_here(P, 0);
             for (const ParamOcc& oc : run.occ) {
                 const int p = oc.param;
-                if (is_res[p]) {
-                    if (!alive[p] && !spawned_here[p]) { A.push_back({psi, slot_of[p], oc.op, false}); spawned_here[p] = 1; }
-                    else acc.push_back({psi, slot_of[p], oc.op, true});
+                if (seen_here[p]) continue;
+                seen_here[p] = 1;
+                if (is_res[p] || (is_str[p] && alive[p])) {
+                    std::vector<SweepCol> items = occurrence_items(r, p, psi, slot_of[p]);
+                    for (size_t k = 0; k < items.size(); k++) {
+                        if (k == 0 && !alive[p]) { items[k].accumulate = false; A.push_back(items[k]); spawned_here[p] = 1; }
+                        else acc.push_back(items[k]);
+                    }
                 } else if (is_str[p]) {
-                    if (alive[p]) acc.push_back({psi, slot_of[p], oc.op, true});
-                    else if (!spawned_here[p]) { born_str.push_back(p); spawned_here[p] = 1; }
+                    born_str.push_back(p); spawned_here[p] = 1;
                 }
             }
             sweep(r, A);
@@ -808,11 +843,10 @@ struct Sched {
                     const int p = born_str[bi++];
                     slot_of[p] = free_str.back(); free_str.pop_back();
                     round.push_back(p);
-                    bool first = true;
-                    for (const ParamOcc& oc : run.occ) {
-                        if (oc.param != p) continue;
-                        if (first) { S.push_back({psi, slot_of[p], oc.op, false}); first = false; }
-                        else sacc.push_back({psi, slot_of[p], oc.op, true});
+                    std::vector<SweepCol> items = occurrence_items(r, p, psi, slot_of[p]);
+                    for (size_t k = 0; k < items.size(); k++) {
+                        if (k == 0) { items[k].accumulate = false; S.push_back(items[k]); }
+                        else sacc.push_back(items[k]);
                     }
                 }
                 sweep(r, S);
@@ -984,7 +1018,11 @@ std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const 
             if (in.kind == INSTR_SWEEP) {
                 o << "{\"k\":\"sweep\",\"run\":" << in.run << ",\"cols\":[";
                 for (size_t j = 0; j < in.cols.size(); j++)
-                    o << (j ? "," : "") << "[" << in.cols[j].src << "," << in.cols[j].dst << "," << in.cols[j].ovr_op << "," << (in.cols[j].accumulate ? 1 : 0) << "]";
+                {
+                    o << (j ? "," : "") << "[" << in.cols[j].src << "," << in.cols[j].dst << "," << in.cols[j].ovr_op << "," << (in.cols[j].accumulate ? 1 : 0) << ",";
+                    jarr(o, in.cols[j].ovr_extra);
+                    o << "]";
+                }
                 o << "]}";
             } else if (in.kind == INSTR_GRAM) {
                 o << "{\"k\":\"gram\",\"a\":"; jarr(o, in.a_slots); o << ",\"aid\":"; jarr(o, in.a_ids);

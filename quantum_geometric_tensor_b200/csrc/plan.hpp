@@ -100,6 +100,8 @@ OpLocation locate_op(const Run& run, int op_index);
 // all variants of a stage's matrix, (re, im) interleaved, row-major 2^R x 2^R each; deriv_op >= 0 replaces
 // that lowered op by its derivative
 void stage_matrices(const Run& run, const SubPass& sp, const Stage& st, int deriv_op, std::vector<double>& out);
+// product rule over several ops of one stage: sum of the single-derivative matrices
+void stage_matrices_sum(const Run& run, const SubPass& sp, const Stage& st, const std::vector<int>& deriv_ops, std::vector<double>& out);
 QgtDevThrDiag make_tdiag(const LoweredOp& op, bool derivative);
 QgtDevCost make_cost(const LoweredOp& op, bool derivative);
 
@@ -107,8 +109,12 @@ QgtDevCost make_cost(const LoweredOp& op, bool derivative);
 enum InstrKind { INSTR_SWEEP = 0, INSTR_GRAM = 1, INSTR_COPY = 2, INSTR_INIT = 3 };
 
 struct SweepCol {
+    SweepCol() {}
+    SweepCol(int s, int d, int o, bool a) : src(s), dst(d), ovr_op(o), accumulate(a) {}
     int src = 0, dst = 0;       // slots
     int ovr_op = -1;            // index into the run's ops, -1 = none
+    std::vector<int> ovr_extra; // further ops of the same parameter inside the same dense stage: the item applies
+                                // the product-rule sum  sum_j (stage with op j replaced by its derivative)
     bool accumulate = false;
 };
 

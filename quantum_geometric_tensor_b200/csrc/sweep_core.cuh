@@ -279,23 +279,151 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
     }
 }
 
-// tile-level pass for the (rare, transcendental-heavy) cost layer: thread `tid` of T handles local
-// indices tid, tid+T, ... directly in shared memory; kept out of the register path to keep that code small.
-QGT_HD void qgt_phase_cost(const QgtDevRun& run, const QgtDevCost& op, cplx* tile, uint64_t tilebase, uint64_t tileg,
-                           int tid, int T, const QgtCostTable& ct) {
-    (void)tilebase;
+// ---- cost layer ---------------------------------------------------------------------------------------
+// E(z) = sum_edges w [z_i != z_j] + sum_q vw_q (1 - 2 z_q) is split by where the qubits live:
+//   ein[idx]   both ends inside the tile (+ vertex terms of tile qubits): a 2^K table built once per CTA;
+//   per tile   edges with both ends outside and outside vertex terms give a constant, edges with one end at
+//              tile position p contribute  z_j + z_p (1 - 2 z_j): a constant plus lin[p] * z_p, folded into
+//              two small tables lo[idx & 63], hi[idx >> 6].
+// So the per-amplitude energy is three shared-memory reads instead of a loop over every edge.
+#define QGT_COST_LO_BITS 6
+#define QGT_COST_MAX_EDGES 1024
+struct QgtCostSmem {
+    double* ein;       // [2^K]
+    double* lo;        // [64]
+    double* hi;        // [2^(K-6)] (at least 1)
+    double* lin;       // [K] slopes, [K] constants, [1] outside constant
+    double* cross_w;   // cross edges (one end at a tile position) grouped by position: weights ...
+    double* out_w;     // edges with both ends outside: weights ...
+    int16_t* cross_start;   // [K+1] CSR offsets into cross_w / cross_q
+    int8_t* cross_q;   // ... and the outside qubit of each
+    int8_t* out_i;     // ... and their two qubits
+    int8_t* out_j;
+    int* n_out;        // [1]
+};
+
+QGT_HD size_t qgt_cost_smem_doubles(int K, int num_edges) {
+    const size_t ne = (size_t)(num_edges > 0 ? num_edges : 1);
+    const size_t bytes_small = 2 * (QGT_MAX_TILE_QUBITS + 2) + 3 * ne + 16;     // int16 starts + three int8 arrays + count
+    return ((size_t)1 << K) + 64 + ((size_t)1 << (K > QGT_COST_LO_BITS ? K - QGT_COST_LO_BITS : 0)) + 2 * QGT_MAX_TILE_QUBITS + 8 +
+           2 * ne + (bytes_small + 7) / 8;
+}
+
+QGT_HD QgtCostSmem qgt_cost_smem_carve(double* base, int K, int num_edges) {
+    const size_t ne = (size_t)(num_edges > 0 ? num_edges : 1);
+    QgtCostSmem c;
+    c.ein = base;
+    c.lo = c.ein + ((size_t)1 << K);
+    c.hi = c.lo + 64;
+    c.lin = c.hi + ((size_t)1 << (K > QGT_COST_LO_BITS ? K - QGT_COST_LO_BITS : 0));
+    c.cross_w = c.lin + 2 * QGT_MAX_TILE_QUBITS + 8;
+    c.out_w = c.cross_w + ne;
+    c.cross_start = reinterpret_cast<int16_t*>(c.out_w + ne);
+    c.cross_q = reinterpret_cast<int8_t*>(c.cross_start + QGT_MAX_TILE_QUBITS + 2);
+    c.out_i = c.cross_q + ne;
+    c.out_j = c.out_i + ne;
+    c.n_out = reinterpret_cast<int*>(reinterpret_cast<uintptr_t>(c.out_j + ne + 3) & ~(uintptr_t)3);
+    return c;
+}
+
+QGT_HD int qgt_local_pos(const QgtDevRun& run, int q) {
+    for (int j = 0; j < run.K; j++) if (run.tq[j] == q) return j;
+    return -1;
+}
+
+// once per CTA: thread `tid` of T fills its share of ein[]; thread 0 also sorts the edges into the cross
+// lists (by tile position) and the outside list
+QGT_HD void qgt_cost_build_ein(const QgtDevRun& run, const QgtCostTable& ct, const QgtCostSmem& cs, int tid, int T) {
     const uint32_t count = 1u << run.K;
     for (uint32_t idx = (uint32_t)tid; idx < count; idx += (uint32_t)T) {
-        const uint64_t g = tileg | qgt_local_to_global(run, idx);
-        const double e = qgt_cost_energy(ct, g);
-        double sn, cs;
+        double e = 0.0;
+        for (int k = 0; k < ct.num_edges; k++) {
+            const int li = qgt_local_pos(run, ct.edges[k].i), lj = qgt_local_pos(run, ct.edges[k].j);
+            if (li >= 0 && lj >= 0 && (((idx >> li) ^ (idx >> lj)) & 1u)) e += ct.edges[k].w;
+        }
+        if (ct.vertex_weights)
+            for (int j = 0; j < run.K; j++) e += ct.vertex_weights[run.tq[j]] * (double)(1 - 2 * (int)((idx >> j) & 1u));
+        cs.ein[idx] = e;
+    }
+    if (tid == 0) {
+        int nc = 0, no = 0;
+        for (int p = 0; p < run.K; p++) {
+            cs.cross_start[p] = (int16_t)nc;
+            const int qp = run.tq[p];
+            for (int k = 0; k < ct.num_edges; k++) {
+                const int i = ct.edges[k].i, j = ct.edges[k].j;
+                const int other = (i == qp) ? j : (j == qp ? i : -1);
+                if (other < 0 || qgt_local_pos(run, other) >= 0) continue;
+                cs.cross_q[nc] = (int8_t)other; cs.cross_w[nc] = ct.edges[k].w; nc++;
+            }
+        }
+        cs.cross_start[run.K] = (int16_t)nc;
+        for (int k = 0; k < ct.num_edges; k++) {
+            const int i = ct.edges[k].i, j = ct.edges[k].j;
+            if (qgt_local_pos(run, i) >= 0 || qgt_local_pos(run, j) >= 0) continue;
+            cs.out_i[no] = (int8_t)i; cs.out_j[no] = (int8_t)j; cs.out_w[no] = ct.edges[k].w; no++;
+        }
+        *cs.n_out = no;
+    }
+}
+
+// per tile, step 1: thread p < K computes lin[p] and its constant from its own cross list; thread K the
+// outside constant
+QGT_HD void qgt_cost_tile_lin(const QgtDevRun& run, const QgtCostTable& ct, const QgtCostSmem& cs, uint64_t tileg, int tid) {
+    if (tid < run.K) {
+        double lin = 0.0, c0 = 0.0;
+        for (int k = cs.cross_start[tid]; k < cs.cross_start[tid + 1]; k++) {
+            const double zj = (double)((tileg >> cs.cross_q[k]) & 1ull);
+            lin += cs.cross_w[k] * (1.0 - 2.0 * zj);
+            c0 += cs.cross_w[k] * zj;
+        }
+        cs.lin[tid] = lin;
+        cs.lin[QGT_MAX_TILE_QUBITS + tid] = c0;
+    } else if (tid == run.K) {
+        double e = 0.0;
+        const int no = *cs.n_out;
+        for (int k = 0; k < no; k++)
+            if (((tileg >> cs.out_i[k]) ^ (tileg >> cs.out_j[k])) & 1ull) e += cs.out_w[k];
+        if (ct.vertex_weights)
+            for (int q = 0; q < ct.n; q++)
+                if (qgt_local_pos(run, q) < 0) e += ct.vertex_weights[q] * (double)(1 - 2 * (int)((tileg >> q) & 1ull));
+        cs.lin[2 * QGT_MAX_TILE_QUBITS] = e;
+    }
+}
+
+// per tile, step 2 (after a barrier): the two small tables; the constants are folded into lo[]
+QGT_HD void qgt_cost_tile_tables(const QgtDevRun& run, const QgtCostSmem& cs, int tid, int T) {
+    const int lo_bits = run.K < QGT_COST_LO_BITS ? run.K : QGT_COST_LO_BITS;
+    const int hi_bits = run.K - lo_bits;
+    for (int x = tid; x < (1 << lo_bits) + (1 << hi_bits); x += T) {
+        if (x < (1 << lo_bits)) {
+            double e = cs.lin[2 * QGT_MAX_TILE_QUBITS];
+            for (int p = 0; p < run.K; p++) e += cs.lin[QGT_MAX_TILE_QUBITS + p];
+            for (int p = 0; p < lo_bits; p++) if ((x >> p) & 1) e += cs.lin[p];
+            cs.lo[x] = e;
+        } else {
+            const int y = x - (1 << lo_bits);
+            double e = 0.0;
+            for (int p = 0; p < hi_bits; p++) if ((y >> p) & 1) e += cs.lin[lo_bits + p];
+            cs.hi[y] = e;
+        }
+    }
+}
+
+// per tile, step 3 (after a barrier): thread `tid` of T handles local indices tid, tid+T, ... in shared memory
+QGT_HD void qgt_phase_cost(const QgtDevRun& run, const QgtDevCost& op, cplx* tile, const QgtCostSmem& cs, int tid, int T) {
+    const uint32_t count = 1u << run.K;
+    const int lo_bits = run.K < QGT_COST_LO_BITS ? run.K : QGT_COST_LO_BITS;
+    for (uint32_t idx = (uint32_t)tid; idx < count; idx += (uint32_t)T) {
+        const double e = cs.ein[idx] + cs.lo[idx & ((1u << lo_bits) - 1u)] + cs.hi[idx >> lo_bits];
+        double sn, cs_;
 #if defined(__CUDA_ARCH__)
-        sincos(-op.angle * e, &sn, &cs);
+        sincos(-op.angle * e, &sn, &cs_);
 #else
-        sn = std::sin(-op.angle * e); cs = std::cos(-op.angle * e);
+        sn = std::sin(-op.angle * e); cs_ = std::cos(-op.angle * e);
 #endif
         const cplx a = tile[qgt_swz(idx)];
-        cplx b; b.x = cs * a.x - sn * a.y; b.y = cs * a.y + sn * a.x;
+        cplx b; b.x = cs_ * a.x - sn * a.y; b.y = cs_ * a.y + sn * a.x;
         if (op.flags & QGT_FLAG_COST_DERIV) {   // times (-i * scale * E)
             const double f = op.dscale * e;
             cplx d; d.x = f * b.y; d.y = -f * b.x; b = d;

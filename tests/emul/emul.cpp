@@ -35,6 +35,9 @@ static void emul_item(const QgtDevRun& run, const PlanImage& img, const QgtSweep
     cx.ovr_mat_off = run.mat_count;
     cx.ovr_kind = it.ovr_kind; cx.ovr_index = it.ovr_index;
     cx.ovr_tdiag = &it.ovr_tdiag;
+    std::vector<double> cost_buf(qgt_cost_smem_doubles(run.K, ct.num_edges));
+    QgtCostSmem cost_sm = qgt_cost_smem_carve(cost_buf.data(), run.K, ct.num_edges);
+    if (run.has_cost) for (int tid = 0; tid < T; tid++) qgt_cost_build_ein(run, ct, cost_sm, tid, T);
     for (uint64_t tau = 0; tau < ntiles; tau++) {
         const uint64_t tilebase = qgt_tile_base(run, tau);
         for (int tid = 0; tid < T; tid++) {
@@ -44,8 +47,13 @@ static void emul_item(const QgtDevRun& run, const PlanImage& img, const QgtSweep
         for (int s = 0; s < run.nsub; s++)
             for (int tid = 0; tid < T; tid++) {
                 if (subs[s].nreg == 0) {
+                    if (tid == 0) {          // the kernel's three barrier-separated steps, all threads of each step in turn
+                        for (int t1 = 0; t1 < T; t1++)
+                            for (int t2 = t1; t2 <= run.K; t2 += T) qgt_cost_tile_lin(run, ct, cost_sm, tilebase, t2);
+                        for (int t2 = 0; t2 < T; t2++) qgt_cost_tile_tables(run, cost_sm, t2, T);
+                    }
                     const QgtDevCost& co = (it.ovr_kind == 3 && subs[s].cost == it.ovr_index) ? it.ovr_cost : img.costs[run.cost_off + subs[s].cost];
-                    qgt_phase_cost(run, co, tile.data(), tilebase, tilebase, tid, T, ct);
+                    qgt_phase_cost(run, co, tile.data(), cost_sm, tid, T);
                 } else {
                     qgt_phase_subpass<R, B>(run, subs[s], cx, tile.data(), tilebase, tid);
                 }
@@ -66,7 +74,7 @@ extern "C" int emul_num_runs(const qgt_b200_circuit* circ, const double* theta, 
 
 // one sweep item: dst (+)= run[run_idx](src) with op `ovr_op` replaced by its derivative (or -1)
 extern "C" int emul_sweep(const qgt_b200_circuit* circ, const double* theta, int K, int R, int run_idx,
-                          const double* src, double* dst, int ovr_op, int accumulate) {
+                          const double* src, double* dst, int ovr_op, int accumulate, const int* extra, int nextra) {
     PlanOptions opt; opt.tile_qubits = K; opt.reg_qubits = R; opt.batch_qubits = g_emul_batch;
     CircuitPlan plan; std::string err;
     if (build_plan(*circ, theta, opt, plan, err)) return -1;
@@ -87,7 +95,9 @@ extern "C" int emul_sweep(const qgt_b200_circuit* circ, const double* theta, int
         if (loc.kind == 1) {
             int first = 0;
             for (int s2 = 0; s2 < loc.sub; s2++) first += (int)run.subs[s2].stages.size();
-            stage_matrices(run, sp, sp.stages[loc.index - first], ovr_op, mats);
+            std::vector<int> dops(1, ovr_op);
+            for (int e = 0; e < nextra; e++) dops.push_back(extra[e]);
+            stage_matrices_sum(run, sp, sp.stages[loc.index - first], dops, mats);
             it.ovr_mat = mats.data();
         } else if (loc.kind == 2) it.ovr_tdiag = make_tdiag(run.ops[ovr_op], true);
         else it.ovr_cost = make_cost(run.ops[ovr_op], true);
@@ -133,7 +143,9 @@ extern "C" double emul_host_plan_ms(const qgt_b200_circuit* circ, const double* 
                 if (loc.kind == 1) {
                     int first = 0;
                     for (int s2 = 0; s2 < loc.sub; s2++) first += (int)run.subs[s2].stages.size();
-                    stage_matrices(run, run.subs[loc.sub], run.subs[loc.sub].stages[loc.index - first], sc.ovr_op, mats);
+                    std::vector<int> dops(1, sc.ovr_op);
+                    dops.insert(dops.end(), sc.ovr_extra.begin(), sc.ovr_extra.end());
+                    stage_matrices_sum(run, run.subs[loc.sub], run.subs[loc.sub].stages[loc.index - first], dops, mats);
                     total += mats.size();
                 }
             }

@@ -26,20 +26,20 @@ def load():
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out] + srcs, check=True)
     L = C.CDLL(out)
-    L.emul_sweep.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int, C.c_int, _DP, _DP, C.c_int, C.c_int]
+    L.emul_sweep.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int, C.c_int, _DP, _DP, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
     L.emul_num_runs.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int]
     _lib = L
     return L
 
 
-def sweep(circ, theta, K, R, run_idx, src, ovr_op=-1, dst=None, accumulate=False):
+def sweep(circ, theta, K, R, run_idx, src, ovr_op=-1, dst=None, accumulate=False, extra=()):
     L = load()
     cc = circ.to_c()
     th = np.ascontiguousarray(theta if len(theta) else np.zeros(1), dtype=np.float64)
     src = np.ascontiguousarray(src, dtype=np.complex128)
     out = np.zeros_like(src) if dst is None else np.array(dst, dtype=np.complex128)
     rc = L.emul_sweep(C.byref(cc), th.ctypes.data_as(_DP), K, R, run_idx, src.ctypes.data_as(_DP),
-                      out.ctypes.data_as(_DP), ovr_op, 1 if accumulate else 0)
+                      out.ctypes.data_as(_DP), ovr_op, 1 if accumulate else 0, (C.c_int * max(1, len(extra)))(*extra), len(extra))
     if rc:
         raise RuntimeError(f"emul_sweep -> {rc}")
     return out

@@ -105,8 +105,11 @@ def run_program(plan: dict, circ):
             srcs_oop = {c[0] for c in ins["cols"] if c[0] != c[1]}
             assert not (srcs_oop & set(dsts)), "a launch reads a column another item of it writes"
             results = []
-            for (src, dst, ovr, acc) in ins["cols"]:
-                results.append((dst, acc, run_sweep(plan, ins["run"], slots[src], ovr, circ)))
+            for (src, dst, ovr, acc, extra) in ins["cols"]:
+                v = run_sweep(plan, ins["run"], slots[src], ovr, circ)
+                for e in extra:                      # product rule inside one dense stage: the item sums the variants
+                    v = v + run_sweep(plan, ins["run"], slots[src], e, circ)
+                results.append((dst, acc, v))
                 counters["sweep_cols"] += 1
             for dst, acc, v in results:
                 slots[dst] = slots[dst] + v if acc else v
@@ -242,13 +245,14 @@ def run_program_sharded(plan, circ, world):
         elif k == "sweep":
             run = plan["runs"][ins["run"]]
             if run["exchange"] >= 0:
-                for (src, dst, ovr, acc) in ins["cols"]:
+                for (src, dst, ovr, acc, extra) in ins["cols"]:
                     assert src == dst and ovr < 0 and not acc
                     cols = [slots[r][dst] for r in range(world)]
                     exchange_all_ranks(cols, run["exchange"])
                 continue
             for r in range(world):
-                res = [(dst, acc, sweep_shard(plan, circ, ins["run"], slots[r][src], r, ovr, tabs)) for (src, dst, ovr, acc) in ins["cols"]]
+                res = [(dst, acc, sum(sweep_shard(plan, circ, ins["run"], slots[r][src], r, o, tabs) for o in [ovr] + list(extra)))
+                       for (src, dst, ovr, acc, extra) in ins["cols"]]
                 for dst, acc, v in res:
                     slots[r][dst] = slots[r][dst] + v if acc else v
         elif k == "gram":

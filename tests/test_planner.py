@@ -26,8 +26,8 @@ def _run_program_emulated(plan, circ, theta, Kt, R):
         elif k == "copy":
             slots[ins["dst"]] = slots[ins["src"]].copy()
         elif k == "sweep":
-            res = [(dst, emul_lib.sweep(circ, theta, Kt, R, ins["run"], slots[src], ovr, slots[dst], bool(acc)))
-                   for (src, dst, ovr, acc) in ins["cols"]]
+            res = [(dst, emul_lib.sweep(circ, theta, Kt, R, ins["run"], slots[src], ovr, slots[dst], bool(acc), extra))
+                   for (src, dst, ovr, acc, extra) in ins["cols"]]
             for dst, v in res:
                 slots[dst] = v
         else:

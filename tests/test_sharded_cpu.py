@@ -86,7 +86,7 @@ def _gloo_worker(rank, world, port, result_path):
                 gbit = run["exchange"]
                 peer, mybit = rank ^ (1 << gbit), (rank >> gbit) & 1
                 half = (1 << nloc) // 2
-                for (src, dst, ovr, acc) in ins["cols"]:
+                for (src, dst, ovr, acc, extra) in ins["cols"]:
                     col = slots[dst]
                     lo = 0 if mybit else half                   # the half that moves (dist.cu: dist_exchange)
                     send = torch.from_numpy(np.ascontiguousarray(col[lo:lo + half]).view(np.float64).copy())
@@ -96,7 +96,8 @@ def _gloo_worker(rank, world, port, result_path):
                         q.wait()
                     col[lo:lo + half] = recv.numpy().view(np.complex128)
                 continue
-            res = [(dst, acc, pi.sweep_shard(plan, c, ins["run"], slots[src], rank, ovr, tabs)) for (src, dst, ovr, acc) in ins["cols"]]
+            res = [(dst, acc, sum(pi.sweep_shard(plan, c, ins["run"], slots[src], rank, o, tabs) for o in [ovr] + list(extra)))
+                   for (src, dst, ovr, acc, extra) in ins["cols"]]
             for dst, acc, v in res:
                 slots[dst] = slots[dst] + v if acc else v
         elif k == "gram":

@@ -9,4 +9,5 @@ c = K.config(sys.argv[1]); th = K.default_angles(c.num_params)
 for i in range(3):
     if i == 2: sys.stderr.write("=== traced eval ===\n")
     q = ctx.qgt(c, th)
-print(ctx.stats())
+st = ctx.stats()
+print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items()})
