@@ -221,13 +221,28 @@ def main():
     import ctypes as C
     cc = circ.to_c()                      # the host-side gate table (POD structs of include/qgt_b200.h)
 
+    # BASELINE config 2 is "QGT + natural-gradient step": the e2e call sequence ends with the regularised solve
+    # (G + lambda I)^-1 grad on the host (reference semantics), fed with a fixed synthetic gradient
+    grad_host = np.random.default_rng(7).normal(size=P)
+    dx_host = np.zeros(P)
+    lam = C.c_double(0)
+    natgrad_ms = [0.0]
+
     def step():
         # the public call: host theta + gate table in, host metric + Berry curvature out
         rc = ctx.L.qgt_b200_qgt(ctx.h, C.byref(cc), theta.ctypes.data_as(api._DP), g_host.ctypes.data_as(api._DP),
                                 b_host.ctypes.data_as(api._DP), None, None)
         if rc:
             raise api.QgtError(rc, ctx.L.qgt_b200_last_error().decode())
-        return ctx.stats()
+        st_ = ctx.stats()
+        if rank == 0 or not sharded:
+            t_ng = time.perf_counter()
+            rc = ctx.L.qgt_b200_natural_gradient(ctx.h, g_host.ctypes.data_as(api._DP), grad_host.ctypes.data_as(api._DP), P, None,
+                                                 dx_host.ctypes.data_as(api._DP), C.byref(lam))
+            natgrad_ms[0] += (time.perf_counter() - t_ng) * 1e3
+            if rc:
+                raise api.QgtError(rc, ctx.L.qgt_b200_last_error().decode())
+        return st_
 
     for _ in range(args.warmup):
         if flush is not None:
@@ -292,7 +307,9 @@ def main():
                                runs=st["num_runs"], resident_columns=st["resident_columns"], blocks=st["blocks"],
                                tile_qubits=st["tile_qubits"]),
                 "e2e": {"value": e2e, "unit": "QGT evals/s", "h2d_bytes_per_step": 8 * P + 32 * len(circ.gates),
-                        "d2h_bytes_per_step": 16 * P * P},
+                        "d2h_bytes_per_step": 16 * P * P,
+                        "includes": "host planning, H2D of the plan, D2H of metric + Berry curvature, natural-gradient solve on the host",
+                        "natgrad_ms_per_step": natgrad_ms[0] / (args.steps + args.warmup)},
                 "gpu_launches": int(agg["sweep_launches"] + 2 * agg["gram_launches"] + agg["other_launches"]),
                 "clocks": clocks, "roofline": dominant, "roofline_secondary": other,
                 "gate_bw_effective_gbs": circ.unfused_bytes() * 0 + 0.0}

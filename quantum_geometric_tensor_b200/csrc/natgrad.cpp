@@ -7,8 +7,8 @@
 //   * adaptive regularisation lambda = max(lambda, 1e-6 * sqrt(kappa)) when kappa > threshold (:2898-2912);
 //   * Tikhonov G + lambda I, solve (:2920-2959); if the regularised matrix is singular and the fallback is
 //     enabled, SVD pseudo-inverse of G with the singular-value cutoff (:2800-2885).
-// P is a few hundred at most, so this stays on the host; one symmetric Jacobi
-// eigen-decomposition G = V diag(w) V^T serves the condition number, the solve and the pseudo-inverse
+// P is a few hundred at most, so this stays on the host; one symmetric
+// eigen-decomposition G = V diag(w) V^T (Householder + QL) serves the condition number, the solve and the pseudo-inverse
 // (for a symmetric matrix the singular values are |w|).
 #include <cmath>
 #include <cstring>
@@ -19,44 +19,142 @@
 
 namespace {
 
-// cyclic Jacobi; A (n x n, symmetric, row-major) is destroyed, V receives the eigenvectors as columns
-void jacobi_eigh(std::vector<double>& A, int n, std::vector<double>& w, std::vector<double>& V) {
-    V.assign((size_t)n * n, 0.0);
-    for (int i = 0; i < n; i++) V[(size_t)i * n + i] = 1.0;
-    for (int sweep = 0; sweep < 64; sweep++) {
-        double off = 0.0, diag = 0.0;
-        for (int p = 0; p < n; p++) {
-            diag += A[(size_t)p * n + p] * A[(size_t)p * n + p];
-            for (int q = p + 1; q < n; q++) off += A[(size_t)p * n + q] * A[(size_t)p * n + q];
+// Symmetric eigen-decomposition A = V diag(w) V^T: Householder reduction to tridiagonal form followed by
+// implicit-shift QL iterations (the classic tred2 / tql2 pair), O(n^3) with a small constant — a 256 x 256
+// metric takes a few milliseconds.  A (row-major) is destroyed; V receives the eigenvectors as columns.
+void sym_eigh(std::vector<double>& A, int n, std::vector<double>& w, std::vector<double>& V, bool want_vectors) {
+    std::vector<double> d(n), e(n);
+    auto a = [&](int i, int j) -> double& { return A[(size_t)i * n + j]; };
+    // --- Householder tridiagonalisation, accumulating the transformation in A
+    for (int i = n - 1; i >= 1; i--) {
+        const int l = i - 1;
+        double h = 0.0, scale = 0.0;
+        if (l > 0) {
+            for (int k = 0; k <= l; k++) scale += std::fabs(a(i, k));
+            if (scale == 0.0) e[i] = a(i, l);
+            else {
+                for (int k = 0; k <= l; k++) { a(i, k) /= scale; h += a(i, k) * a(i, k); }
+                double f = a(i, l);
+                double g = f >= 0.0 ? -std::sqrt(h) : std::sqrt(h);
+                e[i] = scale * g;
+                h -= f * g;
+                a(i, l) = f - g;
+                f = 0.0;
+                for (int j = 0; j <= l; j++) {
+                    a(j, i) = a(i, j) / h;
+                    g = 0.0;
+                    for (int k = 0; k <= j; k++) g += a(j, k) * a(i, k);
+                    for (int k = j + 1; k <= l; k++) g += a(k, j) * a(i, k);
+                    e[j] = g / h;
+                    f += e[j] * a(i, j);
+                }
+                const double hh = f / (h + h);
+                for (int j = 0; j <= l; j++) {
+                    f = a(i, j);
+                    e[j] = g = e[j] - hh * f;
+                    for (int k = 0; k <= j; k++) a(j, k) -= f * e[k] + g * a(i, k);
+                }
+            }
+        } else {
+            e[i] = a(i, l);
         }
-        if (off <= 1e-32 * (diag + off) || off == 0.0) break;
-        for (int p = 0; p < n - 1; p++) {
-            for (int q = p + 1; q < n; q++) {
-                const double apq = A[(size_t)p * n + q];
-                if (apq == 0.0) continue;
-                const double theta = (A[(size_t)q * n + q] - A[(size_t)p * n + p]) / (2.0 * apq);
-                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < n; k++) {
-                    const double akp = A[(size_t)k * n + p], akq = A[(size_t)k * n + q];
-                    A[(size_t)k * n + p] = c * akp - s * akq;
-                    A[(size_t)k * n + q] = s * akp + c * akq;
+        d[i] = h;
+    }
+    d[0] = 0.0; e[0] = 0.0;
+    if (!want_vectors) { for (int i = 0; i < n; i++) d[i] = a(i, i); }
+    else for (int i = 0; i < n; i++) {
+        const int l = i - 1;
+        if (d[i] != 0.0) {
+            for (int j = 0; j <= l; j++) {
+                double g = 0.0;
+                for (int k = 0; k <= l; k++) g += a(i, k) * a(k, j);
+                for (int k = 0; k <= l; k++) a(k, j) -= g * a(k, i);
+            }
+        }
+        d[i] = a(i, i);
+        a(i, i) = 1.0;
+        for (int j = 0; j <= l; j++) a(j, i) = a(i, j) = 0.0;
+    }
+    // --- implicit QL on the tridiagonal matrix (d diagonal, e sub-diagonal); the accumulated transformation is
+    //     kept transposed (rows = vectors) so that every rotation touches two contiguous rows
+    if (want_vectors)
+        for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) std::swap(a(i, j), a(j, i));
+    for (int i = 1; i < n; i++) e[i - 1] = e[i];
+    e[n - 1] = 0.0;
+    for (int l = 0; l < n; l++) {
+        int iter = 0, m;
+        do {
+            for (m = l; m < n - 1; m++) {
+                const double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
+                if (std::fabs(e[m]) <= 2.3e-16 * dd) break;
+            }
+            if (m != l) {
+                if (iter++ == 200) break;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = std::hypot(g, 1.0);
+                g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? std::fabs(r) : -std::fabs(r)));
+                double sn = 1.0, cs = 1.0, p = 0.0;
+                int i;
+                for (i = m - 1; i >= l; i--) {
+                    double f = sn * e[i];
+                    const double bb = cs * e[i];
+                    e[i + 1] = (r = std::hypot(f, g));
+                    if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; break; }
+                    sn = f / r; cs = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * sn + 2.0 * cs * bb;
+                    d[i + 1] = g + (p = sn * r);
+                    g = cs * r - bb;
+                    if (want_vectors) {
+                        double* r1 = &A[(size_t)(i + 1) * n];
+                        double* r0 = &A[(size_t)i * n];
+                        for (int k = 0; k < n; k++) {
+                            f = r1[k];
+                            r1[k] = sn * r0[k] + cs * f;
+                            r0[k] = cs * r0[k] - sn * f;
+                        }
+                    }
                 }
-                for (int k = 0; k < n; k++) {
-                    const double apk = A[(size_t)p * n + k], aqk = A[(size_t)q * n + k];
-                    A[(size_t)p * n + k] = c * apk - s * aqk;
-                    A[(size_t)q * n + k] = s * apk + c * aqk;
-                }
-                for (int k = 0; k < n; k++) {
-                    const double vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
-                    V[(size_t)k * n + p] = c * vkp - s * vkq;
-                    V[(size_t)k * n + q] = s * vkp + c * vkq;
-                }
+                if (r == 0.0 && i >= l) continue;
+                d[l] -= p; e[l] = g; e[m] = 0.0;
+            }
+        } while (m != l);
+    }
+    w = d;
+    if (want_vectors) {
+        V.resize((size_t)n * n);
+        for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[(size_t)j * n + i] = A[(size_t)i * n + j];
+    }
+}
+
+// (G + lambda I) x = g by Cholesky; false when the matrix is not positive definite
+bool cholesky_solve(const double* G, double lambda, const double* g, int n, double* x) {
+    std::vector<double> L((size_t)n * n);
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j <= i; j++) {
+            double s = 0.5 * (G[(size_t)i * n + j] + G[(size_t)j * n + i]) + (i == j ? lambda : 0.0);
+            const double* li = &L[(size_t)i * n];
+            const double* lj = &L[(size_t)j * n];
+            for (int k = 0; k < j; k++) s -= li[k] * lj[k];
+            if (i == j) {
+                if (!(s > 0.0)) return false;
+                L[(size_t)i * n + i] = std::sqrt(s);
+            } else {
+                L[(size_t)i * n + j] = s / L[(size_t)j * n + j];
             }
         }
     }
-    w.resize(n);
-    for (int i = 0; i < n; i++) w[i] = A[(size_t)i * n + i];
+    for (int i = 0; i < n; i++) {
+        double s = g[i];
+        for (int k = 0; k < i; k++) s -= L[(size_t)i * n + k] * x[k];
+        x[i] = s / L[(size_t)i * n + i];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        double s = x[i];
+        for (int k = i + 1; k < n; k++) s -= L[(size_t)k * n + i] * x[k];
+        x[i] = s / L[(size_t)i * n + i];
+    }
+    return true;
 }
 
 }  // namespace
@@ -69,45 +167,46 @@ extern "C" int qgt_b200_natural_gradient(qgt_b200_ctx* ctx, const double* metric
     if (cfg_in) cfg = *cfg_in;
     const int n = (int)num_params;
     std::vector<double> A((size_t)n * n), w, V;
-    for (int i = 0; i < n; i++)
-        for (int j = 0; j < n; j++) A[(size_t)i * n + j] = 0.5 * (metric[(size_t)i * n + j] + metric[(size_t)j * n + i]);
-    jacobi_eigh(A, n, w, V);
-
+    auto load = [&]() {
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) A[(size_t)i * n + j] = 0.5 * (metric[(size_t)i * n + j] + metric[(size_t)j * n + i]);
+    };
     double lambda = cfg.regularization;
     if (cfg.adaptive) {
+        load();
+        sym_eigh(A, n, w, V, false);                    // eigenvalues only: singular values of a symmetric matrix = |w|
         double smax = std::fabs(w[0]), smin = std::fabs(w[0]);
         for (int i = 1; i < n; i++) {
-            const double s = std::fabs(w[i]);
-            if (s > smax) smax = s;
-            if (s < smin && s > 0) smin = s;
+            const double sv = std::fabs(w[i]);
+            if (sv > smax) smax = sv;
+            if (sv < smin && sv > 0) smin = sv;
         }
-        const double kappa = smin > 1e-15 ? smax / smin : std::numeric_limits<double>::infinity();
+        // the reference sets kappa = INFINITY below sigma_min = 1e-15 (gradient.c:2770-2774), which turns its
+        // adaptive lambda into infinity for any rank-deficient metric; kappa is capped at
+        // 1e16 here so the step stays finite
+        double kappa = smin > 1e-15 ? smax / smin : 1e16;
+        if (kappa > 1e16) kappa = 1e16;
         if (kappa > cfg.condition_threshold) {
             const double al = 1e-6 * std::sqrt(kappa);
             if (al > lambda) lambda = al;
         }
     }
     if (lambda_used) *lambda_used = lambda;
-
-    // coefficients of grad in the eigenbasis
+    if (cholesky_solve(metric, lambda, grad, n, out)) return QGT_B200_OK;
+    if (!cfg.pseudoinverse_fallback) return qgt::fail(-55 /* QGT_ERROR_MATRIX_SINGULAR */, "regularised metric is not positive definite");
+    // SVD pseudo-inverse of G with the singular-value cutoff (gradient.c:2800-2885)
+    load();
+    sym_eigh(A, n, w, V, true);
     std::vector<double> coef(n, 0.0);
     for (int k = 0; k < n; k++) {
-        double s = 0.0;
-        for (int i = 0; i < n; i++) s += V[(size_t)i * n + k] * grad[i];
-        coef[k] = s;
-    }
-    bool singular = false;
-    for (int k = 0; k < n; k++) if (std::fabs(w[k] + lambda) < 1e-300) singular = true;
-    if (singular) {
-        if (!cfg.pseudoinverse_fallback) return qgt::fail(-55 /* QGT_ERROR_MATRIX_SINGULAR */, "regularised metric is singular");
-        for (int k = 0; k < n; k++) coef[k] = std::fabs(w[k]) > cfg.singular_cutoff ? coef[k] / w[k] : 0.0;
-    } else {
-        for (int k = 0; k < n; k++) coef[k] /= (w[k] + lambda);
+        double sdot = 0.0;
+        for (int i = 0; i < n; i++) sdot += V[(size_t)i * n + k] * grad[i];
+        coef[k] = std::fabs(w[k]) > cfg.singular_cutoff ? sdot / w[k] : 0.0;
     }
     for (int i = 0; i < n; i++) {
-        double s = 0.0;
-        for (int k = 0; k < n; k++) s += V[(size_t)i * n + k] * coef[k];
-        out[i] = s;
+        double sdot = 0.0;
+        for (int k = 0; k < n; k++) sdot += V[(size_t)i * n + k] * coef[k];
+        out[i] = sdot;
     }
     return QGT_B200_OK;
 }
