@@ -185,6 +185,7 @@ int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
     else if (k == "batch_qubits") c->opt.batch_qubits = (int)value;
     else if (k == "use_mma") c->use_mma = value != 0;
     else if (k == "double_buffer") c->double_buffer = value != 0;
+    else if (k == "debug_skip") c->debug_skip = (int)value;
     else if (k == "gram_tile") set_gram_tile_override((int)value);
     else if (k == "profile") c->timer.enabled = value != 0;
     else if (k == "max_slots") c->max_slots = (size_t)value;
@@ -353,6 +354,7 @@ static int do_sweep(qgt_b200_ctx* c, const CircuitPlan& plan, int run, const Qgt
     a.ntiles = shard_tiles;
     a.use_mma = c->use_mma;
     a.double_buffer = c->double_buffer;
+    a.debug_skip = c->debug_skip;
     a.mma_only = c->use_mma && plan.R == 3 && plan.B == 0;
     int has_cost = 0;
     for (const SubPass& sp : plan.runs[run].subs) {

@@ -34,6 +34,10 @@ enum QgtOpFlags {
 // matrix variants are laid out QGT_VARIANT_STRIDE(N) complex elements apart: the odd padding keeps two
 // variants read by lanes of one quarter-warp in different shared-memory bank groups
 #define QGT_VARIANT_STRIDE(N) ((N) * (N) + 1)
+// element (i, j) of a stage matrix inside its variant.  8x8 matrices are stored in DMMA A-fragment order
+// (lane (r, k) reads M[r][k] and M[r][4+k]: 32 consecutive elements per load, conflict-free); smaller
+// ones row-major.
+#define QGT_MIDX(N, i, j) ((N) == 8 ? ((((j) >> 2) << 5) + ((i) << 2) + ((j) & 3)) : ((i) * (N) + (j)))
 
 // One dense stage of a sub-pass: all gates that touch the sub-pass's R register qubits, multiplied together
 // on the host into a 2^R x 2^R complex matrix.  Gates controlled by (or diagonal on) up to

@@ -19,6 +19,17 @@
 
 namespace qgt {
 
+// Timing experiments (build with -DQGT_DEBUG_SKIP; results are wrong by construction): option debug_skip
+// bit 1 no tile load, 2 no store, 4 no sub-passes, 8 no barrier between sub-passes, 16 no operand
+// loads / result stores inside a sub-pass, 32 no DMMAs.
+#ifdef QGT_DEBUG_SKIP
+#define QGT_DBG(bit) ((a.debug_skip & (bit)) != 0)
+#define QGT_DBGF(bit) ((dbg & (bit)) != 0)
+#else
+#define QGT_DBG(bit) false
+#define QGT_DBGF(bit) false
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // gate sweep
 // ------------------------------------------------------------------------------------------------
@@ -35,48 +46,91 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-// Streamlined tensor-pipe sub-pass for the common shape: exactly one dense stage, no thread diagonals.
-// Same fragment layout as qgt_warp_subpass_mma below, with every slot an XOR of host-precomputed terms.
-__device__ __forceinline__ void qgt_warp_subpass_mma_simple(const QgtDevRun& run, const QgtDevSubPass& sp, const QgtSubCtx& cx,
-                                                            cplx* tile, uint64_t tileg, int warp, int lane) {
-    constexpr int N = 8;
-    const int q = lane >> 2, k = lane & 3;
+// Per-CTA lookup tables of the tensor-only kernel, built once per launch in shared memory: everything a
+// sub-pass needs that depends only on (sub-pass, warp, lane), so the per-tile code is loads + DMMAs + stores.
+struct QgtFastSub {
+    uint64_t vm0, vm1;           // variant-selecting global index bits of the (single) stage, 0 when unused
+    uint32_t mat_off, stage;     // variant 0 in the run's pool; stage index (override test)
+    uint32_t sr2, st0, gx1, gx2; // slot XOR terms: matrix bit 2, thread bit 0, thread bits 3 and 4
+    uint32_t simple, pad;        // exactly one dense stage and no thread diagonal
+};
+struct QgtFastWarp { uint64_t g; uint32_t s; uint32_t pad; };   // warp-index bits: global index / swizzled slot
+#define QGT_FAST_BYTES_PER_SUB (sizeof(QgtFastSub) + 8 * sizeof(QgtFastWarp) + 32 * sizeof(uint32_t))
+
+__device__ __forceinline__ void qgt_fast_build(const QgtDevRun& run, const QgtDevSubPass* subs, const QgtDevStage* stages,
+                                               QgtFastSub* fast, QgtFastWarp* fwarp, uint32_t* flane, int tid, int T) {
     const int nthr_bits = run.K - 3;
-    const uint32_t st0 = sp.s_thr[0], st1 = sp.s_thr[1], st2 = sp.s_thr[2], st3 = sp.s_thr[3], st4 = sp.s_thr[4];
-    const uint32_t sr0 = sp.s_reg[0], sr1 = sp.s_reg[1], sr2 = sp.s_reg[2];
-    uint32_t swarp = 0;
-    uint64_t gwarp = tileg;
-    for (int i = 5; i < nthr_bits; ++i)
-        if ((warp >> (i - 5)) & 1) { swarp ^= sp.s_thr[i]; gwarp |= sp.g_thr[i]; }
-    const uint32_t baseB = swarp ^ ((q & 1) ? st0 : 0u) ^ ((q & 2) ? st1 : 0u) ^ ((q & 4) ? st2 : 0u) ^ ((k & 1) ? sr0 : 0u) ^ ((k & 2) ? sr1 : 0u);
-    const uint32_t baseC = swarp ^ ((k & 1) ? st1 : 0u) ^ ((k & 2) ? st2 : 0u) ^ ((q & 1) ? sr0 : 0u) ^ ((q & 2) ? sr1 : 0u) ^ ((q & 4) ? sr2 : 0u);
-    const int s = sp.stage_begin;
-    const QgtDevStage& st = cx.stages[s];
-    const int off = (cx.ovr_kind == 1 && s == cx.ovr_index) ? cx.ovr_mat_off : st.mat_off;
-    int var = 0;
-    if (st.nvar > 0) var |= (gwarp & st.vmask[0]) != 0;
-    if (st.nvar > 1) var |= ((gwarp & st.vmask[1]) != 0) << 1;
+    for (int w = tid; w < run.nsub * 32; w += T) {
+        const int s = w >> 5, lane = w & 31, q = lane >> 2, k = lane & 3;
+        const QgtDevSubPass& sp = subs[s];
+        const uint32_t b = ((q & 1) ? sp.s_thr[0] : 0u) ^ ((q & 2) ? sp.s_thr[1] : 0u) ^ ((q & 4) ? sp.s_thr[2] : 0u) ^
+                           ((k & 1) ? sp.s_reg[0] : 0u) ^ ((k & 2) ? sp.s_reg[1] : 0u);
+        const uint32_t c = ((k & 1) ? sp.s_thr[1] : 0u) ^ ((k & 2) ? sp.s_thr[2] : 0u) ^ ((q & 1) ? sp.s_reg[0] : 0u) ^
+                           ((q & 2) ? sp.s_reg[1] : 0u) ^ ((q & 4) ? sp.s_reg[2] : 0u);
+        flane[w] = b | (c << 16);
+        if (lane < 8) {
+            QgtFastWarp fw; fw.g = 0; fw.s = 0; fw.pad = 0;
+            for (int i = 5; i < nthr_bits; ++i)
+                if ((lane >> (i - 5)) & 1) { fw.s ^= sp.s_thr[i]; fw.g |= sp.g_thr[i]; }
+            fwarp[s * 8 + lane] = fw;
+        }
+        if (lane == 8) {
+            QgtFastSub f;
+            f.simple = (sp.stage_end - sp.stage_begin == 1 && sp.tdiag_end == sp.tdiag_begin) ? 1u : 0u;
+            f.stage = (uint32_t)sp.stage_begin; f.pad = 0;
+            f.vm0 = f.vm1 = 0; f.mat_off = 0;
+            if (f.simple) {
+                const QgtDevStage& st = stages[sp.stage_begin];
+                f.mat_off = (uint32_t)st.mat_off;
+                if (st.nvar > 0) f.vm0 = st.vmask[0];
+                if (st.nvar > 1) f.vm1 = st.vmask[1];
+            }
+            f.sr2 = sp.s_reg[2]; f.st0 = sp.s_thr[0]; f.gx1 = sp.s_thr[3]; f.gx2 = sp.s_thr[4];
+            fast[s] = f;
+        }
+    }
+}
+
+// Streamlined tensor-pipe sub-pass for the common shape: exactly one dense stage, no thread diagonals.
+// Same fragment layout as qgt_warp_subpass_mma below.  All 8 operand loads are issued before the first
+// DMMA (one __syncwarp for the four groups), so the shared-memory latency is paid once per sub-pass.
+__device__ __forceinline__ void qgt_warp_subpass_fast(const QgtFastSub& f, const QgtFastWarp& fw, uint32_t lt, const QgtSubCtx& cx,
+                                                      cplx* tile, uint64_t tileg, int lane) {
+    constexpr int N = 8;
+    const uint32_t baseB = fw.s ^ (lt & 0xffffu), baseC = fw.s ^ (lt >> 16);
+    const uint64_t gwarp = tileg | fw.g;
+    const int off = (cx.ovr_kind == 1 && (int)f.stage == cx.ovr_index) ? cx.ovr_mat_off : (int)f.mat_off;
+    const int var = ((gwarp & f.vm0) != 0 ? 1 : 0) | ((gwarp & f.vm1) != 0 ? 2 : 0);
     const cplx* M = cx.pool + off + var * QGT_VARIANT_STRIDE(N);
-    const cplx m0 = M[q * N + k], m1 = M[q * N + 4 + k];
+    const cplx m0 = M[lane], m1 = M[32 + lane];           // A fragments: QGT_MIDX(8, q, k) == lane
     const double nm0y = -m0.y, nm1y = -m1.y;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const uint32_t gx = ((g & 1) ? st3 : 0u) ^ ((g & 2) ? st4 : 0u);
-        const cplx v0 = tile[baseB ^ gx], v1 = tile[baseB ^ gx ^ sr2];
-        double cr0 = 0.0, cr1 = 0.0, ci0 = 0.0, ci1 = 0.0;
-        dmma884(cr0, cr1, m0.x, v0.x);
-        dmma884(ci0, ci1, m0.x, v0.y);
-        dmma884(cr0, cr1, m1.x, v1.x);
-        dmma884(ci0, ci1, m1.x, v1.y);
-        dmma884(cr0, cr1, nm0y, v0.y);
-        dmma884(ci0, ci1, m0.y, v0.x);
-        dmma884(cr0, cr1, nm1y, v1.y);
-        dmma884(ci0, ci1, m1.y, v1.x);
-        cplx o0, o1;
-        o0.x = cr0; o0.y = ci0; o1.x = cr1; o1.y = ci1;
-        __syncwarp();                 // every lane has read the group's slots before they are overwritten
-        tile[baseC ^ gx] = o0;
-        tile[baseC ^ gx ^ st0] = o1;
+    for (int h = 0; h < 2; ++h) {     // two groups of 8 vectors at a time: operand loads first, then the DMMAs
+        cplx v0[2], v1[2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const uint32_t gx = (g ? f.gx1 : 0u) ^ (h ? f.gx2 : 0u);
+            v0[g] = tile[baseB ^ gx];
+            v1[g] = tile[baseB ^ gx ^ f.sr2];
+        }
+        __syncwarp();                 // every lane has read its slots before any is overwritten
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const uint32_t gx = (g ? f.gx1 : 0u) ^ (h ? f.gx2 : 0u);
+            double cr0 = 0.0, cr1 = 0.0, ci0 = 0.0, ci1 = 0.0;
+            dmma884(cr0, cr1, m0.x, v0[g].x);
+            dmma884(ci0, ci1, m0.x, v0[g].y);
+            dmma884(cr0, cr1, m1.x, v1[g].x);
+            dmma884(ci0, ci1, m1.x, v1[g].y);
+            dmma884(cr0, cr1, nm0y, v0[g].y);
+            dmma884(ci0, ci1, m0.y, v0[g].x);
+            dmma884(cr0, cr1, nm1y, v1[g].y);
+            dmma884(ci0, ci1, m1.y, v1[g].x);
+            cplx o0, o1;
+            o0.x = cr0; o0.y = ci0; o1.x = cr1; o1.y = ci1;
+            tile[baseC ^ gx] = o0;
+            tile[baseC ^ gx ^ f.st0] = o1;
+        }
     }
 }
 
@@ -134,7 +188,7 @@ __device__ __forceinline__ void qgt_warp_subpass_mma(const QgtDevRun& run, const
         const QgtDevStage& st = cx.stages[s];
         const int off = (cx.ovr_kind == 1 && s == cx.ovr_index) ? cx.ovr_mat_off : st.mat_off;
         const cplx* M = cx.pool + off + qgt_variant_index(st, gwarp) * QGT_VARIANT_STRIDE(N);
-        const cplx m0 = M[q * N + k], m1 = M[q * N + 4 + k];
+        const cplx m0 = M[QGT_MIDX(N, q, k)], m1 = M[QGT_MIDX(N, q, 4 + k)];
         const double nm0y = -m0.y, nm1y = -m1.y;
         const bool last = (s == sp.stage_end - 1);
 #pragma unroll
@@ -196,6 +250,9 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
     cplx* spool = tile + ((size_t)(DB ? 2 : 1) << run.K);
     cplx* sovr = spool + run.mat_count;
     QgtDevSubPass* subs = reinterpret_cast<QgtDevSubPass*>(sovr + OVR_ELEMS);
+    QgtFastSub* fast = reinterpret_cast<QgtFastSub*>(subs + run.nsub);          // tensor-only kernel
+    QgtFastWarp* fwarp = reinterpret_cast<QgtFastWarp*>(fast + run.nsub);
+    uint32_t* flane = reinterpret_cast<uint32_t*>(fwarp + 8 * run.nsub);
     QgtCostSmem cost_sm = qgt_cost_smem_carve(reinterpret_cast<double*>(subs + run.nsub), run.K, a.ct.num_edges);
     {
         const cplx* gpool = a.pool + run.mat_off;
@@ -204,6 +261,10 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
         uint32_t* ss = reinterpret_cast<uint32_t*>(subs);
         for (int i = tid; i < run.nsub * (int)(sizeof(QgtDevSubPass) / 4); i += T) ss[i] = gs[i];
         if (!MMA_ONLY && run.has_cost) qgt_cost_build_ein(run, a.ct, cost_sm, tid, T);
+    }
+    if (MMA_ONLY) {
+        __syncthreads();
+        qgt_fast_build(run, subs, a.stages + run.stage_off, fast, fwarp, flane, tid, T);
     }
     QgtSubCtx cx;
     cx.stages = a.stages + run.stage_off;
@@ -248,15 +309,15 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
             cp_async_commit();
             cp_async_wait<1>();
         } else {
-            prefetch(w, cur);
+            if (!QGT_DBG(1)) prefetch(w, cur);
             cp_async_commit();
             cp_async_wait<0>();
         }
         __syncthreads();
-        for (int s = 0; s < run.nsub; ++s) {
+        for (int s = 0; s < (QGT_DBG(4) ? 0 : run.nsub); ++s) {
             if (MMA_ONLY) {
-                if (subs[s].stage_end - subs[s].stage_begin == 1 && subs[s].tdiag_end == subs[s].tdiag_begin)
-                    qgt_warp_subpass_mma_simple(run, subs[s], cx, cur, tileg, tid >> 5, tid & 31);
+                if (fast[s].simple)
+                    qgt_warp_subpass_fast(fast[s], fwarp[s * 8 + (tid >> 5)], flane[s * 32 + (tid & 31)], cx, cur, tileg, tid & 31);
                 else
                     qgt_warp_subpass_mma(run, subs[s], cx, cur, tileg, tid >> 5, tid & 31);
             } else if (subs[s].nreg == 0) {
@@ -271,9 +332,9 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
             } else {
                 qgt_phase_subpass<R, B>(run, subs[s], cx, cur, tileg, tid);
             }
-            __syncthreads();
+            if (!QGT_DBG(8)) __syncthreads();
         }
-        qgt_phase_store<R + B>(io, cur, reinterpret_cast<cplx*>(it.dst), tilebase, tid, T, it.accumulate != 0);
+        if (!QGT_DBG(2)) qgt_phase_store<R + B>(io, cur, reinterpret_cast<cplx*>(it.dst), tilebase, tid, T, it.accumulate != 0);
         __syncthreads();
     }
     cp_async_wait<0>();
@@ -305,11 +366,13 @@ static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, i
     const int T = 1 << (K - R - B);
     const uint64_t total = a.ntiles * (uint64_t)a.nitems;
     if (total == 0) return cudaSuccess;
-    const size_t fixed = sizeof(cplx) * (size_t)mat_count + sizeof(cplx) * (size_t)(QGT_VARIANT_STRIDE(N) << QGT_MAX_VARIANT_BITS) +
+    const size_t fixed0 = sizeof(cplx) * (size_t)mat_count + sizeof(cplx) * (size_t)(QGT_VARIANT_STRIDE(N) << QGT_MAX_VARIANT_BITS) +
                          (size_t)nsub * sizeof(QgtDevSubPass) + (has_cost ? qgt_cost_smem_doubles(K, a.ct.num_edges) * sizeof(double) : 0);
     const size_t tile_bytes = sizeof(cplx) << K;
-    if (fixed + 2 * tile_bytes > 200 * 1024 || T > 256) return cudaErrorInvalidValue;
+    const size_t fixed = fixed0;
+    if (fixed + (size_t)nsub * QGT_FAST_BYTES_PER_SUB + 2 * tile_bytes > 200 * 1024 || T > 256) return cudaErrorInvalidValue;
     if (R == 3 && B == 0 && a.mma_only && T >= 32) {
+        const size_t fixed = fixed0 + (size_t)nsub * QGT_FAST_BYTES_PER_SUB;
         // single tile buffer: more resident CTAs hide the load latency instead of a second buffer
         if (a.double_buffer) return launch_sweep_cfg<3, 0, true, true, 256, 3>(a, T, fixed + 2 * tile_bytes, total, num_sms, st);
         return launch_sweep_cfg<3, 0, true, false, 256, 4>(a, T, fixed + tile_bytes, total, num_sms, st);

@@ -22,6 +22,7 @@ struct SweepLaunch {
     uint64_t gprefix;            // rank bits of a sharded state, OR-ed into every global index used by masks
     int mma_only;                // every sub-pass of the run qualifies for the tensor-pipe path (host-checked)
     int double_buffer;           // tensor-only kernel: two tile buffers (3 CTAs/SM) instead of one (4 CTAs/SM)
+    int debug_skip;              // timing experiments only: 1 no tile load, 2 no store, 4 no sub-passes
     int use_mma;                 // dense stages on the FP64 tensor pipe (DMMA) where the sub-pass allows it
     QgtCostTable ct;
 };

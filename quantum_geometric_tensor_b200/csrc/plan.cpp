@@ -338,7 +338,12 @@ void stage_matrices(const Run& run, const SubPass& sp, const Stage& st, int deri
             }
             M.swap(T);
         }
-        std::memcpy(&out[(size_t)p * vstride], M.data(), M.size() * sizeof(double));
+        double* dst = &out[(size_t)p * vstride];
+        for (int i = 0; i < N; i++)
+            for (int j = 0; j < N; j++) {
+                dst[2 * QGT_MIDX(N, i, j)] = M[2 * (i * N + j)];
+                dst[2 * QGT_MIDX(N, i, j) + 1] = M[2 * (i * N + j) + 1];
+            }
     }
 }
 

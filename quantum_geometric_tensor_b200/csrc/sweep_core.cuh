@@ -227,7 +227,7 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
                 for (int h = 0; h < NB; ++h) { xr[h] = 0.0; xi[h] = 0.0; }
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    const cplx m = M[0][i * N + j];
+                    const cplx m = M[0][QGT_MIDX(N, i, j)];
 #pragma unroll
                     for (int h = 0; h < NB; ++h) {
                         xr[h] = qgt_fma(m.x, v[h][j].x, xr[h]); xr[h] = qgt_fma(-m.y, v[h][j].y, xr[h]);
@@ -249,7 +249,7 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
                     double xr = 0.0, xi = 0.0;
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
-                        const cplx m = M[h][i * N + j];
+                        const cplx m = M[h][QGT_MIDX(N, i, j)];
                         xr = qgt_fma(m.x, v[h][j].x, xr); xr = qgt_fma(-m.y, v[h][j].y, xr);
                         xi = qgt_fma(m.x, v[h][j].y, xi); xi = qgt_fma(m.y, v[h][j].x, xi);
                     }
