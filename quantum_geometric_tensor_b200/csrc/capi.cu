@@ -479,9 +479,10 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             for (int v : in.b_ids) ids.push_back(v);
             g.symmetric = g.nb >= g.na && std::equal(in.a_slots.begin(), in.a_slots.end(), in.b_slots.begin());
             const GramShape shp = gram_shape(g.na, g.nb);
-            const int mt = (g.na + shp.MT - 1) / shp.MT, nt = (g.nb + shp.NT - 1) / shp.NT;
-            const int ks = gram_ksplit(c, mt * nt, D);
-            partial_bytes = std::max(partial_bytes, (size_t)ks * mt * shp.MT * nt * shp.NT * sizeof(cplx));
+            GramLaunch gl; gl.na = g.na; gl.nb = g.nb; gl.symmetric = g.symmetric ? 1 : 0;
+            const size_t per_split = gram_configure(gl, shp);
+            const int ks = gram_ksplit(c, gl.mtiles * gl.ntiles, D);
+            partial_bytes = std::max(partial_bytes, (size_t)ks * per_split * sizeof(cplx));
         }
     }
     c->ms_prog_pack = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pack0).count();
@@ -544,9 +545,9 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             gl.a_ptrs = d_ptrs + g.a_off; gl.b_ptrs = d_ptrs + g.b_off;
             gl.na = g.na; gl.nb = g.nb; gl.D = D;
             const GramShape shp = gram_shape(g.na, g.nb);
-            gl.mtiles = (g.na + shp.MT - 1) / shp.MT; gl.ntiles = (g.nb + shp.NT - 1) / shp.NT;
-            gl.ksplit = gram_ksplit(c, gl.mtiles * gl.ntiles, D);
             gl.symmetric = g.symmetric ? 1 : 0;
+            gram_configure(gl, shp);
+            gl.ksplit = gram_ksplit(c, gl.mtiles * gl.ntiles, D);
             gl.partial = (cplx*)c->partial.ptr;
             c->timer.begin(c->stream, 1);
             e = launch_gram(gl, shp, c->stream);
@@ -768,10 +769,10 @@ int qgt_b200_gram(qgt_b200_ctx* c, const double* psi, const double* dpsi, size_t
     GramLaunch gl;
     const GramShape shp = gram_shape(P, P + 1);
     gl.na = P; gl.nb = P + 1; gl.D = D;
-    gl.mtiles = (gl.na + shp.MT - 1) / shp.MT; gl.ntiles = (gl.nb + shp.NT - 1) / shp.NT;
-    gl.ksplit = gram_ksplit(c, gl.mtiles * gl.ntiles, D);
     gl.symmetric = 1;
-    if ((rc = c->partial.reserve((size_t)gl.ksplit * gl.mtiles * shp.MT * gl.ntiles * shp.NT * sizeof(cplx)))) return rc;
+    const size_t per_split = gram_configure(gl, shp);
+    gl.ksplit = gram_ksplit(c, gl.mtiles * gl.ntiles, D);
+    if ((rc = c->partial.reserve((size_t)gl.ksplit * per_split * sizeof(cplx)))) return rc;
     gl.partial = (cplx*)c->partial.ptr;
     cudaError_t e = cudaMemcpyAsync(c->aux.ptr, ptrs.data(), ptr_bytes, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync((char*)c->aux.ptr + ptr_bytes, ids.data(), id_bytes, cudaMemcpyHostToDevice, c->stream);

@@ -104,19 +104,20 @@ __device__ __forceinline__ void qgt_warp_subpass_fast(const QgtFastSub& f, const
     const cplx* M = cx.pool + off + var * QGT_VARIANT_STRIDE(N);
     const cplx m0 = M[lane], m1 = M[32 + lane];           // A fragments: QGT_MIDX(8, q, k) == lane
     const double nm0y = -m0.y, nm1y = -m1.y;
+    const uint32_t gx1 = f.gx1, gx2 = f.gx2, sr2 = f.sr2, st0 = f.st0;    // locals: tile stores must not force reloads
 #pragma unroll
     for (int h = 0; h < 2; ++h) {     // two groups of 8 vectors at a time: operand loads first, then the DMMAs
         cplx v0[2], v1[2];
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-            const uint32_t gx = (g ? f.gx1 : 0u) ^ (h ? f.gx2 : 0u);
+            const uint32_t gx = (g ? gx1 : 0u) ^ (h ? gx2 : 0u);
             v0[g] = tile[baseB ^ gx];
-            v1[g] = tile[baseB ^ gx ^ f.sr2];
+            v1[g] = tile[baseB ^ gx ^ sr2];
         }
         __syncwarp();                 // every lane has read its slots before any is overwritten
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-            const uint32_t gx = (g ? f.gx1 : 0u) ^ (h ? f.gx2 : 0u);
+            const uint32_t gx = (g ? gx1 : 0u) ^ (h ? gx2 : 0u);
             double cr0 = 0.0, cr1 = 0.0, ci0 = 0.0, ci1 = 0.0;
             dmma884(cr0, cr1, m0.x, v0[g].x);
             dmma884(ci0, ci1, m0.x, v0[g].y);
@@ -129,7 +130,7 @@ __device__ __forceinline__ void qgt_warp_subpass_fast(const QgtFastSub& f, const
             cplx o0, o1;
             o0.x = cr0; o0.y = ci0; o1.x = cr1; o1.y = ci1;
             tile[baseC ^ gx] = o0;
-            tile[baseC ^ gx ^ f.st0] = o1;
+            tile[baseC ^ gx ^ st0] = o1;
         }
     }
 }
@@ -446,7 +447,8 @@ __global__ void __launch_bounds__(WM * WN * 32, 2) qgt_gram_kernel(GramLaunch g)
     constexpr int ELEMS = (MT + NT) * KC;
     static_assert(ELEMS % NTHR == 0 && NTHR % KC == 0, "tile/threads mismatch");
     constexpr int PER = ELEMS / NTHR;
-    constexpr int STAGE_ELEMS = (MT + NT) * S;
+    constexpr bool STRIP = (WM == 2 && WN == 4 && BM == 2 && BN == 1);     // the 32x32 shape carries the strip
+    constexpr int STAGE_ELEMS = (MT + NT + (STRIP ? 8 : 0)) * S;
     extern __shared__ __align__(16) unsigned char qgt_gram_smem[];
     cplx* sm = reinterpret_cast<cplx*>(qgt_gram_smem);
 
@@ -457,7 +459,12 @@ __global__ void __launch_bounds__(WM * WN * 32, 2) qgt_gram_kernel(GramLaunch g)
     if (g.symmetric && (nt + 1) * NT <= mt * MT) return;   // whole tile below the diagonal: mirrored later
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp / WN, wn = warp % WN;
+    int wm = warp / WN, wn = warp % WN;
+    // diagonal tile of a symmetric launch: warps (1,0) and (1,1) own only blocks below the diagonal; they take
+    // the strip instead (block rows 0-1 / 2-3 of this tile times the 8 strip columns staged behind B)
+    const bool strip_tile = STRIP && g.nstrip > 0 && mt == nt;
+    const bool strip_warp = strip_tile && wm == 1 && wn < 2;
+    if (strip_warp) { wm = wn; wn = WN; }
     uint64_t per = (g.D + (uint64_t)g.ksplit - 1) / (uint64_t)g.ksplit;
     per = (per + KC - 1) / KC * KC;
     const uint64_t k0 = (uint64_t)ks * per;
@@ -475,6 +482,8 @@ __global__ void __launch_bounds__(WM * WN * 32, 2) qgt_gram_kernel(GramLaunch g)
         colptr[j] = ok ? (col < MT ? g.a_ptrs[gc] : g.b_ptrs[gc]) + koff : nullptr;
         soff[j] = col * S + koff;
     }
+    const cplx* strip_ptr = nullptr;                       // threads 0 .. 8*KC-1 stage the strip columns
+    if (strip_tile && tid < 8 * KC && tid / KC < g.nstrip) strip_ptr = g.b_ptrs[g.nb_main + tid / KC] + koff;
     auto issue = [&](uint64_t kb, int stage) {
         cplx* dst = sm + (size_t)stage * STAGE_ELEMS;
         const bool in = kb + (uint64_t)koff < k1;
@@ -482,6 +491,10 @@ __global__ void __launch_bounds__(WM * WN * 32, 2) qgt_gram_kernel(GramLaunch g)
         for (int j = 0; j < PER; ++j) {
             const bool ok = in && colptr[j] != nullptr;
             cp_async16(dst + soff[j], ok ? (const void*)(colptr[j] + kb) : (const void*)g.a_ptrs, ok ? 16 : 0);
+        }
+        if (STRIP && strip_tile && tid < 8 * KC) {
+            const bool ok = in && strip_ptr != nullptr;
+            cp_async16(dst + (MT + NT + tid / KC) * S + koff, ok ? (const void*)(strip_ptr + kb) : (const void*)g.a_ptrs, ok ? 16 : 0);
         }
     };
 
@@ -497,7 +510,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 2) qgt_gram_kernel(GramLaunch g)
 #pragma unroll
         for (int j = 0; j < BN; ++j) {
             const int r0 = mt * MT + (wm * BM + i) * 8, c0 = nt * NT + (wn * BN + j) * 8;
-            blk[i][j] = r0 < g.na && c0 < g.nb && !(g.symmetric && c0 + 8 <= r0);
+            blk[i][j] = strip_warp ? r0 < g.na : (r0 < g.na && c0 < g.nb_main && !(g.symmetric && c0 + 8 <= r0));
         }
     bool all_valid = true;      // warp-uniform: the common case runs without a predicate on every mma.sync
 #pragma unroll
@@ -526,7 +539,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 2) qgt_gram_kernel(GramLaunch g)
         else gram_chunk<WM, WN, BM, BN, KC, false>(sA, sB, wm, wn, fr, fk, blk, cre, cim);
     }
     cp_async_wait<0>();
-    const int Npad = g.ntiles * NT;
+    const int Npad = g.npad;
     const int Mpad = g.mtiles * MT;
     cplx* out = g.partial + (size_t)ks * Mpad * Npad;
 #pragma unroll
@@ -534,7 +547,7 @@ __global__ void __launch_bounds__(WM * WN * 32, 2) qgt_gram_kernel(GramLaunch g)
 #pragma unroll
         for (int j = 0; j < BN; ++j) {
             const int row = mt * MT + (wm * BM + i) * 8 + (lane >> 2);
-            const int col = nt * NT + (wn * BN + j) * 8 + (lane & 3) * 2;
+            const int col = (strip_warp ? g.ntiles * NT : nt * NT + (wn * BN + j) * 8) + (lane & 3) * 2;
             cplx z0, z1;
             z0.x = cre[i][j][0]; z0.y = cim[i][j][0];
             z1.x = cre[i][j][1]; z1.y = cim[i][j][1];
@@ -543,15 +556,16 @@ __global__ void __launch_bounds__(WM * WN * 32, 2) qgt_gram_kernel(GramLaunch g)
         }
 }
 
-__global__ void qgt_gram_reduce_kernel(const cplx* partial, int ksplit, int Mpad, int Npad, int na, int nb,
+__global__ void qgt_gram_reduce_kernel(const cplx* partial, int ksplit, int Mpad, int Npad, int na, int nb, int nb_main, int strip_col0,
                                        const int* a_ids, const int* b_ids, cplx* C, int ldc, int symmetric) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= na * nb) return;
     const int i = idx / nb, j = idx % nb;
     if (symmetric && j < i) return;
+    const int pj = j < nb_main ? j : strip_col0 + (j - nb_main);      // strip columns sit behind the tile grid
     double sr = 0.0, si = 0.0;
     for (int ks = 0; ks < ksplit; ++ks) {           // fixed order: deterministic
-        const cplx z = partial[((size_t)ks * Mpad + i) * Npad + j];
+        const cplx z = partial[((size_t)ks * Mpad + i) * Npad + pj];
         sr += z.x; si += z.y;
     }
     const int ai = a_ids[i], bj = b_ids[j];
@@ -591,10 +605,22 @@ GramShape gram_shape(int na, int nb) {
     return s;
 }
 
+size_t gram_configure(GramLaunch& g, GramShape shp) {
+    g.nstrip = 0;
+    g.nb_main = g.nb;
+    const int extra = g.nb - g.na;
+    if (g.symmetric && shp.MT == 32 && shp.NT == 32 && extra >= 1 && extra <= 8) { g.nstrip = extra; g.nb_main = g.na; }
+    g.mtiles = (g.na + shp.MT - 1) / shp.MT;
+    g.ntiles = (g.nb_main + shp.NT - 1) / shp.NT;
+    g.npad = g.ntiles * shp.NT + (g.nstrip ? 8 : 0);
+    return (size_t)g.mtiles * shp.MT * g.npad;
+}
+
 template <int WM, int WN, int BM, int BN, int KC, int STAGES>
 static cudaError_t launch_gram_t(const GramLaunch& g, cudaStream_t st) {
     constexpr int MT = WM * BM * 8, NT = WN * BN * 8;
-    constexpr size_t smem = (size_t)STAGES * (MT + NT) * (KC + 4) * sizeof(cplx);
+    constexpr bool STRIP = (WM == 2 && WN == 4 && BM == 2 && BN == 1);
+    constexpr size_t smem = (size_t)STAGES * (MT + NT + (STRIP ? 8 : 0)) * (KC + 4) * sizeof(cplx);
     auto kern = qgt_gram_kernel<WM, WN, BM, BN, KC, STAGES>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -618,8 +644,8 @@ cudaError_t launch_gram_reduce(const GramLaunch& g, GramShape shp, const int* a_
                                cplx* C, int ldc, cudaStream_t st) {
     const int total = g.na * g.nb;
     if (total == 0) return cudaSuccess;
-    qgt_gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(g.partial, g.ksplit, g.mtiles * shp.MT, g.ntiles * shp.NT,
-                                                             g.na, g.nb, a_ids, b_ids, C, ldc, g.symmetric);
+    qgt_gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(g.partial, g.ksplit, g.mtiles * shp.MT, g.npad, g.na, g.nb, g.nb_main,
+                                                             g.ntiles * shp.NT, a_ids, b_ids, C, ldc, g.symmetric);
     return cudaGetLastError();
 }
 

@@ -35,7 +35,11 @@ struct GramLaunch {
     int ksplit;
     int mtiles, ntiles;
     int symmetric;               // b list starts with the a list: tiles strictly below the diagonal are skipped
-    cplx* partial;               // [ksplit][mtiles*MT][ntiles*NT]
+    int nb_main;                 // columns of B covered by the tile grid (nb - nstrip)
+    int nstrip;                  // symmetric 32x32 launches: the last <= 8 columns of B (the projection column psi) are
+                                 // contracted by the two warps that idle in diagonal tiles instead of a padded tile column
+    int npad;                    // row stride of `partial`: ntiles*NT (+ 8 strip columns)
+    cplx* partial;               // [ksplit][mtiles*MT][npad]
 };
 
 struct GramShape { int MT, NT; };
@@ -44,6 +48,8 @@ struct GramShape { int MT, NT; };
 cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int has_cost, int num_sms, cudaStream_t st);
 
 GramShape gram_shape(int na, int nb);
+// fills mtiles / ntiles / nb_main / nstrip / npad from na, nb, symmetric; returns the partial elements per k-split
+size_t gram_configure(GramLaunch& g, GramShape shp);
 void set_gram_tile_override(int t);   // tuning: 0 = automatic, 32 or 64 = force that square tile
 cudaError_t launch_gram(const GramLaunch& g, GramShape shp, cudaStream_t st);
 // C[(a_ids[i]), (b_ids[j])] = sum_ks partial ; mirrored conj ; ldc = leading dimension of C
