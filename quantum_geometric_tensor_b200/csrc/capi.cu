@@ -186,6 +186,7 @@ int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
     else if (k == "use_mma") c->use_mma = value != 0;
     else if (k == "double_buffer") c->double_buffer = value != 0;
     else if (k == "debug_skip") c->debug_skip = (int)value;
+    else if (k == "tiles_per_item") c->tiles_per_item = (int)value;
     else if (k == "gram_tile") set_gram_tile_override((int)value);
     else if (k == "profile") c->timer.enabled = value != 0;
     else if (k == "max_slots") c->max_slots = (size_t)value;
@@ -355,6 +356,7 @@ static int do_sweep(qgt_b200_ctx* c, const CircuitPlan& plan, int run, const Qgt
     a.use_mma = c->use_mma;
     a.double_buffer = c->double_buffer;
     a.debug_skip = c->debug_skip;
+    a.tiles_per_item = c->tiles_per_item;
     a.mma_only = c->use_mma && plan.R == 3 && plan.B == 0;
     int has_cost = 0;
     for (const SubPass& sp : plan.runs[run].subs) {
@@ -454,7 +456,7 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                         for (int s2 = 0; s2 < loc.sub; s2++) first += (int)run.subs[s2].stages.size();
                         std::vector<int> dops(1, sc.ovr_op);
                         dops.insert(dops.end(), sc.ovr_extra.begin(), sc.ovr_extra.end());
-                        stage_matrices_sum(run, sp, sp.stages[loc.index - first], dops, mats);
+                        it.ovr_form = stage_matrices_sum(run, sp, sp.stages[loc.index - first], dops, mats);
                         ovr_off.push_back(ovr_pool.size());
                         ovr_item.push_back(items.size());
                         ovr_pool.insert(ovr_pool.end(), mats.begin(), mats.end());

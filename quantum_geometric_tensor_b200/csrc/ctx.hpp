@@ -50,6 +50,7 @@ struct qgt_b200_ctx {
     size_t max_slots = 0;
     int use_mma = 1;
     int double_buffer = 0;
+    int tiles_per_item = 0;      // 0 = automatic
     int debug_skip = 0;          // timing experiments only (results are wrong): 1 no tile load, 2 no store, 4 no sub-passes
     double ms_prog_pack = 0.0;
     qgt::PlanOptions opt;

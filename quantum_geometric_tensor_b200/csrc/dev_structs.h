@@ -33,7 +33,14 @@ enum QgtOpFlags {
 #define QGT_MAX_VARIANT_BITS 2
 // matrix variants are laid out QGT_VARIANT_STRIDE(N) complex elements apart: the odd padding keeps two
 // variants read by lanes of one quarter-warp in different shared-memory bank groups
-#define QGT_VARIANT_STRIDE(N) ((N) * (N) + 1)
+#define QGT_VARIANT_STRIDE(N) ((N) * (N) + (N) + 1)
+// Matrix forms.  QGT_FORM_DENSE: N*N complex elements.  QGT_FORM_DIAG_REAL: the matrix factors as
+// (complex diagonal D) x (real matrix Rm) - true for any stage whose qubits see rotations about Y / CNOT /
+// H before their diagonal gates (RZ, CZ, phases), i.e. for every layer of a hardware-efficient ansatz.
+// Rm sits in the .x of the N*N elements (.y = 0), D in the N elements behind them; the tensor-pipe path
+// then needs 4 DMMAs per 8 vectors instead of 8 and one complex multiply per result.
+#define QGT_FORM_DENSE 0
+#define QGT_FORM_DIAG_REAL 1
 // element (i, j) of a stage matrix inside its variant.  8x8 matrices are stored in DMMA A-fragment order
 // (lane (r, k) reads M[r][k] and M[r][4+k]: 32 consecutive elements per load, conflict-free); smaller
 // ones row-major.
@@ -44,7 +51,8 @@ enum QgtOpFlags {
 // QGT_MAX_VARIANT_BITS non-register qubits give 2^nvar matrix variants; a thread picks its variant from
 // the bits of its global index.
 typedef struct QgtDevStage {
-    int32_t  nvar;                           // number of selecting bits
+    int16_t  nvar;                           // number of selecting bits
+    int16_t  form;                           // QGT_FORM_* of every variant of this stage
     int32_t  mat_off;                        // offset of variant 0 in the run's matrix pool, in complex elements
     uint64_t vmask[QGT_MAX_VARIANT_BITS];    // global index bit selecting variant bit k
 } QgtDevStage;                               // 24 bytes
@@ -105,7 +113,7 @@ typedef struct QgtSweepItem {
     uint32_t    accumulate;              // dst += result instead of dst = result
     int32_t     ovr_kind;                // 0 none, 1 dense stage, 2 thread diagonal, 3 cost
     int32_t     ovr_index;               // which stage / thread diagonal / cost entry of the run is replaced
-    int32_t     pad;
+    int32_t     ovr_form;                // kind 1: QGT_FORM_* of the replacement matrices
     const void* ovr_mat;                 // kind 1: the replacement matrices (all variants) in global memory
     QgtDevThrDiag ovr_tdiag;             // kind 2
     QgtDevCost    ovr_cost;              // kind 3

@@ -52,7 +52,7 @@ struct QgtFastSub {
     uint64_t vm0, vm1;           // variant-selecting global index bits of the (single) stage, 0 when unused
     uint32_t mat_off, stage;     // variant 0 in the run's pool; stage index (override test)
     uint32_t sr2, st0, gx1, gx2; // slot XOR terms: matrix bit 2, thread bit 0, thread bits 3 and 4
-    uint32_t simple, pad;        // exactly one dense stage and no thread diagonal
+    uint32_t simple, form;       // exactly one dense stage and no thread diagonal; QGT_FORM_* of that stage
 };
 struct QgtFastWarp { uint64_t g; uint32_t s; uint32_t pad; };   // warp-index bits: global index / swizzled slot
 #define QGT_FAST_BYTES_PER_SUB (sizeof(QgtFastSub) + 8 * sizeof(QgtFastWarp) + 32 * sizeof(uint32_t))
@@ -77,11 +77,12 @@ __device__ __forceinline__ void qgt_fast_build(const QgtDevRun& run, const QgtDe
         if (lane == 8) {
             QgtFastSub f;
             f.simple = (sp.stage_end - sp.stage_begin == 1 && sp.tdiag_end == sp.tdiag_begin) ? 1u : 0u;
-            f.stage = (uint32_t)sp.stage_begin; f.pad = 0;
+            f.stage = (uint32_t)sp.stage_begin; f.form = QGT_FORM_DENSE;
             f.vm0 = f.vm1 = 0; f.mat_off = 0;
             if (f.simple) {
                 const QgtDevStage& st = stages[sp.stage_begin];
                 f.mat_off = (uint32_t)st.mat_off;
+                f.form = (uint32_t)st.form;
                 if (st.nvar > 0) f.vm0 = st.vmask[0];
                 if (st.nvar > 1) f.vm1 = st.vmask[1];
             }
@@ -99,12 +100,45 @@ __device__ __forceinline__ void qgt_warp_subpass_fast(const QgtFastSub& f, const
     constexpr int N = 8;
     const uint32_t baseB = fw.s ^ (lt & 0xffffu), baseC = fw.s ^ (lt >> 16);
     const uint64_t gwarp = tileg | fw.g;
-    const int off = (cx.ovr_kind == 1 && (int)f.stage == cx.ovr_index) ? cx.ovr_mat_off : (int)f.mat_off;
+    const bool ovr = (cx.ovr_kind == 1 && (int)f.stage == cx.ovr_index);
+    const int off = ovr ? cx.ovr_mat_off : (int)f.mat_off;
+    const bool diag_real = (ovr ? (uint32_t)cx.ovr_form : f.form) == QGT_FORM_DIAG_REAL;
     const int var = ((gwarp & f.vm0) != 0 ? 1 : 0) | ((gwarp & f.vm1) != 0 ? 2 : 0);
     const cplx* M = cx.pool + off + var * QGT_VARIANT_STRIDE(N);
     const cplx m0 = M[lane], m1 = M[32 + lane];           // A fragments: QGT_MIDX(8, q, k) == lane
-    const double nm0y = -m0.y, nm1y = -m1.y;
     const uint32_t gx1 = f.gx1, gx2 = f.gx2, sr2 = f.sr2, st0 = f.st0;    // locals: tile stores must not force reloads
+    if (diag_real) {
+        // M = D * Rm with Rm real: out = D (Rm v_re + i Rm v_im), 4 DMMAs per 8 vectors and one complex multiply
+        // per result (row lane>>2 of the C fragment)
+        const cplx d = M[N * N + (lane >> 2)];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            cplx v0[2], v1[2];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const uint32_t gx = (g ? gx1 : 0u) ^ (h ? gx2 : 0u);
+                v0[g] = tile[baseB ^ gx];
+                v1[g] = tile[baseB ^ gx ^ sr2];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const uint32_t gx = (g ? gx1 : 0u) ^ (h ? gx2 : 0u);
+                double cr0 = 0.0, cr1 = 0.0, ci0 = 0.0, ci1 = 0.0;
+                dmma884(cr0, cr1, m0.x, v0[g].x);
+                dmma884(ci0, ci1, m0.x, v0[g].y);
+                dmma884(cr0, cr1, m1.x, v1[g].x);
+                dmma884(ci0, ci1, m1.x, v1[g].y);
+                cplx o0, o1;
+                o0.x = d.x * cr0 - d.y * ci0; o0.y = d.x * ci0 + d.y * cr0;
+                o1.x = d.x * cr1 - d.y * ci1; o1.y = d.x * ci1 + d.y * cr1;
+                tile[baseC ^ gx] = o0;
+                tile[baseC ^ gx ^ st0] = o1;
+            }
+        }
+        return;
+    }
+    const double nm0y = -m0.y, nm1y = -m1.y;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {     // two groups of 8 vectors at a time: operand loads first, then the DMMAs
         cplx v0[2], v1[2];
@@ -187,9 +221,13 @@ __device__ __forceinline__ void qgt_warp_subpass_mma(const QgtDevRun& run, const
     const int nstage = sp.stage_end - sp.stage_begin;
     for (int s = sp.stage_begin; s < sp.stage_end; ++s) {
         const QgtDevStage& st = cx.stages[s];
-        const int off = (cx.ovr_kind == 1 && s == cx.ovr_index) ? cx.ovr_mat_off : st.mat_off;
+        const bool ovr = (cx.ovr_kind == 1 && s == cx.ovr_index);
+        const int off = ovr ? cx.ovr_mat_off : st.mat_off;
+        const bool diag_real = (ovr ? cx.ovr_form : (int)st.form) == QGT_FORM_DIAG_REAL;
         const cplx* M = cx.pool + off + qgt_variant_index(st, gwarp) * QGT_VARIANT_STRIDE(N);
         const cplx m0 = M[QGT_MIDX(N, q, k)], m1 = M[QGT_MIDX(N, q, 4 + k)];
+        cplx dq; dq.x = 1.0; dq.y = 0.0;
+        if (diag_real) dq = M[N * N + q];                 // M = D * Rm (imaginary parts stored as 0): scale row q afterwards
         const double nm0y = -m0.y, nm1y = -m1.y;
         const bool last = (s == sp.stage_end - 1);
 #pragma unroll
@@ -206,6 +244,11 @@ __device__ __forceinline__ void qgt_warp_subpass_mma(const QgtDevRun& run, const
             dmma884(ci0, ci1, m1.y, v1.x);
             cplx o0, o1;
             o0.x = cr0; o0.y = ci0; o1.x = cr1; o1.y = ci1;
+            if (diag_real) {
+                cplx t0 = o0, t1 = o1;
+                o0.x = dq.x * t0.x - dq.y * t0.y; o0.y = dq.x * t0.y + dq.y * t0.x;
+                o1.x = dq.x * t1.x - dq.y * t1.y; o1.y = dq.x * t1.y + dq.y * t1.x;
+            }
             if (last && has_tdiag) {
                 cplx t0 = o0, t1 = o1;
                 o0.x = pend0[g].x * t0.x - pend0[g].y * t0.y; o0.y = pend0[g].x * t0.y + pend0[g].y * t0.x;
@@ -273,10 +316,14 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
     cx.pool = spool;
     cx.ovr_mat_off = run.mat_count;
     const QgtIoMap<R + B> io = qgt_make_iomap<R + B>(run, tid);
-    const uint64_t total = a.ntiles * (uint64_t)a.nitems;
-    auto prefetch = [&](uint64_t w, cplx* buf) {
+    // work unit = (group of `tpi` consecutive tiles, column item), items fastest: concurrently running CTAs read the
+    // same source tiles (one phi spawns many columns).  The item set-up (descriptor, override matrices) is paid once
+    // per unit.
+    const int tpi = a.tiles_per_item;
+    const uint64_t total = (a.ntiles / (uint64_t)tpi) * (uint64_t)a.nitems;
+    auto prefetch = [&](uint64_t w, int t, cplx* buf) {
         const QgtSweepItem& it = a.items[(int)(w % (uint64_t)a.nitems)];
-        const uint64_t tb = qgt_tile_base(run, w / (uint64_t)a.nitems);
+        const uint64_t tb = qgt_tile_base(run, (w / (uint64_t)a.nitems) * (uint64_t)tpi + (uint64_t)t);
         const cplx* src = reinterpret_cast<const cplx*>(it.src);
 #pragma unroll
         for (int i = 0; i < (1 << (R + B)); ++i) {
@@ -285,32 +332,38 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
         }
     };
     uint64_t w = blockIdx.x;
+    int t = 0;
     if (DB) {
-        if (w < total) prefetch(w, tile);
+        if (w < total) prefetch(w, 0, tile);
         cp_async_commit();
     }
-    for (int par = 0; w < total; w += gridDim.x, par ^= 1) {
+    for (int par = 0; w < total; par ^= 1) {
         cplx* cur = DB ? tile + ((size_t)par << run.K) : tile;
         const int item = (int)(w % (uint64_t)a.nitems);
-        const uint64_t tau = w / (uint64_t)a.nitems;
+        const uint64_t tau = (w / (uint64_t)a.nitems) * (uint64_t)tpi + (uint64_t)t;
         const QgtSweepItem& it = a.items[item];
         const uint64_t tilebase = qgt_tile_base(run, tau);
         const uint64_t tileg = tilebase | a.gprefix;      // global index bits incl. the rank's (sharded states)
         cx.ovr_kind = it.ovr_kind;
         cx.ovr_index = it.ovr_index;
+        cx.ovr_form = it.ovr_form;
         cx.ovr_tdiag = &it.ovr_tdiag;
-        if (it.ovr_kind == 1) {
+        if (t == 0 && it.ovr_kind == 1) {
+            // every warp is past the previous unit's last sub-pass (barrier), so the override buffer is free
             const cplx* g = reinterpret_cast<const cplx*>(it.ovr_mat);
             const int cnt = QGT_VARIANT_STRIDE(N) << cx.stages[it.ovr_index].nvar;
             for (int i = tid; i < cnt && i < OVR_ELEMS; i += T) sovr[i] = g[i];
         }
+        int nt = t + 1;
+        uint64_t nw = w;
+        if (nt == tpi) { nt = 0; nw = w + gridDim.x; }
         if (DB) {
-            // the other buffer was last read by the previous item's store phase, which ended at a barrier
-            if (w + gridDim.x < total) prefetch(w + gridDim.x, tile + ((size_t)(par ^ 1) << run.K));
+            // the other buffer was last read by this thread itself (store phase, same slots as the load)
+            if (nw < total) prefetch(nw, nt, tile + ((size_t)(par ^ 1) << run.K));
             cp_async_commit();
             cp_async_wait<1>();
         } else {
-            if (!QGT_DBG(1)) prefetch(w, cur);
+            if (!QGT_DBG(1)) prefetch(w, t, cur);
             cp_async_commit();
             cp_async_wait<0>();
         }
@@ -335,14 +388,16 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
             }
             if (!QGT_DBG(8)) __syncthreads();
         }
+        // no barrier after the store: the next load of this buffer writes, per thread, exactly the slots the thread
+        // has just read (load and store use the same index map), and the next sub-pass sits behind the load barrier
         if (!QGT_DBG(2)) qgt_phase_store<R + B>(io, cur, reinterpret_cast<cplx*>(it.dst), tilebase, tid, T, it.accumulate != 0);
-        __syncthreads();
+        t = nt; w = nw;
     }
     cp_async_wait<0>();
 }
 
 template <int R, int B, bool MMA_ONLY, bool DB, int MAXT, int MINB>
-static cudaError_t launch_sweep_cfg(const SweepLaunch& a, int T, size_t smem, uint64_t total, int num_sms, cudaStream_t st) {
+static cudaError_t launch_sweep_cfg(const SweepLaunch& a_in, int T, size_t smem, int num_sms, cudaStream_t st) {
     auto kern = qgt_sweep_kernel<R, B, MMA_ONLY, DB, MAXT, MINB>;
     static int ctas_per_sm = 0;
     static size_t smem_seen = 0;
@@ -355,7 +410,18 @@ static cudaError_t launch_sweep_cfg(const SweepLaunch& a, int T, size_t smem, ui
         ctas_per_sm = occ > 0 ? occ : 1;
         smem_seen = smem;
     }
-    const uint64_t cap = (uint64_t)num_sms * ctas_per_sm * 2;
+    SweepLaunch a = a_in;
+    const uint64_t resident = (uint64_t)num_sms * ctas_per_sm;
+    // tiles per item set-up: as many as keep >= 16 work units per resident CTA (tail balance), at most 4
+    int tpi = 1;
+    if (a.tiles_per_item > 0) {
+        while (tpi * 2 <= a.tiles_per_item && a.ntiles % (uint64_t)(tpi * 2) == 0) tpi *= 2;
+    } else {
+        while (tpi < 4 && a.ntiles % (uint64_t)(tpi * 2) == 0 && (a.ntiles / (uint64_t)(tpi * 2)) * (uint64_t)a.nitems >= resident * 16) tpi *= 2;
+    }
+    a.tiles_per_item = tpi;
+    const uint64_t total = (a.ntiles / (uint64_t)tpi) * (uint64_t)a.nitems;
+    const uint64_t cap = resident * 2;
     const unsigned grid = (unsigned)(total < cap ? total : cap);
     kern<<<grid, T, smem, st>>>(a);
     return cudaGetLastError();
@@ -365,8 +431,7 @@ template <int R, int B>
 static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, int nsub, int has_cost, int num_sms, cudaStream_t st) {
     constexpr int N = 1 << R;
     const int T = 1 << (K - R - B);
-    const uint64_t total = a.ntiles * (uint64_t)a.nitems;
-    if (total == 0) return cudaSuccess;
+    if (a.ntiles * (uint64_t)a.nitems == 0) return cudaSuccess;
     const size_t fixed0 = sizeof(cplx) * (size_t)mat_count + sizeof(cplx) * (size_t)(QGT_VARIANT_STRIDE(N) << QGT_MAX_VARIANT_BITS) +
                          (size_t)nsub * sizeof(QgtDevSubPass) + (has_cost ? qgt_cost_smem_doubles(K, a.ct.num_edges) * sizeof(double) : 0);
     const size_t tile_bytes = sizeof(cplx) << K;
@@ -375,12 +440,12 @@ static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, i
     if (R == 3 && B == 0 && a.mma_only && T >= 32) {
         const size_t fixed = fixed0 + (size_t)nsub * QGT_FAST_BYTES_PER_SUB;
         // single tile buffer: more resident CTAs hide the load latency instead of a second buffer
-        if (a.double_buffer) return launch_sweep_cfg<3, 0, true, true, 256, 3>(a, T, fixed + 2 * tile_bytes, total, num_sms, st);
-        return launch_sweep_cfg<3, 0, true, false, 256, 4>(a, T, fixed + tile_bytes, total, num_sms, st);
+        if (a.double_buffer) return launch_sweep_cfg<3, 0, true, true, 256, 3>(a, T, fixed + 2 * tile_bytes, num_sms, st);
+        return launch_sweep_cfg<3, 0, true, false, 256, 4>(a, T, fixed + tile_bytes, num_sms, st);
     }
-    if (B > 0 && T <= 128) return launch_sweep_cfg<R, B, false, true, 128, 3>(a, T, fixed + 2 * tile_bytes, total, num_sms, st);
-    if (B > 0) return launch_sweep_cfg<R, B, false, true, 256, 1>(a, T, fixed + 2 * tile_bytes, total, num_sms, st);
-    return launch_sweep_cfg<R, B, false, true, 256, 2>(a, T, fixed + 2 * tile_bytes, total, num_sms, st);
+    if (B > 0 && T <= 128) return launch_sweep_cfg<R, B, false, true, 128, 3>(a, T, fixed + 2 * tile_bytes, num_sms, st);
+    if (B > 0) return launch_sweep_cfg<R, B, false, true, 256, 1>(a, T, fixed + 2 * tile_bytes, num_sms, st);
+    return launch_sweep_cfg<R, B, false, true, 256, 2>(a, T, fixed + 2 * tile_bytes, num_sms, st);
 }
 
 cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int has_cost, int num_sms, cudaStream_t st) {

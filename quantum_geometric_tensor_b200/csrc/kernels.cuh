@@ -19,6 +19,7 @@ struct SweepLaunch {
     const QgtSweepItem* items;
     int nitems;
     uint64_t ntiles;
+    int tiles_per_item;          // consecutive tiles a CTA processes per item set-up; power of two dividing ntiles
     uint64_t gprefix;            // rank bits of a sharded state, OR-ed into every global index used by masks
     int mma_only;                // every sub-pass of the run qualifies for the tensor-pipe path (host-checked)
     int double_buffer;           // tensor-only kernel: two tile buffers (3 CTAs/SM) instead of one (4 CTAs/SM)

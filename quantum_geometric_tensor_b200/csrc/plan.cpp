@@ -268,12 +268,12 @@ QgtDevCost make_cost(const LoweredOp& op, bool derivative) {
     return c;
 }
 
-void stage_matrices(const Run& run, const SubPass& sp, const Stage& st, int deriv_op, std::vector<double>& out) {
+// all variants of a stage's matrix, row-major N x N complex each (dense[(p*N*N + i*N + j)*2])
+static void stage_dense(const Run& run, const SubPass& sp, const Stage& st, int deriv_op, std::vector<double>& dense) {
     const int R = (int)sp.reg_local.size();
     const int N = 1 << R;
     const int nvar = (int)st.vqubits.size();
-    const size_t vstride = (size_t)QGT_VARIANT_STRIDE(N) * 2;      // doubles per variant (one padding element)
-    out.assign((size_t)(1 << nvar) * vstride, 0.0);
+    dense.assign((size_t)(1 << nvar) * N * N * 2, 0.0);
     // masks of each op over the register combo c and the variant pattern p
     struct Bound { uint32_t creg, cvar, preg, pvar; int j; };
     std::vector<Bound> bound(st.ops.size());
@@ -338,23 +338,66 @@ void stage_matrices(const Run& run, const SubPass& sp, const Stage& st, int deri
             }
             M.swap(T);
         }
-        double* dst = &out[(size_t)p * vstride];
-        for (int i = 0; i < N; i++)
-            for (int j = 0; j < N; j++) {
-                dst[2 * QGT_MIDX(N, i, j)] = M[2 * (i * N + j)];
-                dst[2 * QGT_MIDX(N, i, j) + 1] = M[2 * (i * N + j) + 1];
-            }
+        std::memcpy(&dense[(size_t)p * N * N * 2], M.data(), M.size() * sizeof(double));
     }
 }
 
-void stage_matrices_sum(const Run& run, const SubPass& sp, const Stage& st, const std::vector<int>& deriv_ops, std::vector<double>& out) {
-    std::vector<double> one;
-    out.clear();
-    for (int op : deriv_ops) {
-        stage_matrices(run, sp, st, op, one);
-        if (out.empty()) out = one;
-        else for (size_t i = 0; i < out.size(); i++) out[i] += one[i];
+// Device layout of a stage's variants (see dev_structs.h).  8x8 matrices whose rows all have a constant
+// phase, M[i][j] = d_i * r_ij with r real, are stored in QGT_FORM_DIAG_REAL (decided for all variants of
+// the stage together); everything else dense.
+static int pack_stage(int N, int nvariants, const std::vector<double>& dense, std::vector<double>& out) {
+    const size_t vstride = (size_t)QGT_VARIANT_STRIDE(N) * 2;      // doubles per variant
+    out.assign((size_t)nvariants * vstride, 0.0);
+    bool diag_real = (N == 8);
+    std::vector<double> d((size_t)nvariants * N * 2, 0.0), rm((size_t)nvariants * N * N, 0.0);
+    for (int p = 0; p < nvariants && diag_real; p++) {
+        const double* M = &dense[(size_t)p * N * N * 2];
+        for (int i = 0; i < N && diag_real; i++) {
+            int jm = 0; double best = -1.0;
+            for (int j = 0; j < N; j++) {
+                const double a = M[2 * (i * N + j)] * M[2 * (i * N + j)] + M[2 * (i * N + j) + 1] * M[2 * (i * N + j) + 1];
+                if (a > best) { best = a; jm = j; }
+            }
+            const double mag = std::sqrt(best);
+            double pr = 1.0, pi = 0.0;
+            if (mag > 0.0) { pr = M[2 * (i * N + jm)] / mag; pi = M[2 * (i * N + jm) + 1] / mag; }
+            d[((size_t)p * N + i) * 2] = pr; d[((size_t)p * N + i) * 2 + 1] = pi;
+            for (int j = 0; j < N; j++) {
+                const double xr = M[2 * (i * N + j)], xi = M[2 * (i * N + j) + 1];
+                const double re = xr * pr + xi * pi, im = xi * pr - xr * pi;       // x * conj(phase)
+                if (std::fabs(im) > 1e-14 * mag) { diag_real = false; break; }
+                rm[((size_t)p * N + i) * N + j] = re;
+            }
+        }
     }
+    for (int p = 0; p < nvariants; p++) {
+        double* dst = &out[(size_t)p * vstride];
+        const double* M = &dense[(size_t)p * N * N * 2];
+        for (int i = 0; i < N; i++) {
+            for (int j = 0; j < N; j++) {
+                if (diag_real) dst[2 * QGT_MIDX(N, i, j)] = rm[((size_t)p * N + i) * N + j];
+                else { dst[2 * QGT_MIDX(N, i, j)] = M[2 * (i * N + j)]; dst[2 * QGT_MIDX(N, i, j) + 1] = M[2 * (i * N + j) + 1]; }
+            }
+            if (diag_real) { dst[2 * (N * N + i)] = d[((size_t)p * N + i) * 2]; dst[2 * (N * N + i) + 1] = d[((size_t)p * N + i) * 2 + 1]; }
+        }
+    }
+    return diag_real ? QGT_FORM_DIAG_REAL : QGT_FORM_DENSE;
+}
+
+int stage_matrices(const Run& run, const SubPass& sp, const Stage& st, int deriv_op, std::vector<double>& out) {
+    std::vector<double> dense;
+    stage_dense(run, sp, st, deriv_op, dense);
+    return pack_stage(1 << (int)sp.reg_local.size(), 1 << (int)st.vqubits.size(), dense, out);
+}
+
+int stage_matrices_sum(const Run& run, const SubPass& sp, const Stage& st, const std::vector<int>& deriv_ops, std::vector<double>& out) {
+    std::vector<double> one, sum;
+    for (int op : deriv_ops) {
+        stage_dense(run, sp, st, op, one);
+        if (sum.empty()) sum = one;
+        else for (size_t i = 0; i < sum.size(); i++) sum[i] += one[i];
+    }
+    return pack_stage(1 << (int)sp.reg_local.size(), 1 << (int)st.vqubits.size(), sum, out);
 }
 
 int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions& opt_in, CircuitPlan& plan, std::string& err) {
@@ -547,10 +590,10 @@ void build_image(const CircuitPlan& plan, PlanImage& img) {
             for (const Stage& st : sp.stages) {
                 QgtDevStage d;
                 std::memset(&d, 0, sizeof d);
-                d.nvar = (int)st.vqubits.size();
+                d.nvar = (int16_t)st.vqubits.size();
                 for (int k = 0; k < d.nvar; k++) d.vmask[k] = bit(st.vqubits[k]);
                 d.mat_off = (int)(img.pool.size() / 2) - dr.mat_off;
-                stage_matrices(run, sp, st, -1, mats);
+                d.form = (int16_t)stage_matrices(run, sp, st, -1, mats);
                 img.pool.insert(img.pool.end(), mats.begin(), mats.end());
                 img.stages.push_back(d);
             }
@@ -995,7 +1038,9 @@ std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const 
             o << (s ? "," : "") << "{\"reg\":"; jarr(o, sp.reg_local);
             o << ",\"batch\":"; jarr(o, sp.batch_local);
             o << ",\"tperm\":"; jarr(o, sp.tperm);
-            o << ",\"ops\":[" << sp.op_begin << "," << sp.op_end << "]}";
+            o << ",\"forms\":[";             // QGT_FORM_* of each dense stage (1 = complex diagonal x real matrix)
+            { std::vector<double> tmp; for (size_t k = 0; k < sp.stages.size(); k++) o << (k ? "," : "") << stage_matrices(run, sp, sp.stages[k], -1, tmp); }
+            o << "],\"ops\":[" << sp.op_begin << "," << sp.op_end << "]}";
         }
         o << "],\"ops\":[";
         for (size_t i = 0; i < run.ops.size(); i++) { o << (i ? "," : ""); jop(o, run.ops[i], false); }

@@ -99,9 +99,10 @@ void build_image(const CircuitPlan& plan, PlanImage& img);
 OpLocation locate_op(const Run& run, int op_index);
 // all variants of a stage's matrix, (re, im) interleaved, row-major 2^R x 2^R each; deriv_op >= 0 replaces
 // that lowered op by its derivative
-void stage_matrices(const Run& run, const SubPass& sp, const Stage& st, int deriv_op, std::vector<double>& out);
+// in the device layout of dev_structs.h; returns the QGT_FORM_* chosen
+int stage_matrices(const Run& run, const SubPass& sp, const Stage& st, int deriv_op, std::vector<double>& out);
 // product rule over several ops of one stage: sum of the single-derivative matrices
-void stage_matrices_sum(const Run& run, const SubPass& sp, const Stage& st, const std::vector<int>& deriv_ops, std::vector<double>& out);
+int stage_matrices_sum(const Run& run, const SubPass& sp, const Stage& st, const std::vector<int>& deriv_ops, std::vector<double>& out);
 QgtDevThrDiag make_tdiag(const LoweredOp& op, bool derivative);
 QgtDevCost make_cost(const LoweredOp& op, bool derivative);
 

@@ -156,6 +156,7 @@ struct QgtSubCtx {
     const cplx* pool;            // the run's matrices (element 0 = run.mat_off of the plan-wide pool) ...
     int ovr_mat_off;             // ... followed, at this element offset, by the item's override matrices
     int ovr_kind, ovr_index;
+    int ovr_form;                // QGT_FORM_* of the override matrices
     const QgtDevThrDiag* ovr_tdiag;
 };
 
@@ -205,7 +206,9 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
     const int nstage = sp.stage_end - sp.stage_begin;
     for (int s = sp.stage_begin; s < sp.stage_end; ++s) {
         const QgtDevStage& st = cx.stages[s];
-        const int off = (cx.ovr_kind == 1 && s == cx.ovr_index) ? cx.ovr_mat_off : st.mat_off;
+        const bool ovr = (cx.ovr_kind == 1 && s == cx.ovr_index);
+        const int off = ovr ? cx.ovr_mat_off : st.mat_off;
+        const bool diag_real = (ovr ? cx.ovr_form : (int)st.form) == QGT_FORM_DIAG_REAL;   // M = D * Rm: rows scaled afterwards
         const bool last = (s == sp.stage_end - 1);
         cplx v[NB][N];
 #pragma unroll
@@ -237,6 +240,7 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
 #pragma unroll
                 for (int h = 0; h < NB; ++h) {
                     cplx o; o.x = xr[h]; o.y = xi[h];
+                    if (diag_real) { const cplx d = M[0][N * N + i]; const cplx q = o; o.x = d.x * q.x - d.y * q.y; o.y = d.x * q.y + d.y * q.x; }
                     if (last) { const cplx q = o; o.x = pend[h].x * q.x - pend[h].y * q.y; o.y = pend[h].x * q.y + pend[h].y * q.x; }
                     tile[slot[h][i]] = o;
                 }
@@ -254,6 +258,7 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
                         xi = qgt_fma(m.x, v[h][j].y, xi); xi = qgt_fma(m.y, v[h][j].x, xi);
                     }
                     cplx o; o.x = xr; o.y = xi;
+                    if (diag_real) { const cplx d = M[h][N * N + i]; const cplx q = o; o.x = d.x * q.x - d.y * q.y; o.y = d.x * q.y + d.y * q.x; }
                     if (last) { const cplx q = o; o.x = pend[h].x * q.x - pend[h].y * q.y; o.y = pend[h].x * q.y + pend[h].y * q.x; }
                     uint32_t l = sbase;   // slot[h][i] with a run-time i: recompute instead of indexing registers
 #pragma unroll

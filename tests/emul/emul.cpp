@@ -33,7 +33,7 @@ static void emul_item(const QgtDevRun& run, const PlanImage& img, const QgtSweep
         std::memcpy(pool.data() + run.mat_count, it.ovr_mat, sizeof(cplx) * (QGT_VARIANT_STRIDE(1 << R) << cx.stages[it.ovr_index].nvar));
     cx.pool = pool.data();
     cx.ovr_mat_off = run.mat_count;
-    cx.ovr_kind = it.ovr_kind; cx.ovr_index = it.ovr_index;
+    cx.ovr_kind = it.ovr_kind; cx.ovr_index = it.ovr_index; cx.ovr_form = it.ovr_form;
     cx.ovr_tdiag = &it.ovr_tdiag;
     std::vector<double> cost_buf(qgt_cost_smem_doubles(run.K, ct.num_edges));
     QgtCostSmem cost_sm = qgt_cost_smem_carve(cost_buf.data(), run.K, ct.num_edges);
@@ -97,7 +97,7 @@ extern "C" int emul_sweep(const qgt_b200_circuit* circ, const double* theta, int
             for (int s2 = 0; s2 < loc.sub; s2++) first += (int)run.subs[s2].stages.size();
             std::vector<int> dops(1, ovr_op);
             for (int e = 0; e < nextra; e++) dops.push_back(extra[e]);
-            stage_matrices_sum(run, sp, sp.stages[loc.index - first], dops, mats);
+            it.ovr_form = stage_matrices_sum(run, sp, sp.stages[loc.index - first], dops, mats);
             it.ovr_mat = mats.data();
         } else if (loc.kind == 2) it.ovr_tdiag = make_tdiag(run.ops[ovr_op], true);
         else it.ovr_cost = make_cost(run.ops[ovr_op], true);
