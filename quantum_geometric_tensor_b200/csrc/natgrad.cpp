@@ -22,11 +22,59 @@ namespace {
 // Symmetric eigen-decomposition A = V diag(w) V^T: Householder reduction to tridiagonal form followed by
 // implicit-shift QL iterations (the classic tred2 / tql2 pair), O(n^3) with a small constant — a 256 x 256
 // metric takes a few milliseconds.  A (row-major) is destroyed; V receives the eigenvectors as columns.
+// dot product with four independent accumulators (fixed summation order; lets the compiler keep four
+// multiply-add chains in flight without value-changing flags)
+inline double dot4(const double* a, const double* b, int n) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = 0;
+    for (; k + 4 <= n; k += 4) { s0 += a[k] * b[k]; s1 += a[k + 1] * b[k + 1]; s2 += a[k + 2] * b[k + 2]; s3 += a[k + 3] * b[k + 3]; }
+    for (; k < n; k++) s0 += a[k] * b[k];
+    return (s0 + s1) + (s2 + s3);
+}
+
+// Eigenvalues only: the same Householder reduction on a fully stored symmetric matrix, so that the
+// matrix-vector product and the rank-2 update of every step run over contiguous rows (the lower-triangle
+// form below walks columns); d / e receive the tridiagonal matrix in the layout the QL loop expects.
+void tridiagonalize_values(std::vector<double>& A, int n, std::vector<double>& d, std::vector<double>& e) {
+    std::vector<double> u(n), pv(n);
+    for (int i = n - 1; i >= 1; i--) {
+        const int l = i - 1;
+        double* ai = &A[(size_t)i * n];
+        if (l == 0) { e[i] = ai[0]; continue; }
+        double scale = 0.0;
+        for (int k = 0; k <= l; k++) scale += std::fabs(ai[k]);
+        if (scale == 0.0) { e[i] = ai[l]; continue; }
+        double h = 0.0;
+        for (int k = 0; k <= l; k++) { u[k] = ai[k] / scale; h += u[k] * u[k]; }
+        const double f = u[l];
+        const double g = f >= 0.0 ? -std::sqrt(h) : std::sqrt(h);
+        e[i] = scale * g;
+        h -= f * g;
+        u[l] = f - g;
+        double K = 0.0;
+        for (int j = 0; j <= l; j++) {
+            pv[j] = dot4(&A[(size_t)j * n], u.data(), l + 1) / h;
+            K += pv[j] * u[j];
+        }
+        K /= (h + h);
+        for (int j = 0; j <= l; j++) pv[j] -= K * u[j];
+        for (int j = 0; j <= l; j++) {
+            double* aj = &A[(size_t)j * n];
+            const double uj = u[j], qj = pv[j];
+            for (int k = 0; k <= l; k++) aj[k] -= uj * pv[k] + qj * u[k];
+        }
+    }
+    e[0] = 0.0;
+    for (int i = 0; i < n; i++) d[i] = A[(size_t)i * n + i];
+}
+
 void sym_eigh(std::vector<double>& A, int n, std::vector<double>& w, std::vector<double>& V, bool want_vectors) {
     std::vector<double> d(n), e(n);
     auto a = [&](int i, int j) -> double& { return A[(size_t)i * n + j]; };
+    if (!want_vectors) tridiagonalize_values(A, n, d, e);
+    else
     // --- Householder tridiagonalisation, accumulating the transformation in A
-    for (int i = n - 1; i >= 1; i--) {
+    { for (int i = n - 1; i >= 1; i--) {
         const int l = i - 1;
         double h = 0.0, scale = 0.0;
         if (l > 0) {
@@ -60,9 +108,8 @@ void sym_eigh(std::vector<double>& A, int n, std::vector<double>& w, std::vector
         }
         d[i] = h;
     }
-    d[0] = 0.0; e[0] = 0.0;
-    if (!want_vectors) { for (int i = 0; i < n; i++) d[i] = a(i, i); }
-    else for (int i = 0; i < n; i++) {
+    d[0] = 0.0; e[0] = 0.0; }
+    if (want_vectors) for (int i = 0; i < n; i++) {
         const int l = i - 1;
         if (d[i] != 0.0) {
             for (int j = 0; j <= l; j++) {
@@ -133,9 +180,7 @@ bool cholesky_solve(const double* G, double lambda, const double* g, int n, doub
     for (int i = 0; i < n; i++) {
         for (int j = 0; j <= i; j++) {
             double s = 0.5 * (G[(size_t)i * n + j] + G[(size_t)j * n + i]) + (i == j ? lambda : 0.0);
-            const double* li = &L[(size_t)i * n];
-            const double* lj = &L[(size_t)j * n];
-            for (int k = 0; k < j; k++) s -= li[k] * lj[k];
+            s -= dot4(&L[(size_t)i * n], &L[(size_t)j * n], j);
             if (i == j) {
                 if (!(s > 0.0)) return false;
                 L[(size_t)i * n + i] = std::sqrt(s);
