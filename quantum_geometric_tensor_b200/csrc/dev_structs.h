@@ -37,8 +37,9 @@ enum QgtOpFlags {
 // Matrix forms.  QGT_FORM_DENSE: N*N complex elements.  QGT_FORM_DIAG_REAL: the matrix factors as
 // (complex diagonal D) x (real matrix Rm) - true for any stage whose qubits see rotations about Y / CNOT /
 // H before their diagonal gates (RZ, CZ, phases), i.e. for every layer of a hardware-efficient ansatz.
-// Rm sits in the .x of the N*N elements (.y = 0), D in the N elements behind them; the tensor-pipe path
-// then needs 4 DMMAs per 8 vectors instead of 8 and one complex multiply per result.
+// Rm is stored as N*N packed doubles (element (i, j) at double index QGT_MIDX(N, i, j)) at the start of the
+// variant, D in the N complex elements at index N*N; the tensor-pipe path then needs 4 DMMAs per 8 vectors
+// instead of 8 and one complex multiply per result.
 #define QGT_FORM_DENSE 0
 #define QGT_FORM_DIAG_REAL 1
 // element (i, j) of a stage matrix inside its variant.  8x8 matrices are stored in DMMA A-fragment order

@@ -105,11 +105,12 @@ __device__ __forceinline__ void qgt_warp_subpass_fast(const QgtFastSub& f, const
     const bool diag_real = (ovr ? (uint32_t)cx.ovr_form : f.form) == QGT_FORM_DIAG_REAL;
     const int var = ((gwarp & f.vm0) != 0 ? 1 : 0) | ((gwarp & f.vm1) != 0 ? 2 : 0);
     const cplx* M = cx.pool + off + var * QGT_VARIANT_STRIDE(N);
-    const cplx m0 = M[lane], m1 = M[32 + lane];           // A fragments: QGT_MIDX(8, q, k) == lane
     const uint32_t gx1 = f.gx1, gx2 = f.gx2, sr2 = f.sr2, st0 = f.st0;    // locals: tile stores must not force reloads
     if (diag_real) {
         // M = D * Rm with Rm real: out = D (Rm v_re + i Rm v_im), 4 DMMAs per 8 vectors and one complex multiply
-        // per result (row lane>>2 of the C fragment)
+        // per result (row lane>>2 of the C fragment).  A fragments: QGT_MIDX(8, q, k) == lane, packed doubles
+        cplx m0, m1;
+        m0.x = reinterpret_cast<const double*>(M)[lane]; m1.x = reinterpret_cast<const double*>(M)[32 + lane];
         const cplx d = M[N * N + (lane >> 2)];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -138,6 +139,7 @@ __device__ __forceinline__ void qgt_warp_subpass_fast(const QgtFastSub& f, const
         }
         return;
     }
+    const cplx m0 = M[lane], m1 = M[32 + lane];           // A fragments: QGT_MIDX(8, q, k) == lane
     const double nm0y = -m0.y, nm1y = -m1.y;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {     // two groups of 8 vectors at a time: operand loads first, then the DMMAs
@@ -225,9 +227,15 @@ __device__ __forceinline__ void qgt_warp_subpass_mma(const QgtDevRun& run, const
         const int off = ovr ? cx.ovr_mat_off : st.mat_off;
         const bool diag_real = (ovr ? cx.ovr_form : (int)st.form) == QGT_FORM_DIAG_REAL;
         const cplx* M = cx.pool + off + qgt_variant_index(st, gwarp) * QGT_VARIANT_STRIDE(N);
-        const cplx m0 = M[QGT_MIDX(N, q, k)], m1 = M[QGT_MIDX(N, q, 4 + k)];
-        cplx dq; dq.x = 1.0; dq.y = 0.0;
-        if (diag_real) dq = M[N * N + q];                 // M = D * Rm (imaginary parts stored as 0): scale row q afterwards
+        cplx m0, m1, dq;
+        dq.x = 1.0; dq.y = 0.0;
+        if (diag_real) {                                  // M = D * Rm: real fragments (packed doubles), row q scaled afterwards
+            m0.x = reinterpret_cast<const double*>(M)[QGT_MIDX(N, q, k)]; m1.x = reinterpret_cast<const double*>(M)[QGT_MIDX(N, q, 4 + k)];
+            m0.y = 0.0; m1.y = 0.0;
+            dq = M[N * N + q];
+        } else {
+            m0 = M[QGT_MIDX(N, q, k)]; m1 = M[QGT_MIDX(N, q, 4 + k)];
+        }
         const double nm0y = -m0.y, nm1y = -m1.y;
         const bool last = (s == sp.stage_end - 1);
 #pragma unroll

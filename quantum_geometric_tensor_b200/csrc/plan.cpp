@@ -195,7 +195,9 @@ Dag build_dag(const std::vector<LoweredOp>& ops, int n) {
 //    path loads with lanes spanning {thread bit 0, matrix bits 0,1} and stores with lanes spanning
 //    {matrix bit 0, thread bits 1,2}; the register path spans thread bits 0..2.  Pick thread bits 0..2
 //    so those triples have distinct residues where possible (conflict-free quarter-warps).
-bool make_tperm(int K, const std::vector<int>& reg_local, const std::vector<int>& batch_local,
+//  * the order of the matrix qubits is free (the host builds the matrices in whatever order is chosen), so all
+//    orders are tried together with the thread-bit choice.
+bool make_tperm(int K, std::vector<int>& reg_local, const std::vector<int>& batch_local,
                 const std::vector<int>& variant_local, std::vector<int>& tperm) {
     std::vector<char> taken(K, 0), is_var(K, 0);
     for (int r : reg_local) taken[r] = 1;
@@ -203,18 +205,23 @@ bool make_tperm(int K, const std::vector<int>& reg_local, const std::vector<int>
     for (int v : variant_local) if (!taken[v]) is_var[v] = 1;
     std::vector<int> freep, varp;
     for (int p = 0; p < K; p++) if (!taken[p]) (is_var[p] ? varp : freep).push_back(p);
-    const int r0 = reg_local.size() > 0 ? reg_local[0] % 3 : -1, r1 = reg_local.size() > 1 ? reg_local[1] % 3 : -1;
     int best[3] = {-1, -1, -1}, best_score = -1;
     const int nf = (int)freep.size();
-    for (int a = 0; a < nf; a++) for (int b2 = 0; b2 < nf; b2++) for (int c = 0; c < nf; c++) {
-        if (a == b2 || a == c || b2 == c) continue;
-        const int pa = freep[a] % 3, pb = freep[b2] % 3, pc = freep[c] % 3;
-        int score = 0;
-        if (pa != r0 && pa != r1 && r0 != r1) score += 4;          // tensor-path loads
-        if (pb != r0 && pc != r0 && pb != pc) score += 4;          // tensor-path stores
-        if (pa != pb && pa != pc && pb != pc) score += 2;          // register path
-        if (score > best_score) { best_score = score; best[0] = a; best[1] = b2; best[2] = c; }
-    }
+    std::vector<int> order = reg_local, best_order = reg_local;
+    std::sort(order.begin(), order.end());
+    do {
+        const int r0 = order.size() > 0 ? order[0] % 3 : -1, r1 = order.size() > 1 ? order[1] % 3 : -1;
+        for (int a = 0; a < nf; a++) for (int b2 = 0; b2 < nf; b2++) for (int c = 0; c < nf; c++) {
+            if (a == b2 || a == c || b2 == c) continue;
+            const int pa = freep[a] % 3, pb = freep[b2] % 3, pc = freep[c] % 3;
+            int score = 0;
+            if (pa != r0 && pa != r1 && r0 != r1) score += 4;          // tensor-path loads
+            if (pb != r0 && pc != r0 && pb != pc) score += 4;          // tensor-path stores
+            if (pa != pb && pa != pc && pb != pc) score += 2;          // register path
+            if (score > best_score) { best_score = score; best[0] = a; best[1] = b2; best[2] = c; best_order = order; }
+        }
+    } while (order.size() == 3 && std::next_permutation(order.begin(), order.end()));
+    if (best_score >= 0) reg_local = best_order;
     tperm.clear();
     if (best_score >= 0) {
         for (int k = 0; k < 3; k++) tperm.push_back(freep[best[k]]);
@@ -375,7 +382,7 @@ static int pack_stage(int N, int nvariants, const std::vector<double>& dense, st
         const double* M = &dense[(size_t)p * N * N * 2];
         for (int i = 0; i < N; i++) {
             for (int j = 0; j < N; j++) {
-                if (diag_real) dst[2 * QGT_MIDX(N, i, j)] = rm[((size_t)p * N + i) * N + j];
+                if (diag_real) dst[QGT_MIDX(N, i, j)] = rm[((size_t)p * N + i) * N + j];
                 else { dst[2 * QGT_MIDX(N, i, j)] = M[2 * (i * N + j)]; dst[2 * QGT_MIDX(N, i, j) + 1] = M[2 * (i * N + j) + 1]; }
             }
             if (diag_real) { dst[2 * (N * N + i)] = d[((size_t)p * N + i) * 2]; dst[2 * (N * N + i) + 1] = d[((size_t)p * N + i) * 2 + 1]; }

@@ -230,7 +230,9 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
                 for (int h = 0; h < NB; ++h) { xr[h] = 0.0; xi[h] = 0.0; }
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    const cplx m = M[0][QGT_MIDX(N, i, j)];
+                    cplx m;
+                    if (diag_real) { m.x = reinterpret_cast<const double*>(M[0])[QGT_MIDX(N, i, j)]; m.y = 0.0; }
+                    else m = M[0][QGT_MIDX(N, i, j)];
 #pragma unroll
                     for (int h = 0; h < NB; ++h) {
                         xr[h] = qgt_fma(m.x, v[h][j].x, xr[h]); xr[h] = qgt_fma(-m.y, v[h][j].y, xr[h]);
@@ -253,7 +255,9 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
                     double xr = 0.0, xi = 0.0;
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
-                        const cplx m = M[h][QGT_MIDX(N, i, j)];
+                        cplx m;
+                        if (diag_real) { m.x = reinterpret_cast<const double*>(M[h])[QGT_MIDX(N, i, j)]; m.y = 0.0; }
+                        else m = M[h][QGT_MIDX(N, i, j)];
                         xr = qgt_fma(m.x, v[h][j].x, xr); xr = qgt_fma(-m.y, v[h][j].y, xr);
                         xi = qgt_fma(m.x, v[h][j].y, xi); xi = qgt_fma(m.y, v[h][j].x, xi);
                     }
