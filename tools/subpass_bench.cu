@@ -163,19 +163,6 @@ __global__ void __launch_bounds__(256, 4) k(int iters, const cplx* mats, double*
                 cplx o0, o1; o0.x = cr[g][0]; o0.y = ci[g][0]; o1.x = cr[g][1]; o1.y = ci[g][1];
                 tile[baseC ^ gx] = o0; tile[baseC ^ gx ^ st0] = o1;
             }
-        } else if (V == 4) {             // DMMAs only (operands stay in registers): the pipe's own ceiling in this shape
-            double cr[2][2] = {{0, 0}, {0, 0}}, ci[2][2] = {{0, 0}, {0, 0}};
-            const cplx v0 = tile[baseB], v1 = tile[baseB ^ sr2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    dmma(cr[g][0], cr[g][1], m0.x, v0.x); dmma(ci[g][0], ci[g][1], m0.x, v0.y);
-                    dmma(cr[g][0], cr[g][1], m1.x, v1.x); dmma(ci[g][0], ci[g][1], m1.x, v1.y);
-                    dmma(cr[g][0], cr[g][1], nm0y, v0.y); dmma(ci[g][0], ci[g][1], m0.y, v0.x);
-                    dmma(cr[g][0], cr[g][1], nm1y, v1.y); dmma(ci[g][0], ci[g][1], m1.y, v1.x);
-                }
-            if (cr[0][0] + cr[1][1] + ci[0][1] + ci[1][0] == 1.2345) tile[baseC] = v0;
         }
         __syncthreads();
     }
@@ -211,7 +198,6 @@ int main() {
     run<1>("A-major, 2 groups", p.multiProcessorCount, mats, sink);
     run<2>("chain-major", p.multiProcessorCount, mats, sink);
     run<3>("A-major, 4 groups", p.multiProcessorCount, mats, sink);
-    run<4>("DMMA only", p.multiProcessorCount, mats, sink);
     run<5>("table-driven like the sweep kernel", p.multiProcessorCount, mats, sink);
     return 0;
 }
