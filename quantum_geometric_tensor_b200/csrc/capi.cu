@@ -361,7 +361,7 @@ static int do_sweep(qgt_b200_ctx* c, const CircuitPlan& plan, int run, const Qgt
     int has_cost = 0;
     for (const SubPass& sp : plan.runs[run].subs) {
         if (sp.is_cost) has_cost = 1;
-        if (sp.is_cost || !sp.mma_ok) a.mma_only = 0;
+        if (!sp.is_cost && !sp.mma_ok) a.mma_only = 0;     // cost passes have their own code in the tensor-only kernel
     }
     a.gprefix = (uint64_t)c->rank << plan.nloc;
     a.ct = c->seg_cost.empty() ? c->cost : c->seg_cost[plan.runs[run].segment];
@@ -378,7 +378,7 @@ static int do_sweep(qgt_b200_ctx* c, const CircuitPlan& plan, int run, const Qgt
                  (int)plan.runs[run].subs.size(), nst, (int)plan.runs[run].ops.size(), (unsigned long long)shard_tiles, mat_count);
     }
     c->timer.begin(c->stream, 0, label);
-    cudaError_t e = launch_sweep(a, K, R, plan.B, mat_count, (int)plan.runs[run].subs.size(), a.mma_only ? 0 : has_cost, c->num_sms, c->stream);
+    cudaError_t e = launch_sweep(a, K, R, plan.B, mat_count, (int)plan.runs[run].subs.size(), has_cost, c->num_sms, c->stream);
     c->timer.end(c->stream);
     if (e != cudaSuccess) return cuda_fail(e, "sweep launch");
     c->stats.sweep_launches++;

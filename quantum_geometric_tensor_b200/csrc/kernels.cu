@@ -283,10 +283,11 @@ __device__ __forceinline__ void qgt_warp_subpass_mma(const QgtDevRun& run, const
 // Shared memory: [tile: 2^K amplitudes][matrix pool of the run][override matrices of the current item].
 // The kernel is persistent over (tile, column) work items; the run header and its matrix pool are staged
 // once per CTA.  R = qubits of a stage matrix, B = batch qubits: a thread owns 2^(R+B) amplitudes.
+// COST (with MMA_ONLY): the run also holds cost-layer passes; their energy tables sit behind the lookup tables.
 // MMA_ONLY: every sub-pass of the run takes the tensor-pipe path (no cost pass, warp-uniform variants): the
 // register-FMA code is not instantiated, which halves the register count and doubles the resident warps.
 // DB: two tile buffers with cp.async prefetch of the next work item.
-template <int R, int B, bool MMA_ONLY, bool DB, int MAXT, int MINB>
+template <int R, int B, bool MMA_ONLY, bool DB, int MAXT, int MINB, bool COST = false>
 __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
     constexpr int N = 1 << R;
     constexpr int OVR_ELEMS = QGT_VARIANT_STRIDE(N) << QGT_MAX_VARIANT_BITS;
@@ -302,17 +303,19 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
     cplx* spool = tile + ((size_t)(DB ? 2 : 1) << run.K);
     cplx* sovr = spool + run.mat_count;
     QgtDevSubPass* subs = reinterpret_cast<QgtDevSubPass*>(sovr + OVR_ELEMS);
-    QgtFastSub* fast = reinterpret_cast<QgtFastSub*>(subs + run.nsub);          // tensor-only kernel
+    // [sub-pass descriptors][cost tables (runs with a cost pass)][lookup tables of the tensor-only kernel]
+    QgtCostSmem cost_sm = qgt_cost_smem_carve(reinterpret_cast<double*>(subs + run.nsub), run.K, a.ct.num_edges);
+    QgtFastSub* fast = reinterpret_cast<QgtFastSub*>(reinterpret_cast<double*>(subs + run.nsub) +
+                                                     ((!MMA_ONLY || COST) && run.has_cost ? qgt_cost_smem_doubles(run.K, a.ct.num_edges) : 0));
     QgtFastWarp* fwarp = reinterpret_cast<QgtFastWarp*>(fast + run.nsub);
     uint32_t* flane = reinterpret_cast<uint32_t*>(fwarp + 8 * run.nsub);
-    QgtCostSmem cost_sm = qgt_cost_smem_carve(reinterpret_cast<double*>(subs + run.nsub), run.K, a.ct.num_edges);
     {
         const cplx* gpool = a.pool + run.mat_off;
         for (int i = tid; i < run.mat_count; i += T) spool[i] = gpool[i];
         const uint32_t* gs = reinterpret_cast<const uint32_t*>(a.subs + run.sub_off);
         uint32_t* ss = reinterpret_cast<uint32_t*>(subs);
         for (int i = tid; i < run.nsub * (int)(sizeof(QgtDevSubPass) / 4); i += T) ss[i] = gs[i];
-        if (!MMA_ONLY && run.has_cost) qgt_cost_build_ein(run, a.ct, cost_sm, tid, T);
+        if ((!MMA_ONLY || COST) && run.has_cost) qgt_cost_build_ein(run, a.ct, cost_sm, tid, T);
     }
     if (MMA_ONLY) {
         __syncthreads();
@@ -377,7 +380,14 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
         }
         __syncthreads();
         for (int s = 0; s < (QGT_DBG(4) ? 0 : run.nsub); ++s) {
-            if (MMA_ONLY) {
+            if (MMA_ONLY && COST && subs[s].nreg == 0) {
+                const QgtDevCost& co = (it.ovr_kind == 3 && subs[s].cost == it.ovr_index) ? it.ovr_cost : a.costs[run.cost_off + subs[s].cost];
+                for (int t2 = tid; t2 <= run.K; t2 += T) qgt_cost_tile_lin(run, a.ct, cost_sm, tileg, t2);
+                __syncthreads();
+                qgt_cost_tile_tables(run, cost_sm, tid, T);
+                __syncthreads();
+                qgt_phase_cost(run, co, cur, cost_sm, tid, T);
+            } else if (MMA_ONLY) {
                 if (fast[s].simple)
                     qgt_warp_subpass_fast(fast[s], fwarp[s * 8 + (tid >> 5)], flane[s * 32 + (tid & 31)], cx, cur, tileg, tid & 31);
                 else
@@ -404,9 +414,9 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
     cp_async_wait<0>();
 }
 
-template <int R, int B, bool MMA_ONLY, bool DB, int MAXT, int MINB>
+template <int R, int B, bool MMA_ONLY, bool DB, int MAXT, int MINB, bool COST = false>
 static cudaError_t launch_sweep_cfg(const SweepLaunch& a_in, int T, size_t smem, int num_sms, cudaStream_t st) {
-    auto kern = qgt_sweep_kernel<R, B, MMA_ONLY, DB, MAXT, MINB>;
+    auto kern = qgt_sweep_kernel<R, B, MMA_ONLY, DB, MAXT, MINB, COST>;
     static int ctas_per_sm = 0;
     static size_t smem_seen = 0;
     if (!ctas_per_sm || smem != smem_seen) {
@@ -448,6 +458,7 @@ static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, i
     if (R == 3 && B == 0 && a.mma_only && T >= 32) {
         const size_t fixed = fixed0 + (size_t)nsub * QGT_FAST_BYTES_PER_SUB;
         // single tile buffer: more resident CTAs hide the load latency instead of a second buffer
+        if (has_cost) return launch_sweep_cfg<3, 0, true, false, 256, 3, true>(a, T, fixed + tile_bytes, num_sms, st);
         if (a.double_buffer) return launch_sweep_cfg<3, 0, true, true, 256, 3>(a, T, fixed + 2 * tile_bytes, num_sms, st);
         return launch_sweep_cfg<3, 0, true, false, 256, 4>(a, T, fixed + tile_bytes, num_sms, st);
     }
