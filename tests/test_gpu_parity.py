@@ -152,6 +152,35 @@ def test_qgt_qaoa_matches_oracle(ctx, oracle):
     assert rel_err(ctx.qgt(c, th), oracle.qgt(c, th)) < TOL
 
 
+@pytest.mark.parametrize("n,p,weights", [(12, 2, True), (14, 1, False), (13 + 1, 2, True)])
+def test_qgt_qaoa_multi_tile(ctx, oracle, n, p, weights):
+    # more qubits than a tile holds: cross-tile edges, per-tile energy tables, cost passes on the tensor-only kernel
+    c = K.qaoa_maxcut(n, p)
+    if weights:
+        c.vertex_weights = list(np.linspace(-0.3, 0.7, n))
+        c.edges = [(i, j, 0.5 + 0.25 * ((i + j) % 3)) for (i, j, *_) in c.edges]
+    th = K.default_angles(c.num_params, n)
+    assert rel_err(ctx.qgt(c, th), oracle.qgt(c, th)) < TOL
+    st = ctx.state(n).init(1).apply(c, th)
+    assert np.abs(st.download() - oracle.apply(c, th, oracle.init_state(n, 1))).max() < 1e-13
+    st.close()
+
+
+def test_stage_forms_both_paths(ctx, oracle):
+    # one-layer stages factor as (diagonal) x (real) and take the 4-DMMA path, two fused layers are dense:
+    # both must agree with the oracle, with and without the tensor pipe
+    for layers in (1, 2, 3):
+        c = K.hea_layers(12, layers)
+        th = K.default_angles(c.num_params, layers)
+        ref = oracle.qgt(c, th)
+        for use_mma in (1, 0):
+            ctx.set_option("use_mma", use_mma)
+            try:
+                assert rel_err(ctx.qgt(c, th), ref) < TOL
+            finally:
+                ctx.set_option("use_mma", 1)
+
+
 @pytest.mark.parametrize("slots", [5, 6, 9, 17])
 def test_qgt_blocked_equals_resident(ctx, oracle, slots):
     # force the column-block schedule (what n >= 26 uses) on a size the oracle can check
@@ -195,7 +224,9 @@ def test_derivative_columns_match_oracle(ctx, oracle):
         assert np.abs(ctx.derivative(c, th, mu) - oracle.derivative(c, th, mu)).max() < 1e-13
 
 
-@pytest.mark.parametrize("P,dim", [(1, 64), (5, 1 << 10), (33, 1 << 12), (70, 1 << 11), (130, 1 << 9)])
+# P = 32, 64, 96: the projection column is contracted as the strip of the diagonal tiles; 31 / 33: ragged last tile
+@pytest.mark.parametrize("P,dim", [(1, 64), (5, 1 << 10), (31, 1 << 10), (32, 1 << 11), (33, 1 << 12), (64, 1 << 10), (70, 1 << 11),
+                                   (96, 1 << 12), (130, 1 << 9)])
 def test_gram_entry_point_matches_oracle(ctx, oracle, P, dim):
     rng = np.random.default_rng(P)
     psi = rng.normal(size=dim) + 1j * rng.normal(size=dim)

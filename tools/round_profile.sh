@@ -16,6 +16,8 @@ QGT_B200_TRACE=1 python tools/trace_run.py c2 > $O/${R}_stats_c2.txt 2> $O/${R}_
 grep "cat=" $O/${R}_trace_c2_all.txt | tail -15 > $O/${R}_trace_c2_launches.txt; rm -f $O/${R}_trace_c2_all.txt
 # launch list of one bench step (cold-cache, serialised: compare shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_launches_c2.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/${R}_ncu_launches.log 2>&1
+# DRAM bytes per sweep / Gram launch (source of roofline.traffic; tools/make_traffic.py turns it into profiles/traffic.json)
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --kernel-name regex:"qgt_(sweep|gram)_kernel" -c 52 --csv --log-file $O/${R}_dram_c2.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${R}_ncu_dram.log 2>&1
 # full captures: one dense-stage sweep launch (run 1), one diagonal-real sweep launch (run 5), the Gram
 ncu --set full --import-source on --clock-control none --kernel-name regex:qgt_sweep_kernel --launch-skip 14 --launch-count 1 -o $O/${R}_sweep_run1 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${R}_ncu_a.log 2>&1
 ncu --set full --import-source on --clock-control none --kernel-name regex:qgt_sweep_kernel --launch-skip 22 --launch-count 1 -o $O/${R}_sweep_run5 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${R}_ncu_b.log 2>&1
