@@ -188,6 +188,7 @@ int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
     else if (k == "debug_skip") c->debug_skip = (int)value;
     else if (k == "tiles_per_item") c->tiles_per_item = (int)value;
     else if (k == "gram_tile") set_gram_tile_override((int)value);
+    else if (k == "gram_stages") set_gram_stages((int)value);
     else if (k == "profile") c->timer.enabled = value != 0;
     else if (k == "max_slots") c->max_slots = (size_t)value;
     else return fail(QGT_B200_ERR_INVALID_ARG, "unknown option " + k);
@@ -409,15 +410,6 @@ int apply_plan_inplace(qgt_b200_ctx* c, const CircuitPlan& plan, cplx* d, uint64
     return QGT_B200_OK;
 }
 
-// split-K factor: enough CTAs for ~6 waves at 3 CTAs per SM (fine-grained work keeps the tail short and
-// evens out diagonal / padded tiles that carry fewer blocks), at least 256 amplitudes per CTA
-static int gram_ksplit(const qgt_b200_ctx* c, int tiles, uint64_t D) {
-    const uint64_t by_len = std::max<uint64_t>(1, D / 256);
-    uint64_t want = (uint64_t)std::max(1, (c->num_sms * 18 + tiles - 1) / tiles);
-    want = std::min<uint64_t>(want, by_len);
-    return (int)std::min<uint64_t>(want, 512);
-}
-
 // executes a Program on `nslots` columns of D amplitudes each living at arena + slot*D
 int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan& plan, const Program& prog,
                 cplx* arena, uint64_t D, cplx* cmat /* (P+1)^2 device */) {
@@ -481,9 +473,9 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             for (int v : in.b_ids) ids.push_back(v);
             g.symmetric = g.nb >= g.na && std::equal(in.a_slots.begin(), in.a_slots.end(), in.b_slots.begin());
             const GramShape shp = gram_shape(g.na, g.nb);
-            GramLaunch gl; gl.na = g.na; gl.nb = g.nb; gl.symmetric = g.symmetric ? 1 : 0;
+            GramLaunch gl; gl.na = g.na; gl.nb = g.nb; gl.D = D; gl.symmetric = g.symmetric ? 1 : 0;
             const size_t per_split = gram_configure(gl, shp);
-            const int ks = gram_ksplit(c, gl.mtiles * gl.ntiles, D);
+            const int ks = gram_choose_ksplit(gl, shp, c->num_sms);
             partial_bytes = std::max(partial_bytes, (size_t)ks * per_split * sizeof(cplx));
         }
     }
@@ -549,7 +541,7 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             const GramShape shp = gram_shape(g.na, g.nb);
             gl.symmetric = g.symmetric ? 1 : 0;
             gram_configure(gl, shp);
-            gl.ksplit = gram_ksplit(c, gl.mtiles * gl.ntiles, D);
+            gl.ksplit = gram_choose_ksplit(gl, shp, c->num_sms);
             gl.partial = (cplx*)c->partial.ptr;
             c->timer.begin(c->stream, 1);
             e = launch_gram(gl, shp, c->stream);
@@ -773,7 +765,7 @@ int qgt_b200_gram(qgt_b200_ctx* c, const double* psi, const double* dpsi, size_t
     gl.na = P; gl.nb = P + 1; gl.D = D;
     gl.symmetric = 1;
     const size_t per_split = gram_configure(gl, shp);
-    gl.ksplit = gram_ksplit(c, gl.mtiles * gl.ntiles, D);
+    gl.ksplit = gram_choose_ksplit(gl, shp, c->num_sms);
     if ((rc = c->partial.reserve((size_t)gl.ksplit * per_split * sizeof(cplx)))) return rc;
     gl.partial = (cplx*)c->partial.ptr;
     cudaError_t e = cudaMemcpyAsync(c->aux.ptr, ptrs.data(), ptr_bytes, cudaMemcpyHostToDevice, c->stream);

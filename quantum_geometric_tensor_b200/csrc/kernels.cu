@@ -640,6 +640,61 @@ __global__ void __launch_bounds__(WM * WN * 32, 2) qgt_gram_kernel(GramLaunch g)
         }
 }
 
+// Thin Gram: a handful of column pairs (the blocked schedule at 30 qubits contracts 5 resident with 2 streaming
+// columns at a time).  The tensor-pipe kernel would stage mostly padding and keep only a few KB per SM in
+// flight; here every thread streams amplitudes with coalesced 128-bit loads of all NA + NB columns and keeps the
+// NA x NB complex accumulators in registers, so the kernel runs at HBM speed.  Same partial layout and second
+// stage as the tensor-pipe kernel (one "k-split" per CTA).
+template <int NA, int NB>
+__global__ void __launch_bounds__(256) qgt_gram_thin_kernel(GramLaunch g) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t per = (g.D + (uint64_t)g.ksplit - 1) / (uint64_t)g.ksplit;
+    const uint64_t k0 = (uint64_t)blockIdx.x * per;
+    const uint64_t k1 = (k0 + per < g.D) ? k0 + per : g.D;
+    const cplx* ap[NA];
+    const cplx* bp[NB];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) ap[j] = j < g.na ? g.a_ptrs[j] : nullptr;
+#pragma unroll
+    for (int l = 0; l < NB; ++l) bp[l] = l < g.nb ? g.b_ptrs[l] : nullptr;
+    double cr[NA][NB], ci[NA][NB];
+#pragma unroll
+    for (int j = 0; j < NA; ++j)
+#pragma unroll
+        for (int l = 0; l < NB; ++l) { cr[j][l] = 0.0; ci[j][l] = 0.0; }
+    for (uint64_t i = k0 + (uint64_t)tid; i < k1; i += 256) {
+        cplx a[NA], b[NB];
+#pragma unroll
+        for (int j = 0; j < NA; ++j) { if (ap[j]) a[j] = ap[j][i]; else { a[j].x = 0.0; a[j].y = 0.0; } }
+#pragma unroll
+        for (int l = 0; l < NB; ++l) { if (bp[l]) b[l] = bp[l][i]; else { b[l].x = 0.0; b[l].y = 0.0; } }
+#pragma unroll
+        for (int j = 0; j < NA; ++j)
+#pragma unroll
+            for (int l = 0; l < NB; ++l) {      // conj(a) * b
+                cr[j][l] = fma(a[j].x, b[l].x, cr[j][l]); cr[j][l] = fma(a[j].y, b[l].y, cr[j][l]);
+                ci[j][l] = fma(a[j].x, b[l].y, ci[j][l]); ci[j][l] = fma(-a[j].y, b[l].x, ci[j][l]);
+            }
+    }
+    __shared__ double red[8][NA * NB * 2];
+#pragma unroll
+    for (int j = 0; j < NA; ++j)
+#pragma unroll
+        for (int l = 0; l < NB; ++l) {
+            double xr = cr[j][l], xi = ci[j][l];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { xr += __shfl_down_sync(0xffffffffu, xr, o); xi += __shfl_down_sync(0xffffffffu, xi, o); }
+            if (lane == 0) { red[warp][(j * NB + l) * 2] = xr; red[warp][(j * NB + l) * 2 + 1] = xi; }
+        }
+    __syncthreads();
+    if (tid < NA * NB) {
+        double xr = 0.0, xi = 0.0;
+        for (int w = 0; w < 8; ++w) { xr += red[w][tid * 2]; xi += red[w][tid * 2 + 1]; }      // fixed order: deterministic
+        cplx z; z.x = xr; z.y = xi;
+        g.partial[((size_t)blockIdx.x * NA + tid / NB) * NB + tid % NB] = z;
+    }
+}
+
 __global__ void qgt_gram_reduce_kernel(const cplx* partial, int ksplit, int Mpad, int Npad, int na, int nb, int nb_main, int strip_col0,
                                        const int* a_ids, const int* b_ids, cplx* C, int ldc, int symmetric) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -678,9 +733,17 @@ __global__ void qgt_finalize_kernel(const cplx* C, int P, double* metric, double
 // few-column Grams of the blocked schedule
 static int g_gram_tile_override = 0;
 void set_gram_tile_override(int t) { g_gram_tile_override = t; }
+static int g_gram_stages = 0;
+void set_gram_stages(int s) { g_gram_stages = s; }
 
 GramShape gram_shape(int na, int nb) {
     GramShape s;
+    s.thin = 0;
+    if (g_gram_tile_override == 0) {
+        const int thin_shapes[5][2] = {{8, 2}, {4, 4}, {2, 8}, {16, 1}, {1, 16}};
+        for (const auto& t : thin_shapes)
+            if (na <= t[0] && nb <= t[1]) { s.MT = t[0]; s.NT = t[1]; s.thin = 1; return s; }
+    }
     if (g_gram_tile_override == 64) { s.MT = 64; s.NT = 64; return s; }
     if (g_gram_tile_override == 32) { s.MT = 32; s.NT = 32; return s; }
     if (na <= 32 && nb <= 16) { s.MT = 32; s.NT = 16; return s; }
@@ -692,6 +755,7 @@ GramShape gram_shape(int na, int nb) {
 size_t gram_configure(GramLaunch& g, GramShape shp) {
     g.nstrip = 0;
     g.nb_main = g.nb;
+    if (shp.thin) { g.mtiles = g.ntiles = 1; g.npad = shp.NT; return (size_t)shp.MT * shp.NT; }
     const int extra = g.nb - g.na;
     if (g.symmetric && shp.MT == 32 && shp.NT == 32 && extra >= 1 && extra <= 8) { g.nstrip = extra; g.nb_main = g.na; }
     g.mtiles = (g.na + shp.MT - 1) / shp.MT;
@@ -717,11 +781,79 @@ static cudaError_t launch_gram_t(const GramLaunch& g, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+template <int WM, int WN, int BM, int BN, int KC, int STAGES>
+static int gram_occupancy_t() {
+    constexpr int MT = WM * BM * 8, NT = WN * BN * 8;
+    constexpr bool STRIP = (WM == 2 && WN == 4 && BM == 2 && BN == 1);
+    constexpr size_t smem = (size_t)STAGES * (MT + NT + (STRIP ? 8 : 0)) * (KC + 4) * sizeof(cplx);
+    static int occ = 0;
+    if (!occ) {
+        auto kern = qgt_gram_kernel<WM, WN, BM, BN, KC, STAGES>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, WM * WN * 32, smem) != cudaSuccess || o < 1) o = 1;
+        occ = o;
+    }
+    return occ;
+}
+
+// Split-K factor.  The CTAs that do work (tiles on or above the diagonal of a symmetric launch) times the split
+// should fill a whole number of waves of resident CTAs: ~18 CTAs per SM in total when there is enough work
+// (fine-grained work evens out diagonal / padded tiles), at most 512 splits, at least 256 amplitudes per CTA.  A
+// one-tile streaming Gram with 512 splits on 444 resident CTAs ran 1.15 waves in the time of 2.
+int gram_choose_ksplit(const GramLaunch& g, GramShape shp, int num_sms) {
+    int occ;
+    if (shp.thin) {
+        static int thin_occ[5] = {0, 0, 0, 0, 0};
+        const int which = shp.MT == 8 ? 0 : shp.MT == 4 ? 1 : shp.MT == 2 ? 2 : shp.MT == 16 ? 3 : 4;
+        if (!thin_occ[which]) {
+            int o = 0;
+            cudaError_t e = which == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, qgt_gram_thin_kernel<8, 2>, 256, 0)
+                          : which == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, qgt_gram_thin_kernel<4, 4>, 256, 0)
+                          : which == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, qgt_gram_thin_kernel<2, 8>, 256, 0)
+                          : which == 3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, qgt_gram_thin_kernel<16, 1>, 256, 0)
+                                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, qgt_gram_thin_kernel<1, 16>, 256, 0);
+            thin_occ[which] = (e == cudaSuccess && o > 0) ? o : 1;
+        }
+        occ = thin_occ[which];
+    }
+    else if (shp.MT == 64) occ = gram_occupancy_t<2, 4, 4, 2, 8, 4>();
+    else if (shp.NT == 32) occ = gram_occupancy_t<2, 4, 2, 1, 16, 3>();
+    else occ = gram_occupancy_t<4, 2, 1, 1, 16, 4>();
+    int active = 0;
+    for (int mt = 0; mt < g.mtiles; ++mt)
+        for (int nt = 0; nt < g.ntiles; ++nt)
+            if (!(g.symmetric && (nt + 1) * shp.NT <= mt * shp.MT)) active++;
+    if (active < 1) active = 1;
+    const uint64_t slots = (uint64_t)num_sms * occ;
+    const uint64_t by_len = g.D / 256 > 1 ? g.D / 256 : 1;
+    const uint64_t cap = shp.thin ? 1024 : 512;
+    int waves = shp.thin ? 1 : (18 + occ - 1) / occ;      // thin: pure streaming, one balanced wave
+    uint64_t ks = 1;
+    for (; waves >= 1; --waves) {
+        ks = (uint64_t)waves * slots / (uint64_t)active;
+        if (ks <= cap) break;
+    }
+    if (ks > cap) ks = cap;
+    if (ks > by_len) ks = by_len;
+    return (int)(ks < 1 ? 1 : ks);
+}
+
 cudaError_t launch_gram(const GramLaunch& g, GramShape shp, cudaStream_t st) {
     if (g.mtiles * g.ntiles * g.ksplit == 0) return cudaSuccess;
+    if (shp.thin) {
+        if (shp.MT == 8) qgt_gram_thin_kernel<8, 2><<<g.ksplit, 256, 0, st>>>(g);
+        else if (shp.MT == 4) qgt_gram_thin_kernel<4, 4><<<g.ksplit, 256, 0, st>>>(g);
+        else if (shp.MT == 2) qgt_gram_thin_kernel<2, 8><<<g.ksplit, 256, 0, st>>>(g);
+        else if (shp.MT == 16) qgt_gram_thin_kernel<16, 1><<<g.ksplit, 256, 0, st>>>(g);
+        else qgt_gram_thin_kernel<1, 16><<<g.ksplit, 256, 0, st>>>(g);
+        return cudaGetLastError();
+    }
     if (shp.MT == 64) return launch_gram_t<2, 4, 4, 2, 8, 4>(g, st);
-    if (shp.NT == 32) return launch_gram_t<2, 4, 2, 1, 16, 3>(g, st);
-    return launch_gram_t<4, 2, 1, 1, 16, 4>(g, st);
+    if (shp.NT == 32) return g_gram_stages == 4 ? launch_gram_t<2, 4, 2, 1, 16, 4>(g, st) : launch_gram_t<2, 4, 2, 1, 16, 3>(g, st);
+    if (g_gram_stages == 32) return launch_gram_t<4, 2, 1, 1, 32, 3>(g, st);
+    if (g_gram_stages == 33) return launch_gram_t<4, 2, 1, 1, 32, 4>(g, st);
+    return g_gram_stages == 6 ? launch_gram_t<4, 2, 1, 1, 16, 6>(g, st) : launch_gram_t<4, 2, 1, 1, 16, 4>(g, st);
 }
 
 cudaError_t launch_gram_reduce(const GramLaunch& g, GramShape shp, const int* a_ids, const int* b_ids,

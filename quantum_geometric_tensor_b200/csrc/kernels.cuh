@@ -43,7 +43,7 @@ struct GramLaunch {
     cplx* partial;               // [ksplit][mtiles*MT][npad]
 };
 
-struct GramShape { int MT, NT; };
+struct GramShape { int MT, NT; int thin; };   // thin: few pairs, register accumulators, HBM-bound (MT x NT = operand slots)
 
 // K, R: tile / register qubits of the run; grid is chosen inside
 cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int has_cost, int num_sms, cudaStream_t st);
@@ -51,7 +51,10 @@ cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_coun
 GramShape gram_shape(int na, int nb);
 // fills mtiles / ntiles / nb_main / nstrip / npad from na, nb, symmetric; returns the partial elements per k-split
 size_t gram_configure(GramLaunch& g, GramShape shp);
-void set_gram_tile_override(int t);   // tuning: 0 = automatic, 32 or 64 = force that square tile
+// split-K factor of a configured launch (needs na, nb, D, symmetric and the fields gram_configure fills)
+int gram_choose_ksplit(const GramLaunch& g, GramShape shp, int num_sms);
+void set_gram_tile_override(int t);
+void set_gram_stages(int s);            // tuning: cp.async ring depth override (0 = default)   // tuning: 0 = automatic, 32 or 64 = force that square tile
 cudaError_t launch_gram(const GramLaunch& g, GramShape shp, cudaStream_t st);
 // C[(a_ids[i]), (b_ids[j])] = sum_ks partial ; mirrored conj ; ldc = leading dimension of C
 cudaError_t launch_gram_reduce(const GramLaunch& g, GramShape shp, const int* a_ids, const int* b_ids,
