@@ -116,6 +116,33 @@ int         qgt_b200_device_count(void);                 /* 0 when no usable sm_
 const char* qgt_b200_last_error(void);                   /* thread-local message */
 const char* qgt_b200_error_string(int status);
 
+/* Raw device memory / streams: what the reference's device-memory seam binds (qg_gpu_allocate, gpu_malloc, ...
+ * include/quantum_geometric/core/quantum_geometric_gpu.h:139-276, src/quantum_geometric/core/quantum_geometric_gpu.c).
+ * Device allocations never fall back to host memory: without an sm_100 device every call returns
+ * QGT_B200_ERR_NO_DEVICE. */
+typedef struct qgt_b200_device_info {
+    int    device;                     /* CUDA ordinal */
+    char   name[256];
+    size_t total_memory, free_memory;  /* bytes */
+    int    cc_major, cc_minor;
+    int    num_sms;
+    int    max_threads_per_block;
+    int    max_block_dim[3], max_grid_dim[3];
+    int    unified_addressing;
+} qgt_b200_device_info;
+int qgt_b200_device_info_get(int device, qgt_b200_device_info* out);
+int qgt_b200_set_device(int device);                                   /* for the raw-memory calls of this thread */
+int qgt_b200_mem_alloc(void** ptr, size_t bytes);                      /* device memory */
+int qgt_b200_mem_free(void* ptr);
+int qgt_b200_mem_alloc_pinned(void** ptr, size_t bytes);               /* page-locked host memory */
+int qgt_b200_mem_free_pinned(void* ptr);
+int qgt_b200_memcpy_h2d(void* dst, const void* src, size_t bytes);
+int qgt_b200_memcpy_d2h(void* dst, const void* src, size_t bytes);
+int qgt_b200_stream_create(void** stream);                             /* a cudaStream_t behind void* */
+int qgt_b200_stream_destroy(void* stream);
+int qgt_b200_stream_synchronize(void* stream);
+int qgt_b200_device_synchronize(void);
+
 int  qgt_b200_create(qgt_b200_ctx** out, int device);    /* device = CUDA ordinal */
 void qgt_b200_destroy(qgt_b200_ctx* ctx);
 /* workspace cap in bytes for derivative columns (0 = 85 % of free HBM at first use) */

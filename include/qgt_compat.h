@@ -256,6 +256,61 @@ natural_gradient_config_t get_default_natural_gradient_config(void);
 bool compute_regularized_natural_gradient(const ComplexFloat* gradient, const ComplexFloat* metric, ComplexFloat* natural_gradient,
                                           size_t dimension, const natural_gradient_config_t* config);
 
+/* ---- core/quantum_geometric_gpu.h:28-276: the device-memory seam ------------------------------------------- */
+#define MAX_GPU_NAME_LENGTH 256
+typedef enum {
+    QG_GPU_SUCCESS = 0, QG_GPU_ERROR_NO_DEVICE = -1, QG_GPU_ERROR_NOT_INITIALIZED = -2, QG_GPU_ERROR_OUT_OF_MEMORY = -3,
+    QG_GPU_ERROR_INVALID_DEVICE = -4, QG_GPU_ERROR_INVALID_VALUE = -5, QG_GPU_ERROR_LAUNCH_FAILED = -6,
+    QG_GPU_ERROR_SYNC_FAILED = -7, QG_GPU_ERROR_INTERNAL = -8
+} gpu_error_t;
+#define QGT_ERROR_GPU_NOT_AVAILABLE 300
+#define QGT_ERROR_GPU_OUT_OF_MEMORY 301
+#define QGT_ERROR_GPU_INVALID_VALUE 302
+#define QGT_ERROR_GPU_LAUNCH_FAILED 303
+#define QGT_ERROR_GPU_SYNC_FAILED 304
+#define QGT_ERROR_GPU_INTERNAL 305
+typedef struct {
+    void* device_ptr;       /* device memory (page-locked host memory when is_pinned) */
+    size_t size;
+    bool is_pinned;
+} gpu_buffer_t;
+typedef struct {
+    int device_id;
+    char name[MAX_GPU_NAME_LENGTH];
+    size_t total_memory;
+    size_t free_memory;
+    int compute_capability_major;
+    int compute_capability_minor;
+    int max_threads_per_block;
+    int max_block_dimensions[3];
+    int max_grid_dimensions[3];
+    int compute_units;
+    int backend_type;
+    bool supports_unified_memory;
+} gpu_device_info_t;
+/* device memory only: no host-malloc fallback (the reference falls back when built without a GPU back-end) */
+qgt_error_t gpu_malloc(void** ptr, size_t size);
+qgt_error_t qgt_gpu_free_buffer(void* ptr);
+qgt_error_t gpu_memcpy_host_to_device(void* dst, const void* src, size_t size);
+qgt_error_t gpu_memcpy_device_to_host(void* dst, const void* src, size_t size);
+int qg_gpu_init(void);                          /* QG_GPU_ERROR_NO_DEVICE without an sm_100 device */
+void qg_gpu_cleanup(void);
+void qg_gpu_shutdown(void);
+int qg_gpu_get_device_count(int* count);
+int qg_gpu_get_device_info(int device_id, gpu_device_info_t* info);
+int qg_gpu_set_device(int device_id);
+gpu_error_t qg_gpu_get_last_error(void);
+const char* qg_gpu_get_error_string(gpu_error_t error);
+int qg_gpu_allocate(gpu_buffer_t* buffer, size_t size);
+int qg_gpu_allocate_pinned(gpu_buffer_t* buffer, size_t size);
+int qg_gpu_free(gpu_buffer_t* buffer);
+int qg_gpu_memcpy_to_device(gpu_buffer_t* dst, const void* src, size_t size);
+int qg_gpu_memcpy_to_host(void* dst, const gpu_buffer_t* src, size_t size);
+int qg_gpu_create_stream(int* stream_id);
+int qg_gpu_destroy_stream(int stream_id);
+int qg_gpu_synchronize_stream(int stream_id);
+int qg_gpu_synchronize(void);
+
 /* ---- this layer -------------------------------------------------------------------------------------------- */
 /* CUDA ordinal used by the wrappers (default: $QGT_B200_DEVICE or 0); call before the first compute call */
 int qgt_compat_set_device(int device);

@@ -106,6 +106,117 @@ int qgt_b200_device_count(void) {
 
 const char* qgt_b200_last_error(void) { return g_last_error.c_str(); }
 
+// ---- raw device memory / streams (the reference's qg_gpu_* seam) -----------------------------------------------
+static int raw_need_device(const char* what) {
+    if (qgt_b200_device_count() <= 0) return fail(QGT_B200_ERR_NO_DEVICE, std::string(what) + ": no sm_100 device (there is no host fallback)");
+    return QGT_B200_OK;
+}
+
+int qgt_b200_device_info_get(int device, qgt_b200_device_info* out) {
+    if (!out) return fail(QGT_B200_ERR_INVALID_ARG, "device_info: out is NULL");
+    int rc = raw_need_device("device_info");
+    if (rc) return rc;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { cudaGetLastError(); return fail(QGT_B200_ERR_INVALID_ARG, "device_info: bad device ordinal"); }
+    std::memset(out, 0, sizeof *out);
+    out->device = device;
+    std::snprintf(out->name, sizeof out->name, "%s", p.name);
+    out->total_memory = p.totalGlobalMem;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    size_t fr = 0, tot = 0;
+    if (cudaSetDevice(device) == cudaSuccess && cudaMemGetInfo(&fr, &tot) == cudaSuccess) out->free_memory = fr;
+    cudaSetDevice(cur);
+    out->cc_major = p.major; out->cc_minor = p.minor;
+    out->num_sms = p.multiProcessorCount;
+    out->max_threads_per_block = p.maxThreadsPerBlock;
+    for (int i = 0; i < 3; i++) { out->max_block_dim[i] = p.maxThreadsDim[i]; out->max_grid_dim[i] = p.maxGridSize[i]; }
+    out->unified_addressing = p.unifiedAddressing;
+    return QGT_B200_OK;
+}
+
+int qgt_b200_set_device(int device) {
+    int rc = raw_need_device("set_device");
+    if (rc) return rc;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(QGT_B200_ERR_INVALID_ARG, "set_device: bad device ordinal"); }
+    return QGT_B200_OK;
+}
+
+int qgt_b200_mem_alloc(void** ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return fail(QGT_B200_ERR_INVALID_ARG, "mem_alloc: ptr is NULL or size is 0");
+    *ptr = nullptr;
+    int rc = raw_need_device("mem_alloc");
+    if (rc) return rc;
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(QGT_B200_ERR_NO_MEMORY, "mem_alloc: out of device memory"); }
+    if (e != cudaSuccess) return cuda_fail(e, "mem_alloc");
+    return QGT_B200_OK;
+}
+
+int qgt_b200_mem_free(void* ptr) {
+    if (!ptr) return QGT_B200_OK;
+    cudaError_t e = cudaFree(ptr);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "mem_free");
+}
+
+int qgt_b200_mem_alloc_pinned(void** ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return fail(QGT_B200_ERR_INVALID_ARG, "mem_alloc_pinned: ptr is NULL or size is 0");
+    *ptr = nullptr;
+    int rc = raw_need_device("mem_alloc_pinned");
+    if (rc) return rc;
+    cudaError_t e = cudaMallocHost(ptr, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(QGT_B200_ERR_NO_MEMORY, "mem_alloc_pinned: cudaMallocHost failed"); }
+    return QGT_B200_OK;
+}
+
+int qgt_b200_mem_free_pinned(void* ptr) {
+    if (!ptr) return QGT_B200_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "mem_free_pinned");
+}
+
+int qgt_b200_memcpy_h2d(void* dst, const void* src, size_t bytes) {
+    if (!dst || !src) return fail(QGT_B200_ERR_INVALID_ARG, "memcpy_h2d: NULL pointer");
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "memcpy_h2d");
+}
+
+int qgt_b200_memcpy_d2h(void* dst, const void* src, size_t bytes) {
+    if (!dst || !src) return fail(QGT_B200_ERR_INVALID_ARG, "memcpy_d2h: NULL pointer");
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "memcpy_d2h");
+}
+
+int qgt_b200_stream_create(void** stream) {
+    if (!stream) return fail(QGT_B200_ERR_INVALID_ARG, "stream_create: stream is NULL");
+    *stream = nullptr;
+    int rc = raw_need_device("stream_create");
+    if (rc) return rc;
+    cudaStream_t s;
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return cuda_fail(e, "stream_create");
+    *stream = (void*)s;
+    return QGT_B200_OK;
+}
+
+int qgt_b200_stream_destroy(void* stream) {
+    if (!stream) return QGT_B200_OK;
+    cudaError_t e = cudaStreamDestroy((cudaStream_t)stream);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "stream_destroy");
+}
+
+int qgt_b200_stream_synchronize(void* stream) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "stream_synchronize");
+}
+
+int qgt_b200_device_synchronize(void) {
+    int rc = raw_need_device("device_synchronize");
+    if (rc) return rc;
+    cudaError_t e = cudaDeviceSynchronize();
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "device_synchronize");
+}
+
 const char* qgt_b200_error_string(int s) {
     switch (s) {
     case QGT_B200_OK: return "success";

@@ -228,6 +228,58 @@ static void test_natural_gradient(void) {
     printf("  compute_regularized_natural_gradient: ok\n");
 }
 
+/* the device-memory seam, in the style of the reference's tests/test_quantum_geometric_gpu.c */
+static void test_gpu_memory_seam(void) {
+    CHECK(qg_gpu_init() == QG_GPU_SUCCESS);
+    CHECK(qg_gpu_init() == QG_GPU_SUCCESS);                       /* idempotent */
+    int count = 0;
+    CHECK(qg_gpu_get_device_count(&count) == QG_GPU_SUCCESS && count >= 1);
+    gpu_device_info_t info;
+    CHECK(qg_gpu_get_device_info(0, &info) == QG_GPU_SUCCESS);
+    CHECK(info.compute_capability_major == 10 && info.total_memory > ((size_t)1 << 30) && info.compute_units > 0 && strlen(info.name) > 0);
+    CHECK(qg_gpu_get_device_info(count, &info) == QG_GPU_ERROR_INVALID_DEVICE);
+    CHECK(qg_gpu_get_last_error() == QG_GPU_ERROR_INVALID_DEVICE);
+    CHECK(qg_gpu_set_device(0) == QG_GPU_SUCCESS && qg_gpu_set_device(-1) == QG_GPU_ERROR_INVALID_DEVICE);
+
+    enum { N = 4096 };
+    double src[N], dst[N];
+    for (int i = 0; i < N; i++) { src[i] = 0.5 * i - 7.0; dst[i] = 0.0; }
+    gpu_buffer_t buf = {0};
+    CHECK(qg_gpu_allocate(&buf, 0) == QG_GPU_ERROR_INVALID_VALUE);
+    CHECK(qg_gpu_allocate(&buf, sizeof src) == QG_GPU_SUCCESS && buf.device_ptr && buf.size == sizeof src && !buf.is_pinned);
+    CHECK(qg_gpu_memcpy_to_device(&buf, src, sizeof src + 8) == QG_GPU_ERROR_INVALID_VALUE);   /* larger than the buffer */
+    CHECK(qg_gpu_memcpy_to_device(&buf, src, sizeof src) == QG_GPU_SUCCESS);
+    CHECK(qg_gpu_memcpy_to_host(dst, &buf, sizeof dst) == QG_GPU_SUCCESS);
+    CHECK(memcmp(src, dst, sizeof src) == 0);
+    CHECK(qg_gpu_free(&buf) == QG_GPU_SUCCESS && buf.device_ptr == NULL && buf.size == 0);
+    CHECK(qg_gpu_free(&buf) == QG_GPU_ERROR_INVALID_VALUE);
+
+    gpu_buffer_t pin = {0};
+    CHECK(qg_gpu_allocate_pinned(&pin, sizeof src) == QG_GPU_SUCCESS && pin.is_pinned);
+    CHECK(qg_gpu_memcpy_to_device(&pin, src, sizeof src) == QG_GPU_SUCCESS);
+    memset(dst, 0, sizeof dst);
+    CHECK(qg_gpu_memcpy_to_host(dst, &pin, sizeof dst) == QG_GPU_SUCCESS && memcmp(src, dst, sizeof src) == 0);
+    CHECK(qg_gpu_free(&pin) == QG_GPU_SUCCESS);
+
+    void* raw = NULL;
+    CHECK(gpu_malloc(&raw, sizeof src) == QGT_SUCCESS && raw);
+    CHECK(gpu_malloc(NULL, 16) == QGT_ERROR_INVALID_PARAMETER);
+    CHECK(gpu_memcpy_host_to_device(raw, src, sizeof src) == QGT_SUCCESS);
+    memset(dst, 0, sizeof dst);
+    CHECK(gpu_memcpy_device_to_host(dst, raw, sizeof dst) == QGT_SUCCESS && memcmp(src, dst, sizeof src) == 0);
+    CHECK(qgt_gpu_free_buffer(raw) == QGT_SUCCESS);
+
+    int s0 = -1, s1 = -1;
+    CHECK(qg_gpu_create_stream(&s0) == QG_GPU_SUCCESS && s0 >= 0);
+    CHECK(qg_gpu_create_stream(&s1) == QG_GPU_SUCCESS && s1 >= 0 && s1 != s0);
+    CHECK(qg_gpu_synchronize_stream(s0) == QG_GPU_SUCCESS && qg_gpu_synchronize() == QG_GPU_SUCCESS);
+    CHECK(qg_gpu_destroy_stream(s0) == QG_GPU_SUCCESS && qg_gpu_destroy_stream(s0) == QG_GPU_ERROR_INVALID_VALUE);
+    CHECK(strcmp(qg_gpu_get_error_string(QG_GPU_ERROR_NO_DEVICE), "No GPU device available") == 0);
+    qg_gpu_cleanup();                                              /* destroys the stream still registered */
+    CHECK(qg_gpu_get_device_count(&count) == QG_GPU_ERROR_NOT_INITIALIZED);
+    printf("  qg_gpu_* / gpu_malloc device-memory seam: ok\n");
+}
+
 int main(int argc, char** argv) {
     const int host_only = argc > 1 && !strcmp(argv[1], "--host-only");
     printf("compat entry points (%s)\n", host_only ? "host-only parts" : "with GPU");
@@ -240,6 +292,12 @@ int main(int argc, char** argv) {
         run(st, 2, &h, 1);                       /* no device: reports the error, leaves the state untouched */
         CHECK(creal(st[0]) == 1.0 && cabs(st[1]) == 0.0);
         CHECK(strstr(qgt_compat_last_error(), "no CPU fallback") != NULL);
+        /* the device-memory seam never hands out host memory as "device" memory */
+        CHECK(qg_gpu_init() == QG_GPU_ERROR_NO_DEVICE && qg_gpu_get_last_error() == QG_GPU_ERROR_NO_DEVICE);
+        gpu_buffer_t b = {0};
+        CHECK(qg_gpu_allocate(&b, 64) == QG_GPU_ERROR_INVALID_VALUE && b.device_ptr == NULL);   /* not initialised */
+        void* raw = NULL;
+        CHECK(gpu_malloc(&raw, 64) == QGT_ERROR_GPU_NOT_AVAILABLE && raw == NULL);
         printf("all host-only checks passed\n");
         return 0;
     }
@@ -247,6 +305,7 @@ int main(int argc, char** argv) {
     test_sim_api();
     test_qgt_api();
     test_diffgeo();
+    test_gpu_memory_seam();
     printf("all compat checks passed\n");
     return 0;
 }

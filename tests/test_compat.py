@@ -25,7 +25,11 @@ def test_compat_library_exports_reference_symbols():
                 "create_quantum_geometric_tensor_network", "apply_quantum_gate", "compute_quantum_geometric_tensor", "compute_quantum_metric",
                 "compute_berry_curvature", "geometric_compute_fubini_study_metric", "geometric_compute_berry_curvature",
                 "geometric_compose_qgt", "geometric_compute_full_qgt", "compute_regularized_natural_gradient",
-                "get_default_natural_gradient_config"):
+                "get_default_natural_gradient_config", "gpu_malloc", "qgt_gpu_free_buffer", "gpu_memcpy_host_to_device",
+                "gpu_memcpy_device_to_host", "qg_gpu_init", "qg_gpu_cleanup", "qg_gpu_shutdown", "qg_gpu_get_device_count",
+                "qg_gpu_get_device_info", "qg_gpu_set_device", "qg_gpu_get_last_error", "qg_gpu_get_error_string", "qg_gpu_allocate",
+                "qg_gpu_allocate_pinned", "qg_gpu_free", "qg_gpu_memcpy_to_device", "qg_gpu_memcpy_to_host", "qg_gpu_create_stream",
+                "qg_gpu_destroy_stream", "qg_gpu_synchronize_stream", "qg_gpu_synchronize"):
         assert f" T {sym}\n" in out, sym
 
 
