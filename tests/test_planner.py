@@ -162,3 +162,17 @@ def test_fusion_depth_on_hea():
     assert len(plan["runs"]) <= 24, len(plan["runs"])
     for r in plan["runs"]:
         assert len(r["tile"]) == 11 and r["tile"][:4] == [0, 1, 2, 3]
+
+
+def test_stage_matrix_forms_are_detected():
+    """One ansatz layer per stage factors as (diagonal) x (real); RX layers (QAOA mixer) and two fused layers are dense."""
+    def forms(circ):
+        d = api.plan_dump(circ, K.default_angles(max(1, circ.num_params)))
+        return [f for r in d["runs"] for s in r["subs"] for f in s["forms"]]
+
+    one_layer = forms(K.hea_layers(12, 1))
+    assert one_layer and all(f == 1 for f in one_layer)
+    qaoa = forms(K.qaoa_maxcut(12, 2))
+    assert qaoa and all(f == 0 for f in qaoa)
+    deep = forms(K.config("c2"))
+    assert 0 in deep and 1 in deep              # two fused layers are dense
