@@ -299,7 +299,6 @@ int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
     else if (k == "debug_skip") c->debug_skip = (int)value;
     else if (k == "tiles_per_item") c->tiles_per_item = (int)value;
     else if (k == "gram_tile") set_gram_tile_override((int)value);
-    else if (k == "gram_stages") set_gram_stages((int)value);
     else if (k == "profile") c->timer.enabled = value != 0;
     else if (k == "max_slots") c->max_slots = (size_t)value;
     else return fail(QGT_B200_ERR_INVALID_ARG, "unknown option " + k);

@@ -733,8 +733,6 @@ __global__ void qgt_finalize_kernel(const cplx* C, int P, double* metric, double
 // few-column Grams of the blocked schedule
 static int g_gram_tile_override = 0;
 void set_gram_tile_override(int t) { g_gram_tile_override = t; }
-static int g_gram_stages = 0;
-void set_gram_stages(int s) { g_gram_stages = s; }
 
 GramShape gram_shape(int na, int nb) {
     GramShape s;
@@ -850,10 +848,9 @@ cudaError_t launch_gram(const GramLaunch& g, GramShape shp, cudaStream_t st) {
         return cudaGetLastError();
     }
     if (shp.MT == 64) return launch_gram_t<2, 4, 4, 2, 8, 4>(g, st);
-    if (shp.NT == 32) return g_gram_stages == 4 ? launch_gram_t<2, 4, 2, 1, 16, 4>(g, st) : launch_gram_t<2, 4, 2, 1, 16, 3>(g, st);
-    if (g_gram_stages == 32) return launch_gram_t<4, 2, 1, 1, 32, 3>(g, st);
-    if (g_gram_stages == 33) return launch_gram_t<4, 2, 1, 1, 32, 4>(g, st);
-    return g_gram_stages == 6 ? launch_gram_t<4, 2, 1, 1, 16, 6>(g, st) : launch_gram_t<4, 2, 1, 1, 16, 4>(g, st);
+    if (shp.NT == 32) return launch_gram_t<2, 4, 2, 1, 16, 3>(g, st);
+    // deeper rings (6 stages) and 32-amplitude chunks were measured on the HBM-bound streaming Grams: no gain
+    return launch_gram_t<4, 2, 1, 1, 16, 4>(g, st);
 }
 
 cudaError_t launch_gram_reduce(const GramLaunch& g, GramShape shp, const int* a_ids, const int* b_ids,

@@ -53,8 +53,7 @@ GramShape gram_shape(int na, int nb);
 size_t gram_configure(GramLaunch& g, GramShape shp);
 // split-K factor of a configured launch (needs na, nb, D, symmetric and the fields gram_configure fills)
 int gram_choose_ksplit(const GramLaunch& g, GramShape shp, int num_sms);
-void set_gram_tile_override(int t);
-void set_gram_stages(int s);            // tuning: cp.async ring depth override (0 = default)   // tuning: 0 = automatic, 32 or 64 = force that square tile
+void set_gram_tile_override(int t);   // tuning: 0 = automatic, 32 or 64 = force that square tile
 cudaError_t launch_gram(const GramLaunch& g, GramShape shp, cudaStream_t st);
 // C[(a_ids[i]), (b_ids[j])] = sum_ks partial ; mirrored conj ; ldc = leading dimension of C
 cudaError_t launch_gram_reduce(const GramLaunch& g, GramShape shp, const int* a_ids, const int* b_ids,
