@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -527,8 +528,10 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
     const auto t_pack0 = std::chrono::steady_clock::now();
     // ---- pack every launch's arguments and upload them once ------------------------------------
     std::vector<QgtSweepItem> items;
-    std::vector<double> ovr_pool, mats;          // derivative matrices of the spawn items
-    std::vector<size_t> ovr_off, ovr_item;
+    std::vector<double> ovr_pool;                // derivative matrices of the spawn items
+    struct OvrTask { int run, sub, stage; std::vector<int> dops; size_t item, off; };
+    std::vector<OvrTask> tasks;
+    size_t ovr_doubles = 0;
     std::vector<const cplx*> ptrs;
     std::vector<int> ids;
     struct GramRec { size_t a_off, b_off, aid_off, bid_off; int na, nb; bool symmetric; };
@@ -558,10 +561,13 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                         for (int s2 = 0; s2 < loc.sub; s2++) first += (int)run.subs[s2].stages.size();
                         std::vector<int> dops(1, sc.ovr_op);
                         dops.insert(dops.end(), sc.ovr_extra.begin(), sc.ovr_extra.end());
-                        it.ovr_form = stage_matrices_sum(run, sp, sp.stages[loc.index - first], dops, mats);
-                        ovr_off.push_back(ovr_pool.size());
-                        ovr_item.push_back(items.size());
-                        ovr_pool.insert(ovr_pool.end(), mats.begin(), mats.end());
+                        // the matrices themselves are computed below, in parallel: only the layout is fixed here
+                        const Stage& stg = sp.stages[loc.index - first];
+                        OvrTask task;
+                        task.run = in.run; task.sub = loc.sub; task.stage = loc.index - first; task.dops = std::move(dops);
+                        task.item = items.size(); task.off = ovr_doubles;
+                        ovr_doubles += ((size_t)QGT_VARIANT_STRIDE(1 << (int)sp.reg_local.size()) << stg.vqubits.size()) * 2;
+                        tasks.push_back(std::move(task));
                     } else if (loc.kind == 2) {
                         it.ovr_tdiag = make_tdiag(run.ops[sc.ovr_op], true);
                     } else {
@@ -589,11 +595,35 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             partial_bytes = std::max(partial_bytes, (size_t)ks * per_split * sizeof(cplx));
         }
     }
+    // derivative (product-rule) stage matrices: independent of each other, a few microseconds each, hundreds per
+    // evaluation -> a handful of host threads
+    ovr_pool.assign(ovr_doubles, 0.0);
+    {
+        auto work = [&](size_t lo, size_t hi) {
+            std::vector<double> mats;
+            for (size_t k = lo; k < hi; k++) {
+                const OvrTask& t = tasks[k];
+                const Run& run = plan.runs[t.run];
+                const SubPass& sp = run.subs[t.sub];
+                items[t.item].ovr_form = stage_matrices_sum(run, sp, sp.stages[t.stage], t.dops, mats);
+                std::memcpy(&ovr_pool[t.off], mats.data(), mats.size() * sizeof(double));
+            }
+        };
+        const size_t nthreads = tasks.size() >= 64 ? std::min<size_t>(4, std::max<unsigned>(1u, std::thread::hardware_concurrency())) : 1;
+        if (nthreads <= 1) work(0, tasks.size());
+        else {
+            std::vector<std::thread> pool;
+            const size_t per = (tasks.size() + nthreads - 1) / nthreads;
+            for (size_t t = 1; t < nthreads; t++) pool.emplace_back(work, std::min(tasks.size(), t * per), std::min(tasks.size(), (t + 1) * per));
+            work(0, std::min(tasks.size(), per));
+            for (std::thread& th : pool) th.join();
+        }
+    }
     c->ms_prog_pack = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pack0).count();
     int rc;
     if ((rc = c->ovr_pool.reserve(std::max<size_t>(16, ovr_pool.size() * sizeof(double))))) return rc;
-    for (size_t k = 0; k < ovr_item.size(); k++)
-        items[ovr_item[k]].ovr_mat = (const char*)c->ovr_pool.ptr + ovr_off[k] * sizeof(double);
+    for (const OvrTask& t : tasks)
+        items[t.item].ovr_mat = (const char*)c->ovr_pool.ptr + t.off * sizeof(double);
     if ((rc = c->items.reserve(std::max<size_t>(1, items.size()) * sizeof(QgtSweepItem)))) return rc;
     const size_t ptr_bytes = ptrs.size() * sizeof(cplx*), id_bytes = ids.size() * sizeof(int);
     if ((rc = c->aux.reserve(std::max<size_t>(16, ptr_bytes + id_bytes)))) return rc;
