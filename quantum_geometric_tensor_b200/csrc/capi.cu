@@ -292,6 +292,7 @@ int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
     const std::string k(key);
     if (k == "tile_qubits") { if (value) c->opt.tile_qubits = (int)value; }
     else if (k == "low_qubits") c->opt.low_qubits = (int)value;
+    else if (k == "birth_cut") c->opt.birth_cut = value != 0;
     else if (k == "max_ops_per_run") c->opt.max_ops_per_run = (int)value;
     else if (k == "reg_qubits") c->opt.reg_qubits = (int)value;
     else if (k == "batch_qubits") c->opt.batch_qubits = (int)value;
@@ -614,8 +615,13 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
         else {
             std::vector<std::thread> pool;
             const size_t per = (tasks.size() + nthreads - 1) / nthreads;
-            for (size_t t = 1; t < nthreads; t++) pool.emplace_back(work, std::min(tasks.size(), t * per), std::min(tasks.size(), (t + 1) * per));
+            size_t started = 1;                  // chunk 0 runs on this thread
+            try {
+                for (; started < nthreads; started++)
+                    pool.emplace_back(work, std::min(tasks.size(), started * per), std::min(tasks.size(), (started + 1) * per));
+            } catch (...) {}                     // no thread available: the remaining chunks run here
             work(0, std::min(tasks.size(), per));
+            for (size_t t = started; t < nthreads; t++) work(std::min(tasks.size(), t * per), std::min(tasks.size(), (t + 1) * per));
             for (std::thread& th : pool) th.join();
         }
     }

@@ -417,9 +417,9 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
 template <int R, int B, bool MMA_ONLY, bool DB, int MAXT, int MINB, bool COST = false>
 static cudaError_t launch_sweep_cfg(const SweepLaunch& a_in, int T, size_t smem, int num_sms, cudaStream_t st) {
     auto kern = qgt_sweep_kernel<R, B, MMA_ONLY, DB, MAXT, MINB, COST>;
-    static int ctas_per_sm = 0;
+    static int ctas_per_sm = 0, threads_seen = 0;
     static size_t smem_seen = 0;
-    if (!ctas_per_sm || smem != smem_seen) {
+    if (!ctas_per_sm || smem != smem_seen || T != threads_seen) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         int occ = 0;
@@ -427,6 +427,7 @@ static cudaError_t launch_sweep_cfg(const SweepLaunch& a_in, int T, size_t smem,
         if (e != cudaSuccess) return e;
         ctas_per_sm = occ > 0 ? occ : 1;
         smem_seen = smem;
+        threads_seen = T;
     }
     SweepLaunch a = a_in;
     const uint64_t resident = (uint64_t)num_sms * ctas_per_sm;

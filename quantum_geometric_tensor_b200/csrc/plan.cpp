@@ -443,10 +443,17 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
     std::vector<int> ready;
     for (int i = 0; i < N; i++) if (dag.indeg[i] == 0) ready.push_back(i);
     int scheduled = 0;
+    // Parameters already born before the current run.  A derivative column spawned at sub-pass s of a run
+    // recomputes the s earlier sub-passes phi has been through, so a run in which many parameters are born is cut
+    // short once that waste outweighs the extra pass over the alive columns: with b births in s sub-passes and
+    // `alive` columns entering the run (a pass costs about two stage applications), cut when s > 2 (alive + b) / b.
+    std::vector<char> born(std::max(1, c.num_params), 0);
+    int alive = 1;
 
     while (scheduled < N) {
         Run run;
         run.K = K;
+        std::vector<int> born_here;
         std::vector<char> inS(n, 0);
         int sizeS = 0;
         for (int q = 0; q < L; q++) { inS[q] = 1; sizeS++; }
@@ -484,6 +491,7 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
                     if (!inR[o.target]) { inR[o.target] = 1; sizeR++; sp.regq.push_back(o.target); }
                 }
                 run.ops.push_back(o);
+                if (o.param >= 0 && o.param < (int)born.size() && !born[o.param]) { born[o.param] = 1; born_here.push_back(o.param); }
                 done[best] = 1; scheduled++;
                 ready.erase(std::find(ready.begin(), ready.end(), best));
                 for (int sidx : dag.succ[best]) if (--dag.indeg[sidx] == 0) ready.push_back(sidx);
@@ -492,7 +500,10 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
             sp.e = (int)run.ops.size();
             if (sp.e == sp.b) break;          // nothing fits a fresh sub-pass: the run is complete
             raw.push_back(sp);
+            const int b_run = (int)born_here.size(), s_run = (int)raw.size();
+            if (opt.birth_cut && b_run >= 4 && s_run >= 2 && s_run * b_run > 2 * (alive + b_run)) break;
         }
+        alive += (int)born_here.size();
         if (run.ops.empty()) { err = "planner made no progress"; return QGT_B200_ERR_INTERNAL; }
         // pad the tile to K qubits with the lowest unused ones
         for (int q = 0; q < nl && sizeS < K; q++) if (!inS[q]) { inS[q] = 1; sizeS++; }
@@ -747,6 +758,7 @@ int build_plan_sharded(const qgt_b200_circuit& c, const double* theta, const Pla
         sub.gates = segs[si].gates.data();
         sub.num_gates = segs[si].gates.size();
         CircuitPlan sp;
+        opt.birth_cut = opt_in.birth_cut && si == 0;      // later segments start with columns alive the planner call cannot see
         if ((rc = build_plan(sub, theta, opt, sp, err))) return rc;
         if (si == 0) { plan = sp; plan.runs.clear(); }
         for (Run& r : sp.runs) { r.segment = (int)si; plan.runs.push_back(std::move(r)); }
