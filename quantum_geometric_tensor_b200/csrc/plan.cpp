@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 #include <sstream>
@@ -407,11 +408,69 @@ int stage_matrices_sum(const Run& run, const SubPass& sp, const Stage& st, const
     return pack_stage(1 << (int)sp.reg_local.size(), 1 << (int)st.vqubits.size(), sum, out);
 }
 
+// A derivative column spawned at sub-pass s of a run recomputes the s earlier sub-passes phi has been through (the
+// kernel applies the whole run to every item).  Where many parameters are born inside one long run - the first run
+// of an ansatz, which fuses the light cone of its tile through every layer - the run is executed in pieces: same tile,
+// consecutive sub-pass ranges, so the rest of the plan is unchanged.  Cost model in stage applications: a piece of s
+// sub-passes costs (columns alive at its end) * (s + 1) (one pass over memory is worth about one stage); the cut points
+// minimising the sum are found by dynamic programming; every piece also pays two kernel launches (~10 us, i.e.
+// ~4 stage applications of a 2^20 state), which keeps small states in one piece.  `born` / `alive` carry the
+// parameters seen so far.
+static void split_run_by_births(Run& run, bool enable, int state_qubits, std::vector<char>& born, int& alive, std::vector<Run>& out) {
+    const int S = (int)run.subs.size();
+    std::vector<int> births(S, 0);
+    int total = 0;
+    for (int s = 0; s < S; s++)
+        for (int i = run.subs[s].op_begin; i < run.subs[s].op_end; i++) {
+            const int p = run.ops[i].param;
+            if (p >= 0 && p < (int)born.size() && !born[p]) { born[p] = 1; births[s]++; total++; }
+        }
+    std::vector<int> cuts;                                   // piece boundaries (sub-pass indices), ascending
+    if (enable && S >= 4 && total >= 4) {
+        std::vector<long> cum(S + 1, 0);
+        for (int s = 0; s < S; s++) cum[s + 1] = cum[s] + births[s];
+        const double launch_units = state_qubits < 0 ? 0.0 : 4.2 * std::ldexp(1.0, 20 - std::min(state_qubits, 40));
+        std::vector<double> best(S + 1, 0.0);
+        std::vector<int> from(S + 1, 0);
+        for (int j = 1; j <= S; j++) {
+            best[j] = -1.0;
+            for (int i = 0; i < j; i++) {
+                const double cost = best[i] + (double)(alive + cum[j]) * (j - i + 1) + launch_units;
+                if (best[j] < 0.0 || cost < best[j]) { best[j] = cost; from[j] = i; }
+            }
+        }
+        for (int j = S; j > 0; j = from[j]) cuts.push_back(j);
+        std::reverse(cuts.begin(), cuts.end());
+    } else {
+        cuts.push_back(S);
+    }
+    alive += total;
+    if (cuts.size() <= 1) { out.push_back(std::move(run)); return; }
+    int lo = 0;
+    for (int hi : cuts) {
+        Run piece;
+        piece.K = run.K; piece.tile_qubits = run.tile_qubits; piece.other_qubits = run.other_qubits;
+        piece.exchange_gbit = run.exchange_gbit; piece.segment = run.segment;
+        const int base = run.subs[lo].op_begin, end = run.subs[hi - 1].op_end;
+        piece.ops.assign(run.ops.begin() + base, run.ops.begin() + end);
+        for (int s = lo; s < hi; s++) {
+            SubPass sp = run.subs[s];
+            sp.op_begin -= base; sp.op_end -= base;
+            for (Stage& st : sp.stages) for (int& o : st.ops) o -= base;
+            for (int& o : sp.tdiags) o -= base;
+            piece.subs.push_back(std::move(sp));
+        }
+        out.push_back(std::move(piece));
+        lo = hi;
+    }
+}
+
 int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions& opt_in, CircuitPlan& plan, std::string& err) {
     const int n = c.num_qubits;
     if (n < 1 || n > QGT_MAX_QUBITS) { err = "num_qubits out of range"; return QGT_B200_ERR_INVALID_ARG; }
     if (c.num_gates && !c.gates) { err = "gates is NULL"; return QGT_B200_ERR_INVALID_ARG; }
     PlanOptions opt = opt_in;
+    if (const char* e = std::getenv("QGT_B200_BIRTH_CUT")) opt.birth_cut = std::atoi(e);   // test hook: 2 forces splits on small states
     opt.reg_qubits = std::max(1, std::min(opt.reg_qubits, 3));
     opt.batch_qubits = std::max(0, std::min(opt.batch_qubits, (int)QGT_MAX_REG_QUBITS - opt.reg_qubits));
     opt.tile_qubits = std::max(opt.reg_qubits + opt.batch_qubits + 2,
@@ -443,17 +502,14 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
     std::vector<int> ready;
     for (int i = 0; i < N; i++) if (dag.indeg[i] == 0) ready.push_back(i);
     int scheduled = 0;
-    // Parameters already born before the current run.  A derivative column spawned at sub-pass s of a run
-    // recomputes the s earlier sub-passes phi has been through, so a run in which many parameters are born is cut
-    // short once that waste outweighs the extra pass over the alive columns: with b births in s sub-passes and
-    // `alive` columns entering the run (a pass costs about two stage applications), cut when s > 2 (alive + b) / b.
+    // Parameters already born before the current run (see split_run_by_births).
     std::vector<char> born(std::max(1, c.num_params), 0);
     int alive = 1;
 
     while (scheduled < N) {
         Run run;
         run.K = K;
-        std::vector<int> born_here;
+
         std::vector<char> inS(n, 0);
         int sizeS = 0;
         for (int q = 0; q < L; q++) { inS[q] = 1; sizeS++; }
@@ -491,7 +547,6 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
                     if (!inR[o.target]) { inR[o.target] = 1; sizeR++; sp.regq.push_back(o.target); }
                 }
                 run.ops.push_back(o);
-                if (o.param >= 0 && o.param < (int)born.size() && !born[o.param]) { born[o.param] = 1; born_here.push_back(o.param); }
                 done[best] = 1; scheduled++;
                 ready.erase(std::find(ready.begin(), ready.end(), best));
                 for (int sidx : dag.succ[best]) if (--dag.indeg[sidx] == 0) ready.push_back(sidx);
@@ -500,10 +555,7 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
             sp.e = (int)run.ops.size();
             if (sp.e == sp.b) break;          // nothing fits a fresh sub-pass: the run is complete
             raw.push_back(sp);
-            const int b_run = (int)born_here.size(), s_run = (int)raw.size();
-            if (opt.birth_cut && b_run >= 4 && s_run >= 2 && s_run * b_run > 2 * (alive + b_run)) break;
         }
-        alive += (int)born_here.size();
         if (run.ops.empty()) { err = "planner made no progress"; return QGT_B200_ERR_INTERNAL; }
         // pad the tile to K qubits with the lowest unused ones
         for (int q = 0; q < nl && sizeS < K; q++) if (!inS[q]) { inS[q] = 1; sizeS++; }
@@ -557,15 +609,19 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
             }
             run.subs.push_back(sp);
         }
-        const int ridx = (int)plan.runs.size();
-        for (int i = 0; i < (int)run.ops.size(); i++) {
-            const int p = run.ops[i].param;
-            if (p < 0) continue;
-            run.occ.push_back({p, i});
-            if (plan.first_run[p] < 0) plan.first_run[p] = ridx;
-            plan.last_run[p] = ridx;
+        std::vector<Run> pieces;
+        split_run_by_births(run, opt.birth_cut != 0, opt.birth_cut == 2 ? -1 : nl, born, alive, pieces);
+        for (Run& piece : pieces) {
+            const int ridx = (int)plan.runs.size();
+            for (int i = 0; i < (int)piece.ops.size(); i++) {
+                const int p = piece.ops[i].param;
+                if (p < 0) continue;
+                piece.occ.push_back({p, i});
+                if (plan.first_run[p] < 0) plan.first_run[p] = ridx;
+                plan.last_run[p] = ridx;
+            }
+            plan.runs.push_back(std::move(piece));
         }
-        plan.runs.push_back(std::move(run));
     }
     return QGT_B200_OK;
 }

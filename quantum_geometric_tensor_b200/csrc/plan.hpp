@@ -17,7 +17,7 @@ struct PlanOptions {
     int batch_qubits = 0;   // B: extra amplitudes per thread (2^B halves share every matrix element)
     int low_qubits = 4;     // L: lowest qubits always in the tile (contiguous 16*2^L bytes)
     int max_ops_per_run = 160;
-    int birth_cut = 0;      // end a run early while many parameters are being born in it (see build_plan); measured slower overall, off
+    int birth_cut = 1;      // execute a run in which many parameters are born in pieces (split_run_by_births); 2 = ignore the launch cost
     int local_qubits = 0;   // sharded states: qubits >= local_qubits are rank bits (diagonal use / controls only); 0 = all local
 };
 

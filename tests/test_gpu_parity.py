@@ -181,6 +181,25 @@ def test_stage_forms_both_paths(ctx, oracle):
                 ctx.set_option("use_mma", 1)
 
 
+@pytest.mark.parametrize("slots", [0, 9])
+def test_runs_split_where_parameters_are_born(ctx, oracle, slots):
+    # birth_cut=2 forces on a small state what 20-qubit plans do by themselves: the first run executed in pieces
+    c = K.hea_layers(12, 3)
+    th = K.default_angles(c.num_params, 3)
+    ctx.set_option("birth_cut", 0)
+    ctx.qgt(c, th)
+    runs_whole = ctx.stats()["num_runs"]
+    ctx.set_option("birth_cut", 2)
+    ctx.set_option("max_slots", slots)
+    try:
+        q = ctx.qgt(c, th)
+        assert ctx.stats()["num_runs"] > runs_whole
+    finally:
+        ctx.set_option("birth_cut", 1)
+        ctx.set_option("max_slots", 0)
+    assert rel_err(q, oracle.qgt(c, th)) < TOL
+
+
 @pytest.mark.parametrize("slots", [5, 6, 9, 17])
 def test_qgt_blocked_equals_resident(ctx, oracle, slots):
     # force the column-block schedule (what n >= 26 uses) on a size the oracle can check

@@ -176,3 +176,21 @@ def test_stage_matrix_forms_are_detected():
     assert qaoa and all(f == 0 for f in qaoa)
     deep = forms(K.config("c2"))
     assert 0 in deep and 1 in deep              # two fused layers are dense
+
+
+@pytest.mark.parametrize("slots", [0, 7])
+def test_runs_split_where_parameters_are_born(oracle, slots, monkeypatch):
+    """A long first run is executed in pieces (same tile, consecutive sub-pass ranges); the plan and its column
+    schedule must still reproduce the oracle.  QGT_B200_BIRTH_CUT=2 forces the split on a small state."""
+    c = K.hea_layers(9, 3)
+    th = K.default_angles(c.num_params, 5)
+    monkeypatch.setenv("QGT_B200_BIRTH_CUT", "0")
+    whole = api.plan_dump(c, th, tile_qubits=7)
+    monkeypatch.setenv("QGT_B200_BIRTH_CUT", "2")
+    d = api.plan_dump(c, th, tile_qubits=7, column_slots=slots or c.num_params + 2)
+    assert len(d["runs"]) > len(whole["runs"])
+    assert sum(len(r["subs"]) for r in d["runs"]) == sum(len(r["subs"]) for r in whole["runs"])
+    q, psi, _, seen = pi.run_program(d, c)
+    assert (seen[:c.num_params, :c.num_params] >= 1).all()
+    assert np.abs(q - oracle.qgt(c, th)).max() < 1e-12
+    assert np.abs(psi - oracle.apply(c, th)).max() < 1e-13
