@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """profiles/rNN_dram_c2.csv (ncu dram__bytes_* per launch) -> profiles/traffic.json (what bench.py reports as roofline.traffic).
 
-The csv holds the first 52 sweep / Gram launches of `bench.py --steps 1 --warmup 1` = four identical evaluations of
-13 launches (12 sweeps + 1 Gram); the last complete evaluation is used.  Per-launch averages, like `achieved`.
+The csv holds the first sweep / Gram launches of `bench.py --steps 1 --warmup 1` = a few identical evaluations, each
+ending with its Gram launch; the last complete evaluation is used.  Per-launch averages, like `achieved`.
 """
 import csv
 import json
@@ -18,8 +18,9 @@ for r in rows:
     if metric.startswith("dram__bytes"):
         d["bytes"] += val * scale
 launches = [per[k] for k in sorted(per)]
-evals = len(launches) // 13
-last = launches[(evals - 1) * 13: evals * 13]
+ends = [i for i, l in enumerate(launches) if "gram" in l["name"]]          # an evaluation ends with its Gram
+assert len(ends) >= 2, "need at least two complete evaluations"
+last = launches[ends[-2] + 1: ends[-1] + 1]
 sweeps = [l["bytes"] for l in last if "sweep" in l["name"]]
 grams = [l["bytes"] for l in last if "gram" in l["name"]]
 out = {"c2": {"sweep_bytes_per_launch": sum(sweeps) / max(1, len(sweeps)), "gram_bytes_per_launch": sum(grams) / max(1, len(grams)),
