@@ -13,7 +13,7 @@ python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/${R}_
 python bench.py > $O/${R}_bench_c2.json 2> $O/${R}_bench_c2.err
 python bench.py --impl reference --steps 2 --warmup 1 > $O/${R}_bench_c2_reference.json 2> $O/${R}_bench_c2_reference.err
 QGT_B200_TRACE=1 python tools/trace_run.py c2 > $O/${R}_stats_c2.txt 2> $O/${R}_trace_c2_all.txt
-grep "cat=" $O/${R}_trace_c2_all.txt | tail -15 > $O/${R}_trace_c2_launches.txt; rm -f $O/${R}_trace_c2_all.txt
+grep "cat=" $O/${R}_trace_c2_all.txt | tail -21 > $O/${R}_trace_c2_launches.txt; rm -f $O/${R}_trace_c2_all.txt
 # launch list of one bench step (cold-cache, serialised: compare shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_launches_c2.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/${R}_ncu_launches.log 2>&1
 # DRAM bytes per sweep / Gram launch (source of roofline.traffic; tools/make_traffic.py turns it into profiles/traffic.json)
