@@ -22,6 +22,14 @@ namespace {
 // Symmetric eigen-decomposition A = V diag(w) V^T: Householder reduction to tridiagonal form followed by
 // implicit-shift QL iterations (the classic tred2 / tql2 pair), O(n^3) with a small constant — a 256 x 256
 // metric takes a few milliseconds.  A (row-major) is destroyed; V receives the eigenvectors as columns.
+// sqrt(a^2 + b^2) without std::hypot's slow path; scaled only when squaring could leave the normal range
+inline double pythag(double a, double b) {
+    const double x = std::fabs(a), y = std::fabs(b);
+    const double m = x > y ? x : y;
+    if (m > 1e-140 && m < 1e140) return std::sqrt(a * a + b * b);
+    return std::hypot(a, b);
+}
+
 // dot product with four independent accumulators (fixed summation order; lets the compiler keep four
 // multiply-add chains in flight without value-changing flags)
 inline double dot4(const double* a, const double* b, int n) {
@@ -138,14 +146,14 @@ void sym_eigh(std::vector<double>& A, int n, std::vector<double>& w, std::vector
             if (m != l) {
                 if (iter++ == 200) break;
                 double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
-                double r = std::hypot(g, 1.0);
+                double r = std::sqrt(g * g + 1.0);
                 g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? std::fabs(r) : -std::fabs(r)));
                 double sn = 1.0, cs = 1.0, p = 0.0;
                 int i;
                 for (i = m - 1; i >= l; i--) {
                     double f = sn * e[i];
                     const double bb = cs * e[i];
-                    e[i + 1] = (r = std::hypot(f, g));
+                    e[i + 1] = (r = pythag(f, g));
                     if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; break; }
                     sn = f / r; cs = g / r;
                     g = d[i + 1] - p;
