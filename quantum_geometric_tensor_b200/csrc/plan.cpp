@@ -843,6 +843,7 @@ struct Sched {
     const CircuitPlan& plan;
     Program& prog;
     int psi;                         // slot of the marching state phi
+    int psi_alt = -1;                // spare slot: phi advances out of place inside the columns' launch (resident mode)
     int ckpt;                        // slot of the rolling checkpoint (blocked mode) or -1
     int ckpt_time = 0;               // the checkpoint holds the state BEFORE run ckpt_time
     std::vector<int> res_slots, str_slots;
@@ -937,6 +938,10 @@ struct Sched {
                     born_str.push_back(p); spawned_here[p] = 1;
                 }
             }
+            // phi rides in the same launch, written to the spare slot: the spawns of this run (here and below) keep
+            // reading the old phi, and one launch per run disappears
+            const bool phi_oop = psi_alt >= 0 && run.exchange_gbit < 0;
+            if (phi_oop) A.push_back({psi, psi_alt, -1, false});
             sweep(r, A);
             emit_accumulates(r, acc);
             for (int p = 0; p < P; p++) if (spawned_here[p] && is_res[p]) alive[p] = 1;
@@ -986,7 +991,8 @@ struct Sched {
                 if (round.empty()) break;   // no free slot at all: select_fit() prevents this
             }
             // 4. phi itself
-            sweep(r, {{psi, psi, -1, false}});
+            if (phi_oop) std::swap(psi, psi_alt);
+            else sweep(r, {{psi, psi, -1, false}});
             // 5. resident x (resident, psi) at the first time every resident column is complete
             if (!diag_done && res_complete) {
                 std::vector<int> bs = res_sl, bid = res_ids;
@@ -1043,6 +1049,7 @@ int build_qgt_program(const CircuitPlan& plan, size_t total_slots, bool want_psi
     if (blocked) s.ckpt = next++;
     for (int i = 0; i < b; i++) s.res_slots.push_back(next++);
     for (int i = 0; i < c; i++) s.str_slots.push_back(next++);
+    if (!blocked && Pa > 0 && (size_t)next + 1 <= total_slots) s.psi_alt = next++;
     prog.num_slots = next; prog.psi_slot = s.psi; prog.resident = b; prog.streaming = c;
 
     if (!blocked) {
@@ -1050,6 +1057,7 @@ int build_qgt_program(const CircuitPlan& plan, size_t total_slots, bool want_psi
         prog.blocks = Pa ? 1 : 0;
         s.march(0, ord, {}, true, want_psi);
         if (Pa == 0 && want_psi) for (int r = 0; r < R; r++) s.sweep(r, {{s.psi, s.psi, -1, false}});
+        prog.psi_slot = s.psi;               // phi may have ended in the spare slot
         prog.psi_final = want_psi;
         return QGT_B200_OK;
     }

@@ -18,9 +18,9 @@ grep "cat=" $O/${R}_trace_c2_all.txt | tail -21 > $O/${R}_trace_c2_launches.txt;
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_launches_c2.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/${R}_ncu_launches.log 2>&1
 # DRAM bytes per sweep / Gram launch (source of roofline.traffic; tools/make_traffic.py turns it into profiles/traffic.json)
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --kernel-name regex:"qgt_(sweep|gram)_kernel" -c 80 --csv --log-file $O/${R}_dram_c2.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${R}_ncu_dram.log 2>&1
-# full captures (c2: 18 sweep launches + 1 Gram per evaluation): a dense-stage sweep launch (run 4, 102 columns), a
+# full captures (c2: 9 sweep launches + 1 Gram per evaluation): a dense-stage sweep launch (run 4, 102 columns), a
 # diagonal-real one (run 8, 160 columns), the Gram
-ncu --set full --import-source on --clock-control none --kernel-name regex:qgt_sweep_kernel --launch-skip 26 --launch-count 1 -o $O/${R}_sweep_dense -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${R}_ncu_a.log 2>&1
-ncu --set full --import-source on --clock-control none --kernel-name regex:qgt_sweep_kernel --launch-skip 34 --launch-count 1 -o $O/${R}_sweep_diagreal -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${R}_ncu_b.log 2>&1
+ncu --set full --import-source on --clock-control none --kernel-name regex:qgt_sweep_kernel --launch-skip 13 --launch-count 1 -o $O/${R}_sweep_dense -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${R}_ncu_a.log 2>&1
+ncu --set full --import-source on --clock-control none --kernel-name regex:qgt_sweep_kernel --launch-skip 17 --launch-count 1 -o $O/${R}_sweep_diagreal -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${R}_ncu_b.log 2>&1
 ncu --set full --import-source on --clock-control none --kernel-name regex:qgt_gram_kernel --launch-skip 1 --launch-count 1 -o $O/${R}_gram -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${R}_ncu_c.log 2>&1
 ls -la $O/*.ncu-rep
