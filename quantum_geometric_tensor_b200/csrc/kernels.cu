@@ -527,7 +527,7 @@ __device__ __forceinline__ void gram_chunk(const cplx* __restrict__ sA, const cp
 // keeps the complex numbers interleaved with a row stride of KC+4 elements: one 128-bit load then
 // delivers (re, im) of a fragment element and a quarter-warp touches 8 distinct 16-byte bank groups.
 template <int WM, int WN, int BM, int BN, int KC, int STAGES>
-__global__ void __launch_bounds__(WM * WN * 32, 2) qgt_gram_kernel(GramLaunch g) {
+__global__ void __launch_bounds__(WM * WN * 32, (WM == 2 && WN == 4 && BM == 2 && BN == 1) ? 3 : 2) qgt_gram_kernel(GramLaunch g) {
     constexpr int MT = WM * BM * 8, NT = WN * BN * 8, S = KC + 4, NTHR = WM * WN * 32;
     constexpr int ELEMS = (MT + NT) * KC;
     static_assert(ELEMS % NTHR == 0 && NTHR % KC == 0, "tile/threads mismatch");
