@@ -145,9 +145,18 @@ int qgt_b200_device_synchronize(void);
 
 int  qgt_b200_create(qgt_b200_ctx** out, int device);    /* device = CUDA ordinal */
 void qgt_b200_destroy(qgt_b200_ctx* ctx);
-/* workspace cap in bytes for derivative columns (0 = 85 % of free HBM at first use) */
+/* workspace cap in bytes for derivative columns (0 = 90 % of free HBM at first use) */
 int  qgt_b200_set_workspace_limit(qgt_b200_ctx* ctx, size_t bytes);
-/* tuning knob: tile qubits per sweep (10..12), 0 = default */
+/* Tuning / test knobs (defaults are the measured best; results do not depend on them):
+ *   tile_qubits (11)       amplitudes staged per CTA = 2^tile_qubits       low_qubits (4)   qubits 0..low-1 always in the tile
+ *   reg_qubits (3)         qubits of a stage matrix                         batch_qubits (0) extra amplitudes per thread
+ *   max_ops_per_run (160)  fusion depth cap                                 birth_cut (1)    first run executed in pieces (2 = also on small states)
+ *   use_mma (1)            dense stages on the FP64 tensor pipe             double_buffer (0) two tile buffers per CTA
+ *   tiles_per_item (0)     tiles per work unit, 0 = automatic               gram_tile (0)    force 32 or 64 square Gram tiles
+ *   max_slots (0)          cap on statevector-sized columns (forces the blocked schedule; tests)
+ *   profile (0)            per-category CUDA-event timing into qgt_b200_stats
+ *   debug_skip (0)         timing experiments in builds with -DQGT_DEBUG_SKIP only
+ * Unknown keys return QGT_B200_ERR_INVALID_ARG. */
 int  qgt_b200_set_option(qgt_b200_ctx* ctx, const char* key, double value);
 
 /* ---- statevector ------------------------------------------------------------------------- */
