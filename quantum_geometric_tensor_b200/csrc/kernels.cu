@@ -431,16 +431,19 @@ static cudaError_t launch_sweep_cfg(const SweepLaunch& a_in, int T, size_t smem,
     }
     SweepLaunch a = a_in;
     const uint64_t resident = (uint64_t)num_sms * ctas_per_sm;
-    // tiles per item set-up: as many as keep >= 16 work units per resident CTA (tail balance), at most 4
+    // tiles per item set-up: 1 unless asked for (more tiles per unit measured no faster, and fewer units per launch
+    // leave less room for the multi-wave grid below)
     int tpi = 1;
-    if (a.tiles_per_item > 0) {
+    if (a.tiles_per_item > 0)
         while (tpi * 2 <= a.tiles_per_item && a.ntiles % (uint64_t)(tpi * 2) == 0) tpi *= 2;
-    } else {
-        while (tpi < 4 && a.ntiles % (uint64_t)(tpi * 2) == 0 && (a.ntiles / (uint64_t)(tpi * 2)) * (uint64_t)a.nitems >= resident * 16) tpi *= 2;
-    }
     a.tiles_per_item = tpi;
     const uint64_t total = (a.ntiles / (uint64_t)tpi) * (uint64_t)a.nitems;
-    const uint64_t cap = resident * 2;
+    // grid: several waves of resident CTAs (CTAs that finish early are replaced, which evens out the tail; measured
+    // best at 8-16 waves, 2 waves +3 %), as long as every CTA still gets ~8 work units to amortise its set-up
+    uint64_t waves = total / (resident * 8);
+    waves = waves < 2 ? 2 : (waves > 16 ? 16 : waves);
+    if (COST || a.ct.num_edges > 0) waves = 2;          // cost runs build their energy table once per CTA
+    const uint64_t cap = resident * waves;
     const unsigned grid = (unsigned)(total < cap ? total : cap);
     kern<<<grid, T, smem, st>>>(a);
     return cudaGetLastError();
