@@ -40,9 +40,9 @@ inline double dot4(const double* a, const double* b, int n) {
     return (s0 + s1) + (s2 + s3);
 }
 
-// Eigenvalues only: the same Householder reduction on a fully stored symmetric matrix, so that the
-// matrix-vector product and the rank-2 update of every step run over contiguous rows (the lower-triangle
-// form below walks columns); d / e receive the tridiagonal matrix in the layout the QL loop expects.
+// Eigenvalues only: the same Householder reduction with the matrix-vector product and the rank-2 update of every
+// step running over contiguous row prefixes of the lower triangle (the classic form below walks columns);
+// d / e receive the tridiagonal matrix in the layout the QL loop expects.
 void tridiagonalize_values(std::vector<double>& A, int n, std::vector<double>& d, std::vector<double>& e) {
     std::vector<double> u(n), pv(n);
     for (int i = n - 1; i >= 1; i--) {
@@ -59,17 +59,23 @@ void tridiagonalize_values(std::vector<double>& A, int n, std::vector<double>& d
         e[i] = scale * g;
         h -= f * g;
         u[l] = f - g;
-        double K = 0.0;
+        // p = A u / h from the lower triangle only: row j contributes a dot product to p[j] and an axpy to p[0..j-1],
+        // both over the contiguous row prefix; the rank-2 update then touches the lower triangle only (half the traffic)
+        for (int j = 0; j <= l; j++) pv[j] = 0.0;
         for (int j = 0; j <= l; j++) {
-            pv[j] = dot4(&A[(size_t)j * n], u.data(), l + 1) / h;
-            K += pv[j] * u[j];
+            const double* aj = &A[(size_t)j * n];
+            const double uj = u[j];
+            pv[j] += dot4(aj, u.data(), j) + aj[j] * uj;
+            for (int k = 0; k < j; k++) pv[k] += aj[k] * uj;
         }
+        double K = 0.0;
+        for (int j = 0; j <= l; j++) { pv[j] /= h; K += pv[j] * u[j]; }
         K /= (h + h);
         for (int j = 0; j <= l; j++) pv[j] -= K * u[j];
         for (int j = 0; j <= l; j++) {
             double* aj = &A[(size_t)j * n];
             const double uj = u[j], qj = pv[j];
-            for (int k = 0; k <= l; k++) aj[k] -= uj * pv[k] + qj * u[k];
+            for (int k = 0; k <= j; k++) aj[k] -= uj * pv[k] + qj * u[k];
         }
     }
     e[0] = 0.0;
