@@ -610,7 +610,9 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                 std::memcpy(&ovr_pool[t.off], mats.data(), mats.size() * sizeof(double));
             }
         };
-        const size_t nthreads = tasks.size() >= 64 ? std::min<size_t>(4, std::max<unsigned>(1u, std::thread::hardware_concurrency())) : 1;
+        // threads only for large programs: at a few hundred matrices (< 1 ms serial) a descheduled helper thread on a busy
+        // host costs more than it saves
+        const size_t nthreads = tasks.size() >= 1024 ? std::min<size_t>(4, std::max<unsigned>(1u, std::thread::hardware_concurrency())) : 1;
         if (nthreads <= 1) work(0, tasks.size());
         else {
             std::vector<std::thread> pool;

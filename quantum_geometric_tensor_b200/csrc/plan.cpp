@@ -210,18 +210,25 @@ bool make_tperm(int K, std::vector<int>& reg_local, const std::vector<int>& batc
     const int nf = (int)freep.size();
     std::vector<int> order = reg_local, best_order = reg_local;
     std::sort(order.begin(), order.end());
+    // the score depends on the positions' residues only: try residue triples and take the first free positions of
+    // each class (27 triples x 6 orders instead of nf^3 x 6 position triples)
+    std::vector<int> by_res[3];
+    for (int i = 0; i < nf; i++) by_res[freep[i] % 3].push_back(i);
     do {
         const int r0 = order.size() > 0 ? order[0] % 3 : -1, r1 = order.size() > 1 ? order[1] % 3 : -1;
-        for (int a = 0; a < nf; a++) for (int b2 = 0; b2 < nf; b2++) for (int c = 0; c < nf; c++) {
-            if (a == b2 || a == c || b2 == c) continue;
-            const int pa = freep[a] % 3, pb = freep[b2] % 3, pc = freep[c] % 3;
+        for (int pa = 0; pa < 3 && best_score < 10; pa++) for (int pb = 0; pb < 3 && best_score < 10; pb++) for (int pc = 0; pc < 3; pc++) {
+            int used[3] = {0, 0, 0};
+            const int a = used[pa] < (int)by_res[pa].size() ? by_res[pa][used[pa]++] : -1;
+            const int b2 = used[pb] < (int)by_res[pb].size() ? by_res[pb][used[pb]++] : -1;
+            const int c = used[pc] < (int)by_res[pc].size() ? by_res[pc][used[pc]++] : -1;
+            if (a < 0 || b2 < 0 || c < 0) continue;
             int score = 0;
             if (pa != r0 && pa != r1 && r0 != r1) score += 4;          // tensor-path loads
             if (pb != r0 && pc != r0 && pb != pc) score += 4;          // tensor-path stores
             if (pa != pb && pa != pc && pb != pc) score += 2;          // register path
             if (score > best_score) { best_score = score; best[0] = a; best[1] = b2; best[2] = c; best_order = order; }
         }
-    } while (order.size() == 3 && std::next_permutation(order.begin(), order.end()));
+    } while (best_score < 10 && order.size() == 3 && std::next_permutation(order.begin(), order.end()));
     if (best_score >= 0) reg_local = best_order;
     tperm.clear();
     if (best_score >= 0) {
