@@ -234,17 +234,19 @@ extern "C" int qgt_b200_natural_gradient(qgt_b200_ctx* ctx, const double* metric
     if (cfg.adaptive) {
         load();
         sym_eigh(A, n, w, V, false);                    // eigenvalues only: singular values of a symmetric matrix = |w|
-        double smax = std::fabs(w[0]), smin = std::fabs(w[0]);
-        for (int i = 1; i < n; i++) {
-            const double sv = std::fabs(w[i]);
-            if (sv > smax) smax = sv;
-            if (sv < smin && sv > 0) smin = sv;
-        }
-        // the reference sets kappa = INFINITY below sigma_min = 1e-15 (gradient.c:2770-2774), which turns its
-        // adaptive lambda into infinity for any rank-deficient metric; kappa is capped at
-        // 1e16 here so the step stays finite
-        double kappa = smin > 1e-15 ? smax / smin : 1e16;
-        if (kappa > 1e16) kappa = 1e16;
+        double smax = 0.0;
+        for (int i = 0; i < n; i++) smax = std::max(smax, std::fabs(w[i]));
+        // Condition number over the numerically non-zero spectrum: singular values at or below
+        // max(singular_cutoff, n * eps * sigma_max) - the ones the pseudo-inverse branch below (and the reference's,
+        // gradient.c:2800-2885) treats as zero - do not count.  A rank-deficient metric (redundant ansatz parameters,
+        // QAOA) then keeps the condition number of its range instead of kappa = 1e16 / lambda = 100, which would turn
+        // the natural gradient into 0.01 * gradient.  The reference itself sets kappa = INFINITY below
+        // sigma_min = 1e-15 (gradient.c:2770-2774), i.e. lambda = infinity: BASELINE.md section 4 #17; its
+        // single-precision SVD never resolves sigma below ~1e-7 * sigma_max anyway.
+        const double cut = std::max(cfg.singular_cutoff, (double)n * 2.220446049250313e-16 * smax);
+        double smin = smax;
+        for (int i = 0; i < n; i++) { const double sv = std::fabs(w[i]); if (sv > cut && sv < smin) smin = sv; }
+        const double kappa = smin > 0.0 ? smax / smin : 1.0;
         if (kappa > cfg.condition_threshold) {
             const double al = 1e-6 * std::sqrt(kappa);
             if (al > lambda) lambda = al;

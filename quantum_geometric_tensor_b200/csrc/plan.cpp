@@ -1063,7 +1063,6 @@ int build_qgt_program(const CircuitPlan& plan, size_t total_slots, bool want_psi
         s.init(s.psi);
         prog.blocks = Pa ? 1 : 0;
         s.march(0, ord, {}, true, want_psi);
-        if (Pa == 0 && want_psi) for (int r = 0; r < R; r++) s.sweep(r, {{s.psi, s.psi, -1, false}});
         prog.psi_slot = s.psi;               // phi may have ended in the spare slot
         prog.psi_final = want_psi;
         return QGT_B200_OK;

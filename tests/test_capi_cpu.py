@@ -69,12 +69,32 @@ def test_host_natural_gradient_matches_oracle(oracle):
     assert np.abs(out - x).max() / np.abs(x).max() < 1e-9
     # ill-conditioned metric: adaptive regularisation kicks in identically
     q, _ = np.linalg.qr(A)
-    G2 = q @ np.diag(np.logspace(0, -10, 20)) @ q.T
+    G2 = q @ np.diag(np.logspace(0, -9, 20)) @ q.T
     rc = lib.qgt_b200_natural_gradient(None, G2.ctypes.data_as(dp), g.ctypes.data_as(dp), 20, None, out.ctypes.data_as(dp), C.byref(lam))
     assert rc == 0
     x2, lam2 = oracle.natural_gradient(G2, g)
-    assert lam2 > 1e-4 and abs(lam.value - lam2) / lam2 < 1e-4   # kappa of a 1e10-conditioned matrix is itself ill-determined
+    assert lam2 > 1e-4 and abs(lam.value - lam2) / lam2 < 1e-4   # kappa of a 1e9-conditioned matrix is itself ill-determined
     assert np.abs(out - x2).max() / np.abs(x2).max() < 1e-3
+
+
+def test_natural_gradient_rank_deficient_metric_keeps_a_usable_lambda():
+    """a rank-deficient metric must not push the adaptive lambda to 100 (kappa = 1e16)."""
+    lib = api.load()
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(24, 12))
+    G = A @ A.T / 24 * 0.25                      # rank 12 of 24, eigenvalues <= ~0.25 like a Fubini-Study metric
+    g = G @ rng.normal(size=24)                  # a gradient inside the range
+    out = np.zeros(24)
+    lam = C.c_double(0)
+    dp = C.POINTER(C.c_double)
+    rc = lib.qgt_b200_natural_gradient(None, G.ctypes.data_as(dp), g.ctypes.data_as(dp), 24, None, out.ctypes.data_as(dp), C.byref(lam))
+    assert rc == 0
+    w = np.linalg.eigvalsh(G)
+    kappa_range = w.max() / w[w > 1e-10].min()
+    assert lam.value == max(1e-4, 1e-6 * np.sqrt(kappa_range) if kappa_range > 1e8 else 1e-4)
+    assert lam.value < 1e-2
+    x = np.linalg.solve(G + lam.value * np.eye(24), g)
+    assert np.abs(out - x).max() / np.abs(x).max() < 1e-8
 
 
 def test_error_strings():

@@ -194,3 +194,19 @@ def test_runs_split_where_parameters_are_born(oracle, slots, monkeypatch):
     assert (seen[:c.num_params, :c.num_params] >= 1).all()
     assert np.abs(q - oracle.qgt(c, th)).max() < 1e-12
     assert np.abs(psi - oracle.apply(c, th)).max() < 1e-13
+
+
+def test_parameter_free_circuit_applies_every_run_once(oracle):
+    """with P = 0 and psi requested the program applied the circuit twice (psi = U U|0>)."""
+    c = K.Circuit(3).add(K.H, 1)
+    plan = api.plan_dump(c, np.zeros(1), column_slots=300)
+    kinds = [i["k"] for i in plan["program"]["instrs"]]
+    assert kinds == ["init", "sweep"]
+    Q, psi, _, _ = pi.run_program(plan, c)
+    assert np.abs(psi - oracle.apply(c, np.zeros(1))).max() < 1e-15
+    for seed in range(8):
+        c = K.random_circuit(4, 25, 900 + seed, kinds=[K.X, K.Y, K.Z, K.H, K.S, K.T, K.CNOT, K.CZ, K.SWAP])
+        assert c.num_params == 0
+        plan = api.plan_dump(c, np.zeros(1), tile_qubits=3, reg_qubits=2, column_slots=16)
+        _, psi, _, _ = pi.run_program(plan, c)
+        assert np.abs(psi - oracle.apply(c, np.zeros(1))).max() < 1e-13
