@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define QGT_B200_ABI_VERSION 1
+#define QGT_B200_ABI_VERSION 2
 
 /* ---- status (numerically equal to the reference's qgt_error_t) ------------------------- */
 enum {
@@ -231,6 +231,10 @@ typedef struct qgt_b200_stats {
     int32_t tile_qubits;
     double ms_wall;           /* host wall-clock time of the whole call */
     double ms_host_plan;      /* of which: planning (fusion, stage matrices, schedule, derivative matrices) */
+    double tensor_flops;      /* real flops the sweep / fused kernels issue on the FP64 tensor pipe (stage applications of
+                                 every tile they carry plus the transition-matrix products of the fused schedule) */
+    int32_t fused;            /* 1: the fused schedule ran (transition matrices inside the sweeps, no Gram pass) */
+    int32_t fused_launches;
 } qgt_b200_stats;
 int  qgt_b200_get_stats(qgt_b200_ctx* ctx, qgt_b200_stats* out);
 
@@ -253,6 +257,12 @@ int  qgt_b200_dist_barrier(qgt_b200_ctx* ctx);
  * per-segment logical->physical qubit maps */
 long qgt_b200_plan_dump_sharded(const qgt_b200_circuit* circuit, const double* theta, int world, int restore_identity,
                                 int tile_qubits, int reg_qubits, size_t column_slots, char* buf, size_t buflen);
+
+/* plan_dump with the FUSED column schedule (transition matrices contracted inside the sweeps, no Gram pass; see
+ * plan.hpp) for a state on `world` ranks (1 = unsharded).  Returns QGT_B200_ERR_UNSUPPORTED when the plan does not
+ * qualify (tiles below 8 qubits, a sub-pass off the tensor path, a cost layer). */
+long qgt_b200_plan_dump_fused(const qgt_b200_circuit* circuit, const double* theta, int world, int tile_qubits, int reg_qubits,
+                              size_t column_slots, char* buf, size_t buflen);
 
 #ifdef __cplusplus
 }

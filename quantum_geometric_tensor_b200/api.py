@@ -33,7 +33,8 @@ class Stats(C.Structure):
                 ("sweep_launches", C.c_int64), ("gram_launches", C.c_int64), ("other_launches", C.c_int64),
                 ("sweep_column_passes", C.c_int64),
                 ("num_runs", C.c_int32), ("resident_columns", C.c_int32), ("blocks", C.c_int32), ("tile_qubits", C.c_int32),
-                ("ms_wall", C.c_double), ("ms_host_plan", C.c_double)]
+                ("ms_wall", C.c_double), ("ms_host_plan", C.c_double), ("tensor_flops", C.c_double),
+                ("fused", C.c_int32), ("fused_launches", C.c_int32)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -89,6 +90,8 @@ def load() -> C.CDLL:
     L.qgt_b200_plan_dump_sharded.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t]
     L.qgt_b200_plan_dump_sharded.restype = C.c_long
     L.qgt_b200_dist_barrier.argtypes = [vp]
+    L.qgt_b200_plan_dump_fused.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t]
+    L.qgt_b200_plan_dump_fused.restype = C.c_long
     _lib = L
     return L
 
@@ -134,6 +137,23 @@ def plan_dump_sharded(circ: Circuit, theta: Optional[np.ndarray], world: int, re
         _check(int(n))
     buf = C.create_string_buffer(n + 1)
     n2 = L.qgt_b200_plan_dump_sharded(*args, buf, n + 1)
+    if n2 < 0:
+        _check(int(n2))
+    return json.loads(buf.value.decode())
+
+
+def plan_dump_fused(circ: Circuit, theta: Optional[np.ndarray], column_slots: int, world: int = 1,
+                    tile_qubits: int = 0, reg_qubits: int = 0) -> dict:
+    """Plan with the fused column schedule (transition matrices instead of Gram passes).  Needs no GPU."""
+    L = load()
+    cc = circ.to_c()
+    th = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
+    args = (C.byref(cc), _dp(th), world, tile_qubits, reg_qubits, column_slots)
+    n = L.qgt_b200_plan_dump_fused(*args, None, 0)
+    if n < 0:
+        _check(int(n))
+    buf = C.create_string_buffer(n + 1)
+    n2 = L.qgt_b200_plan_dump_fused(*args, buf, n + 1)
     if n2 < 0:
         _check(int(n2))
     return json.loads(buf.value.decode())

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -275,6 +276,7 @@ void qgt_b200_destroy(qgt_b200_ctx* c) {
     c->img_tdiags.release(); c->img_costs.release(); c->img_pool.release(); c->ovr_pool.release();
     c->items.release(); c->aux.release(); c->partial.release(); c->cmat.release(); c->outbuf.release();
     c->edges.release(); c->vweights.release(); c->scratch.release();
+    c->fx_pool.release(); c->fx_tab.release(); c->rho.release(); c->rho_self.release(); c->amat.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
@@ -303,6 +305,7 @@ int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
     else if (k == "gram_tile") set_gram_tile_override((int)value);
     else if (k == "profile") c->timer.enabled = value != 0;
     else if (k == "max_slots") c->max_slots = (size_t)value;
+    else if (k == "fused") c->fused_mode = (int)value;
     else return fail(QGT_B200_ERR_INVALID_ARG, "unknown option " + k);
     return QGT_B200_OK;
 }
@@ -541,7 +544,7 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
     size_t partial_bytes = 0;
     for (size_t i = 0; i < prog.instrs.size(); i++) {
         const Instr& in = prog.instrs[i];
-        if (in.kind == INSTR_SWEEP) {
+        if (in.kind == INSTR_SWEEP || in.kind == INSTR_FUSED) {
             item_off[i] = items.size();
             const Run& run = plan.runs[in.run];
             for (const SweepCol& sc : in.cols) {
@@ -551,6 +554,8 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                 it.dst = arena + (size_t)sc.dst * D;
                 it.accumulate = sc.accumulate ? 1u : 0u;
                 it.ovr_kind = 0; it.ovr_index = -1;
+                it.self = sc.self ? 1 : 0;
+                it.rho_from = sc.rho_from;
                 if (sc.ovr_op >= 0) {
                     const OpLocation loc = locate_op(run, sc.ovr_op);
                     if (loc.kind == 0) return fail(QGT_B200_ERR_INTERNAL, "override op outside every sub-pass");
@@ -594,6 +599,89 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             const size_t per_split = gram_configure(gl, shp);
             const int ks = gram_choose_ksplit(gl, shp, c->num_sms);
             partial_bytes = std::max(partial_bytes, (size_t)ks * per_split * sizeof(cplx));
+        }
+    }
+    // ---- fused schedule: evolved generators (X pool), contraction tables, layout of the self transition matrices ----
+    struct FusedRec { size_t group_off = 0; int ngroups = 0; int self_item = -1; int tpc = 0, tg = 0; };
+    std::vector<FusedRec> frec(prog.instrs.size());
+    std::vector<QgtContractEntry> centries;
+    std::vector<QgtContractGroup> cgroups;
+    std::vector<double> xpool;
+    std::vector<std::vector<int>> xbase(plan.runs.size());     // per run and stage (run-relative): first X block, -1 = none
+    std::vector<char> xdone(plan.runs.size(), 0);
+    size_t rho_doubles_max = 0;
+    FusedHost& fh = c->fused_host;
+    if (prog.fused) {
+        fh = FusedHost();
+        fh.self_off.assign(plan.runs.size(), (size_t)-1);
+        std::vector<double> gens;
+        for (size_t i = 0; i < prog.instrs.size(); i++) {
+            const Instr& in = prog.instrs[i];
+            if (in.kind != INSTR_FUSED) continue;
+            const Run& run = plan.runs[in.run];
+            if (!xdone[in.run]) {
+                xdone[in.run] = 1;
+                for (const SubPass& sp : run.subs)
+                    for (const Stage& st : sp.stages) {
+                        if (st.params.empty()) { xbase[in.run].push_back(-1); continue; }
+                        xbase[in.run].push_back((int)(xpool.size() / 128));
+                        stage_generators(run, sp, st, gens);
+                        const int nv = 1 << (int)st.vqubits.size();
+                        for (size_t kk = 0; kk < st.params.size(); kk++)
+                            for (int v = 0; v < nv; v++) {
+                                const double* G = &gens[(kk * (size_t)nv + v) * 128];
+                                const size_t base = xpool.size();
+                                xpool.resize(base + 128);
+                                for (int a = 0; a < 8; a++)
+                                    for (int cc = 0; cc < 8; cc++) {          // X(c, a) = Gt[a][c], stored in rho's element order
+                                        xpool[base + rho_index(cc, a, 0)] = G[2 * (a * 8 + cc)];
+                                        xpool[base + rho_index(cc, a, 1)] = G[2 * (a * 8 + cc) + 1];
+                                    }
+                            }
+                        FusedHost::StageGen sg;
+                        sg.run = in.run; sg.rho_off = st.rho_off; sg.nvar = (int)st.vqubits.size(); sg.params = st.params; sg.gens = gens;
+                        fh.stages.push_back(std::move(sg));
+                    }
+            }
+            FusedRec& fr = frec[i];
+            std::map<int, std::vector<QgtContractEntry>> byout;
+            for (size_t j = 0; j < in.cols.size(); j++) {
+                const SweepCol& sc = in.cols[j];
+                if (sc.self) {
+                    if (sc.rho_from == 0) {
+                        fr.self_item = (int)j;
+                        if (fh.self_off[in.run] == (size_t)-1) { fh.self_off[in.run] = fh.self_doubles; fh.self_doubles += (size_t)run.rho_blocks * 128; }
+                    }
+                    continue;
+                }
+                int sidx = 0;
+                for (const SubPass& sp : run.subs)
+                    for (const Stage& st : sp.stages) {
+                        if (st.rho_off >= 0 && sidx >= sc.rho_from) {
+                            const int nv = 1 << (int)st.vqubits.size();
+                            for (size_t kk = 0; kk < st.params.size(); kk++) {
+                                QgtContractEntry en;
+                                en.item = (int)j; en.rho_off = st.rho_off; en.nblocks = nv;
+                                en.x_off = xbase[in.run][sidx] + (int)kk * nv;
+                                byout[sc.id * P + st.params[kk]].push_back(en);
+                            }
+                        }
+                        sidx++;
+                    }
+            }
+            fr.group_off = cgroups.size();
+            for (auto& kv : byout) {
+                QgtContractGroup g;
+                g.begin = (int)centries.size();
+                centries.insert(centries.end(), kv.second.begin(), kv.second.end());
+                g.end = (int)centries.size(); g.out = kv.first; g.pad = 0;
+                cgroups.push_back(g);
+            }
+            fr.ngroups = (int)(cgroups.size() - fr.group_off);
+            fused_geometry(D >> run.K, (int)in.cols.size(), c->num_sms, &fr.tpc, &fr.tg);
+            const size_t per_item = (size_t)run.rho_blocks * 128;
+            rho_doubles_max = std::max(rho_doubles_max, in.cols.size() * per_item);
+            partial_bytes = std::max(partial_bytes, (size_t)fr.tg * in.cols.size() * per_item * sizeof(double));
         }
     }
     // derivative (product-rule) stage matrices: independent of each other, a few microseconds each, hundreds per
@@ -641,8 +729,24 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
     if (e == cudaSuccess && !ovr_pool.empty()) e = cudaMemcpyAsync(c->ovr_pool.ptr, ovr_pool.data(), ovr_pool.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess && ptr_bytes) e = cudaMemcpyAsync(c->aux.ptr, ptrs.data(), ptr_bytes, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess && id_bytes) e = cudaMemcpyAsync((char*)c->aux.ptr + ptr_bytes, ids.data(), id_bytes, cudaMemcpyHostToDevice, c->stream);
+    const size_t entry_bytes = centries.size() * sizeof(QgtContractEntry), group_bytes = cgroups.size() * sizeof(QgtContractGroup);
+    if (prog.fused) {
+        if ((rc = c->fx_pool.reserve(std::max<size_t>(16, xpool.size() * sizeof(double))))) return rc;
+        if ((rc = c->fx_tab.reserve(std::max<size_t>(16, entry_bytes + group_bytes)))) return rc;
+        if ((rc = c->rho.reserve(std::max<size_t>(16, rho_doubles_max * sizeof(double))))) return rc;
+        if ((rc = c->rho_self.reserve(std::max<size_t>(16, fh.self_doubles * sizeof(double))))) return rc;
+        if ((rc = c->amat.reserve(std::max<size_t>(16, (size_t)P * P * sizeof(cplx))))) return rc;
+        if (e == cudaSuccess && !xpool.empty()) e = cudaMemcpyAsync(c->fx_pool.ptr, xpool.data(), xpool.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess && entry_bytes) e = cudaMemcpyAsync(c->fx_tab.ptr, centries.data(), entry_bytes, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess && group_bytes) e = cudaMemcpyAsync((char*)c->fx_tab.ptr + entry_bytes, cgroups.data(), group_bytes, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->amat.ptr, 0, std::max<size_t>(16, (size_t)P * P * sizeof(cplx)), c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->rho_self.ptr, 0, std::max<size_t>(16, fh.self_doubles * sizeof(double)), c->stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // host vectors are locals
     if (e != cudaSuccess) return cuda_fail(e, "program upload");
+    const QgtContractEntry* d_entries = (const QgtContractEntry*)c->fx_tab.ptr;
+    const QgtContractGroup* d_groups = (const QgtContractGroup*)((const char*)c->fx_tab.ptr + entry_bytes);
+    c->stats.fused = prog.fused ? 1 : 0;
     const cplx* const* d_ptrs = (const cplx* const*)c->aux.ptr;
     const int* d_ids = (const int*)((char*)c->aux.ptr + ptr_bytes);
 
@@ -681,6 +785,65 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             for (const SweepCol& sc : in.cols)
                 c->stats.sweep_bytes += (sc.accumulate ? 48.0 : 32.0) * (double)D;
             break; }
+        case INSTR_FUSED: {
+            const Run& run = plan.runs[in.run];
+            const FusedRec& fr = frec[i];
+            const int nitems = (int)in.cols.size();
+            const size_t per_item = (size_t)run.rho_blocks * 128;
+            FusedLaunch a;
+            a.runs = (const QgtDevRun*)c->img_runs.ptr;
+            a.subs = (const QgtDevSubPass*)c->img_subs.ptr;
+            a.stages = (const QgtDevStage*)c->img_stages.ptr;
+            a.tdiags = (const QgtDevThrDiag*)c->img_tdiags.ptr;
+            a.pool = (const cplx*)c->img_pool.ptr;
+            a.run_idx = in.run;
+            a.items = (const QgtSweepItem*)c->items.ptr + item_off[i];
+            a.nitems = nitems;
+            a.phi = arena + (size_t)in.phi * D;
+            a.ntiles = D >> run.K;
+            a.tiles_per_cta = fr.tpc; a.tile_groups = fr.tg;
+            a.gprefix = (uint64_t)c->rank << plan.nloc;
+            a.rho_partial = (double*)c->partial.ptr;
+            int mat_count = 0, nstage_rho = 0;
+            double flops_ab = 0.0;                  // per amplitude: one tile through every stage
+            for (const SubPass& sp : run.subs)
+                for (const Stage& stg : sp.stages) {
+                    mat_count += QGT_VARIANT_STRIDE(8) << stg.vqubits.size();
+                    flops_ab += 64.0;               // counted as dense 4M complex products (the diagonal-real form issues half)
+                    if (stg.rho_off >= 0) nstage_rho++;
+                }
+            char label[160];
+            if (c->timer.trace)
+                snprintf(label, sizeof label, "fused run=%d items=%d subs=%d rho_stages=%d rho_blocks=%d tiles=%llu chunks=%d", in.run, nitems,
+                         (int)run.subs.size(), nstage_rho, run.rho_blocks, (unsigned long long)a.ntiles, fr.tg);
+            c->timer.begin(c->stream, 0, label);
+            e = launch_fused(a, run.K, mat_count, (int)run.subs.size(), run.rho_blocks, c->stream);
+            c->timer.end(c->stream);
+            if (e != cudaSuccess) return cuda_fail(e, "fused launch");
+            c->stats.sweep_launches++; c->stats.fused_launches++;
+            c->stats.sweep_column_passes += nitems;
+            for (const SweepCol& sc : in.cols) {
+                c->stats.sweep_bytes += (sc.accumulate ? 48.0 : 32.0) * (double)D;
+                int sidx = 0, nrho = 0;
+                for (const SubPass& sp : run.subs)
+                    for (const Stage& stg : sp.stages) { if (stg.rho_off >= 0 && sidx >= sc.rho_from) nrho++; sidx++; }
+                const bool use_b = !sc.self && sc.rho_from <= run.last_rho_stage;
+                c->stats.tensor_flops += (double)D * (flops_ab * (use_b ? 2.0 : 1.0) + 64.0 * nrho);
+            }
+            if (per_item > 0) {
+                c->timer.begin(c->stream, 1, "rho reduce + contract");
+                e = launch_rho_reduce((const double*)c->partial.ptr, fr.tg, nitems, (int)per_item, (double*)c->rho.ptr, c->stream);
+                if (e == cudaSuccess && fr.self_item >= 0)
+                    e = cudaMemcpyAsync((double*)c->rho_self.ptr + fh.self_off[in.run], (const double*)c->rho.ptr + (size_t)fr.self_item * per_item,
+                                        per_item * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+                if (e == cudaSuccess)
+                    e = launch_rho_contract((const double*)c->rho.ptr, (int)per_item, (const double*)c->fx_pool.ptr, d_groups + fr.group_off, fr.ngroups,
+                                            d_entries, (cplx*)c->amat.ptr, c->stream);
+                c->timer.end(c->stream);
+                if (e != cudaSuccess) return cuda_fail(e, "rho reduce/contract launch");
+                c->stats.other_launches += 2;
+            }
+            break; }
         case INSTR_GRAM: {
             const GramRec& g = grec[i];
             GramLaunch gl;
@@ -703,6 +866,91 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             break; }
         }
     }
+    return QGT_B200_OK;
+}
+
+bool choose_fused(const qgt_b200_ctx* c, const CircuitPlan& plan, size_t slots) {
+    if (c->fused_mode == 0 || !plan_supports_fused(plan)) return false;
+    size_t Pa = 0;
+    for (int f : plan.first_run) if (f >= 0) Pa++;
+    if (Pa == 0) return false;
+    if (c->fused_mode == 1) return true;
+    return Pa + 2 > slots;       // automatic: the Gram schedule while every column is resident, the fused one otherwise
+}
+
+int fused_finish(qgt_b200_ctx* c, const CircuitPlan& plan, double* metric, double* berry, double* q_full) {
+    const int P = plan.P;
+    const FusedHost& fh = c->fused_host;
+    int rc;
+    if (c->world > 1) {
+        if ((rc = dist_allreduce_device(c, (double*)c->amat.ptr, (size_t)P * P * 2))) return rc;
+        if (fh.self_doubles && (rc = dist_allreduce_device(c, (double*)c->rho_self.ptr, fh.self_doubles))) return rc;
+    }
+    std::vector<double> A((size_t)P * P * 2), rs(fh.self_doubles);
+    cudaError_t e = cudaSuccess;
+    if (P > 0) e = cudaMemcpyAsync(A.data(), c->amat.ptr, A.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && !rs.empty()) e = cudaMemcpyAsync(rs.data(), c->rho_self.ptr, rs.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "fused result download");
+    // C = A + A^H + D,  v_mu = <d_mu psi|psi>;  D (pairs inside one stage, the diagonal) and v from rho of phi with itself
+    std::vector<double> Cr((size_t)P * P), Ci((size_t)P * P), vr(P, 0.0), vi(P, 0.0);
+    for (int m = 0; m < P; m++)
+        for (int n = 0; n < P; n++) {
+            Cr[(size_t)m * P + n] = A[2 * ((size_t)m * P + n)] + A[2 * ((size_t)n * P + m)];
+            Ci[(size_t)m * P + n] = A[2 * ((size_t)m * P + n) + 1] - A[2 * ((size_t)n * P + m) + 1];
+        }
+    for (const FusedHost::StageGen& sg : fh.stages) {
+        if (fh.self_off[sg.run] == (size_t)-1) continue;
+        const int nv = 1 << sg.nvar, np = (int)sg.params.size();
+        for (int v = 0; v < nv; v++) {
+            const double* rho = &rs[fh.self_off[sg.run] + (size_t)(sg.rho_off + v) * 128];
+            // W_k[i][a] = sum_c G_k[i][c] rho[c][a]   (G_k rho), then  D[mu][nu] = sum_{i,a} conj(G_mu[i][a]) W_nu[i][a],  v_mu = sum conj(G_mu[i][a]) rho[i][a]
+            std::vector<double> W((size_t)np * 128, 0.0);
+            for (int k = 0; k < np; k++) {
+                const double* G = &sg.gens[((size_t)k * nv + v) * 128];
+                for (int i = 0; i < 8; i++)
+                    for (int a = 0; a < 8; a++) {
+                        double wr = 0.0, wi = 0.0;
+                        for (int cc = 0; cc < 8; cc++) {
+                            const double gr = G[2 * (i * 8 + cc)], gi = G[2 * (i * 8 + cc) + 1];
+                            const double rr = rho[rho_index(cc, a, 0)], ri = rho[rho_index(cc, a, 1)];
+                            wr += gr * rr - gi * ri; wi += gr * ri + gi * rr;
+                        }
+                        W[((size_t)k * 64 + i * 8 + a) * 2] = wr; W[((size_t)k * 64 + i * 8 + a) * 2 + 1] = wi;
+                    }
+            }
+            for (int km = 0; km < np; km++) {
+                const double* Gm = &sg.gens[((size_t)km * nv + v) * 128];
+                const int mu = sg.params[km];
+                double sr = 0.0, si = 0.0;
+                for (int i = 0; i < 8; i++)
+                    for (int a = 0; a < 8; a++) {
+                        const double gr = Gm[2 * (i * 8 + a)], gi = -Gm[2 * (i * 8 + a) + 1];
+                        const double rr = rho[rho_index(i, a, 0)], ri = rho[rho_index(i, a, 1)];
+                        sr += gr * rr - gi * ri; si += gr * ri + gi * rr;
+                    }
+                vr[mu] += sr; vi[mu] += si;
+                for (int kn = 0; kn < np; kn++) {
+                    const double* Wn = &W[(size_t)kn * 128];
+                    double dr = 0.0, di = 0.0;
+                    for (int x = 0; x < 64; x++) {
+                        const double gr = Gm[2 * x], gi = -Gm[2 * x + 1];
+                        dr += gr * Wn[2 * x] - gi * Wn[2 * x + 1]; di += gr * Wn[2 * x + 1] + gi * Wn[2 * x];
+                    }
+                    Cr[(size_t)mu * P + sg.params[kn]] += dr; Ci[(size_t)mu * P + sg.params[kn]] += di;
+                }
+            }
+        }
+    }
+    for (int m = 0; m < P; m++)
+        for (int n = 0; n < P; n++) {
+            // Q = C - v_mu conj(v_nu)
+            const double qr = Cr[(size_t)m * P + n] - (vr[m] * vr[n] + vi[m] * vi[n]);
+            const double qi = Ci[(size_t)m * P + n] - (vi[m] * vr[n] - vr[m] * vi[n]);
+            if (metric) metric[(size_t)m * P + n] = qr;
+            if (berry) berry[(size_t)m * P + n] = qi;
+            if (q_full) { q_full[2 * ((size_t)m * P + n)] = qr; q_full[2 * ((size_t)m * P + n) + 1] = qi; }
+        }
     return QGT_B200_OK;
 }
 
@@ -787,8 +1035,10 @@ int qgt_b200_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* th
     std::string err;
     if ((rc = build_plan(*circ, theta, c->opt, plan, err))) return fail(rc, err);
     Program prog;
-    const size_t slots = workspace_slots(c, D, (size_t)64 << 20);
-    if ((rc = build_qgt_program(plan, slots, psi_out != nullptr, prog, err))) return fail(rc, err);
+    const size_t slots = workspace_slots(c, D, (size_t)256 << 20);
+    const bool use_fused = choose_fused(c, plan, slots);
+    if ((rc = use_fused ? build_fused_program(plan, slots, psi_out != nullptr, prog, err)
+                        : build_qgt_program(plan, slots, psi_out != nullptr, prog, err))) return fail(rc, err);
     const double ms_plan0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wall0).count();
     if ((rc = c->arena.reserve((size_t)prog.num_slots * D * sizeof(cplx)))) return rc;
     const size_t cm = (size_t)(P + 1) * (P + 1);
@@ -803,13 +1053,17 @@ int qgt_b200_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* th
     double* d_metric = (double*)c->outbuf.ptr;
     double* d_berry = d_metric + (size_t)P * P;
     cplx* d_q = (cplx*)(d_berry + (size_t)P * P);
-    c->timer.begin(c->stream, 2);
-    e = launch_finalize((const cplx*)c->cmat.ptr, P, d_metric, d_berry, d_q, c->stream);
-    c->timer.end(c->stream);
-    if (e != cudaSuccess) return cuda_fail(e, "finalize launch");
-    c->stats.other_launches++;
+    if (prog.fused) {
+        if ((rc = fused_finish(c, plan, metric, berry, q_full))) return rc;
+    } else {
+        c->timer.begin(c->stream, 2);
+        e = launch_finalize((const cplx*)c->cmat.ptr, P, d_metric, d_berry, d_q, c->stream);
+        c->timer.end(c->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "finalize launch");
+        c->stats.other_launches++;
+    }
     const size_t pp = (size_t)P * P;
-    if (P > 0) {
+    if (P > 0 && !prog.fused) {
         if (metric && e == cudaSuccess) e = cudaMemcpyAsync(metric, d_metric, pp * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
         if (berry && e == cudaSuccess) e = cudaMemcpyAsync(berry, d_berry, pp * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
         if (q_full && e == cudaSuccess) e = cudaMemcpyAsync(q_full, d_q, pp * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream);
@@ -1021,6 +1275,30 @@ long qgt_b200_plan_dump_sharded(const qgt_b200_circuit* circ, const double* thet
         pp = &prog;
     }
     const std::string js = dump_json(*circ, plan, pp, &segs);
+    if (buf && buflen > js.size()) std::memcpy(buf, js.c_str(), js.size() + 1);
+    return (long)js.size();
+}
+
+long qgt_b200_plan_dump_fused(const qgt_b200_circuit* circ, const double* theta, int world, int tile_qubits, int reg_qubits,
+                              size_t column_slots, char* buf, size_t buflen) {
+    if (!circ) return fail(QGT_B200_ERR_INVALID_ARG, "circuit is NULL");
+    if (world < 1 || (world & (world - 1))) return fail(QGT_B200_ERR_INVALID_ARG, "world must be a power of two");
+    int gbits = 0;
+    while ((1 << gbits) < world) gbits++;
+    PlanOptions opt;
+    if (tile_qubits) opt.tile_qubits = tile_qubits;
+    if (reg_qubits) opt.reg_qubits = reg_qubits;
+    std::vector<double> zeros((size_t)std::max(1, circ->num_params), 0.0);
+    CircuitPlan plan;
+    std::vector<MappedSegment> segs;
+    std::string err;
+    int rc = world > 1 ? build_plan_sharded(*circ, theta ? theta : zeros.data(), opt, circ->num_qubits - gbits, true, plan, segs, err)
+                       : build_plan(*circ, theta ? theta : zeros.data(), opt, plan, err);
+    if (rc) return fail(rc, err);
+    if (!plan_supports_fused(plan)) return fail(QGT_B200_ERR_UNSUPPORTED, "plan does not qualify for the fused schedule");
+    Program prog;
+    if ((rc = build_fused_program(plan, column_slots, true, prog, err))) return fail(rc, err);
+    const std::string js = dump_json(*circ, plan, &prog, world > 1 ? &segs : nullptr);
     if (buf && buflen > js.size()) std::memcpy(buf, js.c_str(), js.size() + 1);
     return (long)js.size();
 }

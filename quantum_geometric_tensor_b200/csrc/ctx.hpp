@@ -39,6 +39,18 @@ struct Timer {
 
 struct DistState;   // dist.cu
 
+// host side of a fused evaluation: what the final assembly needs besides the device results
+struct FusedHost {
+    struct StageGen {
+        int run = 0, rho_off = 0, nvar = 0;
+        std::vector<int> params;
+        std::vector<double> gens;           // stage_generators(): [param][variant][a][c] complex
+    };
+    std::vector<StageGen> stages;           // every stage with parameters of the runs whose self transition matrices were taken
+    std::vector<size_t> self_off;           // per run: offset (doubles) of its self transition matrices in rho_self, npos = none
+    size_t self_doubles = 0;
+};
+
 }  // namespace qgt
 
 struct qgt_b200_ctx {
@@ -55,6 +67,9 @@ struct qgt_b200_ctx {
     double ms_prog_pack = 0.0;
     qgt::PlanOptions opt;
     qgt::DevBuf arena, img_runs, img_subs, img_stages, img_tdiags, img_costs, img_pool, ovr_pool, items, aux, partial, cmat, outbuf, edges, vweights, scratch;
+    qgt::DevBuf fx_pool, fx_tab, rho, rho_self, amat;     // fused schedule: evolved generators, contraction tables, transition matrices, A
+    qgt::FusedHost fused_host;
+    int fused_mode = -1;         // -1 automatic (fused when the columns do not all fit), 0 never, 1 whenever the plan qualifies
     void* pinned = nullptr;
     QgtCostTable cost = {nullptr, 0, nullptr, 0};
     std::vector<QgtCostTable> seg_cost;      // sharded states: one cost table per mapped segment (remapped qubits)
@@ -82,6 +97,11 @@ int apply_plan_inplace(qgt_b200_ctx* c, const CircuitPlan& plan, cplx* d, uint64
 int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan& plan, const Program& prog,
                 cplx* arena, uint64_t D, cplx* cmat);
 size_t workspace_slots(qgt_b200_ctx* c, uint64_t D, size_t reserve_bytes);
+// fused schedule or the Gram schedule for this plan and slot count (option "fused")
+bool choose_fused(const qgt_b200_ctx* c, const CircuitPlan& plan, size_t slots);
+// after run_program of a fused program: (allreduce over ranks,) download A and the self transition matrices and
+// assemble metric / Berry curvature / full Q on the host; any output may be null
+int fused_finish(qgt_b200_ctx* c, const CircuitPlan& plan, double* metric, double* berry, double* q_full);
 void stats_begin(qgt_b200_ctx* c);
 int stats_end(qgt_b200_ctx* c);
 

@@ -56,7 +56,10 @@ typedef struct QgtDevStage {
     int16_t  form;                           // QGT_FORM_* of every variant of this stage
     int32_t  mat_off;                        // offset of variant 0 in the run's matrix pool, in complex elements
     uint64_t vmask[QGT_MAX_VARIANT_BITS];    // global index bit selecting variant bit k
-} QgtDevStage;                               // 24 bytes
+    int32_t  rho_off;                        // fused kernel: first transition-matrix block of this stage in an item's rho buffer (one
+                                             // block of 64 complex per variant), -1 when no parameter occurs in the stage
+    int32_t  pad;
+} QgtDevStage;                               // 32 bytes
 
 // a diagonal gate (or the derivative of one) that touches no register qubit: one phase per thread
 typedef struct QgtDevThrDiag {
@@ -105,6 +108,9 @@ typedef struct QgtDevRun {
     int8_t  tq[QGT_MAX_TILE_QUBITS];     // tile qubits: local bit j <-> global bit tq[j], ascending
     int8_t  ntq[QGT_MAX_QUBITS];         // the n-K other qubits, ascending (tile id bits are deposited here)
     int32_t has_cost;                    // the run contains a cost-layer pass (energy tables are staged in shared memory)
+    int32_t rho_blocks;                  // fused kernel: transition-matrix blocks per item
+    int32_t last_rho_stage;              // fused kernel: last stage (run-relative) with a parameter occurrence, -1 = none
+    int32_t pad2;
 } QgtDevRun;
 
 // one column of a batched sweep launch
@@ -118,8 +124,20 @@ typedef struct QgtSweepItem {
     const void* ovr_mat;                 // kind 1: the replacement matrices (all variants) in global memory
     QgtDevThrDiag ovr_tdiag;             // kind 2
     QgtDevCost    ovr_cost;              // kind 3
+    // fused kernel only
+    int32_t     self;                    // the item is phi itself: one tile, rho = <phi| . |phi>
+    int32_t     rho_from;                // first stage (run-relative) whose transition matrix is accumulated
 } QgtSweepItem;
 
 typedef struct QgtDevEdge { int32_t i, j; double w; } QgtDevEdge;
+
+// fused schedule: A[out] += sum over entries [begin, end) of  sum_{variant blocks} sum_e X[e] * rho[e]
+typedef struct QgtContractEntry {
+    int32_t item;        // item of the launch whose transition matrices are contracted
+    int32_t rho_off;     // first block of the stage inside the item's rho buffer
+    int32_t nblocks;     // variants of the stage
+    int32_t x_off;       // first block of the evolved generator in the X pool (same element order as rho)
+} QgtContractEntry;
+typedef struct QgtContractGroup { int32_t begin, end, out, pad; } QgtContractGroup;
 
 #endif

@@ -198,7 +198,7 @@ int dist_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
     if (rc) return fail(rc, err);
     Program prog;
     // every rank must build the same program: agree on the smallest slot count
-    size_t slots = workspace_slots(c, D, ((size_t)64 << 20) + (D / 2) * sizeof(cplx));
+    size_t slots = workspace_slots(c, D, ((size_t)256 << 20) + (D / 2) * sizeof(cplx));
     {
         int rc2 = c->dist->red.reserve(sizeof(double));
         if (rc2) return rc2;
@@ -212,7 +212,9 @@ int dist_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
         if (e0 != cudaSuccess) return cuda_fail(e0, "slot readback");
         slots = (size_t)v;
     }
-    if ((rc = build_qgt_program(plan, slots, psi_out != nullptr, prog, err))) return fail(rc, err);
+    const bool use_fused = choose_fused(c, plan, slots);
+    if ((rc = use_fused ? build_fused_program(plan, slots, psi_out != nullptr, prog, err)
+                        : build_qgt_program(plan, slots, psi_out != nullptr, prog, err))) return fail(rc, err);
     if ((rc = c->arena.reserve((size_t)prog.num_slots * D * sizeof(cplx)))) return rc;
     const size_t cm = (size_t)(P + 1) * (P + 1);
     if ((rc = c->cmat.reserve(std::max<size_t>(16, cm * sizeof(cplx))))) return rc;
@@ -224,18 +226,23 @@ int dist_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
     cudaError_t e = cudaMemsetAsync(c->cmat.ptr, 0, cm * sizeof(cplx), c->stream);
     if (e != cudaSuccess) return cuda_fail(e, "memset");
     if ((rc = run_program(c, *circ, plan, prog, (cplx*)c->arena.ptr, D, (cplx*)c->cmat.ptr))) return rc;
-    // partial Gram matrices of the shards -> one allreduce of (P+1)^2 complex numbers
-    c->timer.begin(c->stream, 2, "gram allreduce");
-    rc = dist_allreduce_device(c, (double*)c->cmat.ptr, cm * 2);
-    c->timer.end(c->stream);
-    if (rc) return rc;
     double* d_metric = (double*)c->outbuf.ptr;
     double* d_berry = d_metric + (size_t)P * P;
     cplx* d_q = (cplx*)(d_berry + (size_t)P * P);
-    e = launch_finalize((const cplx*)c->cmat.ptr, P, d_metric, d_berry, d_q, c->stream);
-    if (e != cudaSuccess) return cuda_fail(e, "finalize launch");
+    if (prog.fused) {
+        // partial A and self transition matrices of the shards: two allreduces, then the host assembly (identical on every rank)
+        if ((rc = fused_finish(c, plan, metric, berry, q_full))) return rc;
+    } else {
+        // partial Gram matrices of the shards -> one allreduce of (P+1)^2 complex numbers
+        c->timer.begin(c->stream, 2, "gram allreduce");
+        rc = dist_allreduce_device(c, (double*)c->cmat.ptr, cm * 2);
+        c->timer.end(c->stream);
+        if (rc) return rc;
+        e = launch_finalize((const cplx*)c->cmat.ptr, P, d_metric, d_berry, d_q, c->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "finalize launch");
+    }
     const size_t pp = (size_t)P * P;
-    if (P > 0) {
+    if (P > 0 && !prog.fused) {
         if (metric && e == cudaSuccess) e = cudaMemcpyAsync(metric, d_metric, pp * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
         if (berry && e == cudaSuccess) e = cudaMemcpyAsync(berry, d_berry, pp * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
         if (q_full && e == cudaSuccess) e = cudaMemcpyAsync(q_full, d_q, pp * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream);

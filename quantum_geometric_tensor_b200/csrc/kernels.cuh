@@ -28,6 +28,24 @@ struct SweepLaunch {
     QgtCostTable ct;
 };
 
+// fused sweep + transition-matrix launch (fused.cu): grid = nitems x tile_groups, CTA (chunk, item) handles tiles
+// [chunk * tiles_per_cta, ...) of its item
+struct FusedLaunch {
+    const QgtDevRun* runs;
+    const QgtDevSubPass* subs;
+    const QgtDevStage* stages;
+    const QgtDevThrDiag* tdiags;
+    const cplx* pool;
+    int run_idx;
+    const QgtSweepItem* items;
+    int nitems;
+    const cplx* phi;             // the marching state at the start of the run (second tile of every non-self item)
+    uint64_t ntiles;
+    int tiles_per_cta, tile_groups;
+    uint64_t gprefix;
+    double* rho_partial;         // [tile_groups][nitems][rho_blocks * 128]
+};
+
 struct GramLaunch {
     const cplx* const* a_ptrs;   // device array of na column pointers
     const cplx* const* b_ptrs;   // device array of nb column pointers
@@ -47,6 +65,13 @@ struct GramShape { int MT, NT; int thin; };   // thin: few pairs, register accum
 
 // K, R: tile / register qubits of the run; grid is chosen inside
 cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int has_cost, int num_sms, cudaStream_t st);
+
+void fused_geometry(uint64_t ntiles, int nitems, int num_sms, int* tiles_per_cta, int* tile_groups);
+size_t fused_smem_bytes(int K, int mat_count, int nsub, int rho_blocks);
+cudaError_t launch_fused(const FusedLaunch& a, int K, int mat_count, int nsub, int rho_blocks, cudaStream_t st);
+cudaError_t launch_rho_reduce(const double* partial, int groups, int nitems, int per_item, double* rho, cudaStream_t st);
+cudaError_t launch_rho_contract(const double* rho, int per_item, const double* xpool, const QgtContractGroup* groups, int ngroups,
+                                const QgtContractEntry* entries, cplx* A, cudaStream_t st);
 
 GramShape gram_shape(int na, int nb);
 // fills mtiles / ntiles / nb_main / nstrip / npad from na, nb, symmetric; returns the partial elements per k-split

@@ -585,7 +585,10 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
             for (int i = rs.b; i < rs.e; i++) {
                 const LoweredOp& o = run.ops[i];
                 const uint64_t used_bits = o.cmask | o.pmask | (o.target >= 0 ? bit(o.target) : 0);
-                if (o.type == QGT_OP_DIAG && (used_bits & regmask) == 0) { sp.tdiags.push_back(i); continue; }
+                // a diagonal gate off the matrix qubits is one phase per thread - unless it carries a parameter: its
+                // generator must sit in a dense stage (as an identity x phase matrix selected by variant bits) so that
+                // the fused schedule finds <column| G |phi> in the stage's transition matrix
+                if (o.type == QGT_OP_DIAG && (used_bits & regmask) == 0 && o.param < 0) { sp.tdiags.push_back(i); continue; }
                 std::vector<int> need;               // non-register qubits this op depends on
                 for (int q = 0; q < n; q++) if ((used_bits & ~regmask) >> q & 1) need.push_back(q);
                 bool fits = !sp.stages.empty();
@@ -620,6 +623,24 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
         split_run_by_births(run, opt.birth_cut != 0, opt.birth_cut == 2 ? -1 : nl, born, alive, pieces);
         for (Run& piece : pieces) {
             const int ridx = (int)plan.runs.size();
+            {   // transition-matrix layout of the fused schedule
+                int sidx = 0;
+                for (SubPass& sp : piece.subs)
+                    for (Stage& st : sp.stages) {
+                        st.params.clear();
+                        for (int o : st.ops) {
+                            const int p = piece.ops[o].param;
+                            if (p >= 0 && std::find(st.params.begin(), st.params.end(), p) == st.params.end()) st.params.push_back(p);
+                        }
+                        st.rho_off = -1;
+                        if (!st.params.empty()) {
+                            st.rho_off = piece.rho_blocks;
+                            piece.rho_blocks += 1 << (int)st.vqubits.size();
+                            piece.last_rho_stage = sidx;
+                        }
+                        sidx++;
+                    }
+            }
             for (int i = 0; i < (int)piece.ops.size(); i++) {
                 const int p = piece.ops[i].param;
                 if (p < 0) continue;
@@ -674,6 +695,7 @@ void build_image(const CircuitPlan& plan, PlanImage& img) {
                 d.nvar = (int16_t)st.vqubits.size();
                 for (int k = 0; k < d.nvar; k++) d.vmask[k] = bit(st.vqubits[k]);
                 d.mat_off = (int)(img.pool.size() / 2) - dr.mat_off;
+                d.rho_off = st.rho_off;
                 d.form = (int16_t)stage_matrices(run, sp, st, -1, mats);
                 img.pool.insert(img.pool.end(), mats.begin(), mats.end());
                 img.stages.push_back(d);
@@ -684,6 +706,8 @@ void build_image(const CircuitPlan& plan, PlanImage& img) {
         }
         dr.mat_count = (int)(img.pool.size() / 2) - dr.mat_off;
         for (const SubPass& sp : run.subs) if (sp.is_cost) dr.has_cost = 1;
+        dr.rho_blocks = run.rho_blocks;
+        dr.last_rho_stage = run.last_rho_stage;
         img.runs.push_back(dr);
     }
 }
@@ -1096,6 +1120,149 @@ int build_qgt_program(const CircuitPlan& plan, size_t total_slots, bool want_psi
     return QGT_B200_OK;
 }
 
+void stage_generators(const Run& run, const SubPass& sp, const Stage& st, std::vector<double>& out) {
+    const int R = (int)sp.reg_local.size();
+    const int N = 1 << R;
+    const int nv = 1 << (int)st.vqubits.size();
+    std::vector<double> M, one, Nsum;
+    stage_dense(run, sp, st, -1, M);
+    out.assign(st.params.size() * (size_t)nv * N * N * 2, 0.0);
+    for (size_t k = 0; k < st.params.size(); k++) {
+        Nsum.assign((size_t)nv * N * N * 2, 0.0);
+        for (int o : st.ops) {
+            if (run.ops[o].param != st.params[k]) continue;
+            stage_dense(run, sp, st, o, one);
+            for (size_t i = 0; i < Nsum.size(); i++) Nsum[i] += one[i];
+        }
+        for (int v = 0; v < nv; v++) {
+            const double* Mv = &M[(size_t)v * N * N * 2];
+            const double* Nv = &Nsum[(size_t)v * N * N * 2];
+            double* G = &out[(k * (size_t)nv + v) * N * N * 2];
+            for (int a = 0; a < N; a++)
+                for (int c = 0; c < N; c++) {           // G[a][c] = sum_j N[a][j] conj(M[c][j])
+                    double gr = 0.0, gi = 0.0;
+                    for (int j = 0; j < N; j++) {
+                        const double nr = Nv[2 * (a * N + j)], ni = Nv[2 * (a * N + j) + 1];
+                        const double mr = Mv[2 * (c * N + j)], mi = Mv[2 * (c * N + j) + 1];
+                        gr += nr * mr + ni * mi;
+                        gi += ni * mr - nr * mi;
+                    }
+                    G[2 * (a * N + c)] = gr; G[2 * (a * N + c) + 1] = gi;
+                }
+        }
+    }
+}
+
+// ---- fused schedule --------------------------------------------------------------------------------------
+bool plan_supports_fused(const CircuitPlan& plan) {
+    if (plan.R != 3 || plan.B != 0 || plan.K < 8) return false;
+    for (const Run& run : plan.runs) {
+        if (run.exchange_gbit >= 0) continue;
+        for (const SubPass& sp : run.subs) {
+            if (sp.is_cost) return false;                       // TODO(cost): the QAOA cost pass has no fused form yet
+            if (!sp.mma_ok) return false;
+        }
+        for (const ParamOcc& oc : run.occ)
+            if (locate_op(run, oc.op).kind != 1) return false;
+    }
+    return true;
+}
+
+int build_fused_program(const CircuitPlan& plan, size_t total_slots, bool want_psi, Program& prog, std::string& err) {
+    prog = Program();
+    const int P = plan.P;
+    const int R = (int)plan.runs.size();
+    std::vector<int> ord;
+    for (int p = 0; p < P; p++) if (plan.first_run[p] >= 0) ord.push_back(p);
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return plan.first_run[a] < plan.first_run[b]; });
+    const int Pa = (int)ord.size();
+    if (Pa == 0) return build_qgt_program(plan, total_slots, want_psi, prog, err);
+    int R_last = 0;
+    for (int p : ord) R_last = std::max(R_last, plan.last_run[p]);
+    const bool blocked = (size_t)Pa + 2 > total_slots;
+    if (blocked && total_slots < 4) { err = "workspace too small: need at least 4 statevector-sized columns"; return QGT_B200_ERR_NO_MEMORY; }
+    const int b = blocked ? (int)total_slots - 3 : Pa;
+    Sched s(plan, prog);
+    int next = 0;
+    int phi = next++, phi_alt = next++;
+    const int ckpt = blocked ? next++ : -1;
+    for (int i = 0; i < b; i++) s.res_slots.push_back(next++);
+    prog.num_slots = next; prog.resident = b; prog.streaming = 0; prog.fused = true;
+    const int nblocks = (Pa + b - 1) / b;
+    prog.blocks = nblocks;
+    // block order: 1, 2, ... (the rolling checkpoint only moves forward), then block 0 from a fresh initial state - it
+    // marches through every run, so its phi doubles as the final state and the self transition matrices are its
+    std::vector<int> order;
+    for (int i = 1; i < nblocks; i++) order.push_back(i);
+    order.push_back(0);
+    int ckpt_time = 0;
+    if (blocked && nblocks > 1) s.init(ckpt);
+    auto fused = [&](int run, int phi_slot, std::vector<SweepCol>& cols) {
+        if (cols.empty()) return;
+        Instr in; in.kind = INSTR_FUSED; in.run = run; in.phi = phi_slot; in.cols = cols;
+        prog.instrs.push_back(std::move(in));
+    };
+    for (int blk : order) {
+        const int lo = blk * b, hi = std::min(Pa, lo + b);
+        std::vector<int> slot_of(P, -1);
+        std::vector<char> is_res(P, 0), alive(P, 0);
+        for (int i = lo; i < hi; i++) { slot_of[ord[i]] = s.res_slots[i - lo]; is_res[ord[i]] = 1; }
+        const int r0 = plan.first_run[ord[lo]];
+        if (blk == 0) s.init(phi);
+        else {
+            while (ckpt_time < r0) { s.sweep(ckpt_time, {{ckpt, ckpt, -1, false}}); ckpt_time++; }
+            s.copy(ckpt, phi);
+        }
+        const int r_end = (blk == 0 && want_psi) ? R - 1 : R_last;
+        for (int r = r0; r <= r_end; r++) {
+            const Run& run = plan.runs[r];
+            if (run.exchange_gbit >= 0 || r > R_last) {            // exchange pseudo-run, or phi alone after the last parameter
+                std::vector<SweepCol> A;
+                A.push_back({phi, phi, -1, false});
+                for (int p = 0; p < P; p++) if (alive[p]) A.push_back({slot_of[p], slot_of[p], -1, false});
+                s.sweep(r, A);
+                continue;
+            }
+            std::vector<SweepCol> A, acc;
+            {
+                SweepCol c(phi, phi_alt, -1, false);
+                c.id = P; c.self = true;
+                c.rho_from = (blk == 0) ? 0 : 1 << 20;         // the self transition matrices are taken once, in block 0
+                A.push_back(c);
+            }
+            for (int p = 0; p < P; p++)
+                if (alive[p]) { SweepCol c(slot_of[p], slot_of[p], -1, false); c.id = p; c.rho_from = 0; A.push_back(c); }
+            std::vector<char> seen_here(P, 0);
+            std::vector<int> born;
+            for (const ParamOcc& oc : run.occ) {
+                const int p = oc.param;
+                if (seen_here[p] || !is_res[p]) continue;
+                seen_here[p] = 1;
+                std::vector<SweepCol> items = s.occurrence_items(r, p, phi, slot_of[p]);
+                for (size_t k = 0; k < items.size(); k++) {
+                    items[k].id = p;
+                    items[k].rho_from = locate_op(run, items[k].ovr_op).index + 1;
+                    if (k == 0 && !alive[p]) { items[k].accumulate = false; A.push_back(items[k]); born.push_back(p); }
+                    else acc.push_back(items[k]);
+                }
+            }
+            fused(r, phi, A);
+            while (!acc.empty()) {                                 // no two items of a launch may share a destination
+                std::vector<SweepCol> now, later;
+                std::set<int> dsts;
+                for (const SweepCol& c : acc) (dsts.insert(c.dst).second ? now : later).push_back(c);
+                fused(r, phi, now);
+                acc.swap(later);
+            }
+            for (int p : born) alive[p] = 1;
+            std::swap(phi, phi_alt);
+        }
+    }
+    prog.psi_slot = phi;
+    prog.psi_final = want_psi;
+    return QGT_B200_OK;
+}
+
 // ---- JSON dump (tests interpret this on the CPU) ------------------------------------------------
 static void jarr(std::ostringstream& o, const std::vector<int>& v) {
     o << "[";
@@ -1129,7 +1296,14 @@ std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const 
             o << ",\"tperm\":"; jarr(o, sp.tperm);
             o << ",\"forms\":[";             // QGT_FORM_* of each dense stage (1 = complex diagonal x real matrix)
             { std::vector<double> tmp; for (size_t k = 0; k < sp.stages.size(); k++) o << (k ? "," : "") << stage_matrices(run, sp, sp.stages[k], -1, tmp); }
-            o << "],\"ops\":[" << sp.op_begin << "," << sp.op_end << "]}";
+            o << "],\"stages\":[";
+            for (size_t k = 0; k < sp.stages.size(); k++) {
+                o << (k ? "," : "") << "{\"ops\":"; jarr(o, sp.stages[k].ops);
+                o << ",\"params\":"; jarr(o, sp.stages[k].params);
+                o << ",\"rho_off\":" << sp.stages[k].rho_off << ",\"nvar\":" << sp.stages[k].vqubits.size() << "}";
+            }
+            o << "],\"tdiags\":"; jarr(o, sp.tdiags);
+            o << ",\"ops\":[" << sp.op_begin << "," << sp.op_end << "]}";
         }
         o << "],\"ops\":[";
         for (size_t i = 0; i < run.ops.size(); i++) { o << (i ? "," : ""); jop(o, run.ops[i], false); }
@@ -1150,16 +1324,17 @@ std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const 
     if (prog) {
         o << ",\"program\":{\"slots\":" << prog->num_slots << ",\"psi\":" << prog->psi_slot << ",\"resident\":" << prog->resident
           << ",\"streaming\":" << prog->streaming << ",\"blocks\":" << prog->blocks << ",\"psi_final\":" << (prog->psi_final ? 1 : 0)
-          << ",\"instrs\":[";
+          << ",\"fused\":" << (prog->fused ? 1 : 0) << ",\"instrs\":[";
         for (size_t i = 0; i < prog->instrs.size(); i++) {
             const Instr& in = prog->instrs[i];
             o << (i ? "," : "");
-            if (in.kind == INSTR_SWEEP) {
-                o << "{\"k\":\"sweep\",\"run\":" << in.run << ",\"cols\":[";
+            if (in.kind == INSTR_SWEEP || in.kind == INSTR_FUSED) {
+                o << "{\"k\":\"" << (in.kind == INSTR_FUSED ? "fused" : "sweep") << "\",\"run\":" << in.run << ",\"phi\":" << in.phi << ",\"cols\":[";
                 for (size_t j = 0; j < in.cols.size(); j++)
                 {
                     o << (j ? "," : "") << "[" << in.cols[j].src << "," << in.cols[j].dst << "," << in.cols[j].ovr_op << "," << (in.cols[j].accumulate ? 1 : 0) << ",";
                     jarr(o, in.cols[j].ovr_extra);
+                    if (in.kind == INSTR_FUSED) o << "," << in.cols[j].id << "," << in.cols[j].rho_from << "," << (in.cols[j].self ? 1 : 0);
                     o << "]";
                 }
                 o << "]}";

@@ -41,6 +41,9 @@ struct LoweredOp {
 struct Stage {
     std::vector<int> ops;
     std::vector<int> vqubits;       // global qubit numbers, variant bit k <-> vqubits[k]
+    std::vector<int> params;        // distinct parameters with an occurrence among `ops`, in order of appearance
+    int rho_off = -1;               // fused schedule: first of the stage's 2^nvar transition-matrix blocks inside an
+                                    // item's rho buffer, -1 when no parameter occurs in the stage
 };
 
 struct SubPass {
@@ -66,6 +69,8 @@ struct Run {
     std::vector<ParamOcc> occ;      // parameterised ops in this run
     int exchange_gbit = -1;         // pseudo-run of a sharded state: swap rank bit `exchange_gbit` with the top local qubit
     int segment = 0;                // index of the mapped segment the run belongs to (selects the cost table)
+    int rho_blocks = 0;             // fused schedule: 64-element transition-matrix blocks per item (sum of 2^nvar over stages with parameters)
+    int last_rho_stage = -1;        // run-relative index of the last stage with a parameter occurrence
 };
 
 struct CircuitPlan {
@@ -108,7 +113,7 @@ QgtDevThrDiag make_tdiag(const LoweredOp& op, bool derivative);
 QgtDevCost make_cost(const LoweredOp& op, bool derivative);
 
 // ---- column schedule ---------------------------------------------------------------------------
-enum InstrKind { INSTR_SWEEP = 0, INSTR_GRAM = 1, INSTR_COPY = 2, INSTR_INIT = 3 };
+enum InstrKind { INSTR_SWEEP = 0, INSTR_GRAM = 1, INSTR_COPY = 2, INSTR_INIT = 3, INSTR_FUSED = 4 };
 
 struct SweepCol {
     SweepCol() {}
@@ -118,12 +123,18 @@ struct SweepCol {
     std::vector<int> ovr_extra; // further ops of the same parameter inside the same dense stage: the item applies
                                 // the product-rule sum  sum_j (stage with op j replaced by its derivative)
     bool accumulate = false;
+    // fused schedule (INSTR_FUSED)
+    int id = -1;                // parameter whose column this is; P = the marching state phi itself
+    int rho_from = 0;           // first stage (run-relative) whose transition matrix <column| . |phi> is contracted:
+                                // 0 for a column that merely advances, (stage of the spawning occurrence) + 1 for a spawn
+    bool self = false;          // the item IS phi: one tile, rho = <phi| . |phi>
 };
 
 struct Instr {
     int kind = INSTR_SWEEP;
     int run = -1;
-    std::vector<SweepCol> cols;             // SWEEP
+    int phi = -1;                           // FUSED: slot of phi at the start of the run (second tile of every item)
+    std::vector<SweepCol> cols;             // SWEEP, FUSED
     std::vector<int> a_slots, a_ids;        // GRAM: <a|b> for every pair; id = parameter index, P = psi
     std::vector<int> b_slots, b_ids;
     int src = -1, dst = -1;                 // COPY: dst <- src ; INIT: dst <- initial state
@@ -136,11 +147,32 @@ struct Program {
     int streaming = 0;          // c
     int blocks = 0;
     bool psi_final = false;     // psi_slot holds U(theta)|init> at the end
+    bool fused = false;         // built by build_fused_program: no Gram instructions, Q assembled from transition matrices
     std::vector<Instr> instrs;
 };
 
 // total_slots = number of 2^n-amplitude columns that fit in the workspace
 int build_qgt_program(const CircuitPlan& plan, size_t total_slots, bool want_psi, Program& prog, std::string& err);
+
+// Fused schedule ("apply-gate-and-contract", SURVEY.md section 7 hard-part 1c).  For mu born before nu,
+//   <d_mu psi|d_nu psi> = <lambda_mu(t)| G_nu |phi(t)>   at the time t of nu's gate,
+// lambda_mu = the derivative column propagated to t, G_nu = (dU_nu) U_nu^+.  The kernel advances a column and phi
+// through a run in lockstep (two tiles on chip) and, after every dense stage in which a parameter occurs, accumulates
+// the 8x8 transition matrix rho[c][a] = sum_rest phi'[c, rest] conj(lambda'[a, rest]) over the stage's 3 matrix
+// qubits; <lambda|G|phi> = sum_{a,c} Gt[a][c] rho[c][a] with Gt = (derivative stage matrix) x (stage matrix)^+.
+// No streaming column is ever written and no Gram pass re-reads the resident block: every column costs one pass per
+// run it is alive in, whatever the number of column slots.  Pairs inside one stage, the diagonal and the projections
+// <d_mu psi|psi> come from rho of phi with itself.  b = total_slots - 3 resident columns per block (phi, its
+// out-of-place twin and a rolling checkpoint take three slots).
+bool plan_supports_fused(const CircuitPlan& plan);
+int build_fused_program(const CircuitPlan& plan, size_t total_slots, bool want_psi, Program& prog, std::string& err);
+// index of element (c, a, re/im) inside a 128-double transition-matrix block: the order in which the DMMA C fragments
+// of a warp hold it (lane = c*4 + a/2 owns columns a, a^1)
+static inline int rho_index(int c, int a, int part) { return (c * 4 + (a >> 1)) * 4 + part * 2 + (a & 1); }
+// Evolved generators of one stage: for every parameter of st.params (same order) and every variant, the matrix
+// Gt = N M^+ (N = sum of the stage matrices with one occurrence replaced by its derivative), row-major 8x8 complex
+// (re, im); out[(k * nvariants + v) * 128 + (a * 8 + c) * 2]
+void stage_generators(const Run& run, const SubPass& sp, const Stage& st, std::vector<double>& out);
 
 // ---- sharded states: logical -> physical qubit mapping ------------------------------------------------
 // A state of n qubits sharded over 2^g ranks keeps physical qubits nloc.. (nloc = n - g) in the rank index.

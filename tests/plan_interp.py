@@ -265,3 +265,133 @@ def run_program_sharded(plan, circ, world):
     Q = Cm[:P, :P] - np.outer(v, v.conj())
     psi = np.concatenate([slots[r][prog["psi"]] for r in range(world)]) if prog["psi_final"] else None
     return Q, psi
+
+
+# ---- fused schedule (plan.hpp: build_fused_program) --------------------------------------------------------------
+def _stage_of_op(run):
+    """lowered-op index -> run-relative index of the dense stage holding it"""
+    m, sidx = {}, 0
+    for sp in run["subs"]:
+        for st in sp.get("stages", []):
+            for o in st["ops"]:
+                m[o] = sidx
+            sidx += 1
+    return m
+
+
+def _fused_launch(plan, circ, ins, slots_by_rank, apply_fn, A, D, v):
+    """One INSTR_FUSED.  slots_by_rank[r] = list of this rank's columns; apply_fn(rank, state, op) applies a lowered op.
+    Works at op granularity (no stage matrices): T[mu][b] = <lambda after op b | d(op b) phi before op b>, taken only
+    for occurrences in stages >= rho_from, exactly the terms the device contracts from its transition matrices."""
+    run = plan["runs"][ins["run"]]
+    ops, dops = run["ops"], run["dops"]
+    stage_of = _stage_of_op(run)
+    world = len(slots_by_rank)
+    results = []
+    for (src, dst, ovr, acc, extra, cid, rho_from, self_) in ins["cols"]:
+        ovrs = [ovr] + list(extra) if ovr >= 0 else [None]
+        total = [0 for _ in range(world)]
+        for o in ovrs:
+            for r in range(world):
+                lam = slots_by_rank[r][src].copy()
+                phi = slots_by_rank[r][ins["phi"]].copy()
+                for i, op in enumerate(ops):
+                    phi_prev = phi
+                    phi = apply_fn(r, phi, op)
+                    lam = apply_fn(r, lam, dops[str(i)] if i == o else op)
+                    if op["param"] >= 0 and not self_:
+                        assert i in stage_of, "a parameterised op sits outside every dense stage"
+                        if stage_of[i] >= rho_from:
+                            A[cid, op["param"]] += np.vdot(lam, apply_fn(r, phi_prev, dops[str(i)]))
+                total[r] = total[r] + lam
+        results.append((dst, acc, total))
+        if self_ and rho_from == 0:
+            # pairs inside one stage, the diagonal and the projections: from phi alone
+            for r in range(world):
+                traj = [slots_by_rank[r][ins["phi"]]]
+                for op in ops:
+                    traj.append(apply_fn(r, traj[-1], op))
+                sidx = 0
+                for sp in run["subs"]:
+                    for st in sp.get("stages", []):
+                        if st["params"]:
+                            e = max(st["ops"])
+                            cols = {}
+                            for a in st["ops"]:
+                                p = ops[a]["param"]
+                                if p < 0:
+                                    continue
+                                x = apply_fn(r, traj[a], dops[str(a)])
+                                for j in range(a + 1, e + 1):
+                                    x = apply_fn(r, x, ops[j])
+                                cols[p] = cols.get(p, 0) + x
+                            for mu, cm in cols.items():
+                                v[mu] += np.vdot(cm, traj[e + 1])
+                                for nu, cn in cols.items():
+                                    D[mu, nu] += np.vdot(cm, cn)
+                        sidx += 1
+    dsts = [d for d, _, _ in results]
+    assert len(set(dsts)) == len(dsts), "two items of one launch share a destination"
+    assert ins["phi"] not in dsts, "a fused launch overwrites the phi it reads"
+    for dst, acc, total in results:
+        for r in range(world):
+            slots_by_rank[r][dst] = slots_by_rank[r][dst] + total[r] if acc else total[r]
+
+
+def run_program_fused(plan: dict, circ, world: int = 1):
+    """Returns (Q, psi or None, counters) for a fused program, all ranks simulated in one process."""
+    prog = plan["program"]
+    assert prog["fused"] == 1
+    P, nloc = plan["P"], plan["nloc"]
+    dim = 1 << nloc
+    tabs = segment_cost_tables(plan, circ) if world > 1 else None
+    slots = [[np.zeros(dim, dtype=np.complex128) for _ in range(prog["slots"])] for _ in range(world)]
+    A = np.zeros((P, P), dtype=np.complex128)
+    D = np.zeros((P, P), dtype=np.complex128)
+    v = np.zeros(P, dtype=np.complex128)
+    counters = {"column_passes": 0, "launches": 0}
+
+    def apply_fn_for(run):
+        if world == 1:
+            return lambda r, st, op: apply_op(st, op, circ)
+        edges, vw = tabs[run["segment"]]
+        def f(r, st, op):
+            gidx = (np.uint64(r) << np.uint64(nloc)) | np.arange(st.size, dtype=np.uint64)
+            return _apply_op_shard(st, op, circ, gidx, nloc, edges, vw)
+        return f
+
+    for ins in prog["instrs"]:
+        k = ins["k"]
+        if k == "init":
+            for r in range(world):
+                slots[r][ins["dst"]] = initial_shard(circ, r, nloc) if world > 1 else initial_state(circ)
+        elif k == "copy":
+            for r in range(world):
+                slots[r][ins["dst"]] = slots[r][ins["src"]].copy()
+        elif k == "sweep":
+            run = plan["runs"][ins["run"]]
+            counters["launches"] += 1
+            if run["exchange"] >= 0:
+                for (src, dst, ovr, acc, extra) in ins["cols"]:
+                    assert src == dst and ovr < 0 and not acc
+                    exchange_all_ranks([slots[r][dst] for r in range(world)], run["exchange"])
+                continue
+            f = apply_fn_for(run)
+            for (src, dst, ovr, acc, extra) in ins["cols"]:
+                assert ovr < 0 and not acc
+                counters["column_passes"] += 1
+                for r in range(world):
+                    st = slots[r][src]
+                    for op in run["ops"]:
+                        st = f(r, st, op)
+                    slots[r][dst] = st
+        elif k == "fused":
+            counters["launches"] += 1
+            counters["column_passes"] += len(ins["cols"])
+            _fused_launch(plan, circ, ins, slots, apply_fn_for(plan["runs"][ins["run"]]), A, D, v)
+        else:
+            raise ValueError(k)
+    Cm = A + A.conj().T + D
+    Q = Cm - np.outer(v, v.conj())
+    psi = np.concatenate([slots[r][prog["psi"]] for r in range(world)]) if prog["psi_final"] else None
+    return Q, psi, counters
