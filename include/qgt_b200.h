@@ -258,6 +258,10 @@ int  qgt_b200_dist_barrier(qgt_b200_ctx* ctx);
 long qgt_b200_plan_dump_sharded(const qgt_b200_circuit* circuit, const double* theta, int world, int restore_identity,
                                 int tile_qubits, int reg_qubits, size_t column_slots, char* buf, size_t buflen);
 
+/* Roofline denominators measured on this device: sustained FP64 tensor-pipe throughput (mma.sync m8n8k4 f64, TFLOP/s)
+ * and device-to-device copy bandwidth (read + write bytes, GB/s).  Either output may be NULL. */
+int  qgt_b200_measure_peaks(qgt_b200_ctx* ctx, double* dmma_tflops, double* copy_gbs);
+
 /* plan_dump with the FUSED column schedule (transition matrices contracted inside the sweeps, no Gram pass; see
  * plan.hpp) for a state on `world` ranks (1 = unsharded).  Returns QGT_B200_ERR_UNSUPPORTED when the plan does not
  * qualify (tiles below 8 qubits, a sub-pass off the tensor path, a cost layer). */

@@ -90,6 +90,7 @@ def load() -> C.CDLL:
     L.qgt_b200_plan_dump_sharded.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t]
     L.qgt_b200_plan_dump_sharded.restype = C.c_long
     L.qgt_b200_dist_barrier.argtypes = [vp]
+    L.qgt_b200_measure_peaks.argtypes = [vp, _DP, _DP]
     L.qgt_b200_plan_dump_fused.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t]
     L.qgt_b200_plan_dump_fused.restype = C.c_long
     _lib = L
@@ -299,6 +300,12 @@ class Context:
         g = np.zeros(circ.num_params)
         _check(self.L.qgt_b200_expectation_gradient(self.h, C.byref(cc), _dp(th), C.byref(e), _dp(g)))
         return e.value, g
+
+    def measure_peaks(self) -> dict:
+        """FP64 tensor-pipe peak (TFLOP/s) and D2D copy bandwidth (GB/s) measured on this device."""
+        a, b = C.c_double(0), C.c_double(0)
+        _check(self.L.qgt_b200_measure_peaks(self.h, C.byref(a), C.byref(b)))
+        return {"dmma_tflops": a.value, "copy_gbs": b.value}
 
     def stats(self) -> dict:
         s = Stats()

@@ -306,6 +306,9 @@ int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
     else if (k == "profile") c->timer.enabled = value != 0;
     else if (k == "max_slots") c->max_slots = (size_t)value;
     else if (k == "fused") c->fused_mode = (int)value;
+    else if (k == "fused_traj") c->fused_traj = (int)value;
+    else if (k == "fused_debug") c->fused_debug = (int)value;
+    else if (k == "fused_pipeline") c->fused_pipeline = (int)value;
     else return fail(QGT_B200_ERR_INVALID_ARG, "unknown option " + k);
     return QGT_B200_OK;
 }
@@ -678,7 +681,13 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                 cgroups.push_back(g);
             }
             fr.ngroups = (int)(cgroups.size() - fr.group_off);
-            fused_geometry(D >> run.K, (int)in.cols.size(), c->num_sms, &fr.tpc, &fr.tg);
+            {
+                int mc = 0, ns = 0;
+                for (const SubPass& sp : run.subs)
+                    for (const Stage& stg : sp.stages) { mc += QGT_VARIANT_STRIDE(8) << stg.vqubits.size(); ns++; }
+                const bool pipe = fused_uses_pipe(run.K, in.traj ? 1 : 0, c->fused_pipeline, mc, (int)run.subs.size(), run.rho_blocks, ns);
+                fused_geometry(D >> run.K, (int)in.cols.size(), c->num_sms, pipe, &fr.tpc, &fr.tg);
+            }
             const size_t per_item = (size_t)run.rho_blocks * 128;
             rho_doubles_max = std::max(rho_doubles_max, in.cols.size() * per_item);
             partial_bytes = std::max(partial_bytes, (size_t)fr.tg * in.cols.size() * per_item * sizeof(double));
@@ -804,12 +813,20 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             a.tiles_per_cta = fr.tpc; a.tile_groups = fr.tg;
             a.gprefix = (uint64_t)c->rank << plan.nloc;
             a.rho_partial = (double*)c->partial.ptr;
-            int mat_count = 0, nstage_rho = 0;
+            a.use_traj = in.traj ? 1 : 0;
+            a.debug = c->fused_debug;
+            a.pipeline = c->fused_pipeline;
+            a.all_simple = 1;
+            for (const SubPass& sp : run.subs) if (sp.is_cost || sp.stages.size() != 1 || !sp.tdiags.empty()) a.all_simple = 0;
+            for (int t = 0; t < QGT_MAX_TRAJ; t++)
+                a.traj[t] = t < (int)prog.traj_slots.size() ? arena + (size_t)prog.traj_slots[t] * D : nullptr;
+            int mat_count = 0, nstage_rho = 0, nstages = 0;
             double flops_ab = 0.0;                  // per amplitude: one tile through every stage
             for (const SubPass& sp : run.subs)
                 for (const Stage& stg : sp.stages) {
                     mat_count += QGT_VARIANT_STRIDE(8) << stg.vqubits.size();
                     flops_ab += 64.0;               // counted as dense 4M complex products (the diagonal-real form issues half)
+                    nstages++;
                     if (stg.rho_off >= 0) nstage_rho++;
                 }
             char label[160];
@@ -817,7 +834,7 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                 snprintf(label, sizeof label, "fused run=%d items=%d subs=%d rho_stages=%d rho_blocks=%d tiles=%llu chunks=%d", in.run, nitems,
                          (int)run.subs.size(), nstage_rho, run.rho_blocks, (unsigned long long)a.ntiles, fr.tg);
             c->timer.begin(c->stream, 0, label);
-            e = launch_fused(a, run.K, mat_count, (int)run.subs.size(), run.rho_blocks, c->stream);
+            e = launch_fused(a, run.K, mat_count, (int)run.subs.size(), run.rho_blocks, nstages, c->stream);
             c->timer.end(c->stream);
             if (e != cudaSuccess) return cuda_fail(e, "fused launch");
             c->stats.sweep_launches++; c->stats.fused_launches++;
@@ -827,8 +844,9 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                 int sidx = 0, nrho = 0;
                 for (const SubPass& sp : run.subs)
                     for (const Stage& stg : sp.stages) { if (stg.rho_off >= 0 && sidx >= sc.rho_from) nrho++; sidx++; }
-                const bool use_b = !sc.self && sc.rho_from <= run.last_rho_stage;
-                c->stats.tensor_flops += (double)D * (flops_ab * (use_b ? 2.0 : 1.0) + 64.0 * nrho);
+                const bool use_b = !in.traj && !sc.self && sc.rho_from <= run.last_rho_stage;
+                c->stats.tensor_flops += (double)D * (flops_ab * (use_b ? 2.0 : 1.0) + 48.0 * nrho);      // rho: 3M complex products
+                if (in.traj) c->stats.sweep_bytes += 16.0 * (double)D * nrho;     // phi's tile images: written by the self item, fetched (L2) by the others
             }
             if (per_item > 0) {
                 c->timer.begin(c->stream, 1, "rho reduce + contract");
@@ -1037,7 +1055,7 @@ int qgt_b200_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* th
     Program prog;
     const size_t slots = workspace_slots(c, D, (size_t)256 << 20);
     const bool use_fused = choose_fused(c, plan, slots);
-    if ((rc = use_fused ? build_fused_program(plan, slots, psi_out != nullptr, prog, err)
+    if ((rc = use_fused ? build_fused_program(plan, slots, psi_out != nullptr, prog, err, c->fused_traj)
                         : build_qgt_program(plan, slots, psi_out != nullptr, prog, err))) return fail(rc, err);
     const double ms_plan0 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wall0).count();
     if ((rc = c->arena.reserve((size_t)prog.num_slots * D * sizeof(cplx)))) return rc;
@@ -1279,6 +1297,42 @@ long qgt_b200_plan_dump_sharded(const qgt_b200_circuit* circ, const double* thet
     return (long)js.size();
 }
 
+int qgt_b200_measure_peaks(qgt_b200_ctx* c, double* dmma_tflops, double* copy_gbs) {
+    if (!c) return fail(QGT_B200_ERR_INVALID_ARG, "ctx is NULL");
+    cudaSetDevice(c->device);
+    int rc;
+    if (dmma_tflops) {
+        if ((rc = c->scratch.reserve((size_t)c->num_sms * 1024 * sizeof(double)))) return rc;
+        cudaError_t e = measure_dmma_peak(c->num_sms, (double*)c->scratch.ptr, c->stream, dmma_tflops);
+        if (e != cudaSuccess) return cuda_fail(e, "DMMA peak kernel");
+    }
+    if (copy_gbs) {
+        const size_t bytes = (size_t)1 << 30;
+        void *a = nullptr, *b = nullptr;
+        cudaError_t e = cudaMalloc(&a, bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&b, bytes);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        float best = 1e30f;
+        if (e == cudaSuccess) e = cudaMemsetAsync(a, 1, bytes, c->stream);
+        for (int r = 0; r < 8 && e == cudaSuccess; r++) {
+            cudaEventRecord(e0, c->stream);
+            e = cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice, c->stream);
+            cudaEventRecord(e1, c->stream);
+            if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (r > 0 && ms < best) best = ms;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (a) cudaFree(a);
+        if (b) cudaFree(b);
+        if (e != cudaSuccess) return cuda_fail(e, "copy bandwidth measurement");
+        *copy_gbs = 2.0 * (double)bytes / best * 1e-6;
+    }
+    return QGT_B200_OK;
+}
+
 long qgt_b200_plan_dump_fused(const qgt_b200_circuit* circ, const double* theta, int world, int tile_qubits, int reg_qubits,
                               size_t column_slots, char* buf, size_t buflen) {
     if (!circ) return fail(QGT_B200_ERR_INVALID_ARG, "circuit is NULL");
@@ -1297,7 +1351,9 @@ long qgt_b200_plan_dump_fused(const qgt_b200_circuit* circ, const double* theta,
     if (rc) return fail(rc, err);
     if (!plan_supports_fused(plan)) return fail(QGT_B200_ERR_UNSUPPORTED, "plan does not qualify for the fused schedule");
     Program prog;
-    if ((rc = build_fused_program(plan, column_slots, true, prog, err))) return fail(rc, err);
+    int traj_mode = -1;
+    if (const char* e = std::getenv("QGT_B200_FUSED_TRAJ")) traj_mode = std::atoi(e);      // test hook
+    if ((rc = build_fused_program(plan, column_slots, true, prog, err, traj_mode))) return fail(rc, err);
     const std::string js = dump_json(*circ, plan, &prog, world > 1 ? &segs : nullptr);
     if (buf && buflen > js.size()) std::memcpy(buf, js.c_str(), js.size() + 1);
     return (long)js.size();

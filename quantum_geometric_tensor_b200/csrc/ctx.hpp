@@ -69,6 +69,10 @@ struct qgt_b200_ctx {
     qgt::DevBuf arena, img_runs, img_subs, img_stages, img_tdiags, img_costs, img_pool, ovr_pool, items, aux, partial, cmat, outbuf, edges, vweights, scratch;
     qgt::DevBuf fx_pool, fx_tab, rho, rho_self, amat;     // fused schedule: evolved generators, contraction tables, transition matrices, A
     qgt::FusedHost fused_host;
+    int fused_traj = -1;         // trajectory mode of the fused schedule: -1 automatic, 0 never, 1 whenever it fits
+    int fused_debug = 0;         // timing experiments only
+    int fused_pipeline = 2;      // trajectory mode at K = 11: 2 = lean 2 x 16-warp kernel where the run qualifies, 1 = persistent
+                                 // double-buffered 16-warp kernel, 0 = the generic 8-warp kernel
     int fused_mode = -1;         // -1 automatic (fused when the columns do not all fit), 0 never, 1 whenever the plan qualifies
     void* pinned = nullptr;
     QgtCostTable cost = {nullptr, 0, nullptr, 0};

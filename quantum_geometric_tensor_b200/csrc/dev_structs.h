@@ -14,6 +14,7 @@
 #define QGT_MAX_TILE_QUBITS 12
 #define QGT_MAX_QUBITS 40
 #define QGT_MAX_REG_QUBITS 4
+#define QGT_MAX_TRAJ 8           // transition-matrix stages per run the trajectory mode of the fused kernel supports
 
 // lowered-op types (host side; the device only sees dense stages, thread diagonals and the cost pass)
 enum QgtOpType {
@@ -58,7 +59,7 @@ typedef struct QgtDevStage {
     uint64_t vmask[QGT_MAX_VARIANT_BITS];    // global index bit selecting variant bit k
     int32_t  rho_off;                        // fused kernel: first transition-matrix block of this stage in an item's rho buffer (one
                                              // block of 64 complex per variant), -1 when no parameter occurs in the stage
-    int32_t  pad;
+    int32_t  traj_ord;                       // ordinal of the stage among the run's transition-matrix stages (trajectory column), -1 = none
 } QgtDevStage;                               // 32 bytes
 
 // a diagonal gate (or the derivative of one) that touches no register qubit: one phase per thread

@@ -213,7 +213,7 @@ int dist_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
         slots = (size_t)v;
     }
     const bool use_fused = choose_fused(c, plan, slots);
-    if ((rc = use_fused ? build_fused_program(plan, slots, psi_out != nullptr, prog, err)
+    if ((rc = use_fused ? build_fused_program(plan, slots, psi_out != nullptr, prog, err, c->fused_traj)
                         : build_qgt_program(plan, slots, psi_out != nullptr, prog, err))) return fail(rc, err);
     if ((rc = c->arena.reserve((size_t)prog.num_slots * D * sizeof(cplx)))) return rc;
     const size_t cm = (size_t)(P + 1) * (P + 1);

@@ -914,4 +914,48 @@ cudaError_t launch_cost_dot(const cplx* a, const cplx* b, uint64_t D, QgtCostTab
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// roofline denominators measured in place (MEASURED_PEAKS.json carries no FP64 tensor figure)
+// ------------------------------------------------------------------------------------------------
+// four independent DMMA accumulator chains per warp, each with its own operand registers: the shape that reaches the
+// pipe's peak on B200 (tools/peaks.cu, tools/dmma_ilp.cu)
+__global__ void __launch_bounds__(1024) qgt_peak_dmma_kernel(double* out, int iters) {
+    double a[4], b[4], c[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { a[i] = 1.0 + (threadIdx.x + i) * 1e-9; b[i] = 1.0 - (threadIdx.x + 3 * i) * 1e-9; c[i][0] = 0; c[i][1] = 0; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a[i]), "d"(b[i]));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) s += c[i][0] + c[i][1];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+cudaError_t measure_dmma_peak(int num_sms, double* scratch /* num_sms * 1024 doubles */, cudaStream_t st, double* tflops) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 8192;
+    float best = 1e30f;
+    cudaError_t e = cudaSuccess;
+    for (int r = 0; r < 6 && e == cudaSuccess; r++) {
+        cudaEventRecord(e0, st);
+        qgt_peak_dmma_kernel<<<num_sms, 1024, 0, st>>>(scratch, iters);
+        cudaEventRecord(e1, st);
+        e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    *tflops = (double)num_sms * 32 * iters * 16 * 512.0 / best * 1e-9;      // m8n8k4 = 2*8*8*4 flop
+    return e;
+}
+
 }  // namespace qgt

@@ -44,6 +44,13 @@ struct FusedLaunch {
     int tiles_per_cta, tile_groups;
     uint64_t gprefix;
     double* rho_partial;         // [tile_groups][nitems][rho_blocks * 128]
+    int use_traj;                // phi's tiles after every transition-matrix stage come from the trajectory columns (written
+                                 // by the launch of the self item alone) instead of being recomputed per item
+    int debug;                   // timing experiments only (QGT_FDBG_* bits; results are wrong by construction)
+    int pipeline;                // trajectory mode, K = 11: 1 = the persistent 16-warp kernel with double-buffered tiles,
+                                 // 2 = the lean 2 x 16-warp kernel (runs whose sub-passes are all one stage, no thread diagonal)
+    int all_simple;              // every sub-pass of the run is exactly one dense stage without thread diagonals
+    cplx* traj[QGT_MAX_TRAJ];    // trajectory columns: [ntiles][2^K] images of the swizzled tile
 };
 
 struct GramLaunch {
@@ -66,9 +73,10 @@ struct GramShape { int MT, NT; int thin; };   // thin: few pairs, register accum
 // K, R: tile / register qubits of the run; grid is chosen inside
 cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int has_cost, int num_sms, cudaStream_t st);
 
-void fused_geometry(uint64_t ntiles, int nitems, int num_sms, int* tiles_per_cta, int* tile_groups);
-size_t fused_smem_bytes(int K, int mat_count, int nsub, int rho_blocks);
-cudaError_t launch_fused(const FusedLaunch& a, int K, int mat_count, int nsub, int rho_blocks, cudaStream_t st);
+bool fused_uses_pipe(int K, int use_traj, int pipeline, int mat_count, int nsub, int rho_blocks, int nstages);
+void fused_geometry(uint64_t ntiles, int nitems, int num_sms, bool pipe, int* tiles_per_cta, int* tile_groups);
+size_t fused_smem_bytes(int K, int mat_count, int nsub, int rho_blocks, int nstages);
+cudaError_t launch_fused(const FusedLaunch& a, int K, int mat_count, int nsub, int rho_blocks, int nstages, cudaStream_t st);
 cudaError_t launch_rho_reduce(const double* partial, int groups, int nitems, int per_item, double* rho, cudaStream_t st);
 cudaError_t launch_rho_contract(const double* rho, int per_item, const double* xpool, const QgtContractGroup* groups, int ngroups,
                                 const QgtContractEntry* entries, cplx* A, cudaStream_t st);
@@ -85,6 +93,9 @@ cudaError_t launch_gram_reduce(const GramLaunch& g, GramShape shp, const int* a_
                                cplx* C, int ldc, cudaStream_t st);
 // Q = C[0:P,0:P] - v v^H with v = C[:,P];  any output may be null
 cudaError_t launch_finalize(const cplx* C, int P, double* metric, double* berry, cplx* q_full, cudaStream_t st);
+
+// FP64 tensor-pipe (DMMA.8x8x4) peak of this device, best of 5 timed launches
+cudaError_t measure_dmma_peak(int num_sms, double* scratch, cudaStream_t st, double* tflops);
 
 cudaError_t launch_init_state(cplx* dst, uint64_t D, int initial_state, double plus_amp, uint64_t global_offset, cudaStream_t st);
 cudaError_t launch_norm2(const cplx* src, uint64_t D, double* out /*device, zeroed inside*/, cudaStream_t st);

@@ -632,11 +632,12 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
                             const int p = piece.ops[o].param;
                             if (p >= 0 && std::find(st.params.begin(), st.params.end(), p) == st.params.end()) st.params.push_back(p);
                         }
-                        st.rho_off = -1;
+                        st.rho_off = -1; st.traj_ord = -1;
                         if (!st.params.empty()) {
                             st.rho_off = piece.rho_blocks;
                             piece.rho_blocks += 1 << (int)st.vqubits.size();
                             piece.last_rho_stage = sidx;
+                            st.traj_ord = piece.rho_stages++;
                         }
                         sidx++;
                     }
@@ -696,6 +697,7 @@ void build_image(const CircuitPlan& plan, PlanImage& img) {
                 for (int k = 0; k < d.nvar; k++) d.vmask[k] = bit(st.vqubits[k]);
                 d.mat_off = (int)(img.pool.size() / 2) - dr.mat_off;
                 d.rho_off = st.rho_off;
+                d.traj_ord = st.traj_ord;
                 d.form = (int16_t)stage_matrices(run, sp, st, -1, mats);
                 img.pool.insert(img.pool.end(), mats.begin(), mats.end());
                 img.stages.push_back(d);
@@ -1168,7 +1170,7 @@ bool plan_supports_fused(const CircuitPlan& plan) {
     return true;
 }
 
-int build_fused_program(const CircuitPlan& plan, size_t total_slots, bool want_psi, Program& prog, std::string& err) {
+int build_fused_program(const CircuitPlan& plan, size_t total_slots, bool want_psi, Program& prog, std::string& err, int traj_mode) {
     prog = Program();
     const int P = plan.P;
     const int R = (int)plan.runs.size();
@@ -1179,13 +1181,27 @@ int build_fused_program(const CircuitPlan& plan, size_t total_slots, bool want_p
     if (Pa == 0) return build_qgt_program(plan, total_slots, want_psi, prog, err);
     int R_last = 0;
     for (int p : ord) R_last = std::max(R_last, plan.last_run[p]);
-    const bool blocked = (size_t)Pa + 2 > total_slots;
-    if (blocked && total_slots < 4) { err = "workspace too small: need at least 4 statevector-sized columns"; return QGT_B200_ERR_NO_MEMORY; }
-    const int b = blocked ? (int)total_slots - 3 : Pa;
+    // trajectory mode: Tm extra columns hold phi after every transition-matrix stage of the current run; the items then
+    // fetch those tiles instead of recomputing phi (a third fewer tensor operations per column pass).  Worth it as long as
+    // at least two resident columns remain: per useful column pass and stage ~372 (1 + 1/b) DMMAs against
+    // ~552 + 372/b' when phi is recomputed (b' = b + Tm).
+    int Tm = 0;
+    for (const Run& run : plan.runs) Tm = std::max(Tm, run.rho_stages);
+    bool traj = traj_mode != 0 && Tm >= 1 && Tm <= QGT_MAX_TRAJ;
+    if (traj) {
+        const bool fits_all = (size_t)Pa + 2 + Tm <= total_slots;
+        const long b_traj = (long)total_slots - 3 - Tm;
+        if (!fits_all && b_traj < (traj_mode == 1 ? 1 : 2)) traj = false;
+    }
+    const int extra = traj ? Tm : 0;
+    const bool blocked = (size_t)Pa + 2 + extra > total_slots;
+    if (blocked && total_slots < (size_t)4 + extra) { err = "workspace too small: need at least 4 statevector-sized columns"; return QGT_B200_ERR_NO_MEMORY; }
+    const int b = blocked ? (int)total_slots - 3 - extra : Pa;
     Sched s(plan, prog);
     int next = 0;
     int phi = next++, phi_alt = next++;
     const int ckpt = blocked ? next++ : -1;
+    for (int i = 0; i < extra; i++) prog.traj_slots.push_back(next++);
     for (int i = 0; i < b; i++) s.res_slots.push_back(next++);
     prog.num_slots = next; prog.resident = b; prog.streaming = 0; prog.fused = true;
     const int nblocks = (Pa + b - 1) / b;
@@ -1199,7 +1215,16 @@ int build_fused_program(const CircuitPlan& plan, size_t total_slots, bool want_p
     if (blocked && nblocks > 1) s.init(ckpt);
     auto fused = [&](int run, int phi_slot, std::vector<SweepCol>& cols) {
         if (cols.empty()) return;
-        Instr in; in.kind = INSTR_FUSED; in.run = run; in.phi = phi_slot; in.cols = cols;
+        Instr in; in.kind = INSTR_FUSED; in.run = run; in.phi = phi_slot; in.traj = traj;
+        if (traj && cols.size() > 1 && cols[0].self) {
+            // trajectory mode: phi alone goes first and publishes its tiles, the columns follow in a second launch
+            Instr first = in;
+            first.cols.assign(1, cols[0]);
+            prog.instrs.push_back(std::move(first));
+            in.cols.assign(cols.begin() + 1, cols.end());
+        } else {
+            in.cols = cols;
+        }
         prog.instrs.push_back(std::move(in));
     };
     for (int blk : order) {
@@ -1324,7 +1349,9 @@ std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const 
     if (prog) {
         o << ",\"program\":{\"slots\":" << prog->num_slots << ",\"psi\":" << prog->psi_slot << ",\"resident\":" << prog->resident
           << ",\"streaming\":" << prog->streaming << ",\"blocks\":" << prog->blocks << ",\"psi_final\":" << (prog->psi_final ? 1 : 0)
-          << ",\"fused\":" << (prog->fused ? 1 : 0) << ",\"instrs\":[";
+          << ",\"fused\":" << (prog->fused ? 1 : 0) << ",\"traj\":";
+        jarr(o, prog->traj_slots);
+        o << ",\"instrs\":[";
         for (size_t i = 0; i < prog->instrs.size(); i++) {
             const Instr& in = prog->instrs[i];
             o << (i ? "," : "");

@@ -44,6 +44,7 @@ struct Stage {
     std::vector<int> params;        // distinct parameters with an occurrence among `ops`, in order of appearance
     int rho_off = -1;               // fused schedule: first of the stage's 2^nvar transition-matrix blocks inside an
                                     // item's rho buffer, -1 when no parameter occurs in the stage
+    int traj_ord = -1;              // ordinal among the run's stages with parameters (which trajectory column holds phi after it)
 };
 
 struct SubPass {
@@ -71,6 +72,7 @@ struct Run {
     int segment = 0;                // index of the mapped segment the run belongs to (selects the cost table)
     int rho_blocks = 0;             // fused schedule: 64-element transition-matrix blocks per item (sum of 2^nvar over stages with parameters)
     int last_rho_stage = -1;        // run-relative index of the last stage with a parameter occurrence
+    int rho_stages = 0;             // number of stages with a parameter occurrence
 };
 
 struct CircuitPlan {
@@ -134,6 +136,7 @@ struct Instr {
     int kind = INSTR_SWEEP;
     int run = -1;
     int phi = -1;                           // FUSED: slot of phi at the start of the run (second tile of every item)
+    bool traj = false;                      // FUSED: phi's tiles come from / go to the program's trajectory columns
     std::vector<SweepCol> cols;             // SWEEP, FUSED
     std::vector<int> a_slots, a_ids;        // GRAM: <a|b> for every pair; id = parameter index, P = psi
     std::vector<int> b_slots, b_ids;
@@ -148,6 +151,8 @@ struct Program {
     int blocks = 0;
     bool psi_final = false;     // psi_slot holds U(theta)|init> at the end
     bool fused = false;         // built by build_fused_program: no Gram instructions, Q assembled from transition matrices
+    std::vector<int> traj_slots;// fused schedule, trajectory mode: columns holding phi after every transition-matrix stage of
+                                // the current run (tile images); empty = phi is recomputed next to every column
     std::vector<Instr> instrs;
 };
 
@@ -165,7 +170,8 @@ int build_qgt_program(const CircuitPlan& plan, size_t total_slots, bool want_psi
 // <d_mu psi|psi> come from rho of phi with itself.  b = total_slots - 3 resident columns per block (phi, its
 // out-of-place twin and a rolling checkpoint take three slots).
 bool plan_supports_fused(const CircuitPlan& plan);
-int build_fused_program(const CircuitPlan& plan, size_t total_slots, bool want_psi, Program& prog, std::string& err);
+// traj_mode: 0 never, 1 whenever it fits, -1 automatic (when at least two resident columns remain)
+int build_fused_program(const CircuitPlan& plan, size_t total_slots, bool want_psi, Program& prog, std::string& err, int traj_mode = -1);
 // index of element (c, a, re/im) inside a 128-double transition-matrix block: the order in which the DMMA C fragments
 // of a warp hold it (lane = c*4 + a/2 owns columns a, a^1)
 static inline int rho_index(int c, int a, int part) { return (c * 4 + (a >> 1)) * 4 + part * 2 + (a & 1); }
