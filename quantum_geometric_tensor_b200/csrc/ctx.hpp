@@ -71,8 +71,9 @@ struct qgt_b200_ctx {
     qgt::FusedHost fused_host;
     int fused_traj = -1;         // trajectory mode of the fused schedule: -1 automatic, 0 never, 1 whenever it fits
     int fused_debug = 0;         // timing experiments only
-    int fused_pipeline = 2;      // trajectory mode at K = 11: 2 = lean 2 x 16-warp kernel where the run qualifies, 1 = persistent
-                                 // double-buffered 16-warp kernel, 0 = the generic 8-warp kernel
+    int fused_pipeline = 3;      // trajectory mode at K = 11: 3 = direct kernel (fragment-order trajectory, 3 CTAs x 8 warps) where the
+                                 // run qualifies, 2 = lean 2 x 16-warp kernel, 1 = persistent double-buffered 16-warp kernel,
+                                 // 0 = the generic 8-warp kernel
     int fused_mode = -1;         // -1 automatic (fused when the columns do not all fit), 0 never, 1 whenever the plan qualifies
     void* pinned = nullptr;
     QgtCostTable cost = {nullptr, 0, nullptr, 0};

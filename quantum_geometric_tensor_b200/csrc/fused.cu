@@ -16,10 +16,21 @@
 // src/quantum_geometric/core/quantum_geometric_tensor_network.c:1127-1175) and the P^2 D triple loop of
 // diffgeo_compute_fubini_study / _berry_curvature (distributed/differential_geometry.c:2819-2906) whenever the
 // derivative columns do not all fit in HBM (and, by option, when they do).
+#include <type_traits>
+
 #include "kernels.cuh"
 #include "mma_common.cuh"
 
 namespace qgt {
+
+// mma.sync as a VOLATILE asm: without it the compiler treats the instruction as a pure function and if-converts
+// "diagonal-real form ? 4 DMMAs : 8 DMMAs" into 8 unconditional ones (measured: twice the tensor work on every
+// diagonal-real stage).
+__device__ __forceinline__ void dmma884v(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+#define dmma884 dmma884v
 
 // A fragments of one 8x8 stage matrix for this lane (row lane>>2, columns lane&3 and 4 + lane&3)
 struct StageFrag {
@@ -74,6 +85,28 @@ __device__ __forceinline__ void qgt_rho3(double (&t)[6], const cplx& p, const cp
     dmma884(t[0], t[1], p.x, l.x);
     dmma884(t[2], t[3], p.y, l.y);
     dmma884(t[4], t[5], p.x + p.y, l.x - l.y);
+}
+
+// the same with the matrix form fixed at compile time: callers branch ONCE per stage on the (warp-uniform) form, so the
+// four extra DMMAs of the dense form sit behind a real branch instead of being predicated off one by one (predicated-off
+// DMMAs still travel through the tensor pipe: measured 2x pipe-busy time on diagonal-real stages)
+template <bool DR>
+__device__ __forceinline__ void qgt_apply8t(const StageFrag& f, const cplx& v0, const cplx& v1, cplx& o0, cplx& o1) {
+    double cr0 = 0.0, cr1 = 0.0, ci0 = 0.0, ci1 = 0.0;
+    dmma884(cr0, cr1, f.m0x, v0.x);
+    dmma884(ci0, ci1, f.m0x, v0.y);
+    dmma884(cr0, cr1, f.m1x, v1.x);
+    dmma884(ci0, ci1, f.m1x, v1.y);
+    if (DR) {
+        o0.x = f.dx * cr0 - f.dy * ci0; o0.y = f.dx * ci0 + f.dy * cr0;
+        o1.x = f.dx * cr1 - f.dy * ci1; o1.y = f.dx * ci1 + f.dy * cr1;
+    } else {
+        dmma884(cr0, cr1, -f.m0y, v0.y);
+        dmma884(ci0, ci1, f.m0y, v0.x);
+        dmma884(cr0, cr1, -f.m1y, v1.y);
+        dmma884(ci0, ci1, f.m1y, v1.x);
+        o0.x = cr0; o0.y = ci0; o1.x = cr1; o1.y = ci1;
+    }
 }
 
 __device__ __forceinline__ cplx qgt_cmul(const cplx& a, const cplx& b) {
@@ -307,7 +340,9 @@ __global__ void __launch_bounds__(256, 2) qgt_fused_kernel(FusedLaunch a) {
                         }
                     }
                 } else {
-                    // two halves of two 8-vector groups each: operand loads first, then the tensor work
+                    // two halves of two 8-vector groups each: operand loads first, then the tensor work.  (Instantiating this
+                    // body per matrix form, as the direct kernel does, was measured here: the 128-register kernel spills and
+                    // runs 28 % slower, so the dense form's extra DMMAs stay predicated.)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         cplx va0[2], va1[2], vb0[2], vb1[2];
@@ -839,6 +874,210 @@ size_t fused_lean_smem_bytes(int mat_count, int nsub, int rho_blocks) {
            (size_t)nsub * (sizeof(QgtLeanSub) + 32 * sizeof(uint32_t) + 16 * sizeof(uint2));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Direct form of the trajectory mode (default for 11-qubit tiles whose sub-passes are single stages): phi's tile
+// after a stage is published in FRAGMENT ORDER - element ((warp * 4 + group) * 32 + lane) * 2 + j is the j-th result
+// of that lane - so a consumer lane fetches exactly its own two C-fragment values per group with two coalesced
+// 16-byte read-only loads straight into registers.  No second tile in shared memory, no staging copy: a CTA needs
+// its own 32 KB tile + tables, three CTAs of 8 warps fit on an SM and their barriers / load phases interleave as in
+// the plain sweep kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ cplx qgt_ldg_nc(const cplx* p) {
+    cplx v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(256, 3) qgt_fused_direct_kernel(FusedLaunch a) {
+    constexpr int N = 8, T = 256, NW = 8;
+    constexpr int TILE = 1 << 11;
+    extern __shared__ __align__(128) cplx qgt_dsm[];
+    __shared__ QgtDevRun run;
+    __shared__ int wblk[2 * NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < (int)(sizeof(QgtDevRun) / 4); i += T)
+        reinterpret_cast<uint32_t*>(&run)[i] = reinterpret_cast<const uint32_t*>(&a.runs[a.run_idx])[i];
+    __syncthreads();
+    const int item_idx = (int)(blockIdx.x % (unsigned)a.nitems);
+    const int chunk = (int)(blockIdx.x / (unsigned)a.nitems);
+    const QgtSweepItem& it = a.items[item_idx];
+    const bool self = it.self != 0;
+    const int rho_from = it.rho_from;
+    const int dbg = a.debug;
+    const bool use_b = !self && rho_from <= run.last_rho_stage;
+    const int nsub = run.nsub;
+
+    cplx* tileA = qgt_dsm;
+    cplx* spool = tileA + TILE;
+    double* rho_acc = reinterpret_cast<double*>(spool + run.mat_count);
+    double* scratch = rho_acc + run.rho_blocks * 128;                  // [2][8][128]
+    QgtLeanSub* lsub = reinterpret_cast<QgtLeanSub*>(scratch + 2 * NW * 128);
+    uint32_t* flane = reinterpret_cast<uint32_t*>(lsub + nsub);        // [nsub][32]
+    uint2* fwarp = reinterpret_cast<uint2*>(flane + 32 * nsub);        // [nsub][8]: (slot part, variant bits of the warp)
+    const QgtDevStage* gstages = a.stages + run.stage_off;
+    {
+        const cplx* gpool = a.pool + run.mat_off;
+        for (int i = tid; i < run.mat_count; i += T) spool[i] = gpool[i];
+        for (int i = tid; i < run.rho_blocks * 128; i += T) rho_acc[i] = 0.0;
+        const QgtDevSubPass* gsubs = a.subs + run.sub_off;
+        for (int w = tid; w < nsub * 32; w += T) {
+            const int sI = w >> 5, l = w & 31, q = l >> 2, kk = l & 3;
+            const QgtDevSubPass& sp = gsubs[sI];
+            const QgtDevStage& st = gstages[sp.stage_begin];
+            const uint32_t b = ((q & 1) ? sp.s_thr[0] : 0u) ^ ((q & 2) ? sp.s_thr[1] : 0u) ^ ((q & 4) ? sp.s_thr[2] : 0u) ^
+                               ((kk & 1) ? sp.s_reg[0] : 0u) ^ ((kk & 2) ? sp.s_reg[1] : 0u);
+            const uint32_t c = ((kk & 1) ? sp.s_thr[1] : 0u) ^ ((kk & 2) ? sp.s_thr[2] : 0u) ^ ((q & 1) ? sp.s_reg[0] : 0u) ^
+                               ((q & 2) ? sp.s_reg[1] : 0u) ^ ((q & 4) ? sp.s_reg[2] : 0u);
+            flane[w] = b | (c << 16);
+            if (l < NW) {
+                uint32_t sl = 0; uint64_t g = 0;
+                for (int i = 5; i < 8; ++i)
+                    if ((l >> (i - 5)) & 1) { sl ^= sp.s_thr[i]; g |= sp.g_thr[i]; }
+                uint32_t vb = 0;
+                if (st.nvar > 0 && (g & st.vmask[0])) vb |= 1u;
+                if (st.nvar > 1 && (g & st.vmask[1])) vb |= 2u;
+                fwarp[sI * NW + l] = make_uint2(sl, vb);
+            }
+            if (l == 31) {
+                QgtLeanSub ls;
+                ls.gx1 = sp.s_thr[3]; ls.sr2 = sp.s_reg[2]; ls.st0 = sp.s_thr[0];
+                ls.mat_off = (uint32_t)st.mat_off;
+                ls.vm0 = sp.s_thr[4]; ls.vm1 = 0;                      // vm0 doubles as the second group bit (gx2) here
+                ls.rho_off = st.rho_off;
+                ls.info = (st.form == QGT_FORM_DIAG_REAL ? 1 : 0) | ((st.traj_ord < 0 ? 0xff : st.traj_ord) << 8) | (st.nvar << 4);
+                lsub[sI] = ls;
+            }
+        }
+    }
+    __syncthreads();
+
+    const QgtIoMap<3> io = qgt_make_iomap<3>(run, tid);
+    const int tau0 = chunk * a.tiles_per_cta;
+    const int ntl = (int)((uint64_t)tau0 + a.tiles_per_cta < a.ntiles ? (uint64_t)a.tiles_per_cta : a.ntiles - (uint64_t)tau0);
+    const int ovr_stage = it.ovr_kind == 1 ? it.ovr_index : -1;
+    const bool ovr_dr = it.ovr_form == QGT_FORM_DIAG_REAL;
+    const cplx* ovr_mat = reinterpret_cast<const cplx*>(it.ovr_mat);
+    const cplx* srcA = reinterpret_cast<const cplx*>(it.src);
+    cplx* dstA = reinterpret_cast<cplx*>(it.dst);
+    const int frag_off = (warp * 4 * 32 + lane) * 2;                   // + g * 64 + j
+    int par = 0;
+    for (int ti = 0; ti < ntl; ++ti) {
+        const uint64_t tilebase = qgt_tile_base(run, (uint64_t)(tau0 + ti));
+        const uint64_t tileg = tilebase | a.gprefix;
+        if (!(dbg & QGT_FDBG_NO_GLOBAL)) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t idx = (uint32_t)tid + (uint32_t)i * (uint32_t)T;
+                cp_async16(tileA + qgt_swz(idx), srcA + (tilebase | qgt_io_offset<3>(io, i)), 16);
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        for (int s = 0; s < nsub; ++s) {
+            const QgtLeanSub ls = lsub[s];
+            const uint2 fw = fwarp[s * NW + warp];
+            const uint32_t lt = flane[s * 32 + lane];
+            const uint32_t baseB = fw.x ^ (lt & 0xffffu), baseC = fw.x ^ (lt >> 16);
+            const uint32_t gx1 = ls.gx1, gx2 = ls.vm0;
+            int var = (int)fw.y;
+            const int nvar = (ls.info >> 4) & 3;
+            if (nvar) {                               // tile part of the variant bits
+                const QgtDevStage& st = gstages[s];
+                if (tileg & st.vmask[0]) var |= 1;
+                if (nvar > 1 && (tileg & st.vmask[1])) var |= 2;
+            }
+            const bool ovr = (s == ovr_stage);
+            const bool dr = ovr ? ovr_dr : (ls.info & 1);
+            const StageFrag fa = ovr ? qgt_load_frag(ovr_mat + var * QGT_VARIANT_STRIDE(N), dr, lane)
+                                     : qgt_load_frag(spool + ls.mat_off + var * QGT_VARIANT_STRIDE(N), dr, lane);
+            const bool rho_stage = ls.rho_off >= 0;
+            const bool fetch_b = use_b && rho_stage && s >= rho_from && !(dbg & QGT_FDBG_NO_BCOPY);
+            const bool do_rho = rho_stage && s >= rho_from && (self || use_b) && !(dbg & QGT_FDBG_NO_RHO);
+            cplx* img = rho_stage ? a.traj[(ls.info >> 8) & 0xff] + (size_t)(tau0 + ti) * TILE + frag_off : nullptr;
+            // phi's fragments of this stage: issued now, consumed after the groups have gone through the stage
+            cplx vb[4][2];
+            if (fetch_b) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) { vb[g][0] = qgt_ldg_nc(img + g * 64); vb[g][1] = qgt_ldg_nc(img + g * 64 + 1); }
+            }
+            double t6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            cplx ra0[4], ra1[4];
+            auto groups = [&](auto dr_tag) {
+                constexpr bool DR = decltype(dr_tag)::value;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    cplx va0[2], va1[2];
+#pragma unroll
+                    for (int g2 = 0; g2 < 2; ++g2) {
+                        const uint32_t gx = (g2 ? gx1 : 0u) ^ (h ? gx2 : 0u);
+                        va0[g2] = tileA[baseB ^ gx]; va1[g2] = tileA[baseB ^ gx ^ ls.sr2];
+                    }
+                    __syncwarp();                     // every lane has read the groups' slots before any is overwritten
+#pragma unroll
+                    for (int g2 = 0; g2 < 2; ++g2) {
+                        const int g = h * 2 + g2;
+                        const uint32_t gx = (g2 ? gx1 : 0u) ^ (h ? gx2 : 0u);
+                        qgt_apply8t<DR>(fa, va0[g2], va1[g2], ra0[g], ra1[g]);
+                        tileA[baseC ^ gx] = ra0[g];
+                        tileA[baseC ^ gx ^ ls.st0] = ra1[g];
+                    }
+                }
+            };
+            if (dr) groups(std::true_type{}); else groups(std::false_type{});
+            if (self && rho_stage && !(dbg & QGT_FDBG_NO_GLOBAL)) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) { img[g * 64] = ra0[g]; img[g * 64 + 1] = ra1[g]; }
+            }
+            if (do_rho) {
+                if (self) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) { qgt_rho3(t6, ra0[g], ra0[g]); qgt_rho3(t6, ra1[g], ra1[g]); }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) { qgt_rho3(t6, vb[g][0], ra0[g]); qgt_rho3(t6, vb[g][1], ra1[g]); }
+                }
+            }
+            if (do_rho) {
+                double* sc = scratch + (par * NW + warp) * 128 + lane * 4;
+                *reinterpret_cast<double2*>(sc) = make_double2(t6[0] + t6[2], t6[1] + t6[3]);
+                *reinterpret_cast<double2*>(sc + 2) = make_double2(t6[4] - t6[0] + t6[2], t6[5] - t6[1] + t6[3]);
+                if (lane == 0) wblk[par * NW + warp] = ls.rho_off + var;
+            }
+            __syncthreads();                          // tile coherent for the next stage, scratch complete
+            if (do_rho) {
+                // every warp sums 16 of the 128 doubles over the 8 warps in fixed order (deterministic); a warp's partial
+                // belongs to the block its variant selected.  The scratch is double-buffered: no second barrier.
+                if (lane < 16 && !(dbg & QGT_FDBG_NO_REDUCE)) {
+                    const int e = warp * 16 + lane;
+                    const double* sp = scratch + par * NW * 128 + e;
+                    double x[NW];
+                    int bl[NW];
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) { x[w] = sp[w * 128]; bl[w] = wblk[par * NW + w] - ls.rho_off; }
+                    const int nb = 1 << nvar;
+                    for (int v = 0; v < nb; ++v) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) acc += (bl[w] == v) ? x[w] : 0.0;
+                        rho_acc[(ls.rho_off + v) * 128 + e] += acc;
+                    }
+                }
+                par ^= 1;
+            }
+        }
+        if (!(dbg & QGT_FDBG_NO_GLOBAL)) qgt_phase_store<3>(io, tileA, dstA, tilebase, tid, T, it.accumulate != 0);
+    }
+    __syncthreads();
+    double* out = a.rho_partial + (size_t)blockIdx.x * run.rho_blocks * 128;
+    for (int i = tid; i < run.rho_blocks * 128; i += T) out[i] = rho_acc[i];
+}
+
+size_t fused_direct_smem_bytes(int mat_count, int nsub, int rho_blocks) {
+    return (sizeof(cplx) << 11) + sizeof(cplx) * (size_t)mat_count + (size_t)rho_blocks * 128 * sizeof(double) +
+           (size_t)2 * 8 * 128 * sizeof(double) + (size_t)nsub * (sizeof(QgtLeanSub) + 32 * sizeof(uint32_t) + 8 * sizeof(uint2));
+}
+
 size_t fused_pipe_smem_bytes(int mat_count, int nsub, int rho_blocks, int nstages) {
     return (sizeof(cplx) << 11) * 4 + sizeof(cplx) * (size_t)mat_count + sizeof(cplx) * (size_t)(QGT_VARIANT_STRIDE(8) << QGT_MAX_VARIANT_BITS) +
            (size_t)nsub * (sizeof(QgtDevSubPass) + 16 * sizeof(QgtFastWarp) + 32 * sizeof(uint32_t)) + 16 +
@@ -881,6 +1120,17 @@ cudaError_t launch_fused(const FusedLaunch& a, int K, int mat_count, int nsub, i
         if (e == cudaSuccess) e = cudaFuncSetAttribute(qgt_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
+    }
+    if (a.use_traj && a.pipeline == 3 && K == 11 && a.all_simple && fused_direct_smem_bytes(mat_count, nsub, rho_blocks) <= 110 * 1024) {
+        const size_t dsmem = fused_direct_smem_bytes(mat_count, nsub, rho_blocks);
+        static bool dattr = false;
+        if (!dattr) {
+            cudaError_t e = cudaFuncSetAttribute(qgt_fused_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+            if (e != cudaSuccess) return e;
+            dattr = true;
+        }
+        qgt_fused_direct_kernel<<<(unsigned)a.nitems * (unsigned)a.tile_groups, 256, dsmem, st>>>(a);
+        return cudaGetLastError();
     }
     if (a.use_traj && a.pipeline == 2 && K == 11 && a.all_simple && fused_lean_smem_bytes(mat_count, nsub, rho_blocks) <= 112 * 1024) {
         const size_t lsmem = fused_lean_smem_bytes(mat_count, nsub, rho_blocks);

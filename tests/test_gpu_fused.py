@@ -70,12 +70,12 @@ def test_fused_pipelined_kernel_at_full_tile_size(ctx, oracle):
         q, st = _fused_qgt(ctx, c, th, slots, traj=1)
         assert st["fused"] == 1
         assert rel_err(q, ref) < TOL
-        for pipeline in (0, 1):
+        for pipeline in (0, 1, 2):
             ctx.set_option("fused_pipeline", pipeline)
             try:
                 q2, _ = _fused_qgt(ctx, c, th, slots, traj=1)
             finally:
-                ctx.set_option("fused_pipeline", 2)
+                ctx.set_option("fused_pipeline", 3)
             assert rel_err(q2, ref) < TOL, pipeline
 
 

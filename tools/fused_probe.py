@@ -16,8 +16,8 @@ res = {}
 for mode in modes:
     m, _, dbg = mode.partition(":")
     ctx.set_option("fused", 0 if m == "g" else 1)
-    ctx.set_option("fused_traj", 1 if m in "tpl" else 0)
-    ctx.set_option("fused_pipeline", {"p": 1, "l": 2}.get(m, 0))
+    ctx.set_option("fused_traj", 1 if m in "tpld" else 0)
+    ctx.set_option("fused_pipeline", {"p": 1, "l": 2, "d": 3}.get(m, 0))
     ctx.set_option("fused_debug", float(dbg or 0))
     best = None
     for _ in range(reps):
