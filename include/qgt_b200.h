@@ -235,6 +235,7 @@ typedef struct qgt_b200_stats {
                                  every tile they carry plus the transition-matrix products of the fused schedule) */
     int32_t fused;            /* 1: the fused schedule ran (transition matrices inside the sweeps, no Gram pass) */
     int32_t fused_launches;
+    double ms_exchange;       /* sharded states: time in qubit-swap exchanges over NVLink */
 } qgt_b200_stats;
 int  qgt_b200_get_stats(qgt_b200_ctx* ctx, qgt_b200_stats* out);
 

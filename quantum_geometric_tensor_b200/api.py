@@ -34,7 +34,7 @@ class Stats(C.Structure):
                 ("sweep_column_passes", C.c_int64),
                 ("num_runs", C.c_int32), ("resident_columns", C.c_int32), ("blocks", C.c_int32), ("tile_qubits", C.c_int32),
                 ("ms_wall", C.c_double), ("ms_host_plan", C.c_double), ("tensor_flops", C.c_double),
-                ("fused", C.c_int32), ("fused_launches", C.c_int32)]
+                ("fused", C.c_int32), ("fused_launches", C.c_int32), ("ms_exchange", C.c_double)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -72,8 +72,8 @@ void Timer::end(cudaStream_t st) {
     used += 2;
 }
 
-void Timer::collect(double ms[3]) {
-    ms[0] = ms[1] = ms[2] = 0.0;
+void Timer::collect(double ms[4]) {
+    ms[0] = ms[1] = ms[2] = ms[3] = 0.0;
     for (size_t i = 0; i < cats.size(); i++) {
         float t = 0.f;
         cudaEventElapsedTime(&t, events[2 * i], events[2 * i + 1]);
@@ -414,6 +414,9 @@ static int check_circuit(const qgt_b200_circuit* circ, const double* theta) {
 // upload the device image of a plan and the circuit's cost table
 int upload_plan(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan& plan, PlanImage& img) {
     build_image(plan, img);
+    c->img_stage_form.clear(); c->img_run_stage_off.clear();
+    for (const QgtDevStage& st : img.stages) c->img_stage_form.push_back(st.form);
+    for (const QgtDevRun& r : img.runs) c->img_run_stage_off.push_back(r.stage_off);
     int rc;
     struct Up { DevBuf* buf; const void* src; size_t bytes; };
     const Up ups[] = {
@@ -781,7 +784,7 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
         case INSTR_SWEEP: {
             if (plan.runs[in.run].exchange_gbit >= 0) {      // sharded state: pairwise half-shard exchange per column
                 for (const SweepCol& sc : in.cols) {
-                    c->timer.begin(c->stream, 2, "exchange");
+                    c->timer.begin(c->stream, 3, "exchange");
                     rc = dist_exchange(c, arena + (size_t)sc.dst * D, D, plan.runs[in.run].exchange_gbit);
                     c->timer.end(c->stream);
                     if (rc) return rc;
@@ -825,7 +828,9 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             for (const SubPass& sp : run.subs)
                 for (const Stage& stg : sp.stages) {
                     mat_count += QGT_VARIANT_STRIDE(8) << stg.vqubits.size();
-                    flops_ab += 64.0;               // counted as dense 4M complex products (the diagonal-real form issues half)
+                    // DMMA flops per amplitude of one stage application: 8 complex MACs as 4 real products (64), or the
+                    // diagonal-real form's 2 real products (32)
+                    flops_ab += c->img_stage_form[(size_t)c->img_run_stage_off[in.run] + nstages] == QGT_FORM_DIAG_REAL ? 32.0 : 64.0;
                     nstages++;
                     if (stg.rho_off >= 0) nstage_rho++;
                 }
@@ -994,8 +999,9 @@ int stats_end(qgt_b200_ctx* c) {
     if (e != cudaSuccess) return cuda_fail(e, "stream sync");
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-    double cat[3];
+    double cat[4];
     c->timer.collect(cat);
+    c->stats.ms_exchange = cat[3];
     c->stats.ms_total = ms;
     c->stats.ms_sweep = cat[0]; c->stats.ms_gram = cat[1]; c->stats.ms_other = cat[2];
     return QGT_B200_OK;

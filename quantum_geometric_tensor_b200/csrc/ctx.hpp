@@ -23,7 +23,7 @@ struct DevBuf {
     void release();
 };
 
-// CUDA-event stopwatch on the library's stream; categories 0 = sweep, 1 = gram, 2 = other
+// CUDA-event stopwatch on the library's stream; categories 0 = sweep, 1 = gram / contraction, 2 = other, 3 = exchange
 struct Timer {
     bool enabled = true;
     std::vector<cudaEvent_t> events;
@@ -33,7 +33,7 @@ struct Timer {
     size_t used = 0;
     void begin(cudaStream_t st, int cat, const char* label = nullptr);
     void end(cudaStream_t st);
-    void collect(double ms[3]);
+    void collect(double ms[4]);
     ~Timer();
 };
 
@@ -69,6 +69,7 @@ struct qgt_b200_ctx {
     qgt::DevBuf arena, img_runs, img_subs, img_stages, img_tdiags, img_costs, img_pool, ovr_pool, items, aux, partial, cmat, outbuf, edges, vweights, scratch;
     qgt::DevBuf fx_pool, fx_tab, rho, rho_self, amat;     // fused schedule: evolved generators, contraction tables, transition matrices, A
     qgt::FusedHost fused_host;
+    std::vector<int> img_stage_form, img_run_stage_off;   // QGT_FORM_* of every stage of the uploaded plan (flop accounting)
     int fused_traj = -1;         // trajectory mode of the fused schedule: -1 automatic, 0 never, 1 whenever it fits
     int fused_debug = 0;         // timing experiments only
     int fused_pipeline = 3;      // trajectory mode at K = 11: 3 = direct kernel (fragment-order trajectory, 3 CTAs x 8 warps) where the
