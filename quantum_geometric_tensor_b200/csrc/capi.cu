@@ -521,7 +521,7 @@ int apply_plan_inplace(qgt_b200_ctx* c, const CircuitPlan& plan, cplx* d, uint64
     if (e != cudaSuccess) return cuda_fail(e, "item upload");
     for (size_t r = 0; r < plan.runs.size(); r++) {
         if (plan.runs[r].exchange_gbit >= 0) {
-            if ((rc = dist_exchange(c, d, D, plan.runs[r].exchange_gbit))) return rc;
+            if ((rc = dist_exchange(c, d, D, plan.runs[r].exchange_mask))) return rc;
             continue;
         }
         const uint64_t ntiles = D >> plan.runs[r].K;
@@ -548,16 +548,38 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
     std::vector<size_t> item_off(prog.instrs.size(), 0);
     std::vector<GramRec> grec(prog.instrs.size());
     size_t partial_bytes = 0;
+    // Program slots -> arena columns.  Identity, except that a grouped exchange receives every column into the spare
+    // column (index num_slots) and the column's old place becomes the next spare: the map is rotated statically here.
+    std::vector<int> phys((size_t)prog.num_slots);
+    for (int i = 0; i < prog.num_slots; i++) phys[i] = i;
+    int spare = prog.num_slots;
+    struct Resolved { int a = -1, b = -1; std::vector<std::pair<int, int>> moves; int traj[QGT_MAX_TRAJ]; };
+    std::vector<Resolved> res(prog.instrs.size());
     for (size_t i = 0; i < prog.instrs.size(); i++) {
         const Instr& in = prog.instrs[i];
+        if (in.kind == INSTR_INIT) res[i].b = phys[in.dst];
+        if (in.kind == INSTR_COPY) { res[i].a = phys[in.src]; res[i].b = phys[in.dst]; }
+        if (in.kind == INSTR_FUSED) {
+            res[i].a = phys[in.phi];
+            for (int t = 0; t < QGT_MAX_TRAJ; t++) res[i].traj[t] = t < (int)prog.traj_slots.size() ? phys[prog.traj_slots[t]] : -1;
+        }
+        if (in.kind == INSTR_SWEEP && plan.runs[in.run].exchange_gbit >= 0) {
+            for (const SweepCol& sc : in.cols) {
+                const int from = phys[sc.dst];
+                res[i].moves.push_back({from, spare});
+                phys[sc.dst] = spare;
+                spare = from;
+            }
+            continue;
+        }
         if (in.kind == INSTR_SWEEP || in.kind == INSTR_FUSED) {
             item_off[i] = items.size();
             const Run& run = plan.runs[in.run];
             for (const SweepCol& sc : in.cols) {
                 QgtSweepItem it;
                 std::memset(&it, 0, sizeof it);
-                it.src = arena + (size_t)sc.src * D;
-                it.dst = arena + (size_t)sc.dst * D;
+                it.src = arena + (size_t)phys[sc.src] * D;
+                it.dst = arena + (size_t)phys[sc.dst] * D;
                 it.accumulate = sc.accumulate ? 1u : 0u;
                 it.ovr_kind = 0; it.ovr_index = -1;
                 it.self = sc.self ? 1 : 0;
@@ -592,9 +614,9 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             GramRec& g = grec[i];
             g.na = (int)in.a_slots.size(); g.nb = (int)in.b_slots.size();
             g.a_off = ptrs.size();
-            for (int s : in.a_slots) ptrs.push_back(arena + (size_t)s * D);
+            for (int s : in.a_slots) ptrs.push_back(arena + (size_t)phys[s] * D);
             g.b_off = ptrs.size();
-            for (int s : in.b_slots) ptrs.push_back(arena + (size_t)s * D);
+            for (int s : in.b_slots) ptrs.push_back(arena + (size_t)phys[s] * D);
             g.aid_off = ids.size();
             for (int v : in.a_ids) ids.push_back(v);
             g.bid_off = ids.size();
@@ -762,6 +784,7 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
     const cplx* const* d_ptrs = (const cplx* const*)c->aux.ptr;
     const int* d_ids = (const int*)((char*)c->aux.ptr + ptr_bytes);
 
+    c->psi_phys_slot = prog.psi_slot < (int)phys.size() ? phys[prog.psi_slot] : prog.psi_slot;
     // ---- execute ----------------------------------------------------------------------------------
     const double plus_amp = std::pow(2.0, -0.5 * plan.n);
     for (size_t i = 0; i < prog.instrs.size(); i++) {
@@ -769,23 +792,23 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
         switch (in.kind) {
         case INSTR_INIT: {
             c->timer.begin(c->stream, 2);
-            e = launch_init_state(arena + (size_t)in.dst * D, D, circ.initial_state, plus_amp, (uint64_t)c->rank * D, c->stream);
+            e = launch_init_state(arena + (size_t)res[i].b * D, D, circ.initial_state, plus_amp, (uint64_t)c->rank * D, c->stream);
             c->timer.end(c->stream);
             if (e != cudaSuccess) return cuda_fail(e, "init launch");
             c->stats.other_launches++;
             break; }
         case INSTR_COPY: {
             c->timer.begin(c->stream, 2);
-            e = cudaMemcpyAsync(arena + (size_t)in.dst * D, arena + (size_t)in.src * D, D * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
+            e = cudaMemcpyAsync(arena + (size_t)res[i].b * D, arena + (size_t)res[i].a * D, D * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
             c->timer.end(c->stream);
             if (e != cudaSuccess) return cuda_fail(e, "column copy");
             c->stats.other_launches++;
             break; }
         case INSTR_SWEEP: {
-            if (plan.runs[in.run].exchange_gbit >= 0) {      // sharded state: pairwise half-shard exchange per column
-                for (const SweepCol& sc : in.cols) {
+            if (plan.runs[in.run].exchange_gbit >= 0) {      // sharded state: one grouped all-to-all per column, into the spare column
+                for (const std::pair<int, int>& mv : res[i].moves) {
                     c->timer.begin(c->stream, 3, "exchange");
-                    rc = dist_exchange(c, arena + (size_t)sc.dst * D, D, plan.runs[in.run].exchange_gbit);
+                    rc = dist_exchange_multi(c, arena + (size_t)mv.first * D, arena + (size_t)mv.second * D, D, plan.runs[in.run].exchange_mask);
                     c->timer.end(c->stream);
                     if (rc) return rc;
                     c->stats.other_launches++;
@@ -811,7 +834,7 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             a.run_idx = in.run;
             a.items = (const QgtSweepItem*)c->items.ptr + item_off[i];
             a.nitems = nitems;
-            a.phi = arena + (size_t)in.phi * D;
+            a.phi = arena + (size_t)res[i].a * D;
             a.ntiles = D >> run.K;
             a.tiles_per_cta = fr.tpc; a.tile_groups = fr.tg;
             a.gprefix = (uint64_t)c->rank << plan.nloc;
@@ -822,7 +845,7 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             a.all_simple = 1;
             for (const SubPass& sp : run.subs) if (sp.is_cost || sp.stages.size() != 1 || !sp.tdiags.empty()) a.all_simple = 0;
             for (int t = 0; t < QGT_MAX_TRAJ; t++)
-                a.traj[t] = t < (int)prog.traj_slots.size() ? arena + (size_t)prog.traj_slots[t] * D : nullptr;
+                a.traj[t] = res[i].traj[t] >= 0 ? arena + (size_t)res[i].traj[t] * D : nullptr;
             int mat_count = 0, nstage_rho = 0, nstages = 0;
             double flops_ab = 0.0;                  // per amplitude: one tile through every stage
             for (const SubPass& sp : run.subs)
@@ -1093,7 +1116,7 @@ int qgt_b200_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* th
         if (q_full && e == cudaSuccess) e = cudaMemcpyAsync(q_full, d_q, pp * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream);
     }
     if (psi_out && e == cudaSuccess)
-        e = cudaMemcpyAsync(psi_out->d, (cplx*)c->arena.ptr + (size_t)prog.psi_slot * D, D * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
+        e = cudaMemcpyAsync(psi_out->d, (cplx*)c->arena.ptr + (size_t)c->psi_phys_slot * D, D * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
     if (e != cudaSuccess) return cuda_fail(e, "result copy");
     if ((rc = stats_end(c))) return rc;
     c->stats.num_runs = (int)plan.runs.size();

@@ -69,6 +69,7 @@ struct qgt_b200_ctx {
     qgt::DevBuf arena, img_runs, img_subs, img_stages, img_tdiags, img_costs, img_pool, ovr_pool, items, aux, partial, cmat, outbuf, edges, vweights, scratch;
     qgt::DevBuf fx_pool, fx_tab, rho, rho_self, amat;     // fused schedule: evolved generators, contraction tables, transition matrices, A
     qgt::FusedHost fused_host;
+    int psi_phys_slot = 0;       // arena column holding the program's psi slot after run_program (exchanges rotate columns through a spare)
     std::vector<int> img_stage_form, img_run_stage_off;   // QGT_FORM_* of every stage of the uploaded plan (flop accounting)
     int fused_traj = -1;         // trajectory mode of the fused schedule: -1 automatic, 0 never, 1 whenever it fits
     int fused_debug = 0;         // timing experiments only
@@ -115,7 +116,8 @@ int stats_end(qgt_b200_ctx* c);
 void dist_shutdown(qgt_b200_ctx* c);
 int dist_allreduce_host(qgt_b200_ctx* c, double* v, int n);   // sum over ranks, no-op for world == 1
 int dist_apply_circuit(qgt_b200_state* s, const qgt_b200_circuit* circ, const double* theta);
-int dist_exchange(qgt_b200_ctx* c, cplx* col, uint64_t D, int gbit);   // swap rank bit `gbit` with the top local qubit
+int dist_exchange(qgt_b200_ctx* c, cplx* col, uint64_t D, unsigned mask);   // grouped qubit exchange of one column, in place (via scratch)
+int dist_exchange_multi(qgt_b200_ctx* c, const cplx* src, cplx* dst, uint64_t D, unsigned mask);   // the same, out of place, no extra copy
 int dist_allreduce_device(qgt_b200_ctx* c, double* d_buf, size_t count);   // in place, stream ordered
 int dist_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
              double* metric, double* berry, double* q_full, qgt_b200_state* psi_out);

@@ -106,24 +106,42 @@ int dist_allreduce_host(qgt_b200_ctx* c, double* v, int n) {
     return QGT_B200_OK;
 }
 
-// swap rank bit `gbit` with the top local qubit of the column at `col` (D local amplitudes)
-int dist_exchange(qgt_b200_ctx* c, cplx* col, uint64_t D, int gbit) {
+// One grouped exchange: rank bits b_0 < b_1 < ... of `mask` trade places with the top k local qubits (b_i <-> nloc-k+i).
+// The shard splits into 2^k blocks by its top k local bits; block j goes to the rank whose mask bits spell j and lands
+// there at block index (my mask bits); the block whose index equals my own mask bits stays.  Out of place (src != dst):
+// every block is received straight into its final position - no bounce buffer, no second pass over HBM.
+int dist_exchange_multi(qgt_b200_ctx* c, const cplx* src, cplx* dst, uint64_t D, unsigned mask) {
     if (c->world == 1 || !c->dist) return fail(QGT_B200_ERR_INTERNAL, "exchange on an unsharded state");
-    const int peer = c->rank ^ (1 << gbit);
-    const int mybit = (c->rank >> gbit) & 1;
-    const uint64_t half = D / 2;
-    int rc = c->dist->bounce.reserve(half * sizeof(cplx));
-    if (rc) return rc;
-    // keep the half whose top local bit equals my rank bit; trade the other one with the peer
-    cplx* moving = col + (mybit ? 0 : half);
+    if (!mask || src == dst) return fail(QGT_B200_ERR_INTERNAL, "exchange needs a mask and distinct buffers");
+    int bits[16], k = 0;
+    for (int b = 0; b < 16; b++) if (mask >> b & 1u) bits[k++] = b;
+    const uint64_t blk = D >> k;
+    int mine = 0;
+    for (int i = 0; i < k; i++) mine |= ((c->rank >> bits[i]) & 1) << i;
     ncclResult_t r = g_nccl.GroupStart();
-    if (r == ncclSuccess) r = g_nccl.Send(moving, half * 2, ncclDouble, peer, c->dist->comm, c->stream);
-    if (r == ncclSuccess) r = g_nccl.Recv(c->dist->bounce.ptr, half * 2, ncclDouble, peer, c->dist->comm, c->stream);
+    for (int j = 0; j < (1 << k) && r == ncclSuccess; j++) {
+        if (j == mine) continue;
+        int peer = c->rank;
+        for (int i = 0; i < k; i++) peer = (peer & ~(1 << bits[i])) | (((j >> i) & 1) << bits[i]);
+        r = g_nccl.Send(src + (uint64_t)j * blk, blk * 2, ncclDouble, peer, c->dist->comm, c->stream);
+        if (r == ncclSuccess) r = g_nccl.Recv(dst + (uint64_t)j * blk, blk * 2, ncclDouble, peer, c->dist->comm, c->stream);
+    }
     if (r == ncclSuccess) r = g_nccl.GroupEnd();
     if (r != ncclSuccess) return nccl_fail(r, "exchange send/recv");
-    cudaError_t e = cudaMemcpyAsync(moving, c->dist->bounce.ptr, half * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
+    cudaError_t e = cudaMemcpyAsync(dst + (uint64_t)mine * blk, src + (uint64_t)mine * blk, blk * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "exchange local block");
+    c->stats.exchange_bytes += (double)(((uint64_t)(1 << k) - 1) * blk * sizeof(cplx));
+    return QGT_B200_OK;
+}
+
+// in-place form for a lone state (qgt_b200_apply_circuit): through a scratch column and back
+int dist_exchange(qgt_b200_ctx* c, cplx* col, uint64_t D, unsigned mask) {
+    if (c->world == 1 || !c->dist) return fail(QGT_B200_ERR_INTERNAL, "exchange on an unsharded state");
+    int rc = c->dist->bounce.reserve(D * sizeof(cplx));
+    if (rc) return rc;
+    if ((rc = dist_exchange_multi(c, col, (cplx*)c->dist->bounce.ptr, D, mask))) return rc;
+    cudaError_t e = cudaMemcpyAsync(col, c->dist->bounce.ptr, D * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
     if (e != cudaSuccess) return cuda_fail(e, "exchange copy");
-    c->stats.exchange_bytes += (double)(half * sizeof(cplx));
     return QGT_B200_OK;
 }
 
@@ -198,7 +216,7 @@ int dist_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
     if (rc) return fail(rc, err);
     Program prog;
     // every rank must build the same program: agree on the smallest slot count
-    size_t slots = workspace_slots(c, D, ((size_t)256 << 20) + (D / 2) * sizeof(cplx));
+    size_t slots = workspace_slots(c, D, ((size_t)256 << 20) + D * sizeof(cplx));
     {
         int rc2 = c->dist->red.reserve(sizeof(double));
         if (rc2) return rc2;
@@ -211,11 +229,12 @@ int dist_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
         if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(c->stream);
         if (e0 != cudaSuccess) return cuda_fail(e0, "slot readback");
         slots = (size_t)v;
+        if (slots > 5) slots -= 1;               // one column is the spare the grouped exchanges receive into
     }
     const bool use_fused = choose_fused(c, plan, slots);
     if ((rc = use_fused ? build_fused_program(plan, slots, psi_out != nullptr, prog, err, c->fused_traj)
                         : build_qgt_program(plan, slots, psi_out != nullptr, prog, err))) return fail(rc, err);
-    if ((rc = c->arena.reserve((size_t)prog.num_slots * D * sizeof(cplx)))) return rc;
+    if ((rc = c->arena.reserve(((size_t)prog.num_slots + 1) * D * sizeof(cplx)))) return rc;     // + the spare column of the exchanges
     const size_t cm = (size_t)(P + 1) * (P + 1);
     if ((rc = c->cmat.reserve(std::max<size_t>(16, cm * sizeof(cplx))))) return rc;
     if ((rc = c->outbuf.reserve(std::max<size_t>(16, (size_t)P * P * 4 * sizeof(double))))) return rc;
@@ -248,7 +267,7 @@ int dist_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
         if (q_full && e == cudaSuccess) e = cudaMemcpyAsync(q_full, d_q, pp * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream);
     }
     if (psi_out && e == cudaSuccess)
-        e = cudaMemcpyAsync(psi_out->d, (cplx*)c->arena.ptr + (size_t)prog.psi_slot * D, D * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
+        e = cudaMemcpyAsync(psi_out->d, (cplx*)c->arena.ptr + (size_t)c->psi_phys_slot * D, D * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream);
     if (e != cudaSuccess) return cuda_fail(e, "result copy");
     if ((rc = stats_end(c))) return rc;
     c->stats.num_runs = (int)plan.runs.size();

@@ -457,7 +457,7 @@ static void split_run_by_births(Run& run, bool enable, int state_qubits, std::ve
     for (int hi : cuts) {
         Run piece;
         piece.K = run.K; piece.tile_qubits = run.tile_qubits; piece.other_qubits = run.other_qubits;
-        piece.exchange_gbit = run.exchange_gbit; piece.segment = run.segment;
+        piece.exchange_gbit = run.exchange_gbit; piece.exchange_mask = run.exchange_mask; piece.segment = run.segment;
         const int base = run.subs[lo].op_begin, end = run.subs[hi - 1].op_end;
         piece.ops.assign(run.ops.begin() + base, run.ops.begin() + end);
         for (int s = lo; s < hi; s++) {
@@ -733,60 +733,91 @@ void nondiag_qubits(const qgt_b200_gate& g, int out[2], int& cnt) {
 int map_circuit_sharded(const qgt_b200_circuit& c, int nloc, bool restore_identity,
                         std::vector<MappedSegment>& segs, std::string& err) {
     const int n = c.num_qubits;
+    bool batch_exchanges = true;
+    if (const char* e = std::getenv("QGT_B200_BATCH_EXCHANGES")) batch_exchanges = std::atoi(e) != 0;   // 0: one rank bit per exchange
     segs.clear();
     if (nloc < 2 || nloc > n) { err = "invalid shard size"; return QGT_B200_ERR_INVALID_ARG; }
     std::vector<int> phys(n), logical(n);
     for (int q = 0; q < n; q++) { phys[q] = q; logical[q] = q; }
     MappedSegment cur;
     cur.phys_of_logical = phys;
-    auto close_segment = [&](int gbit) {
-        cur.exchange_gbit = gbit;
+    auto close_segment = [&](unsigned mask) {
+        cur.exchange_mask = mask;
+        cur.exchange_gbit = mask ? __builtin_ctz(mask) : -1;
         segs.push_back(cur);
         cur = MappedSegment();
     };
-    // bring logical qubit q (currently on a rank bit) into physical position nloc-1, evicting `victim`
-    auto bring_in = [&](int q, int victim) {
-        const int top = nloc - 1;
-        if (phys[victim] != top) {             // local SWAP: victim <-> whoever sits at the top local position
-            const int w = logical[top], pv = phys[victim];
-            qgt_b200_gate sw = {QGT_B200_GATE_SWAP, pv, top, -1, 0.0, 1.0};
-            cur.gates.push_back(sw);
-            phys[w] = pv; logical[pv] = w;
-            phys[victim] = top; logical[top] = victim;
+    auto local_swap = [&](int pa, int pb) {          // physical positions, both local
+        if (pa == pb) return;
+        qgt_b200_gate sw = {QGT_B200_GATE_SWAP, pa, pb, -1, 0.0, 1.0};
+        cur.gates.push_back(sw);
+        const int la = logical[pa], lb = logical[pb];
+        phys[la] = pb; logical[pb] = la;
+        phys[lb] = pa; logical[pa] = lb;
+    };
+    // Bring the logical qubits `in` (all on rank bits) into the top local positions in ONE exchange, evicting `out` (local
+    // logical qubits, same count).  The rank bits involved, ascending, pair with local positions nloc-k .. nloc-1.
+    auto bring_in = [&](std::vector<int> in, const std::vector<int>& out) {
+        const int k = (int)in.size();
+        std::sort(in.begin(), in.end(), [&](int a, int b) { return phys[a] < phys[b]; });
+        for (int i = 0; i < k; i++) {                // victim i must sit at local position nloc-k+i
+            const int want = nloc - k + i;
+            // a victim already parked at a wanted position keeps it if possible: place victims greedily
+            local_swap(phys[out[i]], want);
         }
-        const int pg = phys[q];
-        close_segment(pg - nloc);
-        phys[q] = top; logical[top] = q;
-        phys[victim] = pg; logical[pg] = victim;
+        unsigned mask = 0;
+        for (int q : in) mask |= 1u << (phys[q] - nloc);
+        close_segment(mask);
+        for (int i = 0; i < k; i++) {
+            const int q = in[i], v = logical[nloc - k + i];
+            const int pg = phys[q], pl = nloc - k + i;
+            phys[q] = pl; logical[pl] = q;
+            phys[v] = pg; logical[pg] = v;
+        }
         cur.phys_of_logical = phys;
+    };
+    // next gate index >= from at which logical qubit v is acted on non-diagonally
+    auto next_use = [&](int v, size_t from) {
+        for (size_t gj = from; gj < c.num_gates; gj++) {
+            int nd2[2], c2;
+            nondiag_qubits(c.gates[gj], nd2, c2);
+            for (int k2 = 0; k2 < c2; k2++) if (nd2[k2] == v) return gj;
+        }
+        return c.num_gates + 1;
     };
     for (size_t gi = 0; gi < c.num_gates; gi++) {
         const qgt_b200_gate& g = c.gates[gi];
         int nd[2], cnt;
         nondiag_qubits(g, nd, cnt);
+        bool miss = false;
         for (int k = 0; k < cnt; k++) {
-            const int q = nd[k];
-            if (q < 0 || q >= n) { err = "gate qubit out of range"; return QGT_B200_ERR_CIRCUIT; }
-            if (phys[q] < nloc) continue;
-            // victim: a local logical qubit this gate does not need, whose next non-diagonal use is farthest
-            int victim = -1; size_t best = 0;
+            if (nd[k] < 0 || nd[k] >= n) { err = "gate qubit out of range"; return QGT_B200_ERR_CIRCUIT; }
+            if (phys[nd[k]] >= nloc) miss = true;
+        }
+        if (miss) {
+            // candidates to bring in: every logical qubit on a rank bit, soonest next non-diagonal use first (the ones this
+            // gate needs come first by construction); victims: local qubits this gate does not need, farthest next use
+            // first (Belady).  Pair i is part of the batch while the incoming qubit is needed before the outgoing one.
+            std::vector<std::pair<size_t, int>> globals, locals;
             for (int v = 0; v < n; v++) {
-                if (phys[v] >= nloc) continue;
                 bool needed = false;
                 for (int k2 = 0; k2 < cnt; k2++) if (nd[k2] == v) needed = true;
-                if (needed) continue;
-                size_t next = c.num_gates + 1;
-                for (size_t gj = gi + 1; gj < c.num_gates; gj++) {
-                    int nd2[2], c2;
-                    nondiag_qubits(c.gates[gj], nd2, c2);
-                    bool hit = false;
-                    for (int k2 = 0; k2 < c2; k2++) if (nd2[k2] == v) hit = true;
-                    if (hit) { next = gj; break; }
-                }
-                if (victim < 0 || next > best) { victim = v; best = next; }
+                if (phys[v] >= nloc) globals.push_back({needed ? gi : next_use(v, gi + 1), v});
+                else if (!needed) locals.push_back({next_use(v, gi + 1), v});
             }
-            if (victim < 0) { err = "no local qubit available to exchange"; return QGT_B200_ERR_INTERNAL; }
-            bring_in(q, victim);
+            std::sort(globals.begin(), globals.end());
+            std::sort(locals.begin(), locals.end(), [](const std::pair<size_t, int>& a, const std::pair<size_t, int>& b) {
+                return a.first != b.first ? a.first > b.first : a.second < b.second; });
+            std::vector<int> in, out;
+            for (size_t i = 0; i < globals.size() && i < locals.size(); i++) {
+                const bool must = globals[i].first == gi;
+                if (!must && !(batch_exchanges && globals[i].first < locals[i].first)) break;
+                in.push_back(globals[i].second); out.push_back(locals[i].second);
+            }
+            size_t must_count = 0;
+            for (const auto& gl : globals) if (gl.first == gi) must_count++;
+            if (in.size() < must_count) { err = "no local qubit available to exchange"; return QGT_B200_ERR_INTERNAL; }
+            bring_in(in, out);
         }
         qgt_b200_gate pg = g;
         if (g.kind != QGT_B200_GATE_COST) {
@@ -804,7 +835,7 @@ int map_circuit_sharded(const qgt_b200_circuit& c, int nloc, bool restore_identi
                 int victim = -1;
                 for (int v = 0; v < n; v++) if (phys[v] < nloc && v < nloc) { victim = v; break; }
                 if (victim < 0) for (int v = 0; v < n; v++) if (phys[v] < nloc) { victim = v; break; }
-                bring_in(want, victim);
+                bring_in(std::vector<int>(1, want), std::vector<int>(1, victim));
             }
             // now `want` is local: move it to the top and exchange it with rank bit pq
             const int top = nloc - 1;
@@ -816,7 +847,7 @@ int map_circuit_sharded(const qgt_b200_circuit& c, int nloc, bool restore_identi
                 phys[want] = top; logical[top] = want;
             }
             const int other = logical[pq];
-            close_segment(pq - nloc);
+            close_segment(1u << (pq - nloc));
             phys[want] = pq; logical[pq] = want;
             phys[other] = top; logical[top] = other;
             cur.phys_of_logical = phys;
@@ -831,7 +862,7 @@ int map_circuit_sharded(const qgt_b200_circuit& c, int nloc, bool restore_identi
             phys[pq] = pq; logical[pq] = pq;
         }
     }
-    close_segment(-1);
+    close_segment(0);
     return QGT_B200_OK;
 }
 
@@ -855,6 +886,7 @@ int build_plan_sharded(const qgt_b200_circuit& c, const double* theta, const Pla
             Run ex;
             ex.K = plan.K;
             ex.exchange_gbit = segs[si].exchange_gbit;
+            ex.exchange_mask = segs[si].exchange_mask;
             ex.segment = (int)si;
             plan.runs.push_back(ex);
         }
@@ -1312,7 +1344,7 @@ std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const 
       << ",\"initial_state\":" << c.initial_state << ",\"runs\":[";
     for (size_t r = 0; r < plan.runs.size(); r++) {
         const Run& run = plan.runs[r];
-        o << (r ? "," : "") << "{\"exchange\":" << run.exchange_gbit << ",\"segment\":" << run.segment << ",\"tile\":"; jarr(o, run.tile_qubits);
+        o << (r ? "," : "") << "{\"exchange\":" << run.exchange_gbit << ",\"exchange_mask\":" << run.exchange_mask << ",\"segment\":" << run.segment << ",\"tile\":"; jarr(o, run.tile_qubits);
         o << ",\"subs\":[";
         for (size_t s = 0; s < run.subs.size(); s++) {
             const SubPass& sp = run.subs[s];
@@ -1342,7 +1374,7 @@ std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const 
         o << ",\"segments\":[";
         for (size_t i = 0; i < segs->size(); i++) {
             o << (i ? "," : "") << "{\"phys\":"; jarr(o, (*segs)[i].phys_of_logical);
-            o << ",\"exchange\":" << (*segs)[i].exchange_gbit << ",\"gates\":" << (*segs)[i].gates.size() << "}";
+            o << ",\"exchange\":" << (*segs)[i].exchange_gbit << ",\"exchange_mask\":" << (*segs)[i].exchange_mask << ",\"gates\":" << (*segs)[i].gates.size() << "}";
         }
         o << "]";
     }

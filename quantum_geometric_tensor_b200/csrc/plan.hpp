@@ -68,7 +68,9 @@ struct Run {
     std::vector<LoweredOp> ops;     // in execution order
     std::vector<SubPass> subs;
     std::vector<ParamOcc> occ;      // parameterised ops in this run
-    int exchange_gbit = -1;         // pseudo-run of a sharded state: swap rank bit `exchange_gbit` with the top local qubit
+    int exchange_gbit = -1;         // pseudo-run of a sharded state: >= 0 marks an exchange (lowest rank bit of exchange_mask)
+    unsigned exchange_mask = 0;     // rank bits b_0 < b_1 < ... swapped, in ONE grouped all-to-all, with the top local qubits
+                                    // nloc-k, ..., nloc-1 (b_i <-> nloc-k+i); k = popcount
     int segment = 0;                // index of the mapped segment the run belongs to (selects the cost table)
     int rho_blocks = 0;             // fused schedule: 64-element transition-matrix blocks per item (sum of 2^nvar over stages with parameters)
     int last_rho_stage = -1;        // run-relative index of the last stage with a parameter occurrence
@@ -189,7 +191,8 @@ void stage_generators(const Run& run, const SubPass& sp, const Stage& st, std::v
 struct MappedSegment {
     std::vector<qgt_b200_gate> gates;    // physical qubit numbers; targets of non-diagonal gates are < nloc
     std::vector<int> phys_of_logical;    // mapping in force for these gates (cost tables are remapped with it)
-    int exchange_gbit = -1;              // after the gates: swap rank bit with physical qubit nloc-1; -1 = none
+    int exchange_gbit = -1;              // after the gates: an exchange follows (lowest bit of exchange_mask); -1 = none
+    unsigned exchange_mask = 0;          // rank bits swapped with the top popcount(mask) local qubits (see Run::exchange_mask)
 };
 int map_circuit_sharded(const qgt_b200_circuit& c, int nloc, bool restore_identity,
                         std::vector<MappedSegment>& segs, std::string& err);

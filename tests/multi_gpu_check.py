@@ -71,21 +71,35 @@ def main():
     qo = orc.qgt(circ, th)
     check("qgt blocked hea n=11", float(np.abs(q - qo).max() / np.abs(qo).max()), 1e-10)
 
-    # 3. a size no single check needs the oracle for: norm preservation + Hermiticity at 2^26 amplitudes per... n = 26
-    circ = K.hea(26, 24)
-    th = K.default_angles(24)
-    dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    q = ctx.qgt(circ, th)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    st = ctx.stats()
-    check("qgt n=26 hermitian", float(np.abs(q - q.conj().T).max()), 1e-12)
-    check("qgt n=26 first-layer diag", float(np.abs(np.diag(q.real)[:24] - 0.25).max()), 1e-12)
-    if rank == 0:
-        print(f"[rank 0] n=26 P=24 on {world} GPUs: {dt * 1e3:.1f} ms, exchange bytes/rank {st['exchange_bytes']:.3e}, "
-              f"sweep {st['ms_sweep']:.1f} ms gram {st['ms_gram']:.1f} ms other {st['ms_other']:.1f} ms", flush=True)
+    # 3. 22 qubits, 3 full layers (P = 132): every rank qubit is exchanged in and out several times and the columns do
+    #    not all fit per rank on 2 GPUs' worth of slots when capped: a 3 x 3 sub-block against the reference-generated
+    #    golden (tests/golden_big, oracle/_ref), with both schedules
+    z = np.load(os.path.join(ROOT, "tests", "golden_big", "hea_n22_l3_cols.npz"))
+    circ = K.hea_layers(22, 3)
+    th = z["theta"]
+    cols = [int(x) for x in z["cols"]]
+    for label, opts in (("gram schedule", {"fused": 0}), ("fused schedule, capped slots", {"fused": 1, "max_slots": 40})):
+        for k_, v_ in opts.items():
+            ctx.set_option(k_, v_)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        q = ctx.qgt(circ, th)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        st = ctx.stats()
+        ctx.set_option("fused", -1)
+        ctx.set_option("max_slots", 0)
+        sub = q[np.ix_(cols, cols)]
+        check(f"qgt n=22 L=3 sub-block metric ({label})", float(np.abs(sub.real - z["metric"]).max() / np.abs(z["metric"]).max()), 1e-10)
+        check(f"qgt n=22 L=3 sub-block curvature ({label})", float(np.abs(-2 * sub.imag - z["curvature"]).max() / np.abs(z["curvature"]).max()), 1e-10)
+        check(f"qgt n=22 hermitian ({label})", float(np.abs(q - q.conj().T).max()), 1e-12)
+        if st["exchange_bytes"] <= 0:
+            failures.append("no exchange happened at n=22")
+        if rank == 0:
+            print(f"[rank 0] n=22 P=132 on {world} GPUs ({label}): {dt * 1e3:.1f} ms, exchange bytes/rank {st['exchange_bytes']:.3e} "
+                  f"({st['exchange_bytes'] / max(st['ms_exchange'], 1e-9) * 1e-6:.0f} GB/s), sweep {st['ms_sweep']:.1f} ms gram {st['ms_gram']:.1f} ms "
+                  f"exchange {st['ms_exchange']:.1f} ms other {st['ms_other']:.1f} ms blocks {st['blocks']}", flush=True)
 
     ctx.close()
     fl = torch.tensor([len(failures)], device="cuda")

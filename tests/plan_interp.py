@@ -203,18 +203,24 @@ def sweep_shard(plan, circ, run_idx, shard, rank, ovr, tabs):
     return v
 
 
-def exchange_all_ranks(cols, gbit):
-    """cols[rank] = shard; swap rank bit `gbit` with the top local qubit"""
+def exchange_all_ranks(cols, mask):
+    """cols[rank] = shard (modified in place).  Rank bits b_0 < b_1 < ... of `mask` trade places with the top k local
+    qubits (b_i <-> nloc-k+i): one grouped all-to-all (dist.cu: dist_exchange_multi)."""
     world = len(cols)
-    half = cols[0].size // 2
+    dloc = cols[0].size
+    nloc = dloc.bit_length() - 1
+    bits = [b for b in range(16) if (mask >> b) & 1]
+    k = len(bits)
+    full = np.concatenate(cols)
+    idx = np.arange(full.size, dtype=np.int64)
+    src = idx.copy()
+    for i, b in enumerate(bits):                      # new[idx] = old[idx with bit (nloc+b) and bit (nloc-k+i) swapped]
+        hi, lo = nloc + b, nloc - k + i
+        bh, bl = (src >> hi) & 1, (src >> lo) & 1
+        src = src ^ ((bh ^ bl) << hi) ^ ((bh ^ bl) << lo)
+    out = full[src]
     for r in range(world):
-        if (r >> gbit) & 1:
-            continue
-        p = r | (1 << gbit)
-        # rank r (bit 0) keeps its lower half, trades its upper half for the peer's lower half
-        tmp = cols[r][half:].copy()
-        cols[r][half:] = cols[p][:half]
-        cols[p][:half] = tmp
+        cols[r][:] = out[r * dloc:(r + 1) * dloc]
 
 
 def initial_shard(circ, rank, nloc):
@@ -248,7 +254,7 @@ def run_program_sharded(plan, circ, world):
                 for (src, dst, ovr, acc, extra) in ins["cols"]:
                     assert src == dst and ovr < 0 and not acc
                     cols = [slots[r][dst] for r in range(world)]
-                    exchange_all_ranks(cols, run["exchange"])
+                    exchange_all_ranks(cols, run["exchange_mask"])
                 continue
             for r in range(world):
                 res = [(dst, acc, sum(sweep_shard(plan, circ, ins["run"], slots[r][src], r, o, tabs) for o in [ovr] + list(extra)))
@@ -374,7 +380,7 @@ def run_program_fused(plan: dict, circ, world: int = 1):
             if run["exchange"] >= 0:
                 for (src, dst, ovr, acc, extra) in ins["cols"]:
                     assert src == dst and ovr < 0 and not acc
-                    exchange_all_ranks([slots[r][dst] for r in range(world)], run["exchange"])
+                    exchange_all_ranks([slots[r][dst] for r in range(world)], run["exchange_mask"])
                 continue
             f = apply_fn_for(run)
             for (src, dst, ovr, acc, extra) in ins["cols"]:

@@ -48,6 +48,24 @@ def test_sharded_qaoa_cost_tables_follow_the_qubit_map(oracle, world):
     assert np.abs(Q - oracle.qgt(c, th)).max() < 1e-12
 
 
+def test_exchanges_are_batched_over_rank_bits(monkeypatch):
+    """A hardware-efficient ansatz on 8 ranks: the three rank qubits come in with ONE grouped exchange per visit
+    instead of three pairwise ones (fewer exchanges and 7/8 instead of 3/2 of the shard moved)."""
+    c = K.hea_layers(9, 3)
+    th = K.default_angles(c.num_params)
+    def exchanged(plan):
+        ex = [r["exchange_mask"] for r in plan["runs"] if r["exchange"] >= 0]
+        vol = sum(1.0 - 0.5 ** bin(m).count("1") for m in ex)
+        return len(ex), vol
+    monkeypatch.setenv("QGT_B200_BATCH_EXCHANGES", "0")
+    n1, v1 = exchanged(api.plan_dump_sharded(c, th, 8, True, tile_qubits=4, reg_qubits=2))
+    monkeypatch.setenv("QGT_B200_BATCH_EXCHANGES", "1")
+    plan = api.plan_dump_sharded(c, th, 8, True, tile_qubits=4, reg_qubits=2)
+    n2, v2 = exchanged(plan)
+    assert any(bin(r["exchange_mask"]).count("1") > 1 for r in plan["runs"])
+    assert n2 < n1 and v2 < v1
+
+
 def test_diagonal_gates_on_rank_qubits_need_no_exchange():
     c = K.Circuit(6)
     for q in range(6):
@@ -83,18 +101,31 @@ def _gloo_worker(rank, world, port, result_path):
         elif k == "sweep":
             run = plan["runs"][ins["run"]]
             if run["exchange"] >= 0:
-                gbit = run["exchange"]
-                peer, mybit = rank ^ (1 << gbit), (rank >> gbit) & 1
-                half = (1 << nloc) // 2
+                # grouped exchange exactly as dist.cu's dist_exchange_multi: block j of my shard goes to the rank whose
+                # mask bits spell j, the block I receive from it lands at index j; my own block stays
+                bits = [b for b in range(8) if (run["exchange_mask"] >> b) & 1]
+                k = len(bits)
+                blk = (1 << nloc) >> k
+                mine = sum(((rank >> b) & 1) << i for i, b in enumerate(bits))
                 for (src, dst, ovr, acc, extra) in ins["cols"]:
                     col = slots[dst]
-                    lo = 0 if mybit else half                   # the half that moves (dist.cu: dist_exchange)
-                    send = torch.from_numpy(np.ascontiguousarray(col[lo:lo + half]).view(np.float64).copy())
-                    recv = torch.empty_like(send)
-                    reqs = [dist.isend(send, peer), dist.irecv(recv, peer)]
+                    new = col.copy()
+                    reqs, recvs = [], []
+                    for j in range(1 << k):
+                        if j == mine:
+                            continue
+                        peer = rank
+                        for i, b in enumerate(bits):
+                            peer = (peer & ~(1 << b)) | (((j >> i) & 1) << b)
+                        send = torch.from_numpy(np.ascontiguousarray(col[j * blk:(j + 1) * blk]).view(np.float64).copy())
+                        recv = torch.empty_like(send)
+                        reqs += [dist.isend(send, peer), dist.irecv(recv, peer)]
+                        recvs.append((j, recv))
                     for q in reqs:
                         q.wait()
-                    col[lo:lo + half] = recv.numpy().view(np.complex128)
+                    for j, recv in recvs:
+                        new[j * blk:(j + 1) * blk] = recv.numpy().view(np.complex128)
+                    slots[dst] = new
                 continue
             res = [(dst, acc, sum(pi.sweep_shard(plan, c, ins["run"], slots[src], rank, o, tabs) for o in [ovr] + list(extra)))
                    for (src, dst, ovr, acc, extra) in ins["cols"]]
@@ -120,14 +151,15 @@ def _gloo_worker(rank, world, port, result_path):
     dist.destroy_process_group()
 
 
-def test_two_process_gloo_exchange_and_allreduce(tmp_path):
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_process_gloo_exchange_and_allreduce(tmp_path, world):
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     res = str(tmp_path / "res")
-    mp.spawn(_gloo_worker, args=(2, port, res), nprocs=2, join=True)
-    for r in range(2):
+    mp.spawn(_gloo_worker, args=(world, port, res), nprocs=world, join=True)
+    for r in range(world):
         err_q, err_psi = [float(x) for x in open(f"{res}.{r}").read().split()]
         assert err_q < 1e-12 and err_psi < 1e-13
