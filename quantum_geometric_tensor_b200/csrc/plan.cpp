@@ -244,6 +244,15 @@ bool make_tperm(int K, std::vector<int>& reg_local, const std::vector<int>& batc
 
 }  // namespace
 
+// qubit that decides where the scheduler places an op: the target of a 2x2 / permutation op, the lowest local qubit
+// of a PARAMETERISED diagonal op, -1 for free diagonal ops and the cost layer
+static int sched_target(const LoweredOp& o, int nl) {
+    if (o.target >= 0) return o.target;
+    if (o.type == QGT_OP_DIAG && o.param >= 0)
+        for (int q = 0; q < nl; q++) if ((o.pmask | o.cmask) >> q & 1) return q;
+    return -1;
+}
+
 OpLocation locate_op(const Run& run, int op_index) {
     OpLocation loc;
     int stage_base = 0, tdiag_base = 0, cost_base = 0;
@@ -494,8 +503,18 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
     plan.last_run.assign(std::max(0, c.num_params), -1);
 
     std::vector<LoweredOp> ops;
+    std::vector<int> gate_order;
+    {
+        int wf = opt.wavefront;
+        if (const char* e = std::getenv("QGT_B200_WAVEFRONT")) wf = std::atoi(e);
+        if (wf > 0 && nl == n && n - wf >= 2 && c.num_gates > 0) {
+            std::vector<MappedSegment> dummy;
+            std::string werr;
+            if (map_circuit_sharded(c, n - wf, false, dummy, werr, &gate_order) != QGT_B200_OK || gate_order.size() != c.num_gates) gate_order.clear();
+        }
+    }
     for (size_t g = 0; g < c.num_gates; g++) {
-        int rc = lower_gate(c, theta, (int)g, ops, err);
+        int rc = lower_gate(c, theta, gate_order.empty() ? (int)g : gate_order[g], ops, err);
         if (rc) return rc;
     }
     const int N = (int)ops.size();
@@ -536,11 +555,15 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
                     int pri;
                     // 2x2 ops first (on a held register qubit, then a new register qubit of the tile, then a
                     // new tile qubit); diagonal ops last so that those on register qubits end up adjacent
-                    // and merge into one table; the cost layer gets a tile-level pass of its own
+                    // and merge into one table; the cost layer gets a tile-level pass of its own.
+                    // A diagonal gate that carries a parameter is placed like a 2x2 gate on its (lowest local) qubit:
+                    // its generator has to sit in a dense stage, and waiting for a sub-pass that holds the qubit anyway
+                    // costs nothing, whereas taking it "for free" now would add an identity x phase stage of its own.
+                    const int tq = sched_target(o, nl);
                     if (o.type == QGT_OP_COST) pri = (sp.b == (int)run.ops.size()) ? 4 : 99;
-                    else if (o.target < 0) pri = 3;
-                    else if (inR[o.target]) pri = 0;
-                    else if (sizeR < R && inS[o.target]) pri = 1;
+                    else if (tq < 0) pri = 3;
+                    else if (inR[tq]) pri = 0;
+                    else if (sizeR < R && inS[tq]) pri = 1;
                     else if (sizeR < R && sizeS < K) pri = 2;
                     else continue;
                     if (pri == 99) continue;
@@ -549,9 +572,10 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
                 if (best < 0) break;
                 const LoweredOp& o = ops[best];
                 if (o.type == QGT_OP_COST) sp.is_cost = true;
-                if (o.target >= 0) {
-                    if (!inS[o.target]) { inS[o.target] = 1; sizeS++; }
-                    if (!inR[o.target]) { inR[o.target] = 1; sizeR++; sp.regq.push_back(o.target); }
+                const int tqb = sched_target(o, nl);
+                if (tqb >= 0) {
+                    if (!inS[tqb]) { inS[tqb] = 1; sizeS++; }
+                    if (!inR[tqb]) { inR[tqb] = 1; sizeR++; sp.regq.push_back(tqb); }
                 }
                 run.ops.push_back(o);
                 done[best] = 1; scheduled++;
@@ -731,7 +755,7 @@ void nondiag_qubits(const qgt_b200_gate& g, int out[2], int& cnt) {
 }  // namespace
 
 int map_circuit_sharded(const qgt_b200_circuit& c, int nloc, bool restore_identity,
-                        std::vector<MappedSegment>& segs, std::string& err) {
+                        std::vector<MappedSegment>& segs, std::string& err, std::vector<int>* order) {
     const int n = c.num_qubits;
     bool batch_exchanges = true;
     if (const char* e = std::getenv("QGT_B200_BATCH_EXCHANGES")) batch_exchanges = std::atoi(e) != 0;   // 0: one rank bit per exchange
@@ -776,55 +800,103 @@ int map_circuit_sharded(const qgt_b200_circuit& c, int nloc, bool restore_identi
         }
         cur.phys_of_logical = phys;
     };
-    // next gate index >= from at which logical qubit v is acted on non-diagonally
-    auto next_use = [&](int v, size_t from) {
-        for (size_t gj = from; gj < c.num_gates; gj++) {
-            int nd2[2], c2;
-            nondiag_qubits(c.gates[gj], nd2, c2);
-            for (int k2 = 0; k2 < c2; k2++) if (nd2[k2] == v) return gj;
+    // ---- gate DAG: two uses of a qubit commute when both are diagonal on it (controls count as diagonal) ----
+    const size_t NG = c.num_gates;
+    std::vector<std::vector<int>> g_nd(NG), g_dg(NG), succ(NG);
+    std::vector<int> indeg(NG, 0);
+    {
+        std::vector<int> last_nd(n, -1);
+        std::vector<std::vector<int>> diag_since(n);
+        for (size_t gi = 0; gi < NG; gi++) {
+            const qgt_b200_gate& g = c.gates[gi];
+            int nd[2], cnt;
+            nondiag_qubits(g, nd, cnt);
+            for (int k = 0; k < cnt; k++) {
+                if (nd[k] < 0 || nd[k] >= n) { err = "gate qubit out of range"; return QGT_B200_ERR_CIRCUIT; }
+                g_nd[gi].push_back(nd[k]);
+            }
+            auto is_nd = [&](int q) { return std::find(g_nd[gi].begin(), g_nd[gi].end(), q) != g_nd[gi].end(); };
+            if (g.kind == QGT_B200_GATE_COST) { for (int q = 0; q < n; q++) g_dg[gi].push_back(q); }
+            else if (g.kind != QGT_B200_GATE_I) {
+                if (g.target >= 0 && g.target < n && !is_nd(g.target)) g_dg[gi].push_back(g.target);
+                if (is_two_qubit(g.kind) && g.control >= 0 && g.control < n && !is_nd(g.control)) g_dg[gi].push_back(g.control);
+            }
+            std::set<int> preds;
+            for (int q : g_dg[gi]) { if (last_nd[q] >= 0) preds.insert(last_nd[q]); diag_since[q].push_back((int)gi); }
+            for (int q : g_nd[gi]) {
+                if (last_nd[q] >= 0) preds.insert(last_nd[q]);
+                for (int j : diag_since[q]) preds.insert(j);
+                last_nd[q] = (int)gi; diag_since[q].clear();
+            }
+            for (int pgi : preds) { succ[pgi].push_back((int)gi); indeg[gi]++; }
         }
-        return c.num_gates + 1;
+    }
+    std::vector<char> emitted(NG, 0);
+    std::set<int> ready;
+    for (size_t gi = 0; gi < NG; gi++) if (indeg[gi] == 0) ready.insert((int)gi);
+    // next not-yet-emitted gate (by list position) that acts on logical qubit v non-diagonally
+    auto next_use = [&](int v) {
+        for (size_t gj = 0; gj < NG; gj++)
+            if (!emitted[gj] && std::find(g_nd[gj].begin(), g_nd[gj].end(), v) != g_nd[gj].end()) return gj;
+        return NG + 1;
     };
-    for (size_t gi = 0; gi < c.num_gates; gi++) {
-        const qgt_b200_gate& g = c.gates[gi];
-        int nd[2], cnt;
-        nondiag_qubits(g, nd, cnt);
-        bool miss = false;
-        for (int k = 0; k < cnt; k++) {
-            if (nd[k] < 0 || nd[k] >= n) { err = "gate qubit out of range"; return QGT_B200_ERR_CIRCUIT; }
-            if (phys[nd[k]] >= nloc) miss = true;
-        }
-        if (miss) {
-            // candidates to bring in: every logical qubit on a rank bit, soonest next non-diagonal use first (the ones this
-            // gate needs come first by construction); victims: local qubits this gate does not need, farthest next use
-            // first (Belady).  Pair i is part of the batch while the incoming qubit is needed before the outgoing one.
-            std::vector<std::pair<size_t, int>> globals, locals;
-            for (int v = 0; v < n; v++) {
-                bool needed = false;
-                for (int k2 = 0; k2 < cnt; k2++) if (nd[k2] == v) needed = true;
-                if (phys[v] >= nloc) globals.push_back({needed ? gi : next_use(v, gi + 1), v});
-                else if (!needed) locals.push_back({next_use(v, gi + 1), v});
+    size_t done = 0;
+    while (done < NG) {
+        // everything that can run with the current placement, in list order (gates float across exchanges they do not
+        // depend on, so a segment is as long as the data dependencies allow and fuses into few runs)
+        bool progress = true;
+        while (progress) {
+            progress = false;
+            for (auto it = ready.begin(); it != ready.end();) {
+                const int gi = *it;
+                bool local = true;
+                for (int q : g_nd[gi]) if (phys[q] >= nloc) local = false;
+                if (!local) { ++it; continue; }
+                qgt_b200_gate pg = c.gates[gi];
+                if (pg.kind != QGT_B200_GATE_COST) {
+                    pg.target = phys[pg.target];
+                    if (pg.control >= 0 && pg.control < n) pg.control = phys[pg.control];
+                }
+                cur.gates.push_back(pg);
+                if (order) order->push_back(gi);
+                emitted[gi] = 1; done++;
+                it = ready.erase(it);
+                for (int sidx : succ[gi]) if (--indeg[sidx] == 0) { ready.insert(sidx); progress = true; }
             }
-            std::sort(globals.begin(), globals.end());
-            std::sort(locals.begin(), locals.end(), [](const std::pair<size_t, int>& a, const std::pair<size_t, int>& b) {
-                return a.first != b.first ? a.first > b.first : a.second < b.second; });
-            std::vector<int> in, out;
-            for (size_t i = 0; i < globals.size() && i < locals.size(); i++) {
-                const bool must = globals[i].first == gi;
-                if (!must && !(batch_exchanges && globals[i].first < locals[i].first)) break;
-                in.push_back(globals[i].second); out.push_back(locals[i].second);
+        }
+        if (done == NG) break;
+        // every ready gate waits for a qubit on a rank bit.  Bring in: the rank-bit qubits in order of need (those of ready
+        // gates first, by list position); evict: local qubits no ready gate needs, farthest next use first (Belady).  A pair
+        // joins the batch while the incoming qubit is needed before the outgoing one.
+        std::vector<int> need_now(n, 0);
+        for (int gi : ready) for (int q : g_nd[gi]) need_now[q] = 1;
+        const int first_ready = *ready.begin();
+        std::vector<std::pair<size_t, int>> globals, locals;
+        for (int v = 0; v < n; v++) {
+            if (phys[v] >= nloc) {
+                size_t when = next_use(v);
+                if (need_now[v]) {
+                    bool in_first = std::find(g_nd[first_ready].begin(), g_nd[first_ready].end(), v) != g_nd[first_ready].end();
+                    when = in_first ? 0 : std::min(when, (size_t)first_ready + 1);
+                }
+                globals.push_back({when, v});
+            } else if (!need_now[v]) {
+                locals.push_back({next_use(v), v});
             }
-            size_t must_count = 0;
-            for (const auto& gl : globals) if (gl.first == gi) must_count++;
-            if (in.size() < must_count) { err = "no local qubit available to exchange"; return QGT_B200_ERR_INTERNAL; }
-            bring_in(in, out);
         }
-        qgt_b200_gate pg = g;
-        if (g.kind != QGT_B200_GATE_COST) {
-            pg.target = phys[g.target];
-            if (g.control >= 0 && g.control < n) pg.control = phys[g.control];
+        std::sort(globals.begin(), globals.end());
+        std::sort(locals.begin(), locals.end(), [](const std::pair<size_t, int>& x, const std::pair<size_t, int>& y) {
+            return x.first != y.first ? x.first > y.first : x.second < y.second; });
+        std::vector<int> in, out;
+        size_t must_count = 0;
+        for (const auto& gl : globals) if (gl.first == 0) must_count++;
+        for (size_t i = 0; i < globals.size() && i < locals.size(); i++) {
+            const bool must = globals[i].first == 0;
+            if (!must && !(batch_exchanges && globals[i].first < locals[i].first)) break;
+            in.push_back(globals[i].second); out.push_back(locals[i].second);
         }
-        cur.gates.push_back(pg);
+        if (in.size() < must_count || in.empty()) { err = "no local qubit available to exchange"; return QGT_B200_ERR_INTERNAL; }
+        bring_in(in, out);
     }
     if (restore_identity) {
         // undo the permutation: fix the rank bits first (each needs its own logical qubit local at the top)

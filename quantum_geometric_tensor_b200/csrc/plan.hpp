@@ -18,6 +18,9 @@ struct PlanOptions {
     int low_qubits = 4;     // L: lowest qubits always in the tile (contiguous 16*2^L bytes)
     int max_ops_per_run = 160;
     int birth_cut = 1;      // execute a run in which many parameters are born in pieces (split_run_by_births); 2 = ignore the launch cost
+    int wavefront = 2;      // unsharded plans: lower the gates in the order the sharded mapper would emit them with this many
+                            // virtual rank qubits (gates that wait for them are deferred, the rest runs ahead): a dependency-
+                            // respecting reordering that lets the run builder work deep before it works wide
     int local_qubits = 0;   // sharded states: qubits >= local_qubits are rank bits (diagonal use / controls only); 0 = all local
 };
 
@@ -195,7 +198,7 @@ struct MappedSegment {
     unsigned exchange_mask = 0;          // rank bits swapped with the top popcount(mask) local qubits (see Run::exchange_mask)
 };
 int map_circuit_sharded(const qgt_b200_circuit& c, int nloc, bool restore_identity,
-                        std::vector<MappedSegment>& segs, std::string& err);
+                        std::vector<MappedSegment>& segs, std::string& err, std::vector<int>* order = nullptr);
 // plan of a mapped circuit: runs of every segment in order, with exchange pseudo-runs in between
 int build_plan_sharded(const qgt_b200_circuit& c, const double* theta, const PlanOptions& opt, int nloc, bool restore_identity,
                        CircuitPlan& plan, std::vector<MappedSegment>& segs, std::string& err);

@@ -9,7 +9,11 @@ from quantum_geometric_tensor_b200 import api, circuits as K
 name = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 modes = sys.argv[3].split(",") if len(sys.argv) > 3 else ["g", "r", "t", "p"]
+extra = sys.argv[4:]
 ctx = api.Context(0)
+for kv in extra:
+    k_, v_ = kv.split("=")
+    ctx.set_option(k_, float(v_))
 c = K.config(name)
 th = K.default_angles(c.num_params)
 res = {}
