@@ -259,6 +259,30 @@ int  qgt_b200_dist_barrier(qgt_b200_ctx* ctx);
 long qgt_b200_plan_dump_sharded(const qgt_b200_circuit* circuit, const double* theta, int world, int restore_identity,
                                 int tile_qubits, int reg_qubits, size_t column_slots, char* buf, size_t buflen);
 
+/* ---- reductions and element-wise passes on a statevector (device kernels; collective on sharded states) ----------
+ * Replace the serial loops of sim_measure_qubit / sim_get_measurement_counts / sim_get_expectation_value
+ * (src/quantum_geometric/hardware/quantum_simulator.c:563-675, 705-729) and measure_qubit_cpu
+ * (hardware/quantum_simulator_cpu.c:328).  Masks are over GLOBAL amplitude-index bits (bit q = qubit q). */
+/* prob = sum |a_i|^2 over i with (i & mask) == want; norm2 (optional) = sum over all i */
+int  qgt_b200_state_probability(const qgt_b200_state* s, uint64_t mask, uint64_t want, double* prob, double* norm2);
+/* <Z...Z> on the qubits of zmask: sum (-1)^popcount(i & zmask) |a_i|^2  ("Z" of sim_get_expectation_value = all qubits) */
+int  qgt_b200_state_expectation_z(const qgt_b200_state* s, uint64_t zmask, double* out);
+/* out = <a|b> (re, im) */
+int  qgt_b200_state_inner_product(const qgt_b200_state* a, const qgt_b200_state* b, double out[2]);
+int  qgt_b200_state_scale(qgt_b200_state* s, double re, double im);
+int  qgt_b200_state_normalize(qgt_b200_state* s, double* norm_before);
+/* project qubit onto `outcome` and renormalise (no-op scaling when the outcome has probability 0, as the reference) */
+int  qgt_b200_state_collapse(qgt_b200_state* s, int qubit, int outcome, double* prob);
+/* sim_measure_qubit: outcome = uniform < p with p = P(1) mixed with the readout error rate; collapses the state.
+ * The caller supplies the uniform random number (the library holds no RNG state). */
+int  qgt_b200_state_measure(qgt_b200_state* s, int qubit, double uniform, double readout_error, int* outcome, double* prob_one);
+/* sim_get_measurement_counts: shots[k] = first basis index whose cumulative probability exceeds uniforms[k]
+ * (host array of `shots` numbers in [0, 1)); single GPU */
+int  qgt_b200_state_sample(const qgt_b200_state* s, const double* uniforms, size_t shots, uint64_t* indices);
+/* ComplexFloat boundary (core/quantum_state_types.h:20-26): interleaved float pairs, host or device pointer */
+int  qgt_b200_state_upload_c64(qgt_b200_state* s, const float* src);
+int  qgt_b200_state_download_c64(const qgt_b200_state* s, float* dst);
+
 /* Roofline denominators measured on this device: sustained FP64 tensor-pipe throughput (mma.sync m8n8k4 f64, TFLOP/s)
  * and device-to-device copy bandwidth (read + write bytes, GB/s).  Either output may be NULL. */
 int  qgt_b200_measure_peaks(qgt_b200_ctx* ctx, double* dmma_tflops, double* copy_gbs);

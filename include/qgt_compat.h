@@ -149,6 +149,16 @@ bool sim_add_controlled_gate(SimulatorCircuit* circuit, gate_type_t type, uint32
 bool sim_execute_circuit(SimulatorState* state, const SimulatorCircuit* circuit);
 double complex* sim_get_statevector(const SimulatorState* state);
 void sim_cleanup_circuit(SimulatorCircuit* circuit);
+/* measurement / expectation / sampling (quantum_simulator.h:100-118) and the circuit text format (:141-142): the
+ * reductions, the collapse and the inverse-CDF walk run on the device (qgt_b200_state_*) */
+bool sim_measure_qubit(SimulatorState* state, uint32_t qubit, uint32_t classical_bit);
+bool sim_measure_all(SimulatorState* state);
+bool* sim_get_measurement_results(const SimulatorState* state);
+uint64_t* sim_get_measurement_counts(const SimulatorState* state, uint32_t shots);
+double sim_get_expectation_value(const SimulatorState* state, const char* observable);
+bool sim_save_circuit(const SimulatorCircuit* circuit, const char* filename);
+SimulatorCircuit* sim_load_circuit(const char* filename);
+void qgt_compat_seed(unsigned long long seed);       /* seeds the measurement RNG (the reference seeds from the clock) */
 
 /* ---- distributed/differential_geometry.h:237-262, 573-595 ------------------------------------------ */
 typedef struct diffgeo_engine diffgeo_engine_t;

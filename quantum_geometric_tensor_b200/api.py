@@ -91,6 +91,17 @@ def load() -> C.CDLL:
     L.qgt_b200_plan_dump_sharded.restype = C.c_long
     L.qgt_b200_dist_barrier.argtypes = [vp]
     L.qgt_b200_measure_peaks.argtypes = [vp, _DP, _DP]
+    u64 = C.c_uint64
+    L.qgt_b200_state_probability.argtypes = [vp, u64, u64, _DP, _DP]
+    L.qgt_b200_state_expectation_z.argtypes = [vp, u64, _DP]
+    L.qgt_b200_state_inner_product.argtypes = [vp, vp, _DP]
+    L.qgt_b200_state_scale.argtypes = [vp, C.c_double, C.c_double]
+    L.qgt_b200_state_normalize.argtypes = [vp, _DP]
+    L.qgt_b200_state_collapse.argtypes = [vp, C.c_int, C.c_int, _DP]
+    L.qgt_b200_state_measure.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_int), _DP]
+    L.qgt_b200_state_sample.argtypes = [vp, _DP, C.c_size_t, C.POINTER(u64)]
+    L.qgt_b200_state_upload_c64.argtypes = [vp, C.c_void_p]
+    L.qgt_b200_state_download_c64.argtypes = [vp, C.c_void_p]
     L.qgt_b200_plan_dump_fused.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t]
     L.qgt_b200_plan_dump_fused.restype = C.c_long
     _lib = L
@@ -186,6 +197,47 @@ class State:
         v = C.c_double(0)
         _check(self.ctx.L.qgt_b200_state_norm2(self.h, C.byref(v)))
         return v.value
+
+    # -- reductions (device kernels) ---------------------------------------------------------------
+    def probability(self, mask: int, want: int) -> float:
+        v = C.c_double(0)
+        _check(self.ctx.L.qgt_b200_state_probability(self.h, mask, want, C.byref(v), None))
+        return v.value
+
+    def expectation_z(self, zmask: int) -> float:
+        v = C.c_double(0)
+        _check(self.ctx.L.qgt_b200_state_expectation_z(self.h, zmask, C.byref(v)))
+        return v.value
+
+    def inner(self, other: "State") -> complex:
+        out = np.zeros(2)
+        _check(self.ctx.L.qgt_b200_state_inner_product(self.h, other.h, _dp(out)))
+        return complex(out[0], out[1])
+
+    def scale(self, z: complex) -> "State":
+        _check(self.ctx.L.qgt_b200_state_scale(self.h, float(np.real(z)), float(np.imag(z))))
+        return self
+
+    def measure(self, qubit: int, uniform: float, readout_error: float = 0.0):
+        o, p = C.c_int(0), C.c_double(0)
+        _check(self.ctx.L.qgt_b200_state_measure(self.h, qubit, uniform, readout_error, C.byref(o), C.byref(p)))
+        return o.value, p.value
+
+    def sample(self, uniforms: np.ndarray) -> np.ndarray:
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        out = np.zeros(u.size, dtype=np.uint64)
+        _check(self.ctx.L.qgt_b200_state_sample(self.h, _dp(u), u.size, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def upload_c64(self, amps: np.ndarray) -> "State":
+        a = np.ascontiguousarray(amps, dtype=np.complex64)
+        _check(self.ctx.L.qgt_b200_state_upload_c64(self.h, a.ctypes.data))
+        return self
+
+    def download_c64(self) -> np.ndarray:
+        out = np.empty((1 << self.num_qubits) // self.ctx.world, dtype=np.complex64)
+        _check(self.ctx.L.qgt_b200_state_download_c64(self.h, out.ctypes.data))
+        return out
 
     def apply(self, circ: Circuit, theta: np.ndarray) -> "State":
         cc = circ.to_c()

@@ -84,7 +84,7 @@ CPUSimCircuit* cpu_sim_create_circuit(size_t max_gates) {
 }
 
 static int two_qubit_kind(gate_type_t t) {
-    return t == GATE_TYPE_CNOT || t == GATE_TYPE_CZ || t == GATE_TYPE_SWAP || t == GATE_TYPE_ISWAP || t == GATE_TYPE_CRZ ||
+    return t == GATE_TYPE_CNOT || t == GATE_TYPE_CZ || t == GATE_TYPE_SWAP || t == GATE_TYPE_CRZ ||
            t == GATE_TYPE_CRX || t == GATE_TYPE_CRY || t == GATE_TYPE_CY || t == GATE_TYPE_CH || t == GATE_TYPE_ZZ;
 }
 
@@ -131,7 +131,14 @@ void simulate_circuit_cpu(double complex* state, const CPUSimCircuit* circuit, s
     size_t ng = 0;
     for (size_t i = 0; i < circuit->num_gates; i++) {
         const HardwareGate* h = &circuit->gates[i];
-        if (qgt_compat_convert_gate(h->type, h->target, h->control, h->parameter, -1, &gates[ng])) ng++;
+        if (qgt_compat_convert_gate(h->type, h->target, h->control, h->parameter, -1, &gates[ng])) { ng++; continue; }
+        if (h->type == GATE_TYPE_BARRIER) continue;
+        /* MEASURE / RESET / U2 / U3 / ISWAP / CCX / XX / YY / CUSTOM have no statevector-sweep form here: refuse the
+         * whole circuit (state untouched) rather than return a plausible but wrong state */
+        snprintf(g_err, sizeof g_err, "simulate_circuit_cpu: gate %zu has unsupported type %d; circuit not applied", i, (int)h->type);
+        fprintf(stderr, "%s\n", g_err);
+        free(gates);
+        return;
     }
     qgt_b200_circuit c;
     memset(&c, 0, sizeof c);
@@ -231,4 +238,146 @@ void sim_cleanup_circuit(SimulatorCircuit* c) {
     if (!c) return;
     free(c->gates);
     free(c);
+}
+
+/* ---- measurement, expectation values, sampling (quantum_simulator.c:563-729) -----------------------------------
+ * The SimulatorState keeps its amplitudes on the host (callers read state->amplitudes); every call stages them
+ * through the device, where the reductions and the collapse run (qgt_b200_state_*). */
+static unsigned long long g_rng = 0;
+static double compat_uniform(void) {                 /* same LCG as the reference's random_double (:47-51) */
+    if (!g_rng) g_rng = 88172645463325252ull;
+    g_rng = g_rng * 1103515245ull + 12345ull;
+    return (double)(g_rng & 0x7fffffff) / (double)0x7fffffff;
+}
+void qgt_compat_seed(unsigned long long seed) { g_rng = seed ? seed : 1; }
+
+static qgt_b200_state* stage_in(const SimulatorState* s, qgt_b200_ctx** ctx_out) {
+    qgt_b200_ctx* ctx = qgt_compat_ctx();
+    if (!ctx) return NULL;
+    qgt_b200_state* st = NULL;
+    int rc = qgt_b200_state_create(ctx, (int)s->num_qubits, &st);
+    if (!rc) rc = qgt_b200_state_upload(st, (const double*)s->amplitudes);
+    if (rc) { qgt_compat_set_error("state staging", rc); if (st) qgt_b200_state_destroy(st); return NULL; }
+    if (ctx_out) *ctx_out = ctx;
+    return st;
+}
+
+bool sim_measure_qubit(SimulatorState* s, uint32_t qubit, uint32_t classical_bit) {
+    if (!s || qubit >= s->num_qubits) return false;
+    if (classical_bit >= s->num_classical_bits && s->classical_bits) return false;
+    qgt_b200_state* st = stage_in(s, NULL);
+    if (!st) return false;
+    int outcome = 0;
+    int rc = qgt_b200_state_measure(st, (int)qubit, compat_uniform(), s->active_noise.measurement_error_rate, &outcome, NULL);
+    if (!rc) rc = qgt_b200_state_download(st, (double*)s->amplitudes);
+    qgt_b200_state_destroy(st);
+    if (rc) { qgt_compat_set_error("sim_measure_qubit", rc); return false; }
+    if (s->classical_bits && classical_bit < s->num_classical_bits) s->classical_bits[classical_bit] = outcome != 0;
+    return true;
+}
+
+bool sim_measure_all(SimulatorState* s) {
+    if (!s) return false;
+    qgt_b200_state* st = stage_in(s, NULL);
+    if (!st) return false;
+    int rc = 0;
+    for (uint32_t q = 0; q < s->num_qubits && !rc; q++) {          /* one staging for all qubits */
+        int outcome = 0;
+        rc = qgt_b200_state_measure(st, (int)q, compat_uniform(), s->active_noise.measurement_error_rate, &outcome, NULL);
+        const uint32_t cb = q < s->num_classical_bits ? q : 0;
+        if (!rc && s->classical_bits && cb < s->num_classical_bits) s->classical_bits[cb] = outcome != 0;
+    }
+    if (!rc) rc = qgt_b200_state_download(st, (double*)s->amplitudes);
+    qgt_b200_state_destroy(st);
+    if (rc) { qgt_compat_set_error("sim_measure_all", rc); return false; }
+    return true;
+}
+
+bool* sim_get_measurement_results(const SimulatorState* s) {
+    if (!s || !s->classical_bits) return NULL;
+    bool* r = (bool*)malloc(s->num_classical_bits * sizeof(bool));
+    if (r) memcpy(r, s->classical_bits, s->num_classical_bits * sizeof(bool));
+    return r;                                        /* caller frees */
+}
+
+uint64_t* sim_get_measurement_counts(const SimulatorState* s, uint32_t shots) {
+    if (!s) return NULL;
+    const size_t dim = (size_t)1 << s->num_qubits;
+    uint64_t* counts = (uint64_t*)calloc(dim, sizeof(uint64_t));
+    double* u = (double*)malloc((shots ? shots : 1) * sizeof(double));
+    uint64_t* idx = (uint64_t*)malloc((shots ? shots : 1) * sizeof(uint64_t));
+    qgt_b200_state* st = (counts && u && idx) ? stage_in(s, NULL) : NULL;
+    int rc = st ? 0 : -1;
+    if (st) {
+        for (uint32_t k = 0; k < shots; k++) u[k] = compat_uniform();
+        rc = qgt_b200_state_sample(st, u, shots, idx);
+        for (uint32_t k = 0; k < shots && !rc; k++) if (idx[k] < dim) counts[idx[k]]++;
+        qgt_b200_state_destroy(st);
+    }
+    free(u); free(idx);
+    if (rc) { free(counts); return NULL; }
+    return counts;                                   /* dim entries, caller frees */
+}
+
+double sim_get_expectation_value(const SimulatorState* s, const char* observable) {
+    if (!s || !observable) return 0.0;
+    if (strcmp(observable, "Z") != 0) return 0.0;    /* the only observable the reference knows (:708) */
+    qgt_b200_state* st = stage_in(s, NULL);
+    if (!st) return 0.0;
+    double v = 0.0;
+    const uint64_t all = s->num_qubits >= 64 ? ~0ull : (((uint64_t)1 << s->num_qubits) - 1);
+    int rc = qgt_b200_state_expectation_z(st, all, &v);
+    qgt_b200_state_destroy(st);
+    if (rc) { qgt_compat_set_error("sim_get_expectation_value", rc); return 0.0; }
+    return v;
+}
+
+/* ---- circuit text format (quantum_simulator.c:962-1051): "QGT_CIRCUIT v1", qubits / classical_bits / gates, then one
+ * line per gate "type target control [p0 p1 p2 p3]" ------------------------------------------------------------ */
+bool sim_save_circuit(const SimulatorCircuit* c, const char* filename) {
+    if (!c || !filename) return false;
+    FILE* f = fopen(filename, "w");
+    if (!f) return false;
+    fprintf(f, "QGT_CIRCUIT v1\nqubits %u\nclassical_bits %u\ngates %zu\n", c->num_qubits, c->num_classical_bits, c->num_gates);
+    for (size_t i = 0; i < c->num_gates; i++) {
+        const qgt_b200_gate* g = &c->gates[i];
+        fprintf(f, "%d %d %d", (int)g->kind, (int)g->target, g->control < 0 ? 0 : (int)g->control);
+        const int rot = g->kind == GATE_TYPE_RX || g->kind == GATE_TYPE_RY || g->kind == GATE_TYPE_RZ || g->kind == GATE_TYPE_U1 ||
+                        g->kind == GATE_TYPE_PHASE || g->kind == GATE_TYPE_CRX || g->kind == GATE_TYPE_CRY || g->kind == GATE_TYPE_CRZ ||
+                        g->kind == GATE_TYPE_ZZ;
+        if (rot) fprintf(f, " %.17g 0 0 0", g->angle);       /* full precision (the reference prints %g) */
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    return true;
+}
+
+SimulatorCircuit* sim_load_circuit(const char* filename) {
+    if (!filename) return NULL;
+    FILE* f = fopen(filename, "r");
+    if (!f) return NULL;
+    char header[32];
+    if (fscanf(f, "%31s", header) != 1 || strcmp(header, "QGT_CIRCUIT") != 0) { fclose(f); return NULL; }
+    if (fscanf(f, "%*s") != 0) { /* version */ }
+    uint32_t nq = 0, ncb = 0;
+    size_t ng = 0;
+    if (fscanf(f, " qubits %u", &nq) != 1 || fscanf(f, " classical_bits %u", &ncb) != 1 || fscanf(f, " gates %zu", &ng) != 1) { fclose(f); return NULL; }
+    SimulatorCircuit* c = sim_create_circuit(nq, ncb);
+    if (!c) { fclose(f); return NULL; }
+    /* one gate per LINE.  (The reference's loader reads "type target control" and then greedily tries four more numbers
+     * with fscanf, which swallows the next gate's line after every parameter-free gate: quantum_simulator.c:1033-1041,
+     * BASELINE.md section 4 #18.  Not reproduced.) */
+    char line[256];
+    size_t got = 0;
+    while (got < ng && fgets(line, sizeof line, f)) {
+        int type;
+        uint32_t target, control;
+        double params[4] = {0, 0, 0, 0};
+        const int nr = sscanf(line, "%d %u %u %lf %lf %lf %lf", &type, &target, &control, &params[0], &params[1], &params[2], &params[3]);
+        if (nr < 3) continue;                        /* blank line (e.g. the rest of the header line) */
+        sim_add_gate(c, (gate_type_t)type, target, control, nr > 3 ? params : NULL);
+        got++;
+    }
+    fclose(f);
+    return c;
 }

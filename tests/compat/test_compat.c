@@ -280,6 +280,63 @@ static void test_gpu_memory_seam(void) {
     printf("  qg_gpu_* / gpu_malloc device-memory seam: ok\n");
 }
 
+/* measurement / expectation / sampling / circuit text format through the reference's sim_* names */
+static void test_sim_measurement_api(void) {
+    SimulatorState* st = sim_init(3, 3, NULL);
+    SimulatorCircuit* c = sim_create_circuit(3, 3);
+    CHECK(st && c);
+    double t = 1.1;
+    CHECK(sim_add_gate(c, GATE_H, 0, 0, NULL) && sim_add_gate(c, GATE_CNOT, 1, 0, NULL) && sim_add_gate(c, GATE_RY, 2, 0, &t));
+    CHECK(sim_execute_circuit(st, c));
+    /* <ZZZ> of (|00>+|11>)/sqrt2 x RY(t)|0>: parity of the Bell pair is even, so <ZZZ> = cos t */
+    CHECK(fabs(sim_get_expectation_value(st, "Z") - cos(t)) < 1e-12);
+    CHECK(sim_get_expectation_value(st, "X") == 0.0);                       /* unknown observables give 0 like the reference */
+    qgt_compat_seed(12345);
+    uint64_t* counts = sim_get_measurement_counts(st, 4000);
+    CHECK(counts);
+    uint64_t tot = 0;
+    for (int i = 0; i < 8; i++) tot += counts[i];
+    CHECK(tot == 4000);
+    CHECK(counts[1] == 0 && counts[2] == 0 && counts[5] == 0 && counts[6] == 0);      /* qubits 0 and 1 are perfectly correlated */
+    const double p000 = 0.5 * cos(t / 2) * cos(t / 2);
+    CHECK(fabs((double)counts[0] / 4000.0 - p000) < 0.04);
+    free(counts);
+    /* measuring qubit 0 collapses qubit 1 with it */
+    CHECK(sim_measure_qubit(st, 0, 0));
+    bool* bits = sim_get_measurement_results(st);
+    CHECK(bits);
+    const int b0 = bits[0];
+    free(bits);
+    double nrm = 0;
+    for (int i = 0; i < 8; i++) {
+        nrm += creal(st->amplitudes[i] * conj(st->amplitudes[i]));
+        if (((i & 1) != b0) || (((i >> 1) & 1) != b0)) CHECK(cabs(st->amplitudes[i]) < 1e-14);
+    }
+    CHECK(fabs(nrm - 1.0) < 1e-12);
+    CHECK(sim_measure_all(st));
+    int nonzero = 0;
+    for (int i = 0; i < 8; i++) if (cabs(st->amplitudes[i]) > 1e-12) nonzero++;
+    CHECK(nonzero == 1);
+    /* text format round trip */
+    const char* path = "/tmp/qgt_b200_compat_circuit.txt";
+    CHECK(sim_save_circuit(c, path));
+    SimulatorCircuit* c2 = sim_load_circuit(path);
+    CHECK(c2);
+    SimulatorState* s1 = sim_init(3, 0, NULL); SimulatorState* s2 = sim_init(3, 0, NULL);
+    CHECK(sim_execute_circuit(s1, c) && sim_execute_circuit(s2, c2));
+    for (int i = 0; i < 8; i++) CHECK(cabs(s1->amplitudes[i] - s2->amplitudes[i]) < 1e-15);
+    sim_cleanup(s1); sim_cleanup(s2); sim_cleanup_circuit(c2);
+    sim_cleanup_circuit(c); sim_cleanup(st);
+    /* a circuit with a gate outside the supported set is refused as a whole (state untouched) */
+    double complex s4[4];
+    init_simulator_state(s4, 4);
+    QuantumGate bad[2] = { G(GATE_H, 0, 0, 0), G(GATE_TYPE_ISWAP, 1, 0, 0) };
+    run(s4, 2, bad, 2);
+    CHECK(creal(s4[0]) == 1.0 && cabs(s4[1]) == 0.0);
+    CHECK(strstr(qgt_compat_last_error(), "unsupported") != NULL);
+    printf("sim measurement / text format ok\n");
+}
+
 int main(int argc, char** argv) {
     const int host_only = argc > 1 && !strcmp(argv[1], "--host-only");
     printf("compat entry points (%s)\n", host_only ? "host-only parts" : "with GPU");
@@ -306,6 +363,7 @@ int main(int argc, char** argv) {
     test_qgt_api();
     test_diffgeo();
     test_gpu_memory_seam();
+    test_sim_measurement_api();
     printf("all compat checks passed\n");
     return 0;
 }
