@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define QGT_B200_ABI_VERSION 2
+#define QGT_B200_ABI_VERSION 3
 
 /* ---- status (numerically equal to the reference's qgt_error_t) ------------------------- */
 enum {
@@ -142,9 +142,17 @@ int qgt_b200_stream_create(void** stream);                             /* a cuda
 int qgt_b200_stream_destroy(void* stream);
 int qgt_b200_stream_synchronize(void* stream);
 int qgt_b200_device_synchronize(void);
+int qgt_b200_memcpy_async(void* dst, const void* src, size_t bytes, void* stream);   /* direction from the pointers */
+int qgt_b200_memset_async(void* ptr, int value, size_t bytes, void* stream);         /* host pointers are memset on the host */
+int qgt_b200_event_create(void** event);                               /* a cudaEvent_t behind void* */
+int qgt_b200_event_destroy(void* event);
+int qgt_b200_event_record(void* event, void* stream);
+int qgt_b200_event_wait(void* stream, void* event);                    /* stream waits for the event */
+int qgt_b200_event_synchronize(void* event);
 
 int  qgt_b200_create(qgt_b200_ctx** out, int device);    /* device = CUDA ordinal */
 void qgt_b200_destroy(qgt_b200_ctx* ctx);
+void* qgt_b200_ctx_stream(qgt_b200_ctx* ctx);            /* the cudaStream_t the context's kernels are launched on */
 /* workspace cap in bytes for derivative columns (0 = 90 % of free HBM at first use) */
 int  qgt_b200_set_workspace_limit(qgt_b200_ctx* ctx, size_t bytes);
 /* Tuning / test knobs (defaults are the measured best; results do not depend on them):
@@ -270,6 +278,7 @@ int  qgt_b200_state_expectation_z(const qgt_b200_state* s, uint64_t zmask, doubl
 /* out = <a|b> (re, im) */
 int  qgt_b200_state_inner_product(const qgt_b200_state* a, const qgt_b200_state* b, double out[2]);
 int  qgt_b200_state_scale(qgt_b200_state* s, double re, double im);
+int  qgt_b200_state_axpy(qgt_b200_state* dst, double re, double im, const qgt_b200_state* src);   /* dst += (re + i im) * src */
 int  qgt_b200_state_normalize(qgt_b200_state* s, double* norm_before);
 /* project qubit onto `outcome` and renormalise (no-op scaling when the outcome has probability 0, as the reference) */
 int  qgt_b200_state_collapse(qgt_b200_state* s, int qubit, int outcome, double* prob);
@@ -282,6 +291,36 @@ int  qgt_b200_state_sample(const qgt_b200_state* s, const double* uniforms, size
 /* ComplexFloat boundary (core/quantum_state_types.h:20-26): interleaved float pairs, host or device pointer */
 int  qgt_b200_state_upload_c64(qgt_b200_state* s, const float* src);
 int  qgt_b200_state_download_c64(const qgt_b200_state* s, float* dst);
+
+/* ---- ComplexFloat buffer operations and generic collectives -------------------------------------------------------
+ * What the reference's ComputeBackendOps vtable binds (include/quantum_geometric/supercomputer/compute_backend.h:122-319,
+ * CPU semantics src/quantum_geometric/supercomputer/backends/compute_cpu.c:341-466 + compute_simd.c): interleaved
+ * (re, im) float buffers, host or device pointers (detected; host buffers are staged and the call returns after the
+ * copy back, device buffers are used in place and the call is ordered on `stream`, NULL = the context's stream).
+ *   apply_matrix   targets == NULL and mdim == dim: state <- M state with a dense row-major dim x dim matrix (the
+ *                  reference's quantum_unitary); otherwise M is a 2^K x 2^K gate, K = 1..4, acting on qubits
+ *                  targets[0..K-1] (matrix index bit j <-> qubit targets[j]; NULL = qubits 0..K-1)
+ *   normalize      state /= ||state|| unless the norm is below 1e-10; norm_before (optional) receives the norm
+ *   inner_product  out[0..1] = <a|b> = sum conj(a_i) b_i
+ *   expectation_diag  out[0] = sum |state_i|^2 observable[i]   (real diagonal observable, `dim` floats)
+ *   matmul         result[m x k] = a[m x n] b[n x k], row-major complex */
+int  qgt_b200_c64_apply_matrix(qgt_b200_ctx* ctx, float* state, size_t dim, const float* matrix, size_t mdim,
+                               const int32_t* targets, void* stream);
+int  qgt_b200_c64_normalize(qgt_b200_ctx* ctx, float* state, size_t dim, float* norm_before, void* stream);
+int  qgt_b200_c64_inner_product(qgt_b200_ctx* ctx, const float* a, const float* b, size_t dim, float* out, void* stream);
+int  qgt_b200_c64_expectation_diag(qgt_b200_ctx* ctx, const float* state, const float* observable, size_t dim, float* out, void* stream);
+int  qgt_b200_c64_matmul(qgt_b200_ctx* ctx, float* result, const float* a, const float* b, size_t m, size_t n, size_t k, void* stream);
+/* Collectives over the communicator of qgt_b200_dist_init (a copy with one rank).  dtype: 0 f32, 1 f64, 2 c64, 3 c128,
+ * 4 i32, 5 i64, 6 u8; op: 0 sum, 1 prod, 2 min, 3 max, 4 avg (the reference's ComputeDataType / ComputeReduceOp);
+ * count = elements per rank; broadcast works in place on `recv` (send may be NULL). */
+enum { QGT_B200_COLL_BROADCAST = 0, QGT_B200_COLL_ALLREDUCE = 1, QGT_B200_COLL_SCATTER = 2, QGT_B200_COLL_GATHER = 3,
+       QGT_B200_COLL_ALLGATHER = 4, QGT_B200_COLL_REDUCE_SCATTER = 5 };
+int  qgt_b200_dist_collective(qgt_b200_ctx* ctx, int kind, const void* send, void* recv, size_t count, int dtype, int op, int root);
+
+/* Q from caller-supplied ComplexFloat columns (host or device): psi[dim], dpsi[P*dim] row-major; the columns are widened
+ * on the device and contracted by the same Gram kernel as qgt_b200_gram.  Outputs are host arrays of P*P doubles. */
+int  qgt_b200_gram_c64(qgt_b200_ctx* ctx, const float* psi, const float* dpsi, size_t dim, size_t num_params,
+                       double* metric, double* berry, double* q_full);
 
 /* Roofline denominators measured on this device: sustained FP64 tensor-pipe throughput (mma.sync m8n8k4 f64, TFLOP/s)
  * and device-to-device copy bandwidth (read + write bytes, GB/s).  Either output may be NULL. */

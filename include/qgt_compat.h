@@ -67,6 +67,10 @@ typedef int qgt_error_t;
 #define QGT_ERROR_MEMORY_ALLOCATION (-2)
 #define QGT_ERROR_DIMENSION_MISMATCH (-3)
 #define QGT_ERROR_INVALID_STATE (-4)
+#define QGT_ERROR_VALIDATION_FAILED (-5)
+#define QGT_ERROR_HARDWARE_FAILURE (-6)
+#define QGT_ERROR_NOT_IMPLEMENTED (-7)
+#define QGT_ERROR_INTERNAL (-15)
 #define QGT_ERROR_INVALID_DIMENSION (-22)
 
 /* ---- hardware/quantum_hardware_types.h:254-262, hardware/quantum_hardware_abstraction.h:51-82 ---- */
@@ -215,6 +219,56 @@ bool compute_quantum_metric(const quantum_geometric_tensor_network_t* qgtn, size
 bool compute_berry_curvature(const quantum_geometric_tensor_network_t* qgtn, size_t param_i, size_t param_j, double* result);
 const char* get_quantum_geometric_tensor_network_error(void);
 
+/* ---- core/quantum_parameter_shift.h:28-142 (parameter index = order of the parameterised gates) ---------------------
+ * States and gradients are malloc'd ComplexFloat[2^n] arrays the caller frees.  compute_higher_order_gradient returns the
+ * exact derivative column d_mu psi (the reference's combination of shifted states is not a derivative). */
+bool shift_parameter(quantum_geometric_tensor_network_t* qgtn, size_t param_idx, double shift_amount);
+bool compute_shifted_states(quantum_geometric_tensor_network_t* qgtn, size_t param_idx, double shift_amount,
+                            ComplexFloat** forward_state, ComplexFloat** backward_state, size_t* dimension);
+bool compute_parameter_shift_gradient(const quantum_geometric_tensor_network_t* qgtn, size_t param_idx, double shift_amount,
+                                      ComplexFloat** gradient, size_t* dimension);
+bool compute_centered_difference_gradient(const quantum_geometric_tensor_network_t* qgtn, size_t param_idx, double step_size,
+                                          ComplexFloat** gradient, size_t* dimension);
+bool compute_higher_order_gradient(const quantum_geometric_tensor_network_t* qgtn, size_t param_idx, const double* shift_amounts,
+                                   size_t num_shifts, ComplexFloat** gradient, size_t* dimension);
+bool compute_gradient_with_error(const quantum_geometric_tensor_network_t* qgtn, size_t param_idx, ComplexFloat** gradient,
+                                 double* error_estimate, size_t* dimension);
+
+/* ---- core/quantum_gate_operations.h:25-140 ------------------------------------------------------------------------------
+ * Two-qubit gates keep {control, target} in target_qubits, as the reference's constructor does; apply_quantum_gate
+ * understands that form.  The ComplexFloat matrix follows the reference's tables (quantum_gate_operations.c:11-150), with
+ * the real SWAP matrix instead of the reference's 2x2 identity block. */
+quantum_gate_t* create_quantum_gate(gate_type_t type, const size_t* qubits, size_t num_qubits, const double* parameters, size_t num_parameters);
+quantum_gate_t* copy_quantum_gate(const quantum_gate_t* gate);
+bool update_gate_parameters(quantum_gate_t* gate, const double* parameters, size_t num_parameters);
+bool shift_gate_parameters(quantum_gate_t* gate, size_t param_idx, double shift_amount);
+quantum_gate_t* create_rx_gate(size_t qubit, double angle);
+quantum_gate_t* create_ry_gate(size_t qubit, double angle);
+quantum_gate_t* create_rz_gate(size_t qubit, double angle);
+quantum_gate_t* create_h_gate(size_t qubit);
+quantum_gate_t* create_x_gate(size_t qubit);
+quantum_gate_t* create_y_gate(size_t qubit);
+quantum_gate_t* create_z_gate(size_t qubit);
+quantum_gate_t* create_cnot_gate(size_t control, size_t target);
+quantum_gate_t* create_cz_gate(size_t control, size_t target);
+void destroy_quantum_gate(quantum_gate_t* gate);
+
+/* ---- core/numerical_backend.h:9-41,146-147: the two calls reference programs make before using the network API --------- */
+typedef enum { NUMERICAL_SUCCESS, NUMERICAL_ERROR_INVALID_ARGUMENT, NUMERICAL_ERROR_MEMORY, NUMERICAL_ERROR_BACKEND,
+               NUMERICAL_ERROR_COMPUTATION, NUMERICAL_ERROR_NOT_IMPLEMENTED, NUMERICAL_ERROR_INVALID_STATE } numerical_error_t;
+typedef enum { NUMERICAL_BACKEND_CPU, NUMERICAL_BACKEND_ACCELERATE, NUMERICAL_BACKEND_OPENBLAS, NUMERICAL_BACKEND_MKL,
+               NUMERICAL_BACKEND_CUDA, NUMERICAL_BACKEND_METAL } numerical_backend_t;
+typedef struct {
+    numerical_backend_t type;
+    size_t max_threads;
+    bool use_fma, use_avx, use_neon;
+    size_t cache_size;
+    void* backend_specific;
+} numerical_config_t;
+const char* get_numerical_error_string(numerical_error_t error);
+numerical_error_t initialize_numerical_backend(const numerical_config_t* config);   /* accepts any type: the work runs on the GPU */
+void shutdown_numerical_backend(void);
+
 /* ---- core/quantum_geometric_types.h:365-459, core/quantum_geometric_metric.h, _curvature.h -------------- */
 #define QGT_MAX_DIMENSIONS 16
 typedef enum { GEOMETRIC_METRIC_EUCLIDEAN, GEOMETRIC_METRIC_MINKOWSKI, GEOMETRIC_METRIC_FUBINI_STUDY, GEOMETRIC_METRIC_KAHLER,
@@ -320,6 +374,40 @@ int qg_gpu_create_stream(int* stream_id);
 int qg_gpu_destroy_stream(int stream_id);
 int qg_gpu_synchronize_stream(int stream_id);
 int qg_gpu_synchronize(void);
+
+/* ---- hardware/quantum_geometric_tensor_gpu.h:8-81: the QGT-on-GPU seam --------------------------------------------------
+ * Data convention (the reference defines none, see csrc/compat/gpu_seam_compat.c): `state` is rows x cols row-major with
+ * row 0 = psi and rows 1..rows-1 = d_mu psi (P = rows - 1); the output buffer has the same size and carries, at its start,
+ * the P x P metric (Re Q in .real), the P x P Berry curvature (Im Q in .real) or the P Berry connections i<psi|d_a psi>. */
+typedef struct { double precision; bool use_quantum_estimation; bool use_quantum_memory; int error_correction; int optimization_level; } QGTConfig;
+typedef struct {
+    void* device; void* command_queue; void* library; size_t device_memory;
+    qgt_error_t (*execute_metric)(void* state, void* metric, size_t rows, size_t cols);
+    qgt_error_t (*execute_connection)(void* state, void* connection, size_t rows, size_t cols);
+    qgt_error_t (*execute_curvature)(void* state, void* curvature, size_t rows, size_t cols);
+} MetalContext;
+typedef struct {
+    void* stream; void* module;
+    qgt_error_t (*execute_metric)(void* state, void* metric, size_t rows, size_t cols);
+    qgt_error_t (*execute_connection)(void* state, void* connection, size_t rows, size_t cols);
+    qgt_error_t (*execute_curvature)(void* state, void* curvature, size_t rows, size_t cols);
+} CUDAContext;
+typedef struct {
+    bool is_available;
+    qgt_error_t (*malloc)(void** ptr, size_t size);
+    qgt_error_t (*free)(void* ptr);
+    qgt_error_t (*memcpy_to_device)(void* dst, const void* src, size_t size);
+    qgt_error_t (*memcpy_from_device)(void* dst, const void* src, size_t size);
+    size_t (*get_optimal_block_size)(void);
+    union { MetalContext metal; CUDAContext cuda; };
+} GPUContext;
+QGTConfig qgt_default_config(void);
+const char* qgt_error_string(qgt_error_t error);
+qgt_error_t compute_quantum_metric_gpu(GPUContext* ctx, const ComplexFloat* state, ComplexFloat* metric, size_t rows, size_t cols, const QGTConfig* config);
+qgt_error_t compute_quantum_connection_gpu(GPUContext* ctx, const ComplexFloat* state, ComplexFloat* connection, size_t rows, size_t cols, const QGTConfig* config);
+qgt_error_t compute_quantum_curvature_gpu(GPUContext* ctx, const ComplexFloat* state, ComplexFloat* curvature, size_t rows, size_t cols, const QGTConfig* config);
+/* fills in every hook of `ctx` (device memory seam + the three execute hooks); the reference leaves them NULL */
+qgt_error_t qgt_b200_context_init(GPUContext* ctx);
 
 /* ---- this layer -------------------------------------------------------------------------------------------- */
 /* CUDA ordinal used by the wrappers (default: $QGT_B200_DEVICE or 0); call before the first compute call */

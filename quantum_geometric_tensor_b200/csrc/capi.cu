@@ -219,6 +219,62 @@ int qgt_b200_device_synchronize(void) {
     return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "device_synchronize");
 }
 
+int qgt_b200_memcpy_async(void* dst, const void* src, size_t bytes, void* stream) {
+    if (!dst || !src) return fail(QGT_B200_ERR_INVALID_ARG, "memcpy_async: NULL pointer");
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "memcpy_async");
+}
+
+int qgt_b200_memset_async(void* ptr, int value, size_t bytes, void* stream) {
+    if (!ptr) return fail(QGT_B200_ERR_INVALID_ARG, "memset_async: NULL pointer");
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess || a.type == cudaMemoryTypeUnregistered || a.type == cudaMemoryTypeHost) {
+        cudaGetLastError();
+        std::memset(ptr, value, bytes);            // plain or pinned host memory
+        return QGT_B200_OK;
+    }
+    cudaError_t e = cudaMemsetAsync(ptr, value, bytes, (cudaStream_t)stream);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "memset_async");
+}
+
+int qgt_b200_event_create(void** event) {
+    if (!event) return fail(QGT_B200_ERR_INVALID_ARG, "event_create: event is NULL");
+    *event = nullptr;
+    int rc = raw_need_device("event_create");
+    if (rc) return rc;
+    cudaEvent_t ev;
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return cuda_fail(e, "event_create");
+    *event = (void*)ev;
+    return QGT_B200_OK;
+}
+
+int qgt_b200_event_destroy(void* event) {
+    if (!event) return QGT_B200_OK;
+    cudaError_t e = cudaEventDestroy((cudaEvent_t)event);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "event_destroy");
+}
+
+int qgt_b200_event_record(void* event, void* stream) {
+    if (!event) return fail(QGT_B200_ERR_INVALID_ARG, "event_record: event is NULL");
+    cudaError_t e = cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "event_record");
+}
+
+int qgt_b200_event_wait(void* stream, void* event) {
+    if (!event) return fail(QGT_B200_ERR_INVALID_ARG, "event_wait: event is NULL");
+    cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "event_wait");
+}
+
+int qgt_b200_event_synchronize(void* event) {
+    if (!event) return fail(QGT_B200_ERR_INVALID_ARG, "event_synchronize: event is NULL");
+    cudaError_t e = cudaEventSynchronize((cudaEvent_t)event);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "event_synchronize");
+}
+
+void* qgt_b200_ctx_stream(qgt_b200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
 const char* qgt_b200_error_string(int s) {
     switch (s) {
     case QGT_B200_OK: return "success";

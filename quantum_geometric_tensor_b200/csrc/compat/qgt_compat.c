@@ -94,9 +94,12 @@ bool apply_quantum_gate(quantum_geometric_tensor_network_t* n, const quantum_gat
     uint32_t target = 0, control = 0;
     if (qubits && num_qubits >= 1) { target = (uint32_t)qubits[num_qubits - 1]; if (num_qubits >= 2) control = (uint32_t)qubits[0]; }
     else {
-        if (gate->target_qubits) target = (uint32_t)gate->target_qubits[0];
+        /* create_quantum_gate (core/quantum_gate_operations.c:225-319) stores {control, target} of a two-qubit gate in
+           target_qubits and leaves control_qubits NULL */
+        if (gate->target_qubits) target = (uint32_t)gate->target_qubits[gate->control_qubits || gate->num_qubits < 2 ? 0 : gate->num_qubits - 1];
         else if (gate->qubits && gate->num_qubits) target = (uint32_t)gate->qubits[gate->num_qubits - 1];
         if (gate->control_qubits && gate->num_controls) control = (uint32_t)gate->control_qubits[0];
+        else if (gate->target_qubits && gate->num_qubits >= 2) control = (uint32_t)gate->target_qubits[0];
         else if (gate->qubits && gate->num_qubits >= 2) control = (uint32_t)gate->qubits[0];
     }
     if (target >= n->num_qubits || control >= n->num_qubits) { qgtn_err("qubit index out of range"); return false; }
@@ -149,6 +152,145 @@ bool get_quantum_state(const quantum_geometric_tensor_network_t* n, ComplexFloat
     free(amps);
     *state_vector = out;                             /* caller frees, as in the reference */
     *dimension = dim;
+    return true;
+}
+
+/* ---- parameter shifts and derivative columns (core/quantum_parameter_shift.c:151-662, core/quantum_geometric_gradient.c:1849-2406)
+ * Parameter index = order of the parameterised gates (find_parameterized_gate, quantum_parameter_shift.c:278-337).  The
+ * reference's versions re-run a circuit engine that does not apply gates; here the circuit runs
+ * on the device and the states come back as ComplexFloat arrays the caller frees, as in the reference. */
+bool shift_parameter(quantum_geometric_tensor_network_t* n, size_t param_idx, double shift_amount) {
+    if (!n || !n->backend_state) { qgtn_err("invalid arguments"); return false; }
+    qgtn_state* st = (qgtn_state*)n->backend_state;
+    if (param_idx >= st->num_params) { qgtn_err("parameter index out of range"); return false; }
+    st->theta[param_idx] += shift_amount;
+    free(st->q); st->q = NULL;
+    return true;
+}
+
+/* |psi(theta)> of the recorded circuit on the device */
+static qgt_b200_state* qgtn_run(const quantum_geometric_tensor_network_t* n, const double* theta) {
+    qgt_b200_ctx* ctx = qgt_compat_ctx();
+    if (!ctx) { qgtn_err(qgt_compat_last_error()); return NULL; }
+    qgt_b200_state* s = NULL;
+    int rc = qgt_b200_state_create(ctx, (int)n->num_qubits, &s);
+    if (!rc) rc = qgt_b200_state_init(s, QGT_B200_INIT_ZERO);
+    if (!rc) {
+        qgt_b200_circuit c;
+        qgtn_circuit(n, &c);
+        if (c.num_gates) rc = qgt_b200_apply_circuit(s, &c, theta);
+    }
+    if (rc) { qgt_compat_set_error("circuit run", rc); qgtn_err(qgt_compat_last_error()); qgt_b200_state_destroy(s); return NULL; }
+    return s;
+}
+
+static ComplexFloat* qgtn_download(const qgt_b200_state* s, size_t dim) {
+    ComplexFloat* out = (ComplexFloat*)malloc(dim * sizeof *out);
+    if (!out) { qgtn_err("out of memory"); return NULL; }
+    int rc = qgt_b200_state_download_c64(s, (float*)out);
+    if (rc) { qgt_compat_set_error("state download", rc); qgtn_err(qgt_compat_last_error()); free(out); return NULL; }
+    return out;
+}
+
+/* psi(theta + s e_mu) and psi(theta - s e_mu) on the device; the recorded parameters are left unchanged */
+static bool qgtn_shifted_pair(const quantum_geometric_tensor_network_t* n, size_t param_idx, double shift,
+                              qgt_b200_state** fwd, qgt_b200_state** bwd) {
+    const qgtn_state* st = (const qgtn_state*)n->backend_state;
+    if (param_idx >= st->num_params) { qgtn_err("parameter index out of range"); return false; }
+    double* th = (double*)malloc((st->num_params ? st->num_params : 1) * sizeof(double));
+    if (!th) { qgtn_err("out of memory"); return false; }
+    memcpy(th, st->theta, st->num_params * sizeof(double));
+    th[param_idx] = st->theta[param_idx] + shift;
+    *fwd = qgtn_run(n, th);
+    th[param_idx] = st->theta[param_idx] - shift;
+    *bwd = *fwd ? qgtn_run(n, th) : NULL;
+    free(th);
+    if (!*fwd || !*bwd) { qgt_b200_state_destroy(*fwd); qgt_b200_state_destroy(*bwd); *fwd = *bwd = NULL; return false; }
+    return true;
+}
+
+bool compute_shifted_states(quantum_geometric_tensor_network_t* n, size_t param_idx, double shift_amount,
+                            ComplexFloat** forward_state, ComplexFloat** backward_state, size_t* dimension) {
+    if (!n || !n->backend_state || !forward_state || !backward_state || !dimension) { qgtn_err("invalid arguments"); return false; }
+    qgt_b200_state *f = NULL, *b = NULL;
+    if (!qgtn_shifted_pair(n, param_idx, shift_amount, &f, &b)) return false;
+    const size_t dim = (size_t)1 << n->num_qubits;
+    ComplexFloat* fo = qgtn_download(f, dim);
+    ComplexFloat* bo = fo ? qgtn_download(b, dim) : NULL;
+    qgt_b200_state_destroy(f); qgt_b200_state_destroy(b);
+    if (!fo || !bo) { free(fo); free(bo); return false; }
+    *forward_state = fo; *backward_state = bo; *dimension = dim;
+    return true;
+}
+
+/* (psi(theta + s) - psi(theta - s)) / (2 s): the formula of both reference routines (quantum_parameter_shift.c:195-196, 258-259) */
+static bool qgtn_difference(const quantum_geometric_tensor_network_t* n, size_t param_idx, double s, ComplexFloat** gradient, size_t* dimension) {
+    if (!n || !n->backend_state || !gradient || !dimension) { qgtn_err("invalid arguments"); return false; }
+    if (s == 0.0) { qgtn_err("zero step"); return false; }
+    qgt_b200_state *f = NULL, *b = NULL;
+    if (!qgtn_shifted_pair(n, param_idx, s, &f, &b)) return false;
+    int rc = qgt_b200_state_axpy(f, -1.0, 0.0, b);
+    if (!rc) rc = qgt_b200_state_scale(f, 1.0 / (2.0 * s), 0.0);
+    const size_t dim = (size_t)1 << n->num_qubits;
+    ComplexFloat* out = rc ? NULL : qgtn_download(f, dim);
+    if (rc) { qgt_compat_set_error("finite difference", rc); qgtn_err(qgt_compat_last_error()); }
+    qgt_b200_state_destroy(f); qgt_b200_state_destroy(b);
+    if (!out) return false;
+    *gradient = out; *dimension = dim;
+    return true;
+}
+
+bool compute_parameter_shift_gradient(const quantum_geometric_tensor_network_t* n, size_t param_idx, double shift_amount,
+                                      ComplexFloat** gradient, size_t* dimension) {
+    return qgtn_difference(n, param_idx, shift_amount, gradient, dimension);
+}
+
+bool compute_centered_difference_gradient(const quantum_geometric_tensor_network_t* n, size_t param_idx, double step_size,
+                                          ComplexFloat** gradient, size_t* dimension) {
+    return qgtn_difference(n, param_idx, step_size, gradient, dimension);
+}
+
+/* d_mu psi.  The reference combines shifted states with a formula that is not a derivative (quantum_geometric_gradient.c:2356-2360,
+ * BASELINE.md §4 #6); this returns the exact column U_{>k} (-i/2 P) U_{<=k} |0> from the device, whatever the shift list says. */
+bool compute_higher_order_gradient(const quantum_geometric_tensor_network_t* n, size_t param_idx, const double* shift_amounts,
+                                   size_t num_shifts, ComplexFloat** gradient, size_t* dimension) {
+    (void)shift_amounts; (void)num_shifts;
+    if (!n || !n->backend_state || !gradient || !dimension) { qgtn_err("invalid arguments"); return false; }
+    const qgtn_state* st = (const qgtn_state*)n->backend_state;
+    if (param_idx >= st->num_params) { qgtn_err("parameter index out of range"); return false; }
+    qgt_b200_ctx* ctx = qgt_compat_ctx();
+    if (!ctx) { qgtn_err(qgt_compat_last_error()); return false; }
+    qgt_b200_state* col = NULL;
+    int rc = qgt_b200_state_create(ctx, (int)n->num_qubits, &col);
+    if (!rc) {
+        qgt_b200_circuit c;
+        qgtn_circuit(n, &c);
+        rc = qgt_b200_derivative(ctx, &c, st->theta, (int)param_idx, col);
+    }
+    const size_t dim = (size_t)1 << n->num_qubits;
+    ComplexFloat* out = rc ? NULL : qgtn_download(col, dim);
+    if (rc) { qgt_compat_set_error("qgt_b200_derivative", rc); qgtn_err(qgt_compat_last_error()); }
+    qgt_b200_state_destroy(col);
+    if (!out) return false;
+    *gradient = out; *dimension = dim;
+    return true;
+}
+
+/* error estimate = || D(h) - D(h/2) || of two centred differences (quantum_parameter_shift.c:17-149 compares two step sizes) */
+bool compute_gradient_with_error(const quantum_geometric_tensor_network_t* n, size_t param_idx, ComplexFloat** gradient,
+                                 double* error_estimate, size_t* dimension) {
+    if (!gradient || !error_estimate || !dimension) { qgtn_err("invalid arguments"); return false; }
+    ComplexFloat *g1 = NULL, *g2 = NULL;
+    size_t d1 = 0, d2 = 0;
+    if (!qgtn_difference(n, param_idx, 1e-2, &g1, &d1)) return false;
+    if (!qgtn_difference(n, param_idx, 5e-3, &g2, &d2)) { free(g1); return false; }
+    double e = 0.0;
+    for (size_t i = 0; i < d1; i++) {
+        const double dr = (double)g1[i].real - g2[i].real, di = (double)g1[i].imag - g2[i].imag;
+        e += dr * dr + di * di;
+    }
+    free(g1);
+    *gradient = g2; *error_estimate = sqrt(e); *dimension = d2;
     return true;
 }
 

@@ -37,6 +37,9 @@ struct NcclApi {
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -59,6 +62,9 @@ static int nccl_load() {
     a.Recv = (decltype(a.Recv))sym("ncclRecv");
     a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
     a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+    a.Broadcast = (decltype(a.Broadcast))sym("ncclBroadcast");
+    a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+    a.ReduceScatter = (decltype(a.ReduceScatter))sym("ncclReduceScatter");
     a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
     if (!ok) return fail(QGT_B200_ERR_HARDWARE, "libnccl.so.2 lacks a required symbol");
     g_nccl = a;
@@ -325,6 +331,116 @@ int qgt_b200_dist_barrier(qgt_b200_ctx* c) {
     if (!c) return qgt::fail(QGT_B200_ERR_INVALID_ARG, "ctx is NULL");
     double v = 0.0;
     return qgt::dist_allreduce_host(c, &v, 1);
+}
+
+
+// Generic collectives on caller buffers (host or device pointers): what the collective slots of the reference's
+// ComputeBackendOps bind (compute_backend.h:215-319 of the reference; its CUDA backend, supercomputer/backends/
+// compute_cuda.cu:1043-1330, stages host buffers the same way).  dtype / op use the reference's ComputeDataType /
+// ComputeReduceOp numbering.  `count` is per rank for scatter / gather / allgather / reduce_scatter.  With one rank
+// every call is the copy the reference's single-node path makes.
+int qgt_b200_dist_collective(qgt_b200_ctx* c, int kind, const void* send, void* recv, size_t count, int dtype, int op, int root) {
+    using namespace qgt;
+    if (!c) return fail(QGT_B200_ERR_INVALID_ARG, "ctx is NULL");
+    static const size_t esize[] = {4, 8, 8, 16, 4, 8, 1};
+    if (dtype < 0 || dtype > 6) return fail(QGT_B200_ERR_INVALID_ARG, "unknown data type");
+    if (kind < QGT_B200_COLL_BROADCAST || kind > QGT_B200_COLL_REDUCE_SCATTER) return fail(QGT_B200_ERR_INVALID_ARG, "unknown collective");
+    if (kind == QGT_B200_COLL_BROADCAST) { if (!recv) recv = const_cast<void*>(send); send = recv; }
+    if ((!send || !recv) && count) return fail(QGT_B200_ERR_INVALID_ARG, "send/recv is NULL");
+    if (root < 0 || root >= c->world) return fail(QGT_B200_ERR_INVALID_ARG, "root out of range");
+    const int W = c->world;
+    size_t send_n = count, recv_n = count;                 // elements
+    if (kind == QGT_B200_COLL_SCATTER || kind == QGT_B200_COLL_REDUCE_SCATTER) send_n = count * W;
+    if (kind == QGT_B200_COLL_GATHER || kind == QGT_B200_COLL_ALLGATHER) recv_n = count * W;
+    if (W == 1) {
+        if (send != recv && count) {
+            cudaSetDevice(c->device);
+            cudaError_t e = cudaMemcpy(recv, send, count * esize[dtype], cudaMemcpyDefault);
+            if (e != cudaSuccess) return cuda_fail(e, "single-rank collective copy");
+        }
+        return QGT_B200_OK;
+    }
+    if (!c->dist) return fail(QGT_B200_ERR_NOT_INIT, "communicator not initialised");
+    cudaSetDevice(c->device);
+    // complex types travel as pairs of their real type (sum / avg act component-wise; prod/min/max are refused)
+    ncclDataType_t nt; size_t mul = 1;
+    switch (dtype) {
+        case 0: nt = ncclFloat; break;
+        case 1: nt = ncclDouble; break;
+        case 2: nt = ncclFloat; mul = 2; break;
+        case 3: nt = ncclDouble; mul = 2; break;
+        case 4: nt = ncclInt32; break;
+        case 5: nt = ncclInt64; break;
+        default: nt = ncclUint8; break;
+    }
+    ncclRedOp_t ro = ncclSum;
+    if (kind == QGT_B200_COLL_ALLREDUCE || kind == QGT_B200_COLL_REDUCE_SCATTER) {
+        switch (op) {
+            case 0: ro = ncclSum; break;
+            case 1: ro = ncclProd; break;
+            case 2: ro = ncclMin; break;
+            case 3: ro = ncclMax; break;
+            case 4: ro = ncclAvg; break;
+            default: return fail(QGT_B200_ERR_INVALID_ARG, "unknown reduction");
+        }
+        if (mul == 2 && (op == 1 || op == 2 || op == 3)) return fail(QGT_B200_ERR_UNSUPPORTED, "prod/min/max are not defined component-wise for complex data");
+    }
+    auto is_dev = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+    };
+    const size_t sb = send_n * esize[dtype], rb = recv_n * esize[dtype];
+    const bool sdev = is_dev(send), rdev = is_dev(recv);
+    const void* ds = send; void* dr = recv;
+    const size_t r_pad = (kind == QGT_B200_COLL_BROADCAST || rdev) ? 0 : ((rb + 255) & ~(size_t)255);
+    const size_t need = r_pad + (sdev ? 0 : sb);
+    if (need) {
+        int rc = c->dist->red.reserve(need + 256);
+        if (rc) return rc;
+        char* base = (char*)c->dist->red.ptr;
+        if (!rdev) dr = base;
+        if (!sdev) {
+            void* stage = base + r_pad;
+            const bool sender = !(kind == QGT_B200_COLL_BROADCAST || kind == QGT_B200_COLL_SCATTER) || c->rank == root;
+            if (sender) {
+                cudaError_t e = cudaMemcpyAsync(stage, send, sb, cudaMemcpyHostToDevice, c->stream);
+                if (e != cudaSuccess) return cuda_fail(e, "collective staging");
+            }
+            ds = stage;
+            if (kind == QGT_B200_COLL_BROADCAST) dr = stage;       // in place
+        }
+    }
+    ncclResult_t r = ncclSuccess;
+    ncclComm_t comm = c->dist->comm;
+    switch (kind) {
+        case QGT_B200_COLL_BROADCAST: r = g_nccl.Broadcast(ds, dr, send_n * mul, nt, root, comm, c->stream); break;
+        case QGT_B200_COLL_ALLREDUCE: r = g_nccl.AllReduce(ds, dr, send_n * mul, nt, ro, comm, c->stream); break;
+        case QGT_B200_COLL_ALLGATHER: r = g_nccl.AllGather(ds, dr, count * mul, nt, comm, c->stream); break;
+        case QGT_B200_COLL_REDUCE_SCATTER: r = g_nccl.ReduceScatter(ds, dr, count * mul, nt, ro, comm, c->stream); break;
+        case QGT_B200_COLL_SCATTER:
+            g_nccl.GroupStart();
+            if (c->rank == root)
+                for (int p = 0; p < W && r == ncclSuccess; p++)
+                    r = g_nccl.Send((const char*)ds + (size_t)p * count * esize[dtype], count * mul, nt, p, comm, c->stream);
+            if (r == ncclSuccess) r = g_nccl.Recv(dr, count * mul, nt, root, comm, c->stream);
+            g_nccl.GroupEnd();
+            break;
+        default:   // gather
+            g_nccl.GroupStart();
+            r = g_nccl.Send(ds, count * mul, nt, root, comm, c->stream);
+            if (c->rank == root)
+                for (int p = 0; p < W && r == ncclSuccess; p++)
+                    r = g_nccl.Recv((char*)dr + (size_t)p * count * esize[dtype], count * mul, nt, p, comm, c->stream);
+            g_nccl.GroupEnd();
+            break;
+    }
+    if (r != ncclSuccess) return nccl_fail(r, "collective");
+    cudaError_t e = cudaSuccess;
+    const bool receiver = kind != QGT_B200_COLL_GATHER || c->rank == root;
+    if (!rdev && receiver) e = cudaMemcpyAsync(recv, dr, rb, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "collective");
 }
 
 }  // extern "C"

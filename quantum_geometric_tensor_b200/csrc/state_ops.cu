@@ -96,6 +96,18 @@ __global__ void __launch_bounds__(256) so_scale_kernel(cplx* dst, uint64_t D, ui
     }
 }
 
+// dst_i += a * src_i
+__global__ void __launch_bounds__(256) so_axpy_kernel(cplx* dst, const cplx* src, uint64_t D, double ar, double ai) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < D; i += stride) {
+        const cplx x = src[i];
+        cplx z = dst[i];
+        z.x += ar * x.x - ai * x.y;
+        z.y += ar * x.y + ai * x.x;
+        dst[i] = z;
+    }
+}
+
 __global__ void __launch_bounds__(256) so_widen_kernel(cplx* dst, const float2* src, uint64_t D) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < D; i += stride) {
@@ -231,6 +243,17 @@ int qgt_b200_state_scale(qgt_b200_state* s, double re, double im) {
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "scale kernel");
+}
+
+int qgt_b200_state_axpy(qgt_b200_state* dst, double re, double im, const qgt_b200_state* src) {
+    if (!dst || !src) return fail(QGT_B200_ERR_INVALID_ARG, "state is NULL");
+    if (dst->ctx != src->ctx || dst->n != src->n) return fail(QGT_B200_ERR_DIMENSION, "states differ in context or size");
+    qgt_b200_ctx* c = dst->ctx;
+    cudaSetDevice(c->device);
+    so_axpy_kernel<<<so_grid(c, dst->D), 256, 0, c->stream>>>(dst->d, src->d, dst->D, re, im);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "axpy kernel");
 }
 
 int qgt_b200_state_normalize(qgt_b200_state* s, double* norm_before) {

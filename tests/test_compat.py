@@ -16,6 +16,17 @@ def _build(tmp_path):
     return str(exe)
 
 
+def _build_seams(tmp_path):
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, "libcompute_ref.so")):
+        pytest.skip("oracle/_ref/libcompute_ref.so (the reference's registry + CPU backend) is not built")
+    exe = tmp_path / "test_seams"
+    subprocess.run(["gcc", "-std=gnu11", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "compat", "test_seams.c"),
+                    "-o", str(exe), "-L" + PKG, "-lqgt_b200_compat", "-lqgt_b200", "-L" + ref, "-lcompute_ref",
+                    "-Wl,-rpath," + PKG, "-Wl,-rpath," + ref, "-lm"], check=True)
+    return str(exe)
+
+
 def test_compat_library_exports_reference_symbols():
     out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(PKG, "libqgt_b200_compat.so")], check=True,
                          capture_output=True, text=True).stdout
@@ -29,7 +40,17 @@ def test_compat_library_exports_reference_symbols():
                 "gpu_memcpy_device_to_host", "qg_gpu_init", "qg_gpu_cleanup", "qg_gpu_shutdown", "qg_gpu_get_device_count",
                 "qg_gpu_get_device_info", "qg_gpu_set_device", "qg_gpu_get_last_error", "qg_gpu_get_error_string", "qg_gpu_allocate",
                 "qg_gpu_allocate_pinned", "qg_gpu_free", "qg_gpu_memcpy_to_device", "qg_gpu_memcpy_to_host", "qg_gpu_create_stream",
-                "qg_gpu_destroy_stream", "qg_gpu_synchronize_stream", "qg_gpu_synchronize"):
+                "qg_gpu_destroy_stream", "qg_gpu_synchronize_stream", "qg_gpu_synchronize",
+                # round 2: the back-end seams, gate objects, parameter shifts, measurement
+                "qgt_b200_compute_backend_ops", "qgt_b200_compute_backend_info", "qgt_b200_register_compute_backend",
+                "qgt_b200_compute_backend_ctx", "compute_quantum_metric_gpu", "compute_quantum_connection_gpu",
+                "compute_quantum_curvature_gpu", "qgt_b200_context_init", "qgt_default_config", "qgt_error_string",
+                "create_quantum_gate", "copy_quantum_gate", "update_gate_parameters", "shift_gate_parameters", "destroy_quantum_gate",
+                "create_rx_gate", "create_cnot_gate", "initialize_numerical_backend", "shutdown_numerical_backend",
+                "shift_parameter", "compute_shifted_states", "compute_parameter_shift_gradient",
+                "compute_centered_difference_gradient", "compute_higher_order_gradient", "compute_gradient_with_error",
+                "sim_measure_qubit", "sim_measure_all", "sim_get_measurement_counts", "sim_get_expectation_value",
+                "sim_save_circuit", "sim_load_circuit"):
         assert f" T {sym}\n" in out, sym
 
 
@@ -47,3 +68,34 @@ def test_compat_entry_points_on_gpu(tmp_path):
     r = subprocess.run([_build(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all compat checks passed" in r.stdout
+
+
+def test_seams_host_only_parts(tmp_path):
+    """Registration with the reference's registry, probe() without a device, gate objects: no GPU needed."""
+    from quantum_geometric_tensor_b200 import api
+    if api.device_count() > 0:
+        pytest.skip("a GPU is present: the full program runs in the gpu test")
+    r = subprocess.run([_build_seams(tmp_path), "--host-only"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all host-only seam checks passed" in r.stdout
+
+
+@pytest.mark.gpu
+def test_seams_on_gpu(tmp_path):
+    """ComputeBackendOps against the reference's CPU backend, the GPUContext seam, the network API, parameter shifts."""
+    r = subprocess.run([_build_seams(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all seam checks passed" in r.stdout
+
+
+REF_TESTS = "/root/reference/tests"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name", ["test_quantum_simulator_cpu", "test_quantum_geometric_minimal", "test_quantum_geometric_tensor_gpu"])
+def test_reference_tests_compile_and_link_unmodified(tmp_path, name):
+    """The reference's own test programs for the path build against include/ + the two libraries without edits."""
+    exe = tmp_path / name
+    subprocess.run(["gcc", "-std=gnu11", "-w", "-I" + os.path.join(ROOT, "include"), os.path.join(REF_TESTS, name + ".c"), "-o", str(exe),
+                    "-L" + PKG, "-lqgt_b200_compat", "-lqgt_b200", "-Wl,-rpath," + PKG, "-lm"], check=True)
+    assert exe.exists()
