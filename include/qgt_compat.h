@@ -219,6 +219,58 @@ bool compute_quantum_metric(const quantum_geometric_tensor_network_t* qgtn, size
 bool compute_berry_curvature(const quantum_geometric_tensor_network_t* qgtn, size_t param_i, size_t param_j, double* result);
 const char* get_quantum_geometric_tensor_network_error(void);
 
+/* ---- core/quantum_state_types.h:20-26, core/quantum_types.h:52-61,241-271, core/quantum_circuit_operations.h:14-60 ------
+ * The ComplexFloat circuit path.  Gate conventions of this path (quantum_circuit_operations.c:1147-1190): X = RX(pi),
+ * Y = RY(pi), Z = RZ(pi), S = RZ(pi/2); two-qubit gates keep {control, target} in gate->qubits. */
+typedef struct {
+    size_t num_qubits;
+    ComplexFloat* amplitudes;
+    void* workspace;
+    size_t dimension;
+    bool is_normalized;
+} QuantumState;
+typedef QuantumState quantum_state;
+typedef enum { PAULI_I = 0, PAULI_X = 1, PAULI_Y = 2, PAULI_Z = 3 } pauli_type_t;
+typedef pauli_type_t PauliOperator;
+typedef pauli_type_t pauli_type;
+struct circuit_layer_t; struct computational_graph_t; struct quantum_geometric_state_t; struct quantum_compute_node_t;
+struct quantum_circuit_t {
+    size_t num_qubits;
+    bool is_parameterized;
+    struct circuit_layer_t** layers;  size_t num_layers, layers_capacity;        /* unused here: sweeps are fused at execution */
+    quantum_gate_t** gates;  size_t num_gates, max_gates;                          /* the flat list the builders append to */
+    int optimization_level;
+    bool is_compiled;
+    struct computational_graph_t* graph;
+    struct quantum_geometric_state_t* state;
+    struct quantum_compute_node_t** nodes;  size_t num_nodes, capacity;
+};
+typedef struct quantum_circuit_t quantum_circuit_t;
+#define QGT_ERROR_INCOMPATIBLE (-19)
+#define QGT_ERROR_INVALID_OPERATOR (-650)
+quantum_state* init_quantum_state(size_t num_qubits);
+void quantum_state_reset(quantum_state* state);
+void quantum_state_cleanup(quantum_state* state);
+quantum_circuit_t* quantum_circuit_create(size_t num_qubits);
+void quantum_circuit_destroy(quantum_circuit_t* circuit);
+void quantum_circuit_reset(quantum_circuit_t* circuit);
+qgt_error_t quantum_circuit_hadamard(quantum_circuit_t* circuit, size_t qubit);
+qgt_error_t quantum_circuit_pauli_x(quantum_circuit_t* circuit, size_t qubit);
+qgt_error_t quantum_circuit_pauli_y(quantum_circuit_t* circuit, size_t qubit);
+qgt_error_t quantum_circuit_pauli_z(quantum_circuit_t* circuit, size_t qubit);
+qgt_error_t quantum_circuit_phase(quantum_circuit_t* circuit, size_t qubit, double angle);
+qgt_error_t quantum_circuit_rotation(quantum_circuit_t* circuit, size_t qubit, double angle, pauli_type axis);
+qgt_error_t quantum_circuit_cnot(quantum_circuit_t* circuit, size_t control, size_t target);
+qgt_error_t quantum_circuit_cz(quantum_circuit_t* circuit, size_t control, size_t target);
+qgt_error_t quantum_circuit_swap(quantum_circuit_t* circuit, size_t qubit1, size_t qubit2);
+qgt_error_t quantum_circuit_execute(quantum_circuit_t* circuit, quantum_state* state);
+qgt_error_t quantum_circuit_measure(quantum_circuit_t* circuit, quantum_state* state, size_t* results);
+qgt_error_t quantum_circuit_measure_all(quantum_circuit_t* circuit, quantum_state* state, size_t* results);
+qgt_error_t quantum_circuit_optimize(quantum_circuit_t* circuit, int optimization_level);
+qgt_error_t quantum_circuit_validate(quantum_circuit_t* circuit);
+size_t quantum_circuit_depth(const quantum_circuit_t* circuit);
+size_t quantum_circuit_gate_count(const quantum_circuit_t* circuit);
+
 /* ---- core/quantum_parameter_shift.h:28-142 (parameter index = order of the parameterised gates) ---------------------
  * States and gradients are malloc'd ComplexFloat[2^n] arrays the caller frees.  compute_higher_order_gradient returns the
  * exact derivative column d_mu psi (the reference's combination of shifted states is not a derivative). */
