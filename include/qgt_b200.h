@@ -214,8 +214,11 @@ typedef struct qgt_b200_natgrad_config {
 int  qgt_b200_natural_gradient(qgt_b200_ctx* ctx, const double* metric, const double* grad, size_t num_params,
                                const qgt_b200_natgrad_config* cfg, double* out, double* lambda_used);
 
-/* Energy gradient d<E>/d theta for the diagonal cost observable of a COST circuit or a sum of Z_i Z_j /
- * Z_i terms, by the adjoint method on device (feeds the natural-gradient step of config 2). */
+/* Energy E = <psi|H|psi> and its gradient dE/d theta by the adjoint method on the device: one forward circuit and one
+ * backward pass over two states, whatever the number of parameters (replaces the two circuit executions per parameter
+ * of algorithms/qaoa.c:489-558; feeds the natural-gradient step).  H is the diagonal observable defined by the
+ * circuit's edge list and vertex weights, H = sum_edges w (1 - Z_i Z_j)/2 + sum_q v_q Z_q (E_z of qaoa.c:258-289), for
+ * any circuit, with or without COST gates.  Either output may be NULL.  Single GPU. */
 int  qgt_b200_expectation_gradient(qgt_b200_ctx* ctx, const qgt_b200_circuit* circuit, const double* theta,
                                    double* energy, double* grad);
 
@@ -331,6 +334,12 @@ int  qgt_b200_measure_peaks(qgt_b200_ctx* ctx, double* dmma_tflops, double* copy
  * qualify (tiles below 8 qubits, a sub-pass off the tensor path, a cost layer). */
 long qgt_b200_plan_dump_fused(const qgt_b200_circuit* circuit, const double* theta, int world, int tile_qubits, int reg_qubits,
                               size_t column_slots, char* buf, size_t buflen);
+
+/* plan_dump of the INVERSE circuit with the adjoint-gradient program of qgt_b200_expectation_gradient (no device needed):
+ * fused != 0 -> the fused program (QGT_B200_ERR_UNSUPPORTED when the plan does not qualify), else the generic per-run
+ * programs with `scratch_slots` scratch columns.  Slots: 0 = chi, 1 = its twin, 2 = Lambda, 3.. = scratch. */
+long qgt_b200_plan_dump_gradient(const qgt_b200_circuit* circuit, const double* theta, int fused, int scratch_slots, int tile_qubits,
+                                 int reg_qubits, char* buf, size_t buflen);
 
 #ifdef __cplusplus
 }

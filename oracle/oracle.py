@@ -106,6 +106,11 @@ class Oracle:
             raise RuntimeError(f"orc_natural_gradient -> {rc}")
         return out, lam.value
 
+    @staticmethod
+    def energy(circ: Circuit, psi: np.ndarray) -> float:
+        """<psi|H|psi> for the diagonal observable of the circuit's edge list / vertex weights."""
+        return float(((psi.real ** 2 + psi.imag ** 2) * cost_energy_table(circ)).sum())
+
     def expectation_gradient(self, circ: Circuit, theta: np.ndarray) -> Tuple[float, np.ndarray]:
         cc = circ.to_c()
         th = np.ascontiguousarray(theta, dtype=np.float64)
@@ -115,6 +120,18 @@ class Oracle:
         if rc:
             raise RuntimeError(f"orc_expectation_gradient -> {rc}")
         return e.value, g
+
+
+def cost_energy_table(circ: Circuit) -> np.ndarray:
+    """E_z of every basis state: cut weight + vertex terms (reference algorithms/qaoa.c:258-289), plain NumPy."""
+    idx = np.arange(1 << circ.num_qubits, dtype=np.uint64)
+    e = np.zeros(idx.size)
+    for i, j, w in circ.edges:
+        e += w * (((idx >> np.uint64(i)) ^ (idx >> np.uint64(j))) & np.uint64(1)).astype(np.float64)
+    if circ.vertex_weights is not None:
+        for q, v in enumerate(circ.vertex_weights):
+            e += v * (1.0 - 2.0 * ((idx >> np.uint64(q)) & np.uint64(1)).astype(np.float64))
+    return e
 
 
 class Reference:

@@ -104,6 +104,8 @@ def load() -> C.CDLL:
     L.qgt_b200_state_download_c64.argtypes = [vp, C.c_void_p]
     L.qgt_b200_plan_dump_fused.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t]
     L.qgt_b200_plan_dump_fused.restype = C.c_long
+    L.qgt_b200_plan_dump_gradient.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    L.qgt_b200_plan_dump_gradient.restype = C.c_long
     _lib = L
     return L
 
@@ -166,6 +168,23 @@ def plan_dump_fused(circ: Circuit, theta: Optional[np.ndarray], column_slots: in
         _check(int(n))
     buf = C.create_string_buffer(n + 1)
     n2 = L.qgt_b200_plan_dump_fused(*args, buf, n + 1)
+    if n2 < 0:
+        _check(int(n2))
+    return json.loads(buf.value.decode())
+
+
+def plan_dump_gradient(circ: Circuit, theta: Optional[np.ndarray], fused: bool, scratch_slots: int = 2,
+                       tile_qubits: int = 0, reg_qubits: int = 0) -> dict:
+    """Plan of the inverse circuit with the adjoint-gradient program (fused or generic).  Needs no GPU."""
+    L = load()
+    cc = circ.to_c()
+    th = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
+    args = (C.byref(cc), _dp(th), 1 if fused else 0, scratch_slots, tile_qubits, reg_qubits)
+    n = L.qgt_b200_plan_dump_gradient(*args, None, 0)
+    if n < 0:
+        _check(int(n))
+    buf = C.create_string_buffer(n + 1)
+    n2 = L.qgt_b200_plan_dump_gradient(*args, buf, n + 1)
     if n2 < 0:
         _check(int(n2))
     return json.loads(buf.value.decode())

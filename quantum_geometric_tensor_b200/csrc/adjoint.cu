@@ -1,0 +1,134 @@
+// adjoint.cu — energy gradient of a parameterised circuit by the adjoint method:
+// what feeds the natural-gradient step next to the metric.  Replaces the reference's per-parameter re-simulation
+// (algorithms/qaoa.c:489-558: two circuit executions per parameter; core/quantum_geometric_gradient.c:2887 consumes the
+// result) by ONE forward circuit and ONE backward pass over two states, whatever the number of parameters.
+//
+//   E = <psi|H|psi>,  H = E_z of the circuit's edge list / vertex weights (sum of w (1 - Z_i Z_j)/2 and v_q Z_q terms)
+//   backward pass on the inverse circuit: chi_0 = psi, Lambda_0 = H psi,
+//   dE/dtheta_mu = -2 Re sum_j <Lambda_j| (d_mu S_j) S_j^+ |chi_j>                       (plan.hpp)
+//
+// Fusable plans (the ansatz circuits): the fused kernel advances chi and Lambda in lockstep and accumulates the 8x8
+// transition matrices of every stage with a parameter; P dot products collapse into 64-term contractions.  Other plans
+// (QAOA cost layers, registers below 8 qubits): derivative columns are spawned per run and contracted by a Gram.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <vector>
+
+#include "ctx.hpp"
+
+using namespace qgt;
+
+extern "C" int qgt_b200_expectation_gradient(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
+                                              double* energy, double* grad) {
+    if (!c) return fail(QGT_B200_ERR_INVALID_ARG, "ctx is NULL");
+    if (!circ) return fail(QGT_B200_ERR_INVALID_ARG, "circuit is NULL");
+    if (circ->num_params < 0) return fail(QGT_B200_ERR_INVALID_ARG, "num_params < 0");
+    if (circ->num_params > 0 && !theta) return fail(QGT_B200_ERR_INVALID_ARG, "theta is NULL");
+    if (c->world > 1) return fail(QGT_B200_ERR_UNSUPPORTED, "expectation gradient is single-GPU only");
+    cudaSetDevice(c->device);
+    const auto t_wall0 = std::chrono::steady_clock::now();
+    const int n = circ->num_qubits, P = circ->num_params;
+    const uint64_t D = (uint64_t)1 << n;
+    int rc;
+    std::string err;
+
+    // plans of U and of U^+ (same options: same tiles, same fusion rules)
+    CircuitPlan fwd, inv;
+    if ((rc = build_plan(*circ, theta, c->opt, fwd, err))) return fail(rc, err);
+    std::vector<qgt_b200_gate> inv_gates;
+    invert_circuit(*circ, inv_gates);
+    qgt_b200_circuit icirc = *circ;
+    icirc.gates = inv_gates.data(); icirc.num_gates = inv_gates.size();
+    if ((rc = build_plan(icirc, theta, c->opt, inv, err))) return fail(rc, err);
+    const bool want_grad = grad != nullptr && P > 0;
+    const bool fused = want_grad && c->fused_mode != 0 && plan_supports_fused(inv);
+
+    size_t slots = workspace_slots(c, D, (size_t)256 << 20);
+    if (slots < 4) return fail(QGT_B200_ERR_NO_MEMORY, "workspace too small: the adjoint gradient needs 4 statevector-sized columns");
+    int scratch = 0;
+    if (want_grad && !fused) {
+        int most = 1;
+        for (const Run& run : inv.runs) {
+            std::vector<char> seen(P, 0);
+            int cnt = 0;
+            for (const ParamOcc& oc : run.occ) if (!seen[oc.param]) { seen[oc.param] = 1; cnt++; }
+            most = std::max(most, cnt);
+        }
+        scratch = (int)std::min<size_t>((size_t)most, slots - 3);
+    }
+    const int num_slots = 3 + scratch;
+    if ((rc = c->arena.reserve((size_t)(num_slots + 1) * D * sizeof(cplx)))) return rc;
+    const size_t cm = (size_t)(P + 1) * (P + 1);
+    if ((rc = c->cmat.reserve(std::max<size_t>(16, cm * sizeof(cplx))))) return rc;
+    if ((rc = c->scratch.reserve(256))) return rc;
+    cplx* arena = (cplx*)c->arena.ptr;
+    cplx* chi = arena;                  // slot 0
+    cplx* lam = arena + 2 * D;          // slot 2
+
+    stats_begin(c);
+    PlanImage img;
+    // forward: psi = U |init>
+    if ((rc = upload_plan(c, *circ, fwd, img))) return rc;
+    cudaError_t e = launch_init_state(chi, D, circ->initial_state, std::pow(2.0, -0.5 * n), 0, c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "init launch");
+    if ((rc = apply_plan_inplace(c, fwd, chi, D))) return rc;
+    // Lambda = H psi, E = <psi|Lambda>
+    c->timer.begin(c->stream, 2);
+    e = launch_cost_apply(lam, chi, D, c->cost, 0, c->stream);
+    double h[2] = {0.0, 0.0};
+    if (e == cudaSuccess) e = launch_cost_dot(chi, chi, D, c->cost, 0, (double*)c->scratch.ptr, c->stream);
+    c->timer.end(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, c->scratch.ptr, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cost observable");
+    c->stats.other_launches += 2;
+    if (energy) *energy = h[0];
+
+    if (want_grad) {
+        std::fill(grad, grad + P, 0.0);
+        PlanImage iimg;
+        if ((rc = upload_plan(c, icirc, inv, iimg))) return rc;
+        if (fused) {
+            Program prog;
+            if ((rc = build_gradient_fused_program(inv, prog))) return fail(rc, "gradient program");
+            if ((rc = run_program(c, icirc, inv, prog, arena, D, (cplx*)c->cmat.ptr))) return rc;
+            std::vector<double> row((size_t)P * 2);
+            e = cudaMemcpyAsync(row.data(), c->amat.ptr, row.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) return cuda_fail(e, "gradient download");
+            for (int mu = 0; mu < P; mu++) grad[mu] = -2.0 * row[2 * (size_t)mu];
+        } else {
+            std::vector<double> row((size_t)P * 2);
+            std::vector<Program> progs;
+            const cplx* d_row = (const cplx*)c->cmat.ptr + (size_t)P * (P + 1);       // C[P][nu], nu = 0..P-1
+            for (int r = 0; r < (int)inv.runs.size(); r++) {
+                if ((rc = build_gradient_run_programs(inv, r, scratch, progs))) return fail(rc, "gradient program");
+                for (const Program& g : progs) {
+                    bool has_gram = false;
+                    for (const Instr& in : g.instrs) if (in.kind == INSTR_GRAM) has_gram = true;
+                    if (has_gram) {
+                        e = cudaMemsetAsync(c->cmat.ptr, 0, cm * sizeof(cplx), c->stream);
+                        if (e != cudaSuccess) return cuda_fail(e, "memset");
+                    }
+                    if ((rc = run_program(c, icirc, inv, g, arena, D, (cplx*)c->cmat.ptr))) return rc;
+                    if (!has_gram) continue;
+                    e = cudaMemcpyAsync(row.data(), d_row, row.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+                    if (e != cudaSuccess) return cuda_fail(e, "gradient download");
+                    for (int mu = 0; mu < P; mu++) grad[mu] += -2.0 * row[2 * (size_t)mu];
+                }
+            }
+        }
+    }
+    if ((rc = stats_end(c))) return rc;
+    c->stats.num_runs = (int)(fwd.runs.size() + inv.runs.size());
+    c->stats.resident_columns = 1;
+    c->stats.blocks = 1;
+    c->stats.tile_qubits = fwd.runs.empty() ? 0 : fwd.runs[0].K;
+    c->stats.fused = fused ? 1 : 0;
+    c->stats.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wall0).count();
+    return QGT_B200_OK;
+}

@@ -641,6 +641,7 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                 it.ovr_kind = 0; it.ovr_index = -1;
                 it.self = sc.self ? 1 : 0;
                 it.rho_from = sc.rho_from;
+                it.phi_dst = sc.phi_dst >= 0 ? (void*)(arena + (size_t)phys[sc.phi_dst] * D) : nullptr;
                 if (sc.ovr_op >= 0) {
                     const OpLocation loc = locate_op(run, sc.ovr_op);
                     if (loc.kind == 0) return fail(QGT_B200_ERR_INTERNAL, "override op outside every sub-pass");
@@ -1302,39 +1303,6 @@ int qgt_b200_gram(qgt_b200_ctx* c, const double* psi, const double* dpsi, size_t
     return stats_end(c);
 }
 
-int qgt_b200_expectation_gradient(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
-                                  double* energy, double* grad) {
-    if (!c) return fail(QGT_B200_ERR_INVALID_ARG, "ctx is NULL");
-    int rc = check_circuit(circ, theta);
-    if (rc) return rc;
-    if (c->world > 1) return fail(QGT_B200_ERR_UNSUPPORTED, "expectation gradient is single-GPU only");
-    cudaSetDevice(c->device);
-    const int n = circ->num_qubits, P = circ->num_params;
-    qgt_b200_state *psi = nullptr, *col = nullptr;
-    if ((rc = qgt_b200_state_create(c, n, &psi))) return rc;
-    if ((rc = qgt_b200_state_create(c, n, &col))) { qgt_b200_state_destroy(psi); return rc; }
-    rc = qgt_b200_state_init(psi, circ->initial_state);
-    if (!rc) rc = qgt_b200_apply_circuit(psi, circ, theta);
-    if (!rc) rc = c->scratch.reserve(256);
-    double h[2];
-    auto dot = [&](const cplx* a, const cplx* b) -> int {
-        cudaError_t e = launch_cost_dot(a, b, psi->D, c->cost, 0, (double*)c->scratch.ptr, c->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(h, c->scratch.ptr, sizeof h, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "cost dot");
-    };
-    if (!rc) rc = dot(psi->d, psi->d);
-    if (!rc && energy) *energy = h[0];
-    for (int mu = 0; mu < P && !rc && grad; mu++) {
-        rc = qgt_b200_derivative(c, circ, theta, mu, col);
-        if (!rc) rc = dot(col->d, psi->d);
-        if (!rc) grad[mu] = 2.0 * h[0];
-    }
-    qgt_b200_state_destroy(psi);
-    qgt_b200_state_destroy(col);
-    return rc;
-}
-
 long qgt_b200_plan_dump(const qgt_b200_circuit* circ, const double* theta, int tile_qubits, int reg_qubits,
                         size_t column_slots, char* buf, size_t buflen) {
     if (!circ) return fail(QGT_B200_ERR_INVALID_ARG, "circuit is NULL");
@@ -1441,6 +1409,40 @@ long qgt_b200_plan_dump_fused(const qgt_b200_circuit* circ, const double* theta,
     if (const char* e = std::getenv("QGT_B200_FUSED_TRAJ")) traj_mode = std::atoi(e);      // test hook
     if ((rc = build_fused_program(plan, column_slots, true, prog, err, traj_mode))) return fail(rc, err);
     const std::string js = dump_json(*circ, plan, &prog, world > 1 ? &segs : nullptr);
+    if (buf && buflen > js.size()) std::memcpy(buf, js.c_str(), js.size() + 1);
+    return (long)js.size();
+}
+
+// Plan of the inverse circuit with the adjoint-gradient program (adjoint.cu): the fused one when the plan qualifies and
+// `fused` is non-zero, else the per-run programs of the generic path concatenated (scratch_slots scratch columns).
+long qgt_b200_plan_dump_gradient(const qgt_b200_circuit* circ, const double* theta, int fused, int scratch_slots, int tile_qubits,
+                                 int reg_qubits, char* buf, size_t buflen) {
+    if (!circ) return fail(QGT_B200_ERR_INVALID_ARG, "circuit is NULL");
+    PlanOptions opt;
+    if (tile_qubits) opt.tile_qubits = tile_qubits;
+    if (reg_qubits) opt.reg_qubits = reg_qubits;
+    std::vector<double> zeros((size_t)std::max(1, circ->num_params), 0.0);
+    std::vector<qgt_b200_gate> inv_gates;
+    invert_circuit(*circ, inv_gates);
+    qgt_b200_circuit icirc = *circ;
+    icirc.gates = inv_gates.data(); icirc.num_gates = inv_gates.size();
+    CircuitPlan plan;
+    std::string err;
+    int rc = build_plan(icirc, theta ? theta : zeros.data(), opt, plan, err);
+    if (rc) return fail(rc, err);
+    Program prog;
+    if (fused) {
+        if (!plan_supports_fused(plan)) return fail(QGT_B200_ERR_UNSUPPORTED, "plan does not qualify for the fused schedule");
+        if ((rc = build_gradient_fused_program(plan, prog))) return fail(rc, "gradient program");
+    } else {
+        prog.num_slots = 3 + std::max(1, scratch_slots);
+        std::vector<Program> progs;
+        for (int r = 0; r < (int)plan.runs.size(); r++) {
+            if ((rc = build_gradient_run_programs(plan, r, std::max(1, scratch_slots), progs))) return fail(rc, "gradient program");
+            for (const Program& g : progs) prog.instrs.insert(prog.instrs.end(), g.instrs.begin(), g.instrs.end());
+        }
+    }
+    const std::string js = dump_json(icirc, plan, &prog, nullptr);
     if (buf && buflen > js.size()) std::memcpy(buf, js.c_str(), js.size() + 1);
     return (long)js.size();
 }

@@ -128,6 +128,8 @@ typedef struct QgtSweepItem {
     // fused kernel only
     int32_t     self;                    // the item is phi itself: one tile, rho = <phi| . |phi>
     int32_t     rho_from;                // first stage (run-relative) whose transition matrix is accumulated
+    void*       phi_dst;                 // pair mode (adjoint gradient): phi's tile goes through EVERY stage and is stored here
+                                         // (may equal the launch's phi: in place); null = phi is only carried for the matrices
 } QgtSweepItem;
 
 typedef struct QgtDevEdge { int32_t i, j; double w; } QgtDevEdge;

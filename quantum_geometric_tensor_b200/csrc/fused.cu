@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(256, 2) qgt_fused_kernel(FusedLaunch a) {
     const int rho_from = it.rho_from;
     const int dbg = a.debug;
     // phi is only needed while transition matrices remain to be taken
-    const bool use_b = !self && rho_from <= run.last_rho_stage && !(dbg & QGT_FDBG_NO_B);
+    const bool pair = !TRAJ && !self && it.phi_dst != nullptr;       // phi is advanced through the whole run and written back
+    const bool use_b = !self && (pair || rho_from <= run.last_rho_stage) && !(dbg & QGT_FDBG_NO_B);
     const size_t tile_elems = (size_t)1 << run.K;
 
     cplx* tileA = reinterpret_cast<cplx*>(qgt_fsmem_raw);
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(256, 2) qgt_fused_kernel(FusedLaunch a) {
                 const bool last = (sg == sp.stage_end - 1);
                 const bool rho_stage = st.rho_off >= 0;
                 const bool do_rho = rho_stage && sg >= rho_from && (self || use_b) && !(dbg & QGT_FDBG_NO_RHO);
-                const bool apply_b = !TRAJ && use_b && sg <= run.last_rho_stage;
+                const bool apply_b = !TRAJ && use_b && (pair || sg <= run.last_rho_stage);
                 const bool fetch_b = TRAJ && use_b && rho_stage && sg >= rho_from;      // this stage consumes a trajectory image
                 double t6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
                 if (TRAJ) {
@@ -413,8 +414,10 @@ __global__ void __launch_bounds__(256, 2) qgt_fused_kernel(FusedLaunch a) {
                 }
             }
         }
-        if (!(dbg & QGT_FDBG_NO_GLOBAL))
+        if (!(dbg & QGT_FDBG_NO_GLOBAL)) {
             qgt_phase_store<3>(io, tileA, reinterpret_cast<cplx*>(it.dst), tilebase, tid, T, it.accumulate != 0);
+            if (pair && use_b) qgt_phase_store<3>(io, tileB, reinterpret_cast<cplx*>(it.phi_dst), tilebase, tid, T, false);
+        }
     }
     __syncthreads();
     double* out = a.rho_partial + (size_t)blockIdx.x * run.rho_blocks * 128;
@@ -1092,9 +1095,16 @@ bool fused_uses_pipe(int K, int use_traj, int pipeline, int mat_count, int nsub,
 
 void fused_geometry(uint64_t ntiles, int nitems, int num_sms, bool pipe, int* tiles_per_cta, int* tile_groups) {
     // the persistent kernel keeps one CTA per SM: fewer, longer CTAs (its prologue is paid per CTA)
-    const uint64_t target = pipe ? (uint64_t)num_sms * 6 : (uint64_t)num_sms * 2 * 8;
-    uint64_t tpc = (ntiles * (uint64_t)(nitems > 0 ? nitems : 1) + target - 1) / target;
-    if (tpc < 8) tpc = 8;
+    // few items (the adjoint gradient's single pair item): every CTA leaves a partial transition-matrix buffer behind that
+    // the reduce kernel has to walk, so no more CTAs than two waves of resident ones
+    const uint64_t target = pipe ? (uint64_t)num_sms * 6 : nitems <= 2 ? (uint64_t)num_sms * 4 : (uint64_t)num_sms * 2 * 8;
+    const uint64_t work = ntiles * (uint64_t)(nitems > 0 ? nitems : 1);
+    uint64_t tpc = (work + target - 1) / target;
+    if (tpc < 8) {
+        // at least 8 tiles per CTA amortise its prologue - unless that leaves SMs idle (few items on a small state)
+        const uint64_t fill = (work + (uint64_t)num_sms * 2 - 1) / ((uint64_t)num_sms * 2);
+        tpc = fill < 8 ? (fill < 1 ? 1 : fill) : 8;
+    }
     if (tpc > ntiles) tpc = ntiles;
     *tiles_per_cta = (int)tpc;
     *tile_groups = (int)((ntiles + tpc - 1) / tpc);

@@ -905,6 +905,24 @@ __global__ void qgt_cost_dot_kernel(const cplx* a, const cplx* b, uint64_t D, Qg
     }
 }
 
+// dst_i = E_z(goff + i) * src_i: the diagonal cost observable applied to a state (dst may equal src)
+__global__ void __launch_bounds__(256) qgt_cost_apply_kernel(cplx* dst, const cplx* src, uint64_t D, QgtCostTable ct, uint64_t goff) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < D; i += stride) {
+        const double e = qgt_cost_energy(ct, goff + i);
+        cplx z = src[i];
+        z.x *= e; z.y *= e;
+        dst[i] = z;
+    }
+}
+
+cudaError_t launch_cost_apply(cplx* dst, const cplx* src, uint64_t D, QgtCostTable ct, uint64_t goff, cudaStream_t st) {
+    const uint64_t want = (D + 255) / 256;
+    const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+    qgt_cost_apply_kernel<<<grid, 256, 0, st>>>(dst, src, D, ct, goff);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_cost_dot(const cplx* a, const cplx* b, uint64_t D, QgtCostTable ct, uint64_t goff, double* out2, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(double), st);
     if (e != cudaSuccess) return e;

@@ -101,6 +101,7 @@ cudaError_t launch_init_state(cplx* dst, uint64_t D, int initial_state, double p
 cudaError_t launch_norm2(const cplx* src, uint64_t D, double* out /*device, zeroed inside*/, cudaStream_t st);
 cudaError_t launch_axpy(cplx* dst, const cplx* src, uint64_t D, double ar, double ai, cudaStream_t st);   // dst += a*src
 // expectation of the diagonal cost:  out[0] = sum |psi|^2 E ;  out2 = sum conj(a) b E  (re, im)
+cudaError_t launch_cost_apply(cplx* dst, const cplx* src, uint64_t D, QgtCostTable ct, uint64_t global_offset, cudaStream_t st);   // dst = E_z * src
 cudaError_t launch_cost_dot(const cplx* a, const cplx* b, uint64_t D, QgtCostTable ct, uint64_t global_offset,
                             double* out2 /*device, 2 doubles, zeroed inside*/, cudaStream_t st);
 

@@ -1392,6 +1392,102 @@ int build_fused_program(const CircuitPlan& plan, size_t total_slots, bool want_p
     return QGT_B200_OK;
 }
 
+// ---- adjoint-gradient programs (run on the plan of the INVERSE circuit, see adjoint.cu) ---------------------------
+// Slots: 0 = chi (starts as psi = U|init>), 1 = chi's out-of-place twin, 2 = Lambda (starts as H psi), 3.. = scratch.
+void invert_circuit(const qgt_b200_circuit& c, std::vector<qgt_b200_gate>& out) {
+    out.clear();
+    for (size_t k = c.num_gates; k-- > 0;) {
+        qgt_b200_gate g = c.gates[k];
+        switch (g.kind) {
+        case QGT_B200_GATE_S: g.kind = QGT_B200_GATE_SDG; break;
+        case QGT_B200_GATE_SDG: g.kind = QGT_B200_GATE_S; break;
+        case QGT_B200_GATE_T: g.kind = QGT_B200_GATE_TDG; break;
+        case QGT_B200_GATE_TDG: g.kind = QGT_B200_GATE_T; break;
+        case QGT_B200_GATE_SX: out.push_back(g); out.push_back(g); break;          // SX^4 = 1: the inverse is SX^3
+        default:
+            if (is_parametric(g.kind)) { g.angle = -g.angle; g.scale = -g.scale; }  // angle_eff = scale * theta + angle -> its negative
+            break;
+        }
+        out.push_back(g);
+    }
+}
+
+int build_gradient_fused_program(const CircuitPlan& plan, Program& prog) {
+    prog = Program();
+    prog.num_slots = 3; prog.fused = true; prog.resident = 1; prog.blocks = 1;
+    const int chi = 0, lam = 2;
+    for (int r = 0; r < (int)plan.runs.size(); r++) {
+        const Run& run = plan.runs[r];
+        if (run.exchange_gbit >= 0) return QGT_B200_ERR_UNSUPPORTED;
+        Instr in; in.run = r;
+        if (run.rho_stages == 0) {                 // no parameter in this run: both states just advance
+            in.kind = INSTR_SWEEP;
+            in.cols.push_back(SweepCol(chi, chi, -1, false));
+            in.cols.push_back(SweepCol(lam, lam, -1, false));
+            prog.instrs.push_back(std::move(in));
+            continue;
+        }
+        // one item per tile: Lambda and chi are staged together, both go through every stage and both are written back
+        // (pair mode), the transition matrices of the stages with parameters are taken on the way
+        in.kind = INSTR_FUSED; in.phi = chi; in.traj = false;
+        SweepCol col(lam, lam, -1, false);
+        col.id = 0; col.rho_from = 0;              // row 0 of A collects <Lambda| G_nu |chi> for every nu
+        col.phi_dst = chi;
+        in.cols.push_back(col);
+        prog.instrs.push_back(std::move(in));
+    }
+    prog.psi_slot = chi;
+    return QGT_B200_OK;
+}
+
+int build_gradient_run_programs(const CircuitPlan& plan, int r, int scratch_slots, std::vector<Program>& progs) {
+    progs.clear();
+    const Run& run = plan.runs[r];
+    if (run.exchange_gbit >= 0 || scratch_slots < 1) return QGT_B200_ERR_UNSUPPORTED;
+    const int P = plan.P, chi = 0, lam = 2;
+    std::vector<int> params;
+    {
+        std::vector<char> seen(P, 0);
+        for (const ParamOcc& oc : run.occ) if (!seen[oc.param]) { seen[oc.param] = 1; params.push_back(oc.param); }
+    }
+    auto base = [&]() { Program g; g.num_slots = 3 + scratch_slots; return g; };
+    if (params.empty()) {
+        Program g = base();
+        Sched s(plan, g);
+        s.sweep(r, {SweepCol(chi, chi, -1, false), SweepCol(lam, lam, -1, false)});
+        progs.push_back(std::move(g));
+        return QGT_B200_OK;
+    }
+    for (size_t lo = 0; lo < params.size(); lo += (size_t)scratch_slots) {
+        const size_t hi = std::min(params.size(), lo + (size_t)scratch_slots);
+        Program g = base();
+        Sched s(plan, g);
+        std::vector<SweepCol> A, acc;
+        if (lo == 0) A.push_back(SweepCol(lam, lam, -1, false));       // Lambda moves to the end of the run first
+        std::vector<int> slots, ids;
+        for (size_t k = lo; k < hi; k++) {
+            const int slot = 3 + (int)(k - lo);
+            std::vector<SweepCol> items = s.occurrence_items(r, params[k], chi, slot);
+            for (size_t j = 0; j < items.size(); j++) {
+                if (j == 0) { items[j].accumulate = false; A.push_back(items[j]); }
+                else acc.push_back(items[j]);
+            }
+            slots.push_back(slot); ids.push_back(params[k]);
+        }
+        s.sweep(r, A);
+        s.emit_accumulates(r, acc);
+        s.gram({lam}, {P}, slots, ids);                                  // C[P][nu] = <Lambda_after| (d_nu T) chi_before>
+        progs.push_back(std::move(g));
+    }
+    {
+        Program g = base();
+        Sched s(plan, g);
+        s.sweep(r, {SweepCol(chi, chi, -1, false)});
+        progs.push_back(std::move(g));
+    }
+    return QGT_B200_OK;
+}
+
 // ---- JSON dump (tests interpret this on the CPU) ------------------------------------------------
 static void jarr(std::ostringstream& o, const std::vector<int>& v) {
     o << "[";
@@ -1465,7 +1561,7 @@ std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const 
                 {
                     o << (j ? "," : "") << "[" << in.cols[j].src << "," << in.cols[j].dst << "," << in.cols[j].ovr_op << "," << (in.cols[j].accumulate ? 1 : 0) << ",";
                     jarr(o, in.cols[j].ovr_extra);
-                    if (in.kind == INSTR_FUSED) o << "," << in.cols[j].id << "," << in.cols[j].rho_from << "," << (in.cols[j].self ? 1 : 0);
+                    if (in.kind == INSTR_FUSED) o << "," << in.cols[j].id << "," << in.cols[j].rho_from << "," << (in.cols[j].self ? 1 : 0) << "," << in.cols[j].phi_dst;
                     o << "]";
                 }
                 o << "]}";

@@ -135,6 +135,7 @@ struct SweepCol {
     int rho_from = 0;           // first stage (run-relative) whose transition matrix <column| . |phi> is contracted:
                                 // 0 for a column that merely advances, (stage of the spawning occurrence) + 1 for a spawn
     bool self = false;          // the item IS phi: one tile, rho = <phi| . |phi>
+    int phi_dst = -1;           // pair mode: slot the advanced phi is written to by this item (no separate phi item), -1 = none
 };
 
 struct Instr {
@@ -184,6 +185,19 @@ static inline int rho_index(int c, int a, int part) { return (c * 4 + (a >> 1)) 
 // Gt = N M^+ (N = sum of the stage matrices with one occurrence replaced by its derivative), row-major 8x8 complex
 // (re, im); out[(k * nvariants + v) * 128 + (a * 8 + c) * 2]
 void stage_generators(const Run& run, const SubPass& sp, const Stage& st, std::vector<double>& out);
+
+// ---- adjoint energy gradient ---------------------------------------------------------------------------
+// E(theta) = <psi|H|psi>, H diagonal.  With the inverse circuit C' = U^+ run on chi_0 = psi and Lambda_0 = H psi,
+//   dE/dtheta_mu = -2 Re <Lambda_j| (d_mu S_j) S_j^+ |chi_j>   summed over the stages S_j of C' that carry theta_mu
+// (chi_j, Lambda_j = the two states after stage j): the same evolved-generator x transition-matrix contraction as the
+// fused QGT schedule, with Lambda as the only column.  One forward circuit + one backward pass of two states.
+void invert_circuit(const qgt_b200_circuit& c, std::vector<qgt_b200_gate>& out);        // gates of U^+, same parameter indices
+// slots 0 = chi, 1 = chi's twin, 2 = Lambda; row 0 of the A matrix receives <Lambda|G_nu|chi>
+int build_gradient_fused_program(const CircuitPlan& inverse_plan, Program& prog);
+// plans the fused path cannot take (cost layers, tiny tiles): per run, derivative columns (d_nu T) chi are spawned into
+// `scratch_slots` columns (slots 3..) and contracted with the advanced Lambda by a Gram, C[P][nu]; the programs of one
+// run must be executed in order and C read after each
+int build_gradient_run_programs(const CircuitPlan& inverse_plan, int run, int scratch_slots, std::vector<Program>& progs);
 
 // ---- sharded states: logical -> physical qubit mapping ------------------------------------------------
 // A state of n qubits sharded over 2^g ranks keeps physical qubits nloc.. (nloc = n - g) in the rank index.

@@ -294,8 +294,17 @@ def _fused_launch(plan, circ, ins, slots_by_rank, apply_fn, A, D, v):
     stage_of = _stage_of_op(run)
     world = len(slots_by_rank)
     results = []
-    for (src, dst, ovr, acc, extra, cid, rho_from, self_) in ins["cols"]:
+    phi_out = []
+    for (src, dst, ovr, acc, extra, cid, rho_from, self_, phi_dst) in ins["cols"]:
         ovrs = [ovr] + list(extra) if ovr >= 0 else [None]
+        if phi_dst >= 0:                   # pair mode: this item also writes the advanced phi
+            adv = []
+            for r in range(world):
+                st_ = slots_by_rank[r][ins["phi"]]
+                for op in ops:
+                    st_ = apply_fn(r, st_, op)
+                adv.append(st_)
+            phi_out.append((phi_dst, adv))
         total = [0 for _ in range(world)]
         for o in ovrs:
             for r in range(world):
@@ -339,9 +348,13 @@ def _fused_launch(plan, circ, ins, slots_by_rank, apply_fn, A, D, v):
     dsts = [d for d, _, _ in results]
     assert len(set(dsts)) == len(dsts), "two items of one launch share a destination"
     assert ins["phi"] not in dsts, "a fused launch overwrites the phi it reads"
+    assert len(phi_out) <= 1 and (not phi_out or len(ins["cols"]) == 1), "pair mode: one item per launch"
     for dst, acc, total in results:
         for r in range(world):
             slots_by_rank[r][dst] = slots_by_rank[r][dst] + total[r] if acc else total[r]
+    for dst, adv in phi_out:
+        for r in range(world):
+            slots_by_rank[r][dst] = adv[r]
 
 
 def run_program_fused(plan: dict, circ, world: int = 1):
@@ -401,3 +414,49 @@ def run_program_fused(plan: dict, circ, world: int = 1):
     Q = Cm - np.outer(v, v.conj())
     psi = np.concatenate([slots[r][prog["psi"]] for r in range(world)]) if prog["psi_final"] else None
     return Q, psi, counters
+
+
+def run_gradient_program(plan: dict, circ, psi: np.ndarray):
+    """Interprets an adjoint-gradient program (qgt_b200_plan_dump_gradient) on the CPU: slot 0 = psi, slot 2 = H psi.
+    Returns dE/dtheta.  Fused launches contribute A[0, nu] = <Lambda|G_nu|chi>, Gram instructions <Lambda|column>."""
+    prog = plan["program"]
+    P = plan["P"]
+    dim = psi.size
+    slots = [[np.zeros(dim, dtype=np.complex128) for _ in range(prog["slots"])]]
+    idx = np.arange(dim, dtype=np.uint64)
+    slots[0][0] = psi.copy()
+    slots[0][2] = _cost_energy(circ, idx.astype(np.int64)) * psi
+    A = np.zeros((max(P, 1), max(P, 1)), dtype=np.complex128)
+    Dm = np.zeros_like(A)
+    v = np.zeros(max(P, 1), dtype=np.complex128)
+    grad = np.zeros(P)
+    f = lambda r, st, op: apply_op(st, op, circ)
+    for ins in prog["instrs"]:
+        k = ins["k"]
+        if k == "sweep":
+            run = plan["runs"][ins["run"]]
+            ops, dops = run["ops"], run["dops"]
+            results = []
+            for (src, dst, ovr, acc, extra) in ins["cols"]:
+                total = 0
+                for o in ([ovr] + list(extra) if ovr >= 0 else [None]):
+                    st = slots[0][src]
+                    for i, op in enumerate(ops):
+                        st = apply_op(st, dops[str(i)] if i == o else op, circ)
+                    total = total + st
+                results.append((dst, acc, total))
+            dsts = [d for d, _, _ in results]
+            assert len(set(dsts)) == len(dsts)
+            for dst, acc, total in results:
+                slots[0][dst] = slots[0][dst] + total if acc else total
+        elif k == "fused":
+            _fused_launch(plan, circ, ins, slots, f, A, Dm, v)
+        elif k == "gram":
+            assert ins["aid"] == [P] and len(ins["a"]) == 1
+            for b, bid in zip(ins["b"], ins["bid"]):
+                grad[bid] += -2.0 * np.vdot(slots[0][ins["a"][0]], slots[0][b]).real
+        else:
+            raise ValueError(k)
+    if prog["fused"] == 1:
+        grad += -2.0 * A[0, :P].real
+    return grad

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 25
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.qgt_b200_abi_version() == 2
+    assert lib.qgt_b200_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_device():
