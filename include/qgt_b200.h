@@ -291,6 +291,11 @@ int  qgt_b200_state_measure(qgt_b200_state* s, int qubit, double uniform, double
 /* sim_get_measurement_counts: shots[k] = first basis index whose cumulative probability exceeds uniforms[k]
  * (host array of `shots` numbers in [0, 1)); single GPU */
 int  qgt_b200_state_sample(const qgt_b200_state* s, const double* uniforms, size_t shots, uint64_t* indices);
+/* index of the most probable basis state (lowest index on ties) and its probability; single GPU */
+int  qgt_b200_state_argmax(const qgt_b200_state* s, uint64_t* index, double* probability);
+/* <psi|H|psi> for the diagonal observable of `observable`'s edge list and vertex weights (its gates are ignored):
+ * H = sum_edges w [z_i != z_j] + sum_q v_q (1 - 2 z_q), the E_z of algorithms/qaoa.c:258-289 (qaoa_compute_expectation :455) */
+int  qgt_b200_state_cost_expectation(const qgt_b200_state* s, const qgt_b200_circuit* observable, double* out);
 /* ComplexFloat boundary (core/quantum_state_types.h:20-26): interleaved float pairs, host or device pointer */
 int  qgt_b200_state_upload_c64(qgt_b200_state* s, const float* src);
 int  qgt_b200_state_download_c64(const qgt_b200_state* s, float* dst);

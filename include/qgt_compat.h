@@ -271,6 +271,99 @@ qgt_error_t quantum_circuit_validate(quantum_circuit_t* circuit);
 size_t quantum_circuit_depth(const quantum_circuit_t* circuit);
 size_t quantum_circuit_gate_count(const quantum_circuit_t* circuit);
 
+/* ---- core/quantum_state_types.h:28-60 (operator object), algorithms/qaoa.h:29-304: the QAOA driver -----------------------
+ * Served by csrc/compat/qaoa_compat.c: the state lives on the device, qstate->amplitudes is refreshed by the public
+ * apply calls, cost_hamiltonian->matrix stays NULL (E_z is evaluated on the device from the edge list).
+ * Parameter order wherever one vector is used (QGT, exact gradient): (gamma_1, beta_1, ..., gamma_p, beta_p). */
+typedef enum quantum_operator_type_t { QUANTUM_OPERATOR_UNITARY, QUANTUM_OPERATOR_HERMITIAN, QUANTUM_OPERATOR_PROJECTOR,
+                                       QUANTUM_OPERATOR_KRAUS, QUANTUM_OPERATOR_LINDBLAD, QUANTUM_OPERATOR_CUSTOM } quantum_operator_type_t;
+typedef struct quantum_operator_t {
+    quantum_operator_type_t type;
+    size_t dimension;
+    ComplexFloat* matrix;
+    void* auxiliary_data;
+    bool is_hermitian;
+    void* device_data;
+    HardwareType device_type;
+} quantum_operator_t;
+typedef struct { size_t i, j; double weight; } qaoa_edge_t;
+typedef struct { size_t num_vertices, num_edges; qaoa_edge_t* edges; double* vertex_weights; } qaoa_graph_t;
+typedef enum { QAOA_PROBLEM_MAXCUT, QAOA_PROBLEM_QUBO, QAOA_PROBLEM_MAX_INDEPENDENT_SET, QAOA_PROBLEM_VERTEX_COVER,
+               QAOA_PROBLEM_GRAPH_COLORING, QAOA_PROBLEM_TSP, QAOA_PROBLEM_CUSTOM } qaoa_problem_type_t;
+typedef enum { QAOA_MIXER_X, QAOA_MIXER_XY, QAOA_MIXER_GROVER, QAOA_MIXER_CUSTOM } qaoa_mixer_type_t;
+typedef enum { QAOA_OPTIMIZER_COBYLA, QAOA_OPTIMIZER_NELDER_MEAD, QAOA_OPTIMIZER_POWELL, QAOA_OPTIMIZER_BFGS, QAOA_OPTIMIZER_SPSA,
+               QAOA_OPTIMIZER_ADAM, QAOA_OPTIMIZER_GRADIENT_DESCENT } qaoa_optimizer_type_t;
+typedef struct {
+    size_t p;
+    qaoa_problem_type_t problem_type;
+    qaoa_mixer_type_t mixer_type;
+    qaoa_optimizer_type_t optimizer_type;
+    double* initial_gamma;
+    double* initial_beta;
+    size_t max_iterations;
+    double tolerance;
+    double learning_rate;
+    size_t num_shots;
+    bool use_expectation;
+    bool use_gpu;
+    void* backend;
+} qaoa_config_t;
+typedef struct qaoa_state {
+    qaoa_graph_t* graph;
+    quantum_operator_t* cost_hamiltonian;
+    quantum_operator_t* mixer_hamiltonian;
+    double* gamma;
+    double* beta;
+    size_t p;
+    size_t num_qubits;
+    QuantumState* qstate;
+    double current_cost;
+    double best_cost;
+    double* best_gamma;
+    double* best_beta;
+    size_t iteration;
+    qaoa_config_t config;
+    int* best_solution;
+    double* solution_probabilities;
+} qaoa_state_t;
+typedef struct {
+    double optimal_cost;
+    int* optimal_solution;
+    double* optimal_gamma;
+    double* optimal_beta;
+    size_t num_iterations;
+    double* cost_history;
+    size_t history_length;
+    double execution_time;
+    double approximation_ratio;
+} qaoa_result_t;
+qaoa_graph_t* qaoa_create_graph(size_t num_vertices);
+qgt_error_t qaoa_add_edge(qaoa_graph_t* graph, size_t i, size_t j, double weight);
+qgt_error_t qaoa_set_vertex_weight(qaoa_graph_t* graph, size_t vertex, double weight);
+qaoa_graph_t* qaoa_create_random_graph(size_t num_vertices, double edge_probability, double min_weight, double max_weight);
+qaoa_graph_t* qaoa_create_from_adjacency(const double* adjacency, size_t n);
+void qaoa_destroy_graph(qaoa_graph_t* graph);
+qaoa_state_t* qaoa_init(const qaoa_graph_t* graph, const qaoa_config_t* config);       /* NULL without an sm_100 device */
+qgt_error_t qaoa_construct_cost_hamiltonian(qaoa_state_t* state);
+qgt_error_t qaoa_construct_mixer_hamiltonian(qaoa_state_t* state);
+qgt_error_t qaoa_prepare_initial_state(qaoa_state_t* state);
+qgt_error_t qaoa_apply_layer(qaoa_state_t* state, size_t layer_idx);
+qgt_error_t qaoa_apply_circuit(qaoa_state_t* state, const double* gamma, const double* beta);
+qgt_error_t qaoa_compute_expectation(qaoa_state_t* state, double* expectation);
+qgt_error_t qaoa_compute_gradient(qaoa_state_t* state, double* gamma_grad, double* beta_grad);   /* the reference's finite-shift formula */
+qaoa_result_t* qaoa_optimize(qaoa_state_t* state);
+qgt_error_t qaoa_sample(qaoa_state_t* state, int** samples, size_t num_samples);
+double qaoa_evaluate_solution(const qaoa_graph_t* graph, const int* solution);
+void qaoa_destroy(qaoa_state_t* state);
+void qaoa_destroy_result(qaoa_result_t* result);
+qaoa_config_t qaoa_default_config(size_t p);
+size_t qaoa_estimate_optimal_p(size_t num_vertices, size_t num_edges);
+double qaoa_approximation_ratio(const qaoa_graph_t* graph, const int* solution, double optimal_cost);
+void qaoa_print_state(const qaoa_state_t* state);
+void qaoa_print_result(const qaoa_result_t* result);
+/* exact dE/dgamma, dE/dbeta by the adjoint method on the device (not in the reference) */
+qgt_error_t qgt_b200_qaoa_exact_gradient(qaoa_state_t* state, double* energy, double* gamma_grad, double* beta_grad);
+
 /* ---- core/quantum_parameter_shift.h:28-142 (parameter index = order of the parameterised gates) ---------------------
  * States and gradients are malloc'd ComplexFloat[2^n] arrays the caller frees.  compute_higher_order_gradient returns the
  * exact derivative column d_mu psi (the reference's combination of shifted states is not a derivative). */

@@ -468,28 +468,10 @@ static int check_circuit(const qgt_b200_circuit* circ, const double* theta) {
     return QGT_B200_OK;
 }
 
-// upload the device image of a plan and the circuit's cost table
-int upload_plan(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan& plan, PlanImage& img) {
-    build_image(plan, img);
-    c->img_stage_form.clear(); c->img_run_stage_off.clear();
-    for (const QgtDevStage& st : img.stages) c->img_stage_form.push_back(st.form);
-    for (const QgtDevRun& r : img.runs) c->img_run_stage_off.push_back(r.stage_off);
+// the circuit's diagonal cost observable (edge list, vertex weights) on the device: c->cost
+int upload_cost_table(qgt_b200_ctx* c, const qgt_b200_circuit& circ) {
     int rc;
-    struct Up { DevBuf* buf; const void* src; size_t bytes; };
-    const Up ups[] = {
-        {&c->img_runs, img.runs.data(), img.runs.size() * sizeof(QgtDevRun)},
-        {&c->img_subs, img.subs.data(), img.subs.size() * sizeof(QgtDevSubPass)},
-        {&c->img_stages, img.stages.data(), img.stages.size() * sizeof(QgtDevStage)},
-        {&c->img_tdiags, img.tdiags.data(), img.tdiags.size() * sizeof(QgtDevThrDiag)},
-        {&c->img_costs, img.costs.data(), img.costs.size() * sizeof(QgtDevCost)},
-        {&c->img_pool, img.pool.data(), img.pool.size() * sizeof(double)},
-    };
     cudaError_t e = cudaSuccess;
-    for (const Up& u : ups) {
-        if ((rc = u.buf->reserve(std::max<size_t>(16, u.bytes)))) return rc;
-        if (u.bytes && e == cudaSuccess) e = cudaMemcpyAsync(u.buf->ptr, u.src, u.bytes, cudaMemcpyHostToDevice, c->stream);
-    }
-    if (e != cudaSuccess) return cuda_fail(e, "plan upload");
     c->seg_cost.clear();
     c->cost.edges = nullptr; c->cost.num_edges = 0; c->cost.vertex_weights = nullptr; c->cost.n = circ.num_qubits;
     if (circ.num_edges > QGT_COST_MAX_EDGES) return fail(QGT_B200_ERR_UNSUPPORTED, "more than 1024 cost-layer edges");
@@ -514,6 +496,31 @@ int upload_plan(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
         c->cost.vertex_weights = (const double*)c->vweights.ptr;
     }
     return QGT_B200_OK;
+}
+
+// upload the device image of a plan and the circuit's cost table
+int upload_plan(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan& plan, PlanImage& img) {
+    build_image(plan, img);
+    c->img_stage_form.clear(); c->img_run_stage_off.clear();
+    for (const QgtDevStage& st : img.stages) c->img_stage_form.push_back(st.form);
+    for (const QgtDevRun& r : img.runs) c->img_run_stage_off.push_back(r.stage_off);
+    int rc;
+    struct Up { DevBuf* buf; const void* src; size_t bytes; };
+    const Up ups[] = {
+        {&c->img_runs, img.runs.data(), img.runs.size() * sizeof(QgtDevRun)},
+        {&c->img_subs, img.subs.data(), img.subs.size() * sizeof(QgtDevSubPass)},
+        {&c->img_stages, img.stages.data(), img.stages.size() * sizeof(QgtDevStage)},
+        {&c->img_tdiags, img.tdiags.data(), img.tdiags.size() * sizeof(QgtDevThrDiag)},
+        {&c->img_costs, img.costs.data(), img.costs.size() * sizeof(QgtDevCost)},
+        {&c->img_pool, img.pool.data(), img.pool.size() * sizeof(double)},
+    };
+    cudaError_t e = cudaSuccess;
+    for (const Up& u : ups) {
+        if ((rc = u.buf->reserve(std::max<size_t>(16, u.bytes)))) return rc;
+        if (u.bytes && e == cudaSuccess) e = cudaMemcpyAsync(u.buf->ptr, u.src, u.bytes, cudaMemcpyHostToDevice, c->stream);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "plan upload");
+    return upload_cost_table(c, circ);
 }
 
 struct SweepBatch { int run; size_t item_off; int nitems; int out_of_place; };

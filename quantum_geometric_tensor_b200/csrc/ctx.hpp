@@ -100,6 +100,7 @@ namespace qgt {
 
 // executor pieces shared with dist.cu
 int upload_plan(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan& plan, PlanImage& img);
+int upload_cost_table(qgt_b200_ctx* c, const qgt_b200_circuit& circ);
 int apply_plan_inplace(qgt_b200_ctx* c, const CircuitPlan& plan, cplx* d, uint64_t D);
 int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan& plan, const Program& prog,
                 cplx* arena, uint64_t D, cplx* cmat);

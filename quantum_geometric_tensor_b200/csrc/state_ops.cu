@@ -172,6 +172,31 @@ __global__ void __launch_bounds__(256) so_sample_kernel(const cplx* src, uint64_
     }
 }
 
+// per-CTA maximum of |a_i|^2 (first index wins ties): partial[b] = (probability, index)
+__global__ void __launch_bounds__(256) so_argmax_kernel(const cplx* src, uint64_t D, double* pmax, unsigned long long* imax) {
+    double best = -1.0;
+    unsigned long long bi = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < D; i += stride) {
+        const cplx z = src[i];
+        const double p = z.x * z.x + z.y * z.y;
+        if (p > best) { best = p; bi = i; }
+    }
+    __shared__ double sp[256];
+    __shared__ unsigned long long si[256];
+    sp[threadIdx.x] = best; si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const double q = sp[threadIdx.x + o];
+            const unsigned long long qi = si[threadIdx.x + o];
+            if (q > sp[threadIdx.x] || (q == sp[threadIdx.x] && qi < si[threadIdx.x])) { sp[threadIdx.x] = q; si[threadIdx.x] = qi; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { pmax[blockIdx.x] = sp[0]; imax[blockIdx.x] = si[0]; }
+}
+
 static unsigned so_grid(const qgt_b200_ctx* c, uint64_t D) {
     const uint64_t want = (D + 255) / 256;
     const uint64_t cap = (uint64_t)c->num_sms * 8;
@@ -243,6 +268,49 @@ int qgt_b200_state_scale(qgt_b200_state* s, double re, double im) {
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "scale kernel");
+}
+
+int qgt_b200_state_argmax(const qgt_b200_state* s, uint64_t* index, double* probability) {
+    if (!s || !index) return fail(QGT_B200_ERR_INVALID_ARG, "state/index is NULL");
+    qgt_b200_ctx* c = s->ctx;
+    if (c->world > 1) return fail(QGT_B200_ERR_UNSUPPORTED, "argmax is single-GPU only");
+    cudaSetDevice(c->device);
+    const unsigned grid = so_grid(c, s->D);
+    int rc = c->scratch.reserve((size_t)grid * 16 + 64);
+    if (rc) return rc;
+    double* d_p = (double*)c->scratch.ptr;
+    unsigned long long* d_i = (unsigned long long*)(d_p + grid);
+    so_argmax_kernel<<<grid, 256, 0, c->stream>>>(s->d, s->D, d_p, d_i);
+    std::vector<double> hp(grid);
+    std::vector<unsigned long long> hi(grid);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hp.data(), d_p, grid * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hi.data(), d_i, grid * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "argmax kernel");
+    size_t b = 0;
+    for (size_t k = 1; k < grid; k++) if (hp[k] > hp[b] || (hp[k] == hp[b] && hi[k] < hi[b])) b = k;
+    *index = hi[b];
+    if (probability) *probability = hp[b];
+    return QGT_B200_OK;
+}
+
+int qgt_b200_state_cost_expectation(const qgt_b200_state* s, const qgt_b200_circuit* observable, double* out) {
+    if (!s || !observable || !out) return fail(QGT_B200_ERR_INVALID_ARG, "state/observable/out is NULL");
+    if (observable->num_qubits != s->n) return fail(QGT_B200_ERR_DIMENSION, "observable has a different qubit count");
+    qgt_b200_ctx* c = s->ctx;
+    cudaSetDevice(c->device);
+    int rc = upload_cost_table(c, *observable);
+    if (!rc) rc = c->scratch.reserve(256);
+    if (rc) return rc;
+    double h[2] = {0.0, 0.0};
+    cudaError_t e = launch_cost_dot(s->d, s->d, s->D, c->cost, (uint64_t)c->rank * s->D, (double*)c->scratch.ptr, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, c->scratch.ptr, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cost expectation");
+    if ((rc = dist_allreduce_host(c, h, 1))) return rc;
+    *out = h[0];
+    return QGT_B200_OK;
 }
 
 int qgt_b200_state_axpy(qgt_b200_state* dst, double re, double im, const qgt_b200_state* src) {
