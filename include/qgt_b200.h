@@ -222,6 +222,16 @@ int  qgt_b200_natural_gradient(qgt_b200_ctx* ctx, const double* metric, const do
 int  qgt_b200_expectation_gradient(qgt_b200_ctx* ctx, const qgt_b200_circuit* circuit, const double* theta,
                                    double* energy, double* grad);
 
+/* Natural-gradient descent on E(theta) (see qgt_b200_expectation_gradient for H): one step evaluates the metric
+ * (qgt_b200_qgt), the adjoint gradient and the regularised solve, theta_out = theta - learning_rate * (G + lambda I)^-1 grad;
+ * `energy` receives E(theta) BEFORE the step.  The loop form updates theta in place; history (optional, iterations + 1
+ * doubles) receives E before every step and E of the final parameters.  Replaces the host loop around
+ * compute_quantum_geometric_tensor + compute_regularized_natural_gradient (core/quantum_geometric_gradient.c:2887). */
+int  qgt_b200_natural_gradient_step(qgt_b200_ctx* ctx, const qgt_b200_circuit* circuit, const double* theta, double learning_rate,
+                                    const qgt_b200_natgrad_config* cfg, double* theta_out, double* energy, double* lambda_used);
+int  qgt_b200_natural_gradient_descent(qgt_b200_ctx* ctx, const qgt_b200_circuit* circuit, double* theta, int iterations,
+                                       double learning_rate, const qgt_b200_natgrad_config* cfg, double* history);
+
 /* ---- statistics of the last qgt/apply call (for bench.py and the roofline) ----------------- */
 typedef struct qgt_b200_stats {
     double ms_total;          /* device time of the whole call (CUDA events) */

@@ -140,7 +140,15 @@ typedef struct {
     void* device_ptr;      /* qgt_b200_state* once the state lives on the GPU */
     void* custom_state;
 } SimulatorState;
-struct SimulatorConfig;
+struct SimulatorConfig {                 /* hardware/quantum_backend_types.h:107-117 */
+    char* backend_name;
+    uint32_t max_shots, max_qubits;
+    double coupling_map[64][64];
+    double* noise_model;                 /* [gate error rate, measurement error rate, decoherence rate] or NULL */
+    bool optimize_mapping, use_gpu;
+    size_t memory_limit;
+    void* backend_specific_config;
+};
 typedef struct qgt_sim_circuit SimulatorCircuit;   /* opaque; the reference aliases struct quantum_circuit_t */
 
 SimulatorState* sim_init(uint32_t num_qubits, uint32_t num_classical_bits, const struct SimulatorConfig* config);
@@ -555,7 +563,10 @@ qgt_error_t compute_quantum_curvature_gpu(GPUContext* ctx, const ComplexFloat* s
 qgt_error_t qgt_b200_context_init(GPUContext* ctx);
 
 /* ---- this layer -------------------------------------------------------------------------------------------- */
-/* CUDA ordinal used by the wrappers (default: $QGT_B200_DEVICE or 0); call before the first compute call */
+/* Threading: every calling thread gets its own device context (stream, cached buffers) on first use, released when the
+ * thread ends, so the entry points are re-entrant on distinct objects like the reference's; one object must not be used
+ * from two threads at once.
+ * CUDA ordinal used by the wrappers (default: $QGT_B200_DEVICE or 0); call before the first compute call */
 int qgt_compat_set_device(int device);
 const char* qgt_compat_last_error(void);
 

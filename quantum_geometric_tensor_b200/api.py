@@ -372,6 +372,15 @@ class Context:
         _check(self.L.qgt_b200_expectation_gradient(self.h, C.byref(cc), _dp(th), C.byref(e), _dp(g)))
         return e.value, g
 
+    def natural_gradient_descent(self, circ: Circuit, theta: np.ndarray, iterations: int, learning_rate: float) -> Tuple[np.ndarray, np.ndarray]:
+        """`iterations` natural-gradient steps on the device; returns (theta, energy history of length iterations + 1)."""
+        cc = circ.to_c()
+        th = np.array(theta, dtype=np.float64, copy=True)
+        hist = np.zeros(iterations + 1)
+        self.L.qgt_b200_natural_gradient_descent.argtypes = [C.c_void_p, C.POINTER(CCircuit), _DP, C.c_int, C.c_double, C.c_void_p, _DP]
+        _check(self.L.qgt_b200_natural_gradient_descent(self.h, C.byref(cc), _dp(th), iterations, learning_rate, None, _dp(hist)))
+        return th, hist
+
     def measure_peaks(self) -> dict:
         """FP64 tensor-pipe peak (TFLOP/s) and D2D copy bandwidth (GB/s) measured on this device."""
         a, b = C.c_double(0), C.c_double(0)

@@ -132,3 +132,45 @@ extern "C" int qgt_b200_expectation_gradient(qgt_b200_ctx* c, const qgt_b200_cir
     c->stats.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wall0).count();
     return QGT_B200_OK;
 }
+
+// ---- natural-gradient optimiser: metric + adjoint gradient + regularised solve per step --------
+// Replaces the host loop around compute_quantum_geometric_tensor / compute_regularized_natural_gradient
+// (core/quantum_geometric_gradient.c:2887, consumed by hybrid/classical_optimization_engine.c): both device evaluations
+// per step are single calls, the P x P solve stays on the host as in the reference.
+extern "C" int qgt_b200_natural_gradient_step(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta, double learning_rate,
+                                               const qgt_b200_natgrad_config* cfg, double* theta_out, double* energy, double* lambda_used) {
+    if (!c || !circ || !theta_out) return fail(QGT_B200_ERR_INVALID_ARG, "ctx/circuit/theta_out is NULL");
+    const int P = circ->num_params;
+    if (P <= 0) return fail(QGT_B200_ERR_INVALID_ARG, "the circuit has no parameters");
+    if (!theta) return fail(QGT_B200_ERR_INVALID_ARG, "theta is NULL");
+    std::vector<double> metric((size_t)P * P), grad(P), dx(P);
+    int rc = qgt_b200_qgt(c, circ, theta, metric.data(), nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    double e = 0.0;
+    if ((rc = qgt_b200_expectation_gradient(c, circ, theta, &e, grad.data()))) return rc;
+    if ((rc = qgt_b200_natural_gradient(c, metric.data(), grad.data(), (size_t)P, cfg, dx.data(), lambda_used))) return rc;
+    for (int i = 0; i < P; i++) theta_out[i] = theta[i] - learning_rate * dx[i];
+    if (energy) *energy = e;
+    return QGT_B200_OK;
+}
+
+extern "C" int qgt_b200_natural_gradient_descent(qgt_b200_ctx* c, const qgt_b200_circuit* circ, double* theta, int iterations,
+                                                  double learning_rate, const qgt_b200_natgrad_config* cfg, double* history) {
+    if (!c || !circ || !theta) return fail(QGT_B200_ERR_INVALID_ARG, "ctx/circuit/theta is NULL");
+    if (iterations < 0) return fail(QGT_B200_ERR_INVALID_ARG, "iterations < 0");
+    const int P = circ->num_params;
+    std::vector<double> next((size_t)std::max(1, P));
+    int rc;
+    for (int it = 0; it < iterations; it++) {
+        double e = 0.0;
+        if ((rc = qgt_b200_natural_gradient_step(c, circ, theta, learning_rate, cfg, next.data(), &e, nullptr))) return rc;
+        if (history) history[it] = e;
+        std::copy(next.begin(), next.begin() + P, theta);
+    }
+    if (history) {
+        double e = 0.0;
+        if ((rc = qgt_b200_expectation_gradient(c, circ, theta, &e, nullptr))) return rc;
+        history[iterations] = e;
+    }
+    return QGT_B200_OK;
+}

@@ -452,20 +452,47 @@ natural_gradient_config_t get_default_natural_gradient_config(void) {
     return c;
 }
 
+/* The metric may be the real symmetric Fubini-Study metric (the intended input) or a complex Hermitian matrix such as the
+ * full Q = g + i Omega that geometric_compute_full_qgt produces (the reference inverts whatever complex matrix it is given,
+ * quantum_geometric_gradient.c:2902-2950).  Hermitian input is solved exactly through its real symmetric embedding
+ * [[Re, -Im], [Im, Re]]; a matrix that is not Hermitian (to 1e-5 of its largest entry, float data) is refused. */
 bool compute_regularized_natural_gradient(const ComplexFloat* gradient, const ComplexFloat* metric, ComplexFloat* natural_gradient,
                                           size_t dimension, const natural_gradient_config_t* config) {
     if (!gradient || !metric || !natural_gradient || !config || dimension == 0) return false;
     const size_t P = dimension;
-    double* G = (double*)malloc(P * P * sizeof(double));
+    double scale = 0.0, max_imag = 0.0, defect = 0.0;
+    for (size_t i = 0; i < P; i++)
+        for (size_t j = 0; j < P; j++) {
+            const ComplexFloat a = metric[i * P + j], b = metric[j * P + i];
+            scale = fmax(scale, fmax(fabs(a.real), fabs(a.imag)));
+            max_imag = fmax(max_imag, fabs(a.imag));
+            defect = fmax(defect, fmax(fabs((double)a.real - b.real), fabs((double)a.imag + b.imag)));
+        }
+    if (defect > 1e-5 * fmax(scale, 1e-30)) { qgt_compat_set_error("compute_regularized_natural_gradient: metric is not Hermitian", QGT_ERROR_INVALID_PARAMETER); return false; }
+    const bool complex_metric = max_imag > 1e-7 * fmax(scale, 1e-30);
+    const size_t N = complex_metric ? 2 * P : P;
+    double* G = (double*)malloc(N * N * sizeof(double));
     double* g = (double*)malloc(2 * P * sizeof(double));
     double* x = (double*)malloc(2 * P * sizeof(double));
     if (!G || !g || !x) { free(G); free(g); free(x); return false; }
-    for (size_t i = 0; i < P * P; i++) G[i] = metric[i].real;          /* the Fubini-Study metric is real symmetric */
     for (size_t i = 0; i < P; i++) { g[i] = gradient[i].real; g[P + i] = gradient[i].imag; }
     qgt_b200_natgrad_config cfg = {config->regularization_param, config->condition_threshold, config->use_adaptive_regularization,
                                    config->use_pseudoinverse_fallback, config->singular_value_cutoff};
-    int rc = qgt_b200_natural_gradient(NULL, G, g, P, &cfg, x, NULL);            /* real and imaginary parts: the solve is linear */
-    if (!rc) rc = qgt_b200_natural_gradient(NULL, G, g + P, P, &cfg, x + P, NULL);
+    int rc;
+    if (!complex_metric) {
+        for (size_t i = 0; i < P * P; i++) G[i] = metric[i].real;
+        rc = qgt_b200_natural_gradient(NULL, G, g, P, &cfg, x, NULL);                /* real and imaginary parts: the solve is linear */
+        if (!rc) rc = qgt_b200_natural_gradient(NULL, G, g + P, P, &cfg, x + P, NULL);
+    } else {
+        for (size_t i = 0; i < P; i++)
+            for (size_t j = 0; j < P; j++) {
+                const double re = 0.5 * ((double)metric[i * P + j].real + metric[j * P + i].real);
+                const double im = 0.5 * ((double)metric[i * P + j].imag - metric[j * P + i].imag);
+                G[i * N + j] = re;          G[i * N + P + j] = -im;
+                G[(P + i) * N + j] = im;    G[(P + i) * N + P + j] = re;
+            }
+        rc = qgt_b200_natural_gradient(NULL, G, g, N, &cfg, x, NULL);               /* (Re x, Im x) of the complex system */
+    }
     if (!rc) for (size_t i = 0; i < P; i++) { natural_gradient[i].real = (float)x[i]; natural_gradient[i].imag = (float)x[P + i]; }
     free(G); free(g); free(x);
     return rc == 0;

@@ -16,10 +16,17 @@
 
 #include "compat_common.h"
 
-static qgt_b200_ctx* g_ctx = NULL;
+/* One context per calling thread (its own stream and device buffers), created on first use and destroyed when the thread
+ * ends: the reference's entry points are re-entrant on distinct objects, and a context's cached buffers are not. */
 static int g_device = -1;
+static int g_any_ctx = 0;
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static pthread_key_t g_ctx_key;
+static pthread_once_t g_ctx_once = PTHREAD_ONCE_INIT;
 static __thread char g_err[512];
+
+static void ctx_destructor(void* p) { if (p) qgt_b200_destroy((qgt_b200_ctx*)p); }
+static void ctx_key_init(void) { pthread_key_create(&g_ctx_key, ctx_destructor); }
 
 void qgt_compat_set_error(const char* where, int status) {
     snprintf(g_err, sizeof g_err, "%s: %s (%s)", where, qgt_b200_error_string(status), qgt_b200_last_error());
@@ -30,22 +37,24 @@ const char* qgt_compat_last_error(void) { return g_err; }
 int qgt_compat_set_device(int device) {
     pthread_mutex_lock(&g_lock);
     int rc = 0;
-    if (g_ctx) rc = -17;            /* QGT_ERROR_ALREADY_INITIALIZED */
+    if (g_any_ctx) rc = -17;        /* QGT_ERROR_ALREADY_INITIALIZED */
     else g_device = device;
     pthread_mutex_unlock(&g_lock);
     return rc;
 }
 
 qgt_b200_ctx* qgt_compat_ctx(void) {
+    pthread_once(&g_ctx_once, ctx_key_init);
+    qgt_b200_ctx* c = (qgt_b200_ctx*)pthread_getspecific(g_ctx_key);
+    if (c) return c;
     pthread_mutex_lock(&g_lock);
-    if (!g_ctx) {
-        int dev = g_device;
-        if (dev < 0) { const char* e = getenv("QGT_B200_DEVICE"); dev = e ? atoi(e) : 0; }
-        int rc = qgt_b200_create(&g_ctx, dev);
-        if (rc) { g_ctx = NULL; qgt_compat_set_error("qgt_b200_create", rc); }
-    }
-    qgt_b200_ctx* c = g_ctx;
+    int dev = g_device;
+    if (dev < 0) { const char* e = getenv("QGT_B200_DEVICE"); dev = e ? atoi(e) : 0; }
+    int rc = qgt_b200_create(&c, dev);
+    if (rc) { c = NULL; qgt_compat_set_error("qgt_b200_create", rc); }
+    else g_any_ctx = 1;
     pthread_mutex_unlock(&g_lock);
+    if (c) pthread_setspecific(g_ctx_key, c);
     return c;
 }
 
@@ -156,7 +165,6 @@ struct qgt_sim_circuit {
 };
 
 SimulatorState* sim_init(uint32_t num_qubits, uint32_t num_classical_bits, const struct SimulatorConfig* config) {
-    (void)config;                                   /* noise models are outside the hot path */
     if (num_qubits == 0 || num_qubits > 32) return NULL;      /* MAX_QUBITS, quantum_simulator.h:16 */
     SimulatorState* s = (SimulatorState*)calloc(1, sizeof *s);
     if (!s) return NULL;
@@ -167,6 +175,12 @@ SimulatorState* sim_init(uint32_t num_qubits, uint32_t num_classical_bits, const
     if (num_classical_bits) s->classical_bits = (bool*)calloc(num_classical_bits, sizeof(bool));
     s->fidelity = 1.0;
     s->active_noise.type = NOISE_NONE;
+    if (config && config->noise_model) {            /* [gate error, measurement error, decoherence rate] (quantum_simulator.c:100-109) */
+        s->active_noise.gate_error_rate = config->noise_model[0];
+        s->active_noise.measurement_error_rate = config->noise_model[1];
+        s->active_noise.decoherence_rate = config->noise_model[2];
+        if (config->noise_model[0] > 0) s->active_noise.type = NOISE_DEPOLARIZING;
+    }
     return s;
 }
 
@@ -214,6 +228,8 @@ bool sim_add_controlled_gate(SimulatorCircuit* c, gate_type_t type, uint32_t tar
     return sim_add_gate(c, type, target, control, parameters);
 }
 
+static double compat_uniform(void);
+
 bool sim_execute_circuit(SimulatorState* s, const SimulatorCircuit* c) {
     if (!s || !c) return false;
     qgt_b200_ctx* ctx = qgt_compat_ctx();
@@ -221,7 +237,30 @@ bool sim_execute_circuit(SimulatorState* s, const SimulatorCircuit* c) {
     qgt_b200_circuit qc;
     memset(&qc, 0, sizeof qc);
     qc.num_qubits = (int32_t)s->num_qubits; qc.gates = c->gates; qc.num_gates = c->num_gates;
+    qgt_b200_gate* noisy = NULL;
+    if (s->active_noise.type != NOISE_NONE && s->active_noise.gate_error_rate > 0 && c->num_gates) {
+        /* depolarizing noise after every gate (quantum_simulator.c:290-311, 525-529): with probability gate_error_rate a
+           Pauli drawn from {X, Y, Z, I} hits the gate's target.  The draws happen here, in the reference's order (one
+           for the event, one for the Pauli), and the chosen Paulis join the gate list, so one noisy trajectory is still
+           a single fused device circuit. */
+        noisy = (qgt_b200_gate*)malloc(2 * c->num_gates * sizeof *noisy);
+        if (!noisy) return false;
+        size_t k = 0;
+        for (size_t i = 0; i < c->num_gates; i++) {
+            noisy[k++] = c->gates[i];
+            if (compat_uniform() < s->active_noise.gate_error_rate) {
+                const double pick = compat_uniform();
+                const int kind = pick < 0.25 ? QGT_B200_GATE_X : pick < 0.5 ? QGT_B200_GATE_Y : pick < 0.75 ? QGT_B200_GATE_Z : -1;
+                if (kind >= 0) {
+                    qgt_b200_gate e = {kind, c->gates[i].target, -1, -1, 0.0, 1.0};
+                    noisy[k++] = e;
+                }
+            }
+        }
+        qc.gates = noisy; qc.num_gates = k;
+    }
     int rc = qgt_b200_simulate_host(ctx, (double*)s->amplitudes, (int)s->num_qubits, &qc, NULL);
+    free(noisy);
     if (rc) { qgt_compat_set_error("sim_execute_circuit", rc); return false; }
     return true;
 }

@@ -225,7 +225,48 @@ static void test_natural_gradient(void) {
         for (size_t j = 0; j < P; j++) { double a = G[i * P + j].real + (i == j ? 1e-4 : 0.0); re += a * x[j].real; im += a * x[j].imag; }
         CHECK(fabs(re - g[i].real) < 1e-5 && fabs(im - g[i].imag) < 1e-5);
     }
+    /* a complex Hermitian "metric" (the full Q = g + i Omega): the complex system is solved, as the reference's general
+       inverse would; a non-Hermitian matrix is refused */
+    ComplexFloat H[36], y[6];
+    for (size_t i = 0; i < P; i++)
+        for (size_t j = 0; j < P; j++) { H[i * P + j] = G[i * P + j]; H[i * P + j].imag = i == j ? 0.0f : (i < j ? 0.01f : -0.01f) * (float)(i + j); }
+    CHECK(compute_regularized_natural_gradient(g, H, y, P, &cfg));
+    for (size_t i = 0; i < P; i++) {
+        double re = 0, im = 0;
+        for (size_t j = 0; j < P; j++) {
+            const double ar = H[i * P + j].real + (i == j ? 1e-4 : 0.0), ai = H[i * P + j].imag;
+            re += ar * y[j].real - ai * y[j].imag; im += ar * y[j].imag + ai * y[j].real;
+        }
+        CHECK(fabs(re - g[i].real) < 1e-5 && fabs(im - g[i].imag) < 1e-5);
+    }
+    H[1].real += 0.1f;                                   /* H[0][1] != conj(H[1][0]) */
+    CHECK(!compute_regularized_natural_gradient(g, H, y, P, &cfg));
     printf("  compute_regularized_natural_gradient: ok\n");
+}
+
+/* two threads drive independent circuits at the same time: each thread owns its own device context */
+#include <pthread.h>
+static void* thread_body(void* arg) {
+    const int id = (int)(size_t)arg;
+    for (int rep = 0; rep < 20; rep++) {
+        const size_t nq = 10 + (size_t)id;
+        double complex* st = malloc(((size_t)1 << nq) * sizeof *st);
+        init_simulator_state(st, (size_t)1 << nq);
+        QuantumGate gs[3] = { G(GATE_H, 0, 0, 0), G(GATE_CNOT, (uint32_t)nq - 1, 0, 0), G(GATE_RZ, (uint32_t)id, 0, 0.3 * (id + 1)) };
+        run(st, nq, gs, 3);
+        const size_t hi = ((size_t)1 << (nq - 1)) | 1;
+        if (fabs(cabs(st[0]) - S2) > 1e-12 || fabs(cabs(st[hi]) - S2) > 1e-12) { free(st); return (void*)1; }
+        free(st);
+    }
+    return NULL;
+}
+static void test_two_threads(void) {
+    pthread_t t[2];
+    void* r[2] = {NULL, NULL};
+    for (size_t i = 0; i < 2; i++) CHECK(pthread_create(&t[i], NULL, thread_body, (void*)i) == 0);
+    for (size_t i = 0; i < 2; i++) pthread_join(t[i], &r[i]);
+    CHECK(r[0] == NULL && r[1] == NULL);
+    printf("  two threads, two contexts: ok\n");
 }
 
 /* the device-memory seam, in the style of the reference's tests/test_quantum_geometric_gpu.c */
@@ -364,6 +405,7 @@ int main(int argc, char** argv) {
     test_diffgeo();
     test_gpu_memory_seam();
     test_sim_measurement_api();
+    test_two_threads();
     printf("all compat checks passed\n");
     return 0;
 }

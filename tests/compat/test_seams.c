@@ -14,6 +14,8 @@
 #include "quantum_geometric/core/quantum_gate_operations.h"
 #include "quantum_geometric/core/quantum_parameter_shift.h"
 #include "quantum_geometric/core/numerical_backend.h"
+#include "quantum_geometric/hardware/quantum_simulator.h"
+#include <complex.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -408,6 +410,63 @@ static void test_minimal_network(void) {
     printf("network API + parameter shifts: ok\n");
 }
 
+/* ---- 5. depolarizing-noise trajectories of sim_execute_circuit (quantum_simulator.c:290-311, 525-529) ------------------ */
+static unsigned long long lcg_state;
+static double lcg(void) { lcg_state = lcg_state * 1103515245ull + 12345ull; return (double)(lcg_state & 0x7fffffff) / (double)0x7fffffff; }
+
+static void test_noise_trajectory(void) {
+    const uint32_t n = 5;
+    const int ng = 40;
+    gate_type_t kinds[40]; uint32_t tg[40], ct[40]; double ang[40];
+    unsigned long long r = 777;
+    for (int i = 0; i < ng; i++) {
+        r = r * 6364136223846793005ull + 1442695040888963407ull;
+        const int k = (int)((r >> 33) % 5);
+        kinds[i] = k == 0 ? GATE_TYPE_H : k == 1 ? GATE_TYPE_RX : k == 2 ? GATE_TYPE_RZ : k == 3 ? GATE_TYPE_CNOT : GATE_TYPE_RY;
+        tg[i] = (uint32_t)((r >> 40) % n); ct[i] = (tg[i] + 1 + (uint32_t)((r >> 50) % (n - 1))) % n;
+        ang[i] = (double)((r >> 20) % 1000) / 200.0 - 2.5;
+    }
+    double model[3] = {0.6, 0.0, 0.0};
+    struct SimulatorConfig cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.noise_model = model;
+    SimulatorState* noisy = sim_init(n, 0, &cfg);
+    SimulatorState* clean = sim_init(n, 0, NULL);
+    CHECK(noisy && clean && noisy->active_noise.type == NOISE_DEPOLARIZING && noisy->active_noise.gate_error_rate == 0.6);
+    CHECK(clean->active_noise.type == NOISE_NONE);
+    SimulatorCircuit* c = sim_create_circuit(n, 0);
+    SimulatorCircuit* replay = sim_create_circuit(n, 0);
+    lcg_state = 4242;
+    int injected = 0;
+    for (int i = 0; i < ng; i++) {
+        CHECK(sim_add_gate(c, kinds[i], tg[i], ct[i], &ang[i]));
+        CHECK(sim_add_gate(replay, kinds[i], tg[i], ct[i], &ang[i]));
+        if (lcg() < 0.6) {                       /* the same two draws per event, in the same order */
+            const double pick = lcg();
+            if (pick < 0.75) { CHECK(sim_add_gate(replay, pick < 0.25 ? GATE_TYPE_X : pick < 0.5 ? GATE_TYPE_Y : GATE_TYPE_Z, tg[i], 0, NULL)); injected++; }
+        }
+    }
+    CHECK(injected > 5);
+    qgt_compat_seed(4242);
+    CHECK(sim_execute_circuit(noisy, c));
+    CHECK(sim_execute_circuit(clean, replay));
+    double nrm = 0, diff = 0;
+    for (size_t i = 0; i < ((size_t)1 << n); i++) {
+        nrm += creal(noisy->amplitudes[i] * conj(noisy->amplitudes[i]));
+        const double d = cabs(noisy->amplitudes[i] - clean->amplitudes[i]);
+        if (d > diff) diff = d;
+    }
+    CHECK(fabs(nrm - 1.0) < 1e-12 && diff < 1e-14);            /* Pauli errors keep the state normalised; trajectory = replay */
+    /* and the noise did something: the noiseless circuit ends elsewhere */
+    sim_reset_state(clean);
+    CHECK(sim_execute_circuit(clean, c));
+    diff = 0;
+    for (size_t i = 0; i < ((size_t)1 << n); i++) { const double d = cabs(noisy->amplitudes[i] - clean->amplitudes[i]); if (d > diff) diff = d; }
+    CHECK(diff > 1e-3);
+    sim_cleanup_circuit(c); sim_cleanup_circuit(replay); sim_cleanup(noisy); sim_cleanup(clean);
+    printf("depolarizing-noise trajectory: equals its replay\n");
+}
+
 int main(int argc, char** argv) {
     const int host_only = argc > 1 && strcmp(argv[1], "--host-only") == 0;
     test_gate_objects();
@@ -416,6 +475,7 @@ int main(int argc, char** argv) {
     test_backend_ops();
     test_gpu_seam();
     test_minimal_network();
+    test_noise_trajectory();
     printf("all seam checks passed\n");
     return 0;
 }

@@ -12,7 +12,7 @@ PKG = os.path.join(ROOT, "quantum_geometric_tensor_b200")
 def _build(tmp_path):
     exe = tmp_path / "test_compat"
     subprocess.run(["gcc", "-std=gnu11", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "compat", "test_compat.c"),
-                    "-o", str(exe), "-L" + PKG, "-lqgt_b200_compat", "-lqgt_b200", "-Wl,-rpath," + PKG, "-lm"], check=True)
+                    "-o", str(exe), "-L" + PKG, "-lqgt_b200_compat", "-lqgt_b200", "-Wl,-rpath," + PKG, "-lm", "-lpthread"], check=True)
     return str(exe)
 
 
