@@ -998,49 +998,52 @@ __global__ void __launch_bounds__(256, 3) qgt_fused_direct_kernel(FusedLaunch a)
             const bool fetch_b = use_b && rho_stage && s >= rho_from && !(dbg & QGT_FDBG_NO_BCOPY);
             const bool do_rho = rho_stage && s >= rho_from && (self || use_b) && !(dbg & QGT_FDBG_NO_RHO);
             cplx* img = rho_stage ? a.traj[(ls.info >> 8) & 0xff] + (size_t)(tau0 + ti) * TILE + frag_off : nullptr;
-            // phi's fragments of this stage: issued now, consumed after the groups have gone through the stage
-            cplx vb[4][2];
+            // phi's fragments of this stage, one half (two groups) at a time: the first half is requested now, the second
+            // while the first half's groups go through the stage, and each half is contracted right after its groups, so
+            // only two groups of results and two halves of phi are live (the four-group form spilled phi's fragments to
+            // local memory straight after the load, which made every warp wait for L2 where the prefetch was meant to hide it)
+            cplx vb[2][2][2];
             if (fetch_b) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) { vb[g][0] = qgt_ldg_nc(img + g * 64); vb[g][1] = qgt_ldg_nc(img + g * 64 + 1); }
+                for (int g2 = 0; g2 < 2; ++g2) { vb[0][g2][0] = qgt_ldg_nc(img + g2 * 64); vb[0][g2][1] = qgt_ldg_nc(img + g2 * 64 + 1); }
             }
             double t6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            cplx ra0[4], ra1[4];
             auto groups = [&](auto dr_tag) {
                 constexpr bool DR = decltype(dr_tag)::value;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    cplx va0[2], va1[2];
+                    cplx va0[2], va1[2], ra0[2], ra1[2];
 #pragma unroll
                     for (int g2 = 0; g2 < 2; ++g2) {
                         const uint32_t gx = (g2 ? gx1 : 0u) ^ (h ? gx2 : 0u);
                         va0[g2] = tileA[baseB ^ gx]; va1[g2] = tileA[baseB ^ gx ^ ls.sr2];
                     }
                     __syncwarp();                     // every lane has read the groups' slots before any is overwritten
+                    if (h == 0 && fetch_b) {          // behind the barrier: the compiler must not hoist these next to the first half
+#pragma unroll
+                        for (int g2 = 0; g2 < 2; ++g2) { vb[1][g2][0] = qgt_ldg_nc(img + (2 + g2) * 64); vb[1][g2][1] = qgt_ldg_nc(img + (2 + g2) * 64 + 1); }
+                    }
 #pragma unroll
                     for (int g2 = 0; g2 < 2; ++g2) {
-                        const int g = h * 2 + g2;
                         const uint32_t gx = (g2 ? gx1 : 0u) ^ (h ? gx2 : 0u);
-                        qgt_apply8t<DR>(fa, va0[g2], va1[g2], ra0[g], ra1[g]);
-                        tileA[baseC ^ gx] = ra0[g];
-                        tileA[baseC ^ gx ^ ls.st0] = ra1[g];
+                        qgt_apply8t<DR>(fa, va0[g2], va1[g2], ra0[g2], ra1[g2]);
+                        tileA[baseC ^ gx] = ra0[g2];
+                        tileA[baseC ^ gx ^ ls.st0] = ra1[g2];
+                    }
+                    if (self && rho_stage && !(dbg & QGT_FDBG_NO_GLOBAL)) {
+#pragma unroll
+                        for (int g2 = 0; g2 < 2; ++g2) { img[(h * 2 + g2) * 64] = ra0[g2]; img[(h * 2 + g2) * 64 + 1] = ra1[g2]; }
+                    }
+                    if (do_rho) {
+#pragma unroll
+                        for (int g2 = 0; g2 < 2; ++g2) {
+                            if (self) { qgt_rho3(t6, ra0[g2], ra0[g2]); qgt_rho3(t6, ra1[g2], ra1[g2]); }
+                            else { qgt_rho3(t6, vb[h][g2][0], ra0[g2]); qgt_rho3(t6, vb[h][g2][1], ra1[g2]); }
+                        }
                     }
                 }
             };
             if (dr) groups(std::true_type{}); else groups(std::false_type{});
-            if (self && rho_stage && !(dbg & QGT_FDBG_NO_GLOBAL)) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) { img[g * 64] = ra0[g]; img[g * 64 + 1] = ra1[g]; }
-            }
-            if (do_rho) {
-                if (self) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) { qgt_rho3(t6, ra0[g], ra0[g]); qgt_rho3(t6, ra1[g], ra1[g]); }
-                } else {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) { qgt_rho3(t6, vb[g][0], ra0[g]); qgt_rho3(t6, vb[g][1], ra1[g]); }
-                }
-            }
             if (do_rho) {
                 double* sc = scratch + (par * NW + warp) * 128 + lane * 4;
                 *reinterpret_cast<double2*>(sc) = make_double2(t6[0] + t6[2], t6[1] + t6[3]);
