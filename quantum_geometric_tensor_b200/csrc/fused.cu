@@ -665,6 +665,7 @@ __global__ void __launch_bounds__(512, 1) qgt_fused_pipe_kernel(FusedLaunch a) {
 // warps hide each other's barriers and shared-memory latencies, as the 4 x 8-warp plain sweep kernel does); all
 // per-stage constants come from small shared-memory tables built once per CTA.
 // ------------------------------------------------------------------------------------------------
+constexpr int QGT_DIRECT_MAX_SUBS = 48;       // sub-passes (= stages) of a run the direct kernel keeps variant masks for
 struct QgtLeanSub {          // 32 bytes per sub-pass (= per stage)
     uint32_t gx1, sr2, st0;  // slot XOR terms: thread bit 3 (second group), matrix bit 2, thread bit 0
     uint32_t mat_off;        // variant 0 of the stage matrix in the run's pool (complex elements)
@@ -897,6 +898,7 @@ __global__ void __launch_bounds__(256, 3) qgt_fused_direct_kernel(FusedLaunch a)
     extern __shared__ __align__(128) cplx qgt_dsm[];
     __shared__ QgtDevRun run;
     __shared__ int wblk[2 * NW];
+    __shared__ uint64_t svm[QGT_DIRECT_MAX_SUBS][2];     // the stages' variant masks: read per tile and stage, so not from global memory
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < (int)(sizeof(QgtDevRun) / 4); i += T)
         reinterpret_cast<uint32_t*>(&run)[i] = reinterpret_cast<const uint32_t*>(&a.runs[a.run_idx])[i];
@@ -923,6 +925,10 @@ __global__ void __launch_bounds__(256, 3) qgt_fused_direct_kernel(FusedLaunch a)
         for (int i = tid; i < run.mat_count; i += T) spool[i] = gpool[i];
         for (int i = tid; i < run.rho_blocks * 128; i += T) rho_acc[i] = 0.0;
         const QgtDevSubPass* gsubs = a.subs + run.sub_off;
+        for (int i = tid; i < nsub * 2; i += T) {
+            const QgtDevStage& st = gstages[gsubs[i >> 1].stage_begin];
+            svm[i >> 1][i & 1] = (i & 1) < st.nvar ? st.vmask[i & 1] : 0ull;
+        }
         for (int w = tid; w < nsub * 32; w += T) {
             const int sI = w >> 5, l = w & 31, q = l >> 2, kk = l & 3;
             const QgtDevSubPass& sp = gsubs[sI];
@@ -986,9 +992,8 @@ __global__ void __launch_bounds__(256, 3) qgt_fused_direct_kernel(FusedLaunch a)
             int var = (int)fw.y;
             const int nvar = (ls.info >> 4) & 3;
             if (nvar) {                               // tile part of the variant bits
-                const QgtDevStage& st = gstages[s];
-                if (tileg & st.vmask[0]) var |= 1;
-                if (nvar > 1 && (tileg & st.vmask[1])) var |= 2;
+                if (tileg & svm[s][0]) var |= 1;
+                if (tileg & svm[s][1]) var |= 2;
             }
             const bool ovr = (s == ovr_stage);
             const bool dr = ovr ? ovr_dr : (ls.info & 1);
@@ -1134,7 +1139,8 @@ cudaError_t launch_fused(const FusedLaunch& a, int K, int mat_count, int nsub, i
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (a.use_traj && a.pipeline == 3 && K == 11 && a.all_simple && fused_direct_smem_bytes(mat_count, nsub, rho_blocks) <= 110 * 1024) {
+    if (a.use_traj && a.pipeline == 3 && K == 11 && a.all_simple && nsub <= QGT_DIRECT_MAX_SUBS &&
+        fused_direct_smem_bytes(mat_count, nsub, rho_blocks) <= 110 * 1024) {
         const size_t dsmem = fused_direct_smem_bytes(mat_count, nsub, rho_blocks);
         static bool dattr = false;
         if (!dattr) {
