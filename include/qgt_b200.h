@@ -218,7 +218,8 @@ int  qgt_b200_natural_gradient(qgt_b200_ctx* ctx, const double* metric, const do
  * backward pass over two states, whatever the number of parameters (replaces the two circuit executions per parameter
  * of algorithms/qaoa.c:489-558; feeds the natural-gradient step).  H is the diagonal observable defined by the
  * circuit's edge list and vertex weights, H = sum_edges w (1 - Z_i Z_j)/2 + sum_q v_q Z_q (E_z of qaoa.c:258-289), for
- * any circuit, with or without COST gates.  Either output may be NULL.  Single GPU. */
+ * any circuit, with or without COST gates.  Either output may be NULL.  Collective on a sharded state (every rank makes
+ * the same call and receives the same energy and gradient). */
 int  qgt_b200_expectation_gradient(qgt_b200_ctx* ctx, const qgt_b200_circuit* circuit, const double* theta,
                                    double* energy, double* grad);
 

@@ -27,27 +27,41 @@ extern "C" int qgt_b200_expectation_gradient(qgt_b200_ctx* c, const qgt_b200_cir
     if (!circ) return fail(QGT_B200_ERR_INVALID_ARG, "circuit is NULL");
     if (circ->num_params < 0) return fail(QGT_B200_ERR_INVALID_ARG, "num_params < 0");
     if (circ->num_params > 0 && !theta) return fail(QGT_B200_ERR_INVALID_ARG, "theta is NULL");
-    if (c->world > 1) return fail(QGT_B200_ERR_UNSUPPORTED, "expectation gradient is single-GPU only");
     cudaSetDevice(c->device);
     const auto t_wall0 = std::chrono::steady_clock::now();
     const int n = circ->num_qubits, P = circ->num_params;
-    const uint64_t D = (uint64_t)1 << n;
+    // a state sharded over the ranks of the communicator: every rank holds 2^nloc amplitudes, runs the same programs and
+    // contributes partial transition matrices / dot products, summed with one allreduce each
+    const bool sharded = c->world > 1;
+    int gbits = 0;
+    while ((1 << gbits) < c->world) gbits++;
+    const int nloc = n - gbits;
+    if (sharded && nloc < 4) return fail(QGT_B200_ERR_INVALID_ARG, "state too small for this many ranks");
+    const uint64_t D = (uint64_t)1 << nloc;
+    const uint64_t goff = (uint64_t)c->rank << nloc;
     int rc;
     std::string err;
 
     // plans of U and of U^+ (same options: same tiles, same fusion rules)
     CircuitPlan fwd, inv;
-    if ((rc = build_plan(*circ, theta, c->opt, fwd, err))) return fail(rc, err);
+    std::vector<MappedSegment> fsegs, isegs;
     std::vector<qgt_b200_gate> inv_gates;
     invert_circuit(*circ, inv_gates);
     qgt_b200_circuit icirc = *circ;
     icirc.gates = inv_gates.data(); icirc.num_gates = inv_gates.size();
-    if ((rc = build_plan(icirc, theta, c->opt, inv, err))) return fail(rc, err);
+    if (sharded) {
+        // the forward plan restores the identity qubit layout (H and the inverse plan assume it); the inverse plan need not
+        if ((rc = build_plan_sharded(*circ, theta, c->opt, nloc, true, fwd, fsegs, err))) return fail(rc, err);
+        if ((rc = build_plan_sharded(icirc, theta, c->opt, nloc, false, inv, isegs, err))) return fail(rc, err);
+    } else {
+        if ((rc = build_plan(*circ, theta, c->opt, fwd, err))) return fail(rc, err);
+        if ((rc = build_plan(icirc, theta, c->opt, inv, err))) return fail(rc, err);
+    }
     const bool want_grad = grad != nullptr && P > 0;
     const bool fused = want_grad && c->fused_mode != 0 && plan_supports_fused(inv);
 
     size_t slots = workspace_slots(c, D, (size_t)256 << 20);
-    if (slots < 4) return fail(QGT_B200_ERR_NO_MEMORY, "workspace too small: the adjoint gradient needs 4 statevector-sized columns");
+    if (slots < 5) return fail(QGT_B200_ERR_NO_MEMORY, "workspace too small: the adjoint gradient needs 5 statevector-sized columns");
     int scratch = 0;
     if (want_grad && !fused) {
         int most = 1;
@@ -57,10 +71,11 @@ extern "C" int qgt_b200_expectation_gradient(qgt_b200_ctx* c, const qgt_b200_cir
             for (const ParamOcc& oc : run.occ) if (!seen[oc.param]) { seen[oc.param] = 1; cnt++; }
             most = std::max(most, cnt);
         }
-        scratch = (int)std::min<size_t>((size_t)most, slots - 3);
+        // sharded: every rank must build the same programs, whatever its free memory
+        scratch = sharded ? std::min(most, 1) : (int)std::min<size_t>((size_t)most, slots - 4);
     }
     const int num_slots = 3 + scratch;
-    if ((rc = c->arena.reserve((size_t)(num_slots + 1) * D * sizeof(cplx)))) return rc;
+    if ((rc = c->arena.reserve((size_t)(num_slots + 1) * D * sizeof(cplx)))) return rc;      // + the spare column of the exchanges
     const size_t cm = (size_t)(P + 1) * (P + 1);
     if ((rc = c->cmat.reserve(std::max<size_t>(16, cm * sizeof(cplx))))) return rc;
     if ((rc = c->scratch.reserve(256))) return rc;
@@ -72,18 +87,20 @@ extern "C" int qgt_b200_expectation_gradient(qgt_b200_ctx* c, const qgt_b200_cir
     PlanImage img;
     // forward: psi = U |init>
     if ((rc = upload_plan(c, *circ, fwd, img))) return rc;
-    cudaError_t e = launch_init_state(chi, D, circ->initial_state, std::pow(2.0, -0.5 * n), 0, c->stream);
+    if (sharded && (rc = upload_segment_costs(c, *circ, fsegs))) return rc;
+    cudaError_t e = launch_init_state(chi, D, circ->initial_state, std::pow(2.0, -0.5 * n), goff, c->stream);
     if (e != cudaSuccess) return cuda_fail(e, "init launch");
     if ((rc = apply_plan_inplace(c, fwd, chi, D))) return rc;
-    // Lambda = H psi, E = <psi|Lambda>
+    // Lambda = H psi, E = <psi|Lambda>   (identity layout: global index = rank bits | local index)
     c->timer.begin(c->stream, 2);
-    e = launch_cost_apply(lam, chi, D, c->cost, 0, c->stream);
+    e = launch_cost_apply(lam, chi, D, c->cost, goff, c->stream);
     double h[2] = {0.0, 0.0};
-    if (e == cudaSuccess) e = launch_cost_dot(chi, chi, D, c->cost, 0, (double*)c->scratch.ptr, c->stream);
+    if (e == cudaSuccess) e = launch_cost_dot(chi, chi, D, c->cost, goff, (double*)c->scratch.ptr, c->stream);
     c->timer.end(c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h, c->scratch.ptr, sizeof h, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return cuda_fail(e, "cost observable");
+    if ((rc = dist_allreduce_host(c, h, 1))) return rc;
     c->stats.other_launches += 2;
     if (energy) *energy = h[0];
 
@@ -91,20 +108,28 @@ extern "C" int qgt_b200_expectation_gradient(qgt_b200_ctx* c, const qgt_b200_cir
         std::fill(grad, grad + P, 0.0);
         PlanImage iimg;
         if ((rc = upload_plan(c, icirc, inv, iimg))) return rc;
+        if (sharded && (rc = upload_segment_costs(c, icirc, isegs))) return rc;
+        std::vector<double> row((size_t)P * 2);
         if (fused) {
             Program prog;
             if ((rc = build_gradient_fused_program(inv, prog))) return fail(rc, "gradient program");
             if ((rc = run_program(c, icirc, inv, prog, arena, D, (cplx*)c->cmat.ptr))) return rc;
-            std::vector<double> row((size_t)P * 2);
+            if ((rc = dist_allreduce_device(c, (double*)c->amat.ptr, row.size()))) return rc;       // row 0 of A
             e = cudaMemcpyAsync(row.data(), c->amat.ptr, row.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
             if (e != cudaSuccess) return cuda_fail(e, "gradient download");
             for (int mu = 0; mu < P; mu++) grad[mu] = -2.0 * row[2 * (size_t)mu];
         } else {
-            std::vector<double> row((size_t)P * 2);
             std::vector<Program> progs;
-            const cplx* d_row = (const cplx*)c->cmat.ptr + (size_t)P * (P + 1);       // C[P][nu], nu = 0..P-1
+            cplx* d_row = (cplx*)c->cmat.ptr + (size_t)P * (P + 1);       // C[P][nu], nu = 0..P-1
             for (int r = 0; r < (int)inv.runs.size(); r++) {
+                if (inv.runs[r].exchange_gbit >= 0) {
+                    // sharded state: both states go through the exchange in place (the per-run programs below assume every
+                    // slot stays where it is, so the exchange is not left to run_program's column rotation)
+                    if ((rc = dist_exchange(c, chi, D, inv.runs[r].exchange_mask))) return rc;
+                    if ((rc = dist_exchange(c, lam, D, inv.runs[r].exchange_mask))) return rc;
+                    continue;
+                }
                 if ((rc = build_gradient_run_programs(inv, r, scratch, progs))) return fail(rc, "gradient program");
                 for (const Program& g : progs) {
                     bool has_gram = false;
@@ -115,6 +140,7 @@ extern "C" int qgt_b200_expectation_gradient(qgt_b200_ctx* c, const qgt_b200_cir
                     }
                     if ((rc = run_program(c, icirc, inv, g, arena, D, (cplx*)c->cmat.ptr))) return rc;
                     if (!has_gram) continue;
+                    if ((rc = dist_allreduce_device(c, (double*)d_row, row.size()))) return rc;
                     e = cudaMemcpyAsync(row.data(), d_row, row.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
                     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
                     if (e != cudaSuccess) return cuda_fail(e, "gradient download");

@@ -120,6 +120,7 @@ int dist_apply_circuit(qgt_b200_state* s, const qgt_b200_circuit* circ, const do
 int dist_exchange(qgt_b200_ctx* c, cplx* col, uint64_t D, unsigned mask);   // grouped qubit exchange of one column, in place (via scratch)
 int dist_exchange_multi(qgt_b200_ctx* c, const cplx* src, cplx* dst, uint64_t D, unsigned mask);   // the same, out of place, no extra copy
 int dist_allreduce_device(qgt_b200_ctx* c, double* d_buf, size_t count);   // in place, stream ordered
+int upload_segment_costs(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const std::vector<MappedSegment>& segs);   // per-segment cost tables (remapped qubits)
 int dist_qgt(qgt_b200_ctx* c, const qgt_b200_circuit* circ, const double* theta,
              double* metric, double* berry, double* q_full, qgt_b200_state* psi_out);
 

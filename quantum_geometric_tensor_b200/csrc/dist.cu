@@ -152,7 +152,7 @@ int dist_exchange(qgt_b200_ctx* c, cplx* col, uint64_t D, unsigned mask) {
 }
 
 // cost tables with qubits renamed by each segment's logical -> physical map
-static int upload_segment_costs(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const std::vector<MappedSegment>& segs) {
+int upload_segment_costs(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const std::vector<MappedSegment>& segs) {
     c->seg_cost.clear();
     if (!circ.num_edges && !circ.vertex_weights) return QGT_B200_OK;
     const int n = circ.num_qubits;

@@ -1418,9 +1418,8 @@ int build_gradient_fused_program(const CircuitPlan& plan, Program& prog) {
     const int chi = 0, lam = 2;
     for (int r = 0; r < (int)plan.runs.size(); r++) {
         const Run& run = plan.runs[r];
-        if (run.exchange_gbit >= 0) return QGT_B200_ERR_UNSUPPORTED;
         Instr in; in.run = r;
-        if (run.rho_stages == 0) {                 // no parameter in this run: both states just advance
+        if (run.exchange_gbit >= 0 || run.rho_stages == 0) {   // an exchange of a sharded state, or no parameter in this run: both states just move
             in.kind = INSTR_SWEEP;
             in.cols.push_back(SweepCol(chi, chi, -1, false));
             in.cols.push_back(SweepCol(lam, lam, -1, false));
@@ -1443,8 +1442,15 @@ int build_gradient_fused_program(const CircuitPlan& plan, Program& prog) {
 int build_gradient_run_programs(const CircuitPlan& plan, int r, int scratch_slots, std::vector<Program>& progs) {
     progs.clear();
     const Run& run = plan.runs[r];
-    if (run.exchange_gbit >= 0 || scratch_slots < 1) return QGT_B200_ERR_UNSUPPORTED;
+    if (scratch_slots < 1) return QGT_B200_ERR_UNSUPPORTED;
     const int P = plan.P, chi = 0, lam = 2;
+    if (run.exchange_gbit >= 0) {                  // sharded state: both states go through the exchange
+        Program g; g.num_slots = 3 + scratch_slots;
+        Sched s(plan, g);
+        s.sweep(r, {SweepCol(chi, chi, -1, false), SweepCol(lam, lam, -1, false)});
+        progs.push_back(std::move(g));
+        return QGT_B200_OK;
+    }
     std::vector<int> params;
     {
         std::vector<char> seen(P, 0);

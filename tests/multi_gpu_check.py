@@ -101,6 +101,24 @@ def main():
                   f"({st['exchange_bytes'] / max(st['ms_exchange'], 1e-9) * 1e-6:.0f} GB/s), sweep {st['ms_sweep']:.1f} ms gram {st['ms_gram']:.1f} ms "
                   f"exchange {st['ms_exchange']:.1f} ms other {st['ms_other']:.1f} ms blocks {st['blocks']}", flush=True)
 
+    # 4. adjoint energy gradient on sharded states: fused pair path (ansatz, exchanges inside one program) and the per-run
+    #    path (QAOA cost layers, exchanges between programs), against the oracle's per-parameter derivative columns
+    def ring(c, seed=3):
+        rng = np.random.default_rng(seed)
+        n = c.num_qubits
+        c.edges = [(q, (q + 1) % n, float(rng.uniform(0.5, 1.5))) for q in range(n)]
+        c.vertex_weights = [float(v) for v in rng.uniform(-1, 1, n)]
+        return c
+    for circ, want_fused in ((ring(K.hea_layers(14, 2)), 1), (K.qaoa_maxcut(12, 2), 0), (ring(K.hea_layers(13, 1)), 1)):
+        th = K.default_angles(circ.num_params, 17)
+        e, g = ctx.expectation_gradient(circ, th)
+        st = ctx.stats()
+        eo, go = orc.expectation_gradient(circ, th)
+        check(f"gradient energy {circ.name}", abs(e - eo) / max(1.0, abs(eo)), 1e-10)
+        check(f"gradient {circ.name} (fused={st['fused']})", float(np.abs(g - go).max() / max(1.0, np.abs(go).max())), 1e-10)
+        if world <= 4 and st["fused"] != want_fused:
+            failures.append(f"gradient path of {circ.name}: fused={st['fused']}")
+
     ctx.close()
     fl = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(fl)
