@@ -355,7 +355,7 @@ long qgt_b200_plan_dump_fused(const qgt_b200_circuit* circuit, const double* the
  * fused != 0 -> the fused program (QGT_B200_ERR_UNSUPPORTED when the plan does not qualify), else the generic per-run
  * programs with `scratch_slots` scratch columns.  Slots: 0 = chi, 1 = its twin, 2 = Lambda, 3.. = scratch. */
 long qgt_b200_plan_dump_gradient(const qgt_b200_circuit* circuit, const double* theta, int fused, int scratch_slots, int tile_qubits,
-                                 int reg_qubits, char* buf, size_t buflen);
+                                 int reg_qubits, int world, char* buf, size_t buflen);     /* world > 1: the sharded plan with its exchanges */
 
 #ifdef __cplusplus
 }

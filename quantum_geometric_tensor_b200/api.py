@@ -104,7 +104,7 @@ def load() -> C.CDLL:
     L.qgt_b200_state_download_c64.argtypes = [vp, C.c_void_p]
     L.qgt_b200_plan_dump_fused.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t]
     L.qgt_b200_plan_dump_fused.restype = C.c_long
-    L.qgt_b200_plan_dump_gradient.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    L.qgt_b200_plan_dump_gradient.argtypes = [C.POINTER(CCircuit), _DP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
     L.qgt_b200_plan_dump_gradient.restype = C.c_long
     _lib = L
     return L
@@ -174,12 +174,12 @@ def plan_dump_fused(circ: Circuit, theta: Optional[np.ndarray], column_slots: in
 
 
 def plan_dump_gradient(circ: Circuit, theta: Optional[np.ndarray], fused: bool, scratch_slots: int = 2,
-                       tile_qubits: int = 0, reg_qubits: int = 0) -> dict:
+                       tile_qubits: int = 0, reg_qubits: int = 0, world: int = 1) -> dict:
     """Plan of the inverse circuit with the adjoint-gradient program (fused or generic).  Needs no GPU."""
     L = load()
     cc = circ.to_c()
     th = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
-    args = (C.byref(cc), _dp(th), 1 if fused else 0, scratch_slots, tile_qubits, reg_qubits)
+    args = (C.byref(cc), _dp(th), 1 if fused else 0, scratch_slots, tile_qubits, reg_qubits, world)
     n = L.qgt_b200_plan_dump_gradient(*args, None, 0)
     if n < 0:
         _check(int(n))

@@ -1423,8 +1423,11 @@ long qgt_b200_plan_dump_fused(const qgt_b200_circuit* circ, const double* theta,
 // Plan of the inverse circuit with the adjoint-gradient program (adjoint.cu): the fused one when the plan qualifies and
 // `fused` is non-zero, else the per-run programs of the generic path concatenated (scratch_slots scratch columns).
 long qgt_b200_plan_dump_gradient(const qgt_b200_circuit* circ, const double* theta, int fused, int scratch_slots, int tile_qubits,
-                                 int reg_qubits, char* buf, size_t buflen) {
+                                 int reg_qubits, int world, char* buf, size_t buflen) {
     if (!circ) return fail(QGT_B200_ERR_INVALID_ARG, "circuit is NULL");
+    if (world < 1 || (world & (world - 1))) return fail(QGT_B200_ERR_INVALID_ARG, "world must be a power of two");
+    int gbits = 0;
+    while ((1 << gbits) < world) gbits++;
     PlanOptions opt;
     if (tile_qubits) opt.tile_qubits = tile_qubits;
     if (reg_qubits) opt.reg_qubits = reg_qubits;
@@ -1434,8 +1437,10 @@ long qgt_b200_plan_dump_gradient(const qgt_b200_circuit* circ, const double* the
     qgt_b200_circuit icirc = *circ;
     icirc.gates = inv_gates.data(); icirc.num_gates = inv_gates.size();
     CircuitPlan plan;
+    std::vector<MappedSegment> segs;
     std::string err;
-    int rc = build_plan(icirc, theta ? theta : zeros.data(), opt, plan, err);
+    int rc = world > 1 ? build_plan_sharded(icirc, theta ? theta : zeros.data(), opt, circ->num_qubits - gbits, false, plan, segs, err)
+                       : build_plan(icirc, theta ? theta : zeros.data(), opt, plan, err);
     if (rc) return fail(rc, err);
     Program prog;
     if (fused) {
@@ -1449,7 +1454,7 @@ long qgt_b200_plan_dump_gradient(const qgt_b200_circuit* circ, const double* the
             for (const Program& g : progs) prog.instrs.insert(prog.instrs.end(), g.instrs.begin(), g.instrs.end());
         }
     }
-    const std::string js = dump_json(icirc, plan, &prog, nullptr);
+    const std::string js = dump_json(icirc, plan, &prog, world > 1 ? &segs : nullptr);
     if (buf && buflen > js.size()) std::memcpy(buf, js.c_str(), js.size() + 1);
     return (long)js.size();
 }

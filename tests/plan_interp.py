@@ -460,3 +460,66 @@ def run_gradient_program(plan: dict, circ, psi: np.ndarray):
     if prog["fused"] == 1:
         grad += -2.0 * A[0, :P].real
     return grad
+
+
+def run_gradient_program_sharded(plan: dict, circ, psi: np.ndarray, world: int):
+    """The same for a state sharded over `world` ranks (all simulated in this process): psi arrives in the identity qubit
+    layout (what the forward plan restores), Lambda = H psi is formed shard by shard, exchanges move both states, the
+    partial results of the ranks are summed (the allreduce)."""
+    prog = plan["program"]
+    P, nloc = plan["P"], plan["nloc"]
+    dim = 1 << nloc
+    tabs = segment_cost_tables(plan, circ)
+    energy = _cost_energy(circ, np.arange(psi.size, dtype=np.int64))
+    slots = [[np.zeros(dim, dtype=np.complex128) for _ in range(prog["slots"])] for _ in range(world)]
+    for r in range(world):
+        slots[r][0] = psi[r * dim:(r + 1) * dim].copy()
+        slots[r][2] = (energy * psi)[r * dim:(r + 1) * dim].copy()
+    A = np.zeros((max(P, 1), max(P, 1)), dtype=np.complex128)
+    Dm = np.zeros_like(A)
+    v = np.zeros(max(P, 1), dtype=np.complex128)
+    grad = np.zeros(P)
+
+    def apply_fn_for(run):
+        edges, vw = tabs[run["segment"]]
+        def f(r, st, op):
+            gidx = (np.uint64(r) << np.uint64(nloc)) | np.arange(st.size, dtype=np.uint64)
+            return _apply_op_shard(st, op, circ, gidx, nloc, edges, vw)
+        return f
+
+    for ins in prog["instrs"]:
+        k = ins["k"]
+        run = plan["runs"][ins["run"]] if "run" in ins else None
+        if k == "sweep":
+            if run["exchange"] >= 0:
+                for col in ins["cols"]:
+                    src, dst, ovr, acc = col[0], col[1], col[2], col[3]
+                    assert src == dst and ovr < 0 and not acc
+                    exchange_all_ranks([slots[r][dst] for r in range(world)], run["exchange_mask"])
+                continue
+            f = apply_fn_for(run)
+            ops, dops = run["ops"], run["dops"]
+            for r in range(world):
+                results = []
+                for col in ins["cols"]:
+                    src, dst, ovr, acc, extra = col[0], col[1], col[2], col[3], col[4]
+                    total = 0
+                    for o in ([ovr] + list(extra) if ovr >= 0 else [None]):
+                        st = slots[r][src]
+                        for i, op in enumerate(ops):
+                            st = f(r, st, dops[str(i)] if i == o else op)
+                        total = total + st
+                    results.append((dst, acc, total))
+                for dst, acc, total in results:
+                    slots[r][dst] = slots[r][dst] + total if acc else total
+        elif k == "fused":
+            _fused_launch(plan, circ, ins, slots, apply_fn_for(run), A, Dm, v)
+        elif k == "gram":
+            assert ins["aid"] == [P] and len(ins["a"]) == 1
+            for b, bid in zip(ins["b"], ins["bid"]):
+                grad[bid] += -2.0 * sum(np.vdot(slots[r][ins["a"][0]], slots[r][b]) for r in range(world)).real
+        else:
+            raise ValueError(k)
+    if prog["fused"] == 1:
+        grad += -2.0 * A[0, :P].real
+    return grad

@@ -68,3 +68,27 @@ def test_inverse_circuit_restores_the_initial_state(oracle):
         for op in run["ops"]:
             st = plan_interp.apply_op(st, op, c)
     assert abs(st[0] - 1.0) < 1e-12 and np.abs(st[1:]).max() < 1e-12
+
+
+SHARDED = [("hea11_w2_fused", lambda: ring(K.hea_layers(11, 2)), True, 2), ("hea12_w4_fused", lambda: ring(K.hea_layers(12, 1)), True, 4),
+           ("qaoa8_w2", lambda: K.qaoa_maxcut(8, 2), False, 2), ("mixed9_w4", lambda: mixed_circuit(9, 4), False, 4),
+           ("hea10_w2_generic", lambda: ring(K.hea_layers(10, 2)), False, 2)]
+
+
+@pytest.mark.parametrize("name,make,fused,world", SHARDED, ids=[c[0] for c in SHARDED])
+def test_sharded_gradient_program_matches_oracle(oracle, name, make, fused, world):
+    """The inverse circuit mapped onto `world` ranks (exchanges included) with the gradient program of adjoint.cu, all ranks
+    interpreted in one process, against the oracle's gradient of the unsharded circuit."""
+    c = make()
+    th = K.default_angles(c.num_params, 13)
+    try:
+        plan = api.plan_dump_gradient(c, th, fused, scratch_slots=1, world=world)
+    except api.QgtError as e:
+        if fused and e.status == -7:
+            pytest.skip("this circuit's sharded inverse plan does not qualify for the fused schedule")
+        raise
+    assert plan["nloc"] == c.num_qubits - {2: 1, 4: 2}[world]
+    psi = oracle.apply(c, th)
+    g = plan_interp.run_gradient_program_sharded(plan, c, psi, world)
+    eo, go = oracle.expectation_gradient(c, th)
+    assert np.abs(g - go).max() < 1e-11 * max(1.0, np.abs(go).max())
