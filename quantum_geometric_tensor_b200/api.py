@@ -381,6 +381,12 @@ class Context:
         _check(self.L.qgt_b200_natural_gradient_descent(self.h, C.byref(cc), _dp(th), iterations, learning_rate, None, _dp(hist)))
         return th, hist
 
+    def collective(self, kind: int, send: Optional[np.ndarray], recv: np.ndarray, count: int, dtype: int, op: int = 0, root: int = 0) -> None:
+        """qgt_b200_dist_collective on host arrays (kind: 0 broadcast, 1 allreduce, 2 scatter, 3 gather, 4 allgather, 5 reduce_scatter)."""
+        self.L.qgt_b200_dist_collective.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int]
+        sp = None if send is None else send.ctypes.data_as(C.c_void_p)
+        _check(self.L.qgt_b200_dist_collective(self.h, kind, sp, recv.ctypes.data_as(C.c_void_p), count, dtype, op, root))
+
     def measure_peaks(self) -> dict:
         """FP64 tensor-pipe peak (TFLOP/s) and D2D copy bandwidth (GB/s) measured on this device."""
         a, b = C.c_double(0), C.c_double(0)

@@ -119,6 +119,32 @@ def main():
         if world <= 4 and st["fused"] != want_fused:
             failures.append(f"gradient path of {circ.name}: fused={st['fused']}")
 
+    # 5. the generic collectives behind the ComputeBackendOps table (host buffers staged, NCCL underneath)
+    x = np.arange(6, dtype=np.float64) + 10.0 * rank
+    out = np.zeros(6)
+    ctx.collective(1, x, out, 6, 1, 0)                                       # allreduce sum, f64
+    check("collective allreduce", float(np.abs(out - (world * np.arange(6) + 10.0 * sum(range(world)))).max()), 1e-12)
+    z = (np.arange(4) + 1j * rank).astype(np.complex64)
+    zo = np.zeros(4, dtype=np.complex64)
+    ctx.collective(1, z, zo, 4, 2, 0)                                        # allreduce sum, complex64 (pairs of f32)
+    check("collective allreduce c64", float(np.abs(zo - (world * np.arange(4) + 1j * sum(range(world)))).max()), 1e-6)
+    b = np.full(5, float(rank + 1))
+    ctx.collective(0, None, b, 5, 1, 0, root=world - 1)                      # broadcast in place from the last rank
+    check("collective broadcast", float(np.abs(b - world).max()), 0.5)
+    ag = np.zeros(3 * world)
+    ctx.collective(4, np.full(3, float(rank)), ag, 3, 1)                     # allgather
+    check("collective allgather", float(np.abs(ag - np.repeat(np.arange(world), 3)).max()), 0.5)
+    rs = np.zeros(2)
+    ctx.collective(5, np.arange(2 * world, dtype=np.float64), rs, 2, 1, 0)   # reduce_scatter sum
+    check("collective reduce_scatter", float(np.abs(rs - world * (np.arange(2) + 2 * rank)).max()), 1e-12)
+    sc = np.zeros(2)
+    ctx.collective(2, np.arange(2 * world, dtype=np.float64) if rank == 0 else np.zeros(2 * world), sc, 2, 1, 0, root=0)   # scatter
+    check("collective scatter", float(np.abs(sc - (np.arange(2) + 2 * rank)).max()), 0.5)
+    ga = np.zeros(2 * world)
+    ctx.collective(3, np.full(2, float(rank)), ga, 2, 1, 0, root=0)          # gather
+    if rank == 0:
+        check("collective gather", float(np.abs(ga - np.repeat(np.arange(world), 2)).max()), 0.5)
+
     ctx.close()
     fl = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(fl)
