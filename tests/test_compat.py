@@ -50,7 +50,13 @@ def test_compat_library_exports_reference_symbols():
                 "shift_parameter", "compute_shifted_states", "compute_parameter_shift_gradient",
                 "compute_centered_difference_gradient", "compute_higher_order_gradient", "compute_gradient_with_error",
                 "sim_measure_qubit", "sim_measure_all", "sim_get_measurement_counts", "sim_get_expectation_value",
-                "sim_save_circuit", "sim_load_circuit"):
+                "sim_save_circuit", "sim_load_circuit",
+                "quantum_circuit_create", "quantum_circuit_destroy", "quantum_circuit_hadamard", "quantum_circuit_rotation",
+                "quantum_circuit_cnot", "quantum_circuit_execute", "quantum_circuit_measure_all", "quantum_circuit_depth",
+                "init_quantum_state", "quantum_state_cleanup",
+                "qaoa_create_graph", "qaoa_add_edge", "qaoa_init", "qaoa_apply_circuit", "qaoa_apply_layer", "qaoa_compute_expectation",
+                "qaoa_compute_gradient", "qaoa_optimize", "qaoa_sample", "qaoa_evaluate_solution", "qaoa_destroy",
+                "qgt_b200_qaoa_exact_gradient"):
         assert f" T {sym}\n" in out, sym
 
 
