@@ -528,6 +528,53 @@ int qg_gpu_destroy_stream(int stream_id);
 int qg_gpu_synchronize_stream(int stream_id);
 int qg_gpu_synchronize(void);
 
+/* ---- core/quantum_geometric_types.h:239-250,290-353, core/quantum_geometric_tensor.h:13-100: generic rank-N tensors ----------
+ * Small host algebra (csrc/compat/tensor_compat.c): the entry points the reference's tests/test_quantum_geometric_tensor.c
+ * and tests/test_quantum_geometric_tensor_init.c drive. */
+typedef enum { GEOMETRIC_TENSOR_SCALAR, GEOMETRIC_TENSOR_VECTOR, GEOMETRIC_TENSOR_COVECTOR, GEOMETRIC_TENSOR_BIVECTOR,
+               GEOMETRIC_TENSOR_TRIVECTOR, GEOMETRIC_TENSOR_UNITARY, GEOMETRIC_TENSOR_HERMITIAN, GEOMETRIC_TENSOR_SYMMETRIC,
+               GEOMETRIC_TENSOR_CUSTOM } geometric_tensor_type_t;
+typedef enum { QGT_MEM_STANDARD = 0, QGT_MEM_HUGE_PAGES, QGT_MEM_PINNED, QGT_MEM_UNIFIED } qgt_memory_type_t;
+typedef struct quantum_geometric_tensor_t {
+    geometric_tensor_type_t type;
+    size_t* dimensions;
+    size_t rank;
+    size_t dimension;
+    ComplexFloat* components;
+    size_t num_spins;
+    void* auxiliary_data;
+    bool is_symmetric, is_unitary, is_hermitian;
+    HardwareType hardware;
+    qgt_memory_type_t mem_type;
+    size_t total_elements, aligned_elements;
+} quantum_geometric_tensor_t;
+#define QGT_ERROR_NUMERICAL_INSTABILITY (-24)
+qgt_error_t geometric_tensor_create(quantum_geometric_tensor_t** tensor, geometric_tensor_type_t type, const size_t* dimensions, size_t rank);
+void geometric_tensor_destroy(quantum_geometric_tensor_t* tensor);
+qgt_error_t geometric_tensor_clone(quantum_geometric_tensor_t** dest, const quantum_geometric_tensor_t* src);
+qgt_error_t geometric_tensor_initialize(quantum_geometric_tensor_t* tensor, const ComplexFloat* data);
+qgt_error_t geometric_tensor_initialize_zero(quantum_geometric_tensor_t* tensor);
+qgt_error_t geometric_tensor_initialize_random(quantum_geometric_tensor_t* tensor, float min_val, float max_val);
+qgt_error_t geometric_tensor_initialize_identity(quantum_geometric_tensor_t* tensor);
+qgt_error_t geometric_tensor_add(quantum_geometric_tensor_t* result, const quantum_geometric_tensor_t* a, const quantum_geometric_tensor_t* b);
+qgt_error_t geometric_tensor_subtract(quantum_geometric_tensor_t* result, const quantum_geometric_tensor_t* a, const quantum_geometric_tensor_t* b);
+qgt_error_t geometric_tensor_multiply(quantum_geometric_tensor_t* result, const quantum_geometric_tensor_t* a, const quantum_geometric_tensor_t* b);
+qgt_error_t geometric_tensor_contract(quantum_geometric_tensor_t* result, const quantum_geometric_tensor_t* a, const quantum_geometric_tensor_t* b,
+                                      const size_t* indices_a, const size_t* indices_b, size_t num_indices);
+qgt_error_t geometric_tensor_outer_product(quantum_geometric_tensor_t* result, const quantum_geometric_tensor_t* a, const quantum_geometric_tensor_t* b);
+qgt_error_t geometric_tensor_inner_product(ComplexFloat* result, const quantum_geometric_tensor_t* a, const quantum_geometric_tensor_t* b);
+qgt_error_t geometric_tensor_transpose(quantum_geometric_tensor_t* result, const quantum_geometric_tensor_t* tensor, const size_t* permutation);
+qgt_error_t geometric_tensor_conjugate(quantum_geometric_tensor_t* result, const quantum_geometric_tensor_t* tensor);
+qgt_error_t geometric_tensor_scale(quantum_geometric_tensor_t* result, const quantum_geometric_tensor_t* tensor, ComplexFloat scalar);
+qgt_error_t geometric_tensor_adjoint(quantum_geometric_tensor_t* result, const quantum_geometric_tensor_t* tensor);
+qgt_error_t geometric_tensor_norm(float* norm, const quantum_geometric_tensor_t* tensor);
+qgt_error_t geometric_tensor_trace(ComplexFloat* trace, const quantum_geometric_tensor_t* tensor);
+bool geometric_tensor_is_hermitian(const quantum_geometric_tensor_t* tensor);
+bool geometric_tensor_is_unitary(const quantum_geometric_tensor_t* tensor);
+qgt_error_t geometric_tensor_validate(const quantum_geometric_tensor_t* tensor);
+qgt_error_t geometric_tensor_validate_dimensions(const quantum_geometric_tensor_t* tensor);
+qgt_error_t geometric_tensor_validate_compatibility(const quantum_geometric_tensor_t* a, const quantum_geometric_tensor_t* b);
+
 /* ---- hardware/quantum_geometric_tensor_gpu.h:8-81: the QGT-on-GPU seam --------------------------------------------------
  * Data convention (the reference defines none, see csrc/compat/gpu_seam_compat.c): `state` is rows x cols row-major with
  * row 0 = psi and rows 1..rows-1 = d_mu psi (P = rows - 1); the output buffer has the same size and carries, at its start,

@@ -56,7 +56,10 @@ def test_compat_library_exports_reference_symbols():
                 "init_quantum_state", "quantum_state_cleanup",
                 "qaoa_create_graph", "qaoa_add_edge", "qaoa_init", "qaoa_apply_circuit", "qaoa_apply_layer", "qaoa_compute_expectation",
                 "qaoa_compute_gradient", "qaoa_optimize", "qaoa_sample", "qaoa_evaluate_solution", "qaoa_destroy",
-                "qgt_b200_qaoa_exact_gradient"):
+                "qgt_b200_qaoa_exact_gradient",
+                "geometric_tensor_create", "geometric_tensor_destroy", "geometric_tensor_add", "geometric_tensor_multiply",
+                "geometric_tensor_contract", "geometric_tensor_transpose", "geometric_tensor_conjugate", "geometric_tensor_norm",
+                "geometric_tensor_validate", "geometric_tensor_initialize_random", "geometric_tensor_is_hermitian"):
         assert f" T {sym}\n" in out, sym
 
 
@@ -105,3 +108,16 @@ def test_reference_tests_compile_and_link_unmodified(tmp_path, name):
     subprocess.run(["gcc", "-std=gnu11", "-w", "-I" + os.path.join(ROOT, "include"), os.path.join(REF_TESTS, name + ".c"), "-o", str(exe),
                     "-L" + PKG, "-lqgt_b200_compat", "-lqgt_b200", "-Wl,-rpath," + PKG, "-lm"], check=True)
     assert exe.exists()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name", ["test_quantum_geometric_tensor", "test_quantum_geometric_tensor_init"])
+def test_reference_tensor_tests_pass_unmodified(tmp_path, name):
+    """The reference's own tests of the generic tensor objects (host algebra, no GPU involved) build against include/ and
+    pass against the compat library."""
+    exe = tmp_path / name
+    subprocess.run(["gcc", "-std=gnu11", "-w", "-I" + os.path.join(ROOT, "include"), os.path.join(REF_TESTS, name + ".c"), "-o", str(exe),
+                    "-L" + PKG, "-lqgt_b200_compat", "-lqgt_b200", "-Wl,-rpath," + PKG, "-lm"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "All tests passed!" in r.stdout
