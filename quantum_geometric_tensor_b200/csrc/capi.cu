@@ -776,7 +776,10 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                 for (const SubPass& sp : run.subs)
                     for (const Stage& stg : sp.stages) { mc += QGT_VARIANT_STRIDE(8) << stg.vqubits.size(); ns++; }
                 const bool pipe = fused_uses_pipe(run.K, in.traj ? 1 : 0, c->fused_pipeline, mc, (int)run.subs.size(), run.rho_blocks, ns);
-                fused_geometry(D >> run.K, (int)in.cols.size(), c->num_sms, pipe, &fr.tpc, &fr.tg);
+                int simple = 1;
+                for (const SubPass& sp : run.subs) if (sp.is_cost || sp.stages.size() != 1 || !sp.tdiags.empty()) simple = 0;
+                const bool direct = fused_uses_direct(run.K, in.traj ? 1 : 0, c->fused_pipeline, simple, mc, (int)run.subs.size(), run.rho_blocks);
+                fused_geometry(D >> run.K, (int)in.cols.size(), c->num_sms, direct ? 2 : pipe ? 1 : 0, in.traj, &fr.tpc, &fr.tg);
             }
             const size_t per_item = (size_t)run.rho_blocks * 128;
             rho_doubles_max = std::max(rho_doubles_max, in.cols.size() * per_item);

@@ -1101,18 +1101,36 @@ bool fused_uses_pipe(int K, int use_traj, int pipeline, int mat_count, int nsub,
     return use_traj && pipeline == 1 && K == 11 && fused_pipe_smem_bytes(mat_count, nsub, rho_blocks, nstages) <= 220 * 1024;
 }
 
-void fused_geometry(uint64_t ntiles, int nitems, int num_sms, bool pipe, int* tiles_per_cta, int* tile_groups) {
-    // the persistent kernel keeps one CTA per SM: fewer, longer CTAs (its prologue is paid per CTA)
-    // few items (the adjoint gradient's single pair item): every CTA leaves a partial transition-matrix buffer behind that
-    // the reduce kernel has to walk, so no more CTAs than two waves of resident ones
-    const uint64_t target = pipe ? (uint64_t)num_sms * 6 : nitems <= 2 ? (uint64_t)num_sms * 4 : (uint64_t)num_sms * 2 * 8;
-    const uint64_t work = ntiles * (uint64_t)(nitems > 0 ? nitems : 1);
-    uint64_t tpc = (work + target - 1) / target;
-    if (tpc < 8) {
-        // at least 8 tiles per CTA amortise its prologue - unless that leaves SMs idle (few items on a small state)
-        const uint64_t fill = (work + (uint64_t)num_sms * 2 - 1) / ((uint64_t)num_sms * 2);
-        tpc = fill < 8 ? (fill < 1 ? 1 : fill) : 8;
+bool fused_uses_direct(int K, int use_traj, int pipeline, int all_simple, int mat_count, int nsub, int rho_blocks) {
+    return use_traj && pipeline == 3 && K == 11 && all_simple && nsub <= QGT_DIRECT_MAX_SUBS &&
+           fused_direct_smem_bytes(mat_count, nsub, rho_blocks) <= 110 * 1024;
+}
+
+// kind: 0 = generic 8-warp kernel (2 CTAs per SM), 1 = persistent pipelined kernel (1 CTA per SM), 2 = direct kernel (3 CTAs per SM)
+void fused_geometry(uint64_t ntiles, int nitems, int num_sms, int kind, bool use_traj, int* tiles_per_cta, int* tile_groups) {
+    const uint64_t items = (uint64_t)(nitems > 0 ? nitems : 1);
+    const uint64_t work = ntiles * items;
+    uint64_t tpc;
+    if (kind == 2 && work >= (uint64_t)num_sms * 3 * 5 * 8) {
+        // all CTAs of a launch do the same amount of work, so they finish wave by wave: a whole number of waves of resident
+        // CTAs (3 per SM) leaves no SM idle in the last one (2368 CTAs on 444 slots ran 5.3 waves in the time of 6)
+        const uint64_t slots = (uint64_t)num_sms * 3 * 5;
+        uint64_t tg = slots / items;
+        if (tg < 1) tg = 1;
+        tpc = (ntiles + tg - 1) / tg;
+    } else {
+        // the persistent kernel keeps one CTA per SM: fewer, longer CTAs (its prologue is paid per CTA); the adjoint gradient's
+        // single pair item (no trajectory): every CTA leaves a partial transition-matrix buffer behind that the reduce kernel
+        // has to walk, so no more CTAs than two waves of resident ones
+        const uint64_t target = kind == 1 ? (uint64_t)num_sms * 6 : (nitems <= 2 && !use_traj) ? (uint64_t)num_sms * 4 : (uint64_t)num_sms * 2 * 8;
+        tpc = (work + target - 1) / target;
+        if (tpc < 8) {
+            // at least 8 tiles per CTA amortise its prologue - unless that leaves SMs idle (few items on a small state)
+            const uint64_t fill = (work + (uint64_t)num_sms * 2 - 1) / ((uint64_t)num_sms * 2);
+            tpc = fill < 8 ? (fill < 1 ? 1 : fill) : 8;
+        }
     }
+    if (tpc < 1) tpc = 1;
     if (tpc > ntiles) tpc = ntiles;
     *tiles_per_cta = (int)tpc;
     *tile_groups = (int)((ntiles + tpc - 1) / tpc);
@@ -1139,8 +1157,7 @@ cudaError_t launch_fused(const FusedLaunch& a, int K, int mat_count, int nsub, i
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (a.use_traj && a.pipeline == 3 && K == 11 && a.all_simple && nsub <= QGT_DIRECT_MAX_SUBS &&
-        fused_direct_smem_bytes(mat_count, nsub, rho_blocks) <= 110 * 1024) {
+    if (fused_uses_direct(K, a.use_traj, a.pipeline, a.all_simple, mat_count, nsub, rho_blocks)) {
         const size_t dsmem = fused_direct_smem_bytes(mat_count, nsub, rho_blocks);
         static bool dattr = false;
         if (!dattr) {
@@ -1190,9 +1207,26 @@ __global__ void qgt_rho_reduce_kernel(const double* partial, int groups, int nit
     }
 }
 
+// few outputs, many partials (the adjoint gradient's single pair item): one warp per output element, the lanes walk the
+// CTA partials with stride 32 and are combined in a fixed order, so the result is still reproducible
+__global__ void __launch_bounds__(256) qgt_rho_reduce_warp_kernel(const double* partial, int groups, size_t total, double* rho) {
+    const size_t i = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= total) return;
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int g = lane; g < groups; g += 32) s += partial[(size_t)g * total + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) rho[i] = s;
+}
+
 cudaError_t launch_rho_reduce(const double* partial, int groups, int nitems, int per_item, double* rho, cudaStream_t st) {
     const size_t total = (size_t)nitems * per_item;
     if (total == 0) return cudaSuccess;
+    if (total <= 16384 && groups >= 64) {
+        qgt_rho_reduce_warp_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(partial, groups, total, rho);
+        return cudaGetLastError();
+    }
     const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
     qgt_rho_reduce_kernel<<<grid, 256, 0, st>>>(partial, groups, nitems, per_item, rho);
     return cudaGetLastError();

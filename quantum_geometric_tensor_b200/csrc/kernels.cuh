@@ -74,7 +74,9 @@ struct GramShape { int MT, NT; int thin; };   // thin: few pairs, register accum
 cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int has_cost, int num_sms, cudaStream_t st);
 
 bool fused_uses_pipe(int K, int use_traj, int pipeline, int mat_count, int nsub, int rho_blocks, int nstages);
-void fused_geometry(uint64_t ntiles, int nitems, int num_sms, bool pipe, int* tiles_per_cta, int* tile_groups);
+bool fused_uses_direct(int K, int use_traj, int pipeline, int all_simple, int mat_count, int nsub, int rho_blocks);
+// kind: 0 generic kernel, 1 persistent pipelined kernel, 2 direct kernel
+void fused_geometry(uint64_t ntiles, int nitems, int num_sms, int kind, bool use_traj, int* tiles_per_cta, int* tile_groups);
 size_t fused_smem_bytes(int K, int mat_count, int nsub, int rho_blocks, int nstages);
 cudaError_t launch_fused(const FusedLaunch& a, int K, int mat_count, int nsub, int rho_blocks, int nstages, cudaStream_t st);
 cudaError_t launch_rho_reduce(const double* partial, int groups, int nitems, int per_item, double* rho, cudaStream_t st);
