@@ -121,3 +121,36 @@ def test_reference_tensor_tests_pass_unmodified(tmp_path, name):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "All tests passed!" in r.stdout
+
+
+def _declared(header):
+    import re
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"#define[^\n]*(\\\n[^\n]*)*", "", src)
+    names = set()
+    for stmt in src.split(";"):
+        s = stmt.strip()
+        if "{" in s or "}" in s or s.startswith("typedef"):
+            continue
+        m = re.match(r"^(?:[\w\s\*]+?)\b([a-z_][a-z0-9_]*)\s*\([^()]*(\([^()]*\)[^()]*)*\)\s*$", s, flags=re.S)
+        if m and "(*" not in s.split("(")[0]:
+            names.add(m.group(1))
+    return names
+
+
+def test_every_declared_compat_function_is_exported():
+    """Every function include/qgt_compat.h and include/qgt_compute_backend.h declare is defined by libqgt_b200_compat.so; the
+    only exceptions are the registry / engine functions, which the reference's supercomputer/compute_backend.c provides."""
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(PKG, "libqgt_b200_compat.so")], check=True,
+                         capture_output=True, text=True).stdout
+    defined = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    compat = _declared("qgt_compat.h")
+    assert len(compat) >= 160
+    assert sorted(n for n in compat if n not in defined) == []
+    backend = _declared("qgt_compute_backend.h")
+    registry = {"compute_register_backend", "compute_get_backend_count", "compute_get_backend_info", "compute_get_backend_by_type",
+                "compute_select_backend", "compute_backend_available", "compute_engine_init", "compute_engine_cleanup",
+                "compute_engine_get_backend_type", "compute_engine_get_ops", "compute_engine_get_backend"}
+    assert sorted(n for n in backend if n not in defined and n not in registry) == []
+    assert {"qgt_b200_compute_backend_ops", "qgt_b200_register_compute_backend"} <= backend & defined
