@@ -898,7 +898,8 @@ __global__ void __launch_bounds__(256, 3) qgt_fused_direct_kernel(FusedLaunch a)
     extern __shared__ __align__(128) cplx qgt_dsm[];
     __shared__ QgtDevRun run;
     __shared__ int wblk[2 * NW];
-    __shared__ uint64_t svm[QGT_DIRECT_MAX_SUBS][2];     // the stages' variant masks: read per tile and stage, so not from global memory
+    __shared__ uint64_t svm[QGT_DIRECT_MAX_SUBS][2];     // the stages' variant masks (not read from global memory per stage)
+    __shared__ int tvar[QGT_DIRECT_MAX_SUBS];            // per tile: the tile's part of every stage's variant index
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < (int)(sizeof(QgtDevRun) / 4); i += T)
         reinterpret_cast<uint32_t*>(&run)[i] = reinterpret_cast<const uint32_t*>(&a.runs[a.run_idx])[i];
@@ -981,6 +982,9 @@ __global__ void __launch_bounds__(256, 3) qgt_fused_direct_kernel(FusedLaunch a)
             }
         }
         cp_async_commit();
+        // the tile's variant bits of all stages, once per tile (after the last stage's barrier nobody reads the previous
+        // tile's entries any more); the stage loop then needs neither the tile's global index nor the 64-bit masks
+        if (tid < nsub) tvar[tid] = ((tileg & svm[tid][0]) ? 1 : 0) | ((tileg & svm[tid][1]) ? 2 : 0);
         cp_async_wait<0>();
         __syncthreads();
         for (int s = 0; s < nsub; ++s) {
@@ -989,12 +993,8 @@ __global__ void __launch_bounds__(256, 3) qgt_fused_direct_kernel(FusedLaunch a)
             const uint32_t lt = flane[s * 32 + lane];
             const uint32_t baseB = fw.x ^ (lt & 0xffffu), baseC = fw.x ^ (lt >> 16);
             const uint32_t gx1 = ls.gx1, gx2 = ls.vm0;
-            int var = (int)fw.y;
+            const int var = (int)fw.y | tvar[s];
             const int nvar = (ls.info >> 4) & 3;
-            if (nvar) {                               // tile part of the variant bits
-                if (tileg & svm[s][0]) var |= 1;
-                if (tileg & svm[s][1]) var |= 2;
-            }
             const bool ovr = (s == ovr_stage);
             const bool dr = ovr ? ovr_dr : (ls.info & 1);
             const StageFrag fa = ovr ? qgt_load_frag(ovr_mat + var * QGT_VARIANT_STRIDE(N), dr, lane)
