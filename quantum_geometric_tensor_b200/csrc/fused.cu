@@ -1113,11 +1113,17 @@ void fused_geometry(uint64_t ntiles, int nitems, int num_sms, int kind, bool use
     uint64_t tpc;
     if (kind == 2 && work >= (uint64_t)num_sms * 3 * 5 * 8) {
         // all CTAs of a launch do the same amount of work, so they finish wave by wave: a whole number of waves of resident
-        // CTAs (3 per SM) leaves no SM idle in the last one (2368 CTAs on 444 slots ran 5.3 waves in the time of 6)
-        const uint64_t slots = (uint64_t)num_sms * 3 * 5;
+        // CTAs (3 per SM) leaves no SM idle in the last one.  Many short waves beat few long ones (28 qubits, 29 columns:
+        // 5 waves 9.93 s, 16 waves 9.43 s, 64-128 waves 9.23 s, 512 waves 9.41 s per evaluation): concurrently running CTAs then
+        // work on a narrow band of tiles and share phi's trajectory images in L2.  At least 16 tiles per CTA pay for its
+        // prologue (stage matrices and lookup tables into shared memory).
+        static int waves = 0;
+        if (!waves) { const char* e = std::getenv("QGT_B200_DIRECT_WAVES"); waves = e ? std::atoi(e) : 64; if (waves < 1) waves = 64; }
+        const uint64_t slots = (uint64_t)num_sms * 3 * (uint64_t)waves;
         uint64_t tg = slots / items;
         if (tg < 1) tg = 1;
         tpc = (ntiles + tg - 1) / tg;
+        if (tpc < 16) tpc = 16;
     } else {
         // the persistent kernel keeps one CTA per SM: fewer, longer CTAs (its prologue is paid per CTA); the adjoint gradient's
         // single pair item (no trajectory): every CTA leaves a partial transition-matrix buffer behind that the reduce kernel
