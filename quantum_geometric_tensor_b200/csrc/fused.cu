@@ -1128,7 +1128,10 @@ void fused_geometry(uint64_t ntiles, int nitems, int num_sms, int kind, bool use
         // the persistent kernel keeps one CTA per SM: fewer, longer CTAs (its prologue is paid per CTA); the adjoint gradient's
         // single pair item (no trajectory): every CTA leaves a partial transition-matrix buffer behind that the reduce kernel
         // has to walk, so no more CTAs than two waves of resident ones
-        const uint64_t target = kind == 1 ? (uint64_t)num_sms * 6 : (nitems <= 2 && !use_traj) ? (uint64_t)num_sms * 4 : (uint64_t)num_sms * 2 * 8;
+        // generic kernel: 64 waves as well (30 qubits, 6 columns per launch: 8 waves 74.1 s, 32 waves 71.0 s, 128 waves 70.2 s)
+        static int gwaves = 0;
+        if (!gwaves) { const char* e = std::getenv("QGT_B200_GENERIC_WAVES"); gwaves = e ? std::atoi(e) : 64; if (gwaves < 1) gwaves = 64; }
+        const uint64_t target = kind == 1 ? (uint64_t)num_sms * 6 : (nitems <= 2 && !use_traj) ? (uint64_t)num_sms * 4 : (uint64_t)num_sms * 2 * (uint64_t)gwaves;
         tpc = (work + target - 1) / target;
         if (tpc < 8) {
             // at least 8 tiles per CTA amortise its prologue - unless that leaves SMs idle (few items on a small state)
