@@ -1057,21 +1057,33 @@ __global__ void __launch_bounds__(256, 3) qgt_fused_direct_kernel(FusedLaunch a)
             }
             __syncthreads();                          // tile coherent for the next stage, scratch complete
             if (do_rho) {
-                // every warp sums 16 of the 128 doubles over the 8 warps in fixed order (deterministic); a warp's partial
-                // belongs to the block its variant selected.  The scratch is double-buffered: no second barrier.
-                if (lane < 16 && !(dbg & QGT_FDBG_NO_REDUCE)) {
-                    const int e = warp * 16 + lane;
+                // every warp sums 16 of the 128 doubles over the 8 warps as a fixed tree (deterministic); a warp's partial
+                // belongs to the block its variant selected: the lower half-warp collects variant 0 (2), the upper one
+                // variant 1 (3), so one pass serves both blocks of a one-bit stage and a stage without variants needs no
+                // selection at all.  (The serial 8-term chain per block, run by 16 lanes, cost 9 % of the kernel: its
+                // additions queue behind the other warps' DMMAs on the FP64 pipe.)  The scratch is double-buffered: no
+                // second barrier.
+                if (!(dbg & QGT_FDBG_NO_REDUCE)) {
+                    const int e = warp * 16 + (lane & 15);
                     const double* sp = scratch + par * NW * 128 + e;
-                    double x[NW];
-                    int bl[NW];
+                    if (nvar == 0) {
+                        if (lane < 16) {
+                            double x[NW];
 #pragma unroll
-                    for (int w = 0; w < NW; ++w) { x[w] = sp[w * 128]; bl[w] = wblk[par * NW + w] - ls.rho_off; }
-                    const int nb = 1 << nvar;
-                    for (int v = 0; v < nb; ++v) {
-                        double acc = 0.0;
+                            for (int w = 0; w < NW; ++w) x[w] = sp[w * 128];
+                            rho_acc[ls.rho_off * 128 + e] += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+                        }
+                    } else {
+                        double x[NW];
+                        int bl[NW];
 #pragma unroll
-                        for (int w = 0; w < NW; ++w) acc += (bl[w] == v) ? x[w] : 0.0;
-                        rho_acc[(ls.rho_off + v) * 128 + e] += acc;
+                        for (int w = 0; w < NW; ++w) { x[w] = sp[w * 128]; bl[w] = wblk[par * NW + w] - ls.rho_off; }
+                        for (int v = lane >> 4; v < (1 << nvar); v += 2) {
+                            double y[NW];
+#pragma unroll
+                            for (int w = 0; w < NW; ++w) y[w] = (bl[w] == v) ? x[w] : 0.0;
+                            rho_acc[(ls.rho_off + v) * 128 + e] += ((y[0] + y[1]) + (y[2] + y[3])) + ((y[4] + y[5]) + (y[6] + y[7]));
+                        }
                     }
                 }
                 par ^= 1;
