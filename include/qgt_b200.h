@@ -300,9 +300,11 @@ int  qgt_b200_state_collapse(qgt_b200_state* s, int qubit, int outcome, double* 
  * The caller supplies the uniform random number (the library holds no RNG state). */
 int  qgt_b200_state_measure(qgt_b200_state* s, int qubit, double uniform, double readout_error, int* outcome, double* prob_one);
 /* sim_get_measurement_counts: shots[k] = first basis index whose cumulative probability exceeds uniforms[k]
- * (host array of `shots` numbers in [0, 1)); single GPU */
+ * (host array of `shots` numbers in [0, 1)).  Sharded state: collective - every rank passes the same uniforms and receives
+ * all `shots` global indices (a shot is walked on the rank whose share of the probability mass holds it) */
 int  qgt_b200_state_sample(const qgt_b200_state* s, const double* uniforms, size_t shots, uint64_t* indices);
-/* index of the most probable basis state (lowest index on ties) and its probability; single GPU */
+/* index of the most probable basis state (lowest index on ties) and its probability; collective on a sharded state
+ * (every rank receives the global winner) */
 int  qgt_b200_state_argmax(const qgt_b200_state* s, uint64_t* index, double* probability);
 /* <psi|H|psi> for the diagonal observable of `observable`'s edge list and vertex weights (its gates are ignored):
  * H = sum_edges w [z_i != z_j] + sum_q v_q (1 - 2 z_q), the E_z of algorithms/qaoa.c:258-289 (qaoa_compute_expectation :455) */

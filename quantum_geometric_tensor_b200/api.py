@@ -248,6 +248,11 @@ class State:
         _check(self.ctx.L.qgt_b200_state_sample(self.h, _dp(u), u.size, out.ctypes.data_as(C.POINTER(C.c_uint64))))
         return out
 
+    def argmax(self):
+        i, p = C.c_uint64(0), C.c_double(0)
+        _check(self.ctx.L.qgt_b200_state_argmax(self.h, C.byref(i), C.byref(p)))
+        return int(i.value), p.value
+
     def upload_c64(self, amps: np.ndarray) -> "State":
         a = np.ascontiguousarray(amps, dtype=np.complex64)
         _check(self.ctx.L.qgt_b200_state_upload_c64(self.h, a.ctypes.data))

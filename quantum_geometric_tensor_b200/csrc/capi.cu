@@ -904,6 +904,7 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             a.nitems = nitems;
             a.phi = arena + (size_t)res[i].a * D;
             a.ntiles = D >> run.K;
+            a.tile_off = 0;
             a.tiles_per_cta = fr.tpc; a.tile_groups = fr.tg;
             a.gprefix = (uint64_t)c->rank << plan.nloc;
             a.rho_partial = (double*)c->partial.ptr;

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256, 2) qgt_fused_kernel(FusedLaunch a) {
     if (TRAJ && nrs > 0 && tid == 0 && tau0 < tau1) issue_b(tau0, rs_first);
     int par = 0;                                     // scratch buffer the next transition matrix goes to
     for (uint64_t tau = tau0; tau < tau1; ++tau) {
-        const uint64_t tilebase = qgt_tile_base(run, tau);
+        const uint64_t tilebase = qgt_tile_base(run, a.tile_off + tau);
         const uint64_t tileg = tilebase | a.gprefix;
         if (!(dbg & QGT_FDBG_NO_GLOBAL)) {
             const cplx* srcA = reinterpret_cast<const cplx*>(it.src);
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(512, 1) qgt_fused_pipe_kernel(FusedLaunch a) {
     if (tid == 0 && !(dbg & QGT_FDBG_NO_BCOPY)) { if (total_images > 0) issue_b(0); if (total_images > 1) issue_b(1); }
     int jc = 0;                                       // next image to consume (uniform over the CTA)
     auto load_tile = [&](uint64_t tau, cplx* buf) {
-        const uint64_t tb = qgt_tile_base(run, tau);
+        const uint64_t tb = qgt_tile_base(run, a.tile_off + tau);
         const cplx* srcA = reinterpret_cast<const cplx*>(it.src);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(512, 1) qgt_fused_pipe_kernel(FusedLaunch a) {
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const uint64_t tilebase = qgt_tile_base(run, tau);
+        const uint64_t tilebase = qgt_tile_base(run, a.tile_off + tau);
         const uint64_t tileg = tilebase | a.gprefix;
         for (int s = 0; s < run.nsub; ++s) {
             const QgtDevSubPass& sp = subs[s];
@@ -779,7 +779,7 @@ __global__ void __launch_bounds__(512, 2) qgt_fused_lean_kernel(FusedLaunch a) {
     const cplx* srcA = reinterpret_cast<const cplx*>(it.src);
     cplx* dstA = reinterpret_cast<cplx*>(it.dst);
     for (int ti = 0; ti < ntl; ++ti) {
-        const uint64_t tilebase = qgt_tile_base(run, (uint64_t)(tau0 + ti));
+        const uint64_t tilebase = qgt_tile_base(run, a.tile_off + (uint64_t)(tau0 + ti));
         const uint64_t tileg = tilebase | a.gprefix;
         if (!(dbg & QGT_FDBG_NO_GLOBAL)) {
 #pragma unroll
@@ -972,7 +972,7 @@ __global__ void __launch_bounds__(256, 3) qgt_fused_direct_kernel(FusedLaunch a)
     const int frag_off = (warp * 4 * 32 + lane) * 2;                   // + g * 64 + j
     int par = 0;
     for (int ti = 0; ti < ntl; ++ti) {
-        const uint64_t tilebase = qgt_tile_base(run, (uint64_t)(tau0 + ti));
+        const uint64_t tilebase = qgt_tile_base(run, a.tile_off + (uint64_t)(tau0 + ti));
         const uint64_t tileg = tilebase | a.gprefix;
         if (!(dbg & QGT_FDBG_NO_GLOBAL)) {
 #pragma unroll

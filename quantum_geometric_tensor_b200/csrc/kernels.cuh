@@ -40,7 +40,8 @@ struct FusedLaunch {
     const QgtSweepItem* items;
     int nitems;
     const cplx* phi;             // the marching state at the start of the run (second tile of every non-self item)
-    uint64_t ntiles;
+    uint64_t ntiles;             // tiles of this launch: tile_off .. tile_off + ntiles - 1 of the state
+    uint64_t tile_off;           // (a launch may cover one range of the tiles only: ranged trajectory mode, see capi.cu)
     int tiles_per_cta, tile_groups;
     uint64_t gprefix;
     double* rho_partial;         // [tile_groups][nitems][rho_blocks * 128]
@@ -50,7 +51,7 @@ struct FusedLaunch {
     int pipeline;                // trajectory mode, K = 11: 1 = the persistent 16-warp kernel with double-buffered tiles,
                                  // 2 = the lean 2 x 16-warp kernel (runs whose sub-passes are all one stage, no thread diagonal)
     int all_simple;              // every sub-pass of the run is exactly one dense stage without thread diagonals
-    cplx* traj[QGT_MAX_TRAJ];    // trajectory columns: [ntiles][2^K] images of the swizzled tile
+    cplx* traj[QGT_MAX_TRAJ];    // trajectory images: [ntiles][2^K] images of the swizzled tile, indexed from the launch's first tile
 };
 
 struct GramLaunch {

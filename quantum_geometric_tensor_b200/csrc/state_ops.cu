@@ -273,7 +273,6 @@ int qgt_b200_state_scale(qgt_b200_state* s, double re, double im) {
 int qgt_b200_state_argmax(const qgt_b200_state* s, uint64_t* index, double* probability) {
     if (!s || !index) return fail(QGT_B200_ERR_INVALID_ARG, "state/index is NULL");
     qgt_b200_ctx* c = s->ctx;
-    if (c->world > 1) return fail(QGT_B200_ERR_UNSUPPORTED, "argmax is single-GPU only");
     cudaSetDevice(c->device);
     const unsigned grid = so_grid(c, s->D);
     int rc = c->scratch.reserve((size_t)grid * 16 + 64);
@@ -290,8 +289,22 @@ int qgt_b200_state_argmax(const qgt_b200_state* s, uint64_t* index, double* prob
     if (e != cudaSuccess) return cuda_fail(e, "argmax kernel");
     size_t b = 0;
     for (size_t k = 1; k < grid; k++) if (hp[k] > hp[b] || (hp[k] == hp[b] && hi[k] < hi[b])) b = k;
-    *index = hi[b];
-    if (probability) *probability = hp[b];
+    double best_p = hp[b];
+    uint64_t best_i = ((uint64_t)c->rank * s->D) | hi[b];
+    if (c->world > 1) {
+        // sharded state: every rank contributes (probability, global index) in its own slot of a summed table, so all ranks
+        // see all candidates and pick the same one (indices below 2^53 are exact as doubles)
+        std::vector<double> tab((size_t)c->world * 2, 0.0);
+        tab[(size_t)c->rank * 2] = best_p;
+        tab[(size_t)c->rank * 2 + 1] = (double)best_i;
+        if ((rc = dist_allreduce_host(c, tab.data(), c->world * 2))) return rc;
+        int br = 0;
+        for (int r = 1; r < c->world; r++) if (tab[(size_t)r * 2] > tab[(size_t)br * 2]) br = r;     // ties: the lower rank = the lower index
+        best_p = tab[(size_t)br * 2];
+        best_i = (uint64_t)tab[(size_t)br * 2 + 1];
+    }
+    *index = best_i;
+    if (probability) *probability = best_p;
     return QGT_B200_OK;
 }
 
@@ -366,7 +379,6 @@ int qgt_b200_state_measure(qgt_b200_state* s, int qubit, double uniform, double 
 int qgt_b200_state_sample(const qgt_b200_state* s, const double* uniforms, size_t shots, uint64_t* indices) {
     if (!s || !uniforms || !indices) return fail(QGT_B200_ERR_INVALID_ARG, "state/uniforms/indices is NULL");
     qgt_b200_ctx* c = s->ctx;
-    if (c->world > 1) return fail(QGT_B200_ERR_UNSUPPORTED, "sampling is single-GPU only");
     if (shots == 0) return QGT_B200_OK;
     cudaSetDevice(c->device);
     const uint64_t D = s->D;
@@ -384,26 +396,58 @@ int qgt_b200_state_sample(const qgt_b200_state* s, const double* uniforms, size_
     // inverse CDF over the chunk masses on the host (2^(n-14) entries), the walk inside a chunk on the device
     std::vector<double> cum(nch + 1, 0.0);
     for (size_t i = 0; i < nch; i++) cum[i + 1] = cum[i] + mass[i];
-    std::vector<uint32_t> chunk(shots);
-    std::vector<double> resid(shots);
+    // sharded state (collective call, the same uniforms on every rank): the ranks' masses are laid end to end in rank order
+    // = global index order; a shot belongs to the rank whose interval holds it and is walked there with the interval's start
+    // taken off; every rank computes the same interval ends from the same summed table, so exactly one rank claims a shot
+    double base = 0.0, top = cum[nch];
+    if (c->world > 1) {
+        std::vector<double> rm((size_t)c->world, 0.0);
+        rm[(size_t)c->rank] = cum[nch];
+        if ((rc = dist_allreduce_host(c, rm.data(), c->world))) return rc;
+        for (int r = 0; r < c->rank; r++) base += rm[(size_t)r];
+        top = base + rm[(size_t)c->rank];
+    }
+    std::vector<size_t> own;
+    std::vector<uint32_t> chunk;
+    std::vector<double> resid;
     for (size_t k = 0; k < shots; k++) {
-        const double r = uniforms[k];
+        const double u = uniforms[k];
+        if (c->world > 1 && !((c->rank == 0 || u >= base) && (c->rank == c->world - 1 || u < top))) continue;
+        const double r = u - base;
         size_t ci = (size_t)(std::upper_bound(cum.begin() + 1, cum.end(), r) - (cum.begin() + 1));
         if (ci >= nch) ci = nch - 1;
-        chunk[k] = (uint32_t)ci;
-        resid[k] = r - cum[ci];
+        own.push_back(k);
+        chunk.push_back((uint32_t)ci);
+        resid.push_back(r - cum[ci]);
     }
-    double* d_resid = d_mass + nch;
-    uint64_t* d_out = (uint64_t*)(d_resid + shots);
-    uint32_t* d_chunk = (uint32_t*)(d_out + shots);
-    e = cudaMemcpyAsync(d_resid, resid.data(), shots * sizeof(double), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_chunk, chunk.data(), shots * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
-    if (e != cudaSuccess) return cuda_fail(e, "sample staging");
-    so_sample_kernel<<<(unsigned)shots, 256, 0, c->stream>>>(s->d, D, d_chunk, d_resid, d_out);
-    e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(indices, d_out, shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    return e == cudaSuccess ? QGT_B200_OK : cuda_fail(e, "sample kernel");
+    const size_t nown = own.size();
+    std::vector<uint64_t> local(nown);
+    if (nown > 0) {
+        double* d_resid = d_mass + nch;
+        uint64_t* d_out = (uint64_t*)(d_resid + shots);
+        uint32_t* d_chunk = (uint32_t*)(d_out + shots);
+        e = cudaMemcpyAsync(d_resid, resid.data(), nown * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_chunk, chunk.data(), nown * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "sample staging");
+        so_sample_kernel<<<(unsigned)nown, 256, 0, c->stream>>>(s->d, D, d_chunk, d_resid, d_out);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(local.data(), d_out, nown * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "sample kernel");
+    }
+    if (c->world == 1) {
+        for (size_t j = 0; j < nown; j++) indices[own[j]] = local[j];
+        return QGT_B200_OK;
+    }
+    // every rank receives every shot: owned entries as global indices (exact as doubles below 2^53), zeros elsewhere, summed
+    std::vector<double> all(shots, 0.0);
+    for (size_t j = 0; j < nown; j++) all[own[j]] = (double)(((uint64_t)c->rank * D) | local[j]);
+    for (size_t off = 0; off < shots; off += (size_t)1 << 20) {
+        const size_t cnt = std::min(shots - off, (size_t)1 << 20);
+        if ((rc = dist_allreduce_host(c, all.data() + off, (int)cnt))) return rc;
+    }
+    for (size_t k = 0; k < shots; k++) indices[k] = (uint64_t)all[k];
+    return QGT_B200_OK;
 }
 
 static bool so_is_device(const void* p) {

@@ -145,6 +145,29 @@ def main():
     if rank == 0:
         check("collective gather", float(np.abs(ga - np.repeat(np.arange(world), 2)).max()), 0.5)
 
+    # 6. sampling and argmax on a sharded state: every rank uploads its slice of one seeded vector and must receive the
+    #    inverse-CDF indices / the global winner of the whole vector
+    for n in (16, 19):
+        rng = np.random.default_rng(100 + n)
+        full = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+        full[(5 << (n - 3)) + 77] *= 40.0                                   # a clear maximum, in a high shard
+        full /= np.linalg.norm(full)
+        L = (1 << n) // world
+        s = ctx.state(n).upload(full[rank * L:(rank + 1) * L])
+        u = np.concatenate([rng.uniform(0, 1, 300), [0.0, 1e-12, 0.5, 1 - 1e-12]])
+        got = s.sample(u).astype(np.int64)
+        cdf = np.cumsum(np.abs(full) ** 2)
+        ref = np.searchsorted(cdf, u, side="right")
+        gap = np.minimum(np.abs(cdf[np.minimum(ref, cdf.size - 1)] - u), np.abs(u - np.where(ref > 0, cdf[np.maximum(ref, 1) - 1], 0)))
+        far = gap > 1e-10
+        bad = int(np.count_nonzero(got[far] != np.minimum(ref[far], cdf.size - 1)))
+        lo = np.where(got > 0, cdf[np.maximum(got, 1) - 1], 0.0)
+        bad += int(np.count_nonzero(~((lo - 1e-11 <= u) & (u < cdf[got] + 1e-11))))
+        check(f"sharded sampling n={n}", float(bad), 0.5)
+        idx, p = s.argmax()
+        check(f"sharded argmax n={n}", float(abs(idx - int(np.argmax(np.abs(full) ** 2))) + abs(p - np.max(np.abs(full) ** 2))), 1e-12)
+        s.close()
+
     ctx.close()
     fl = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(fl)
