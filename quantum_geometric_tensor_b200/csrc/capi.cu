@@ -779,7 +779,8 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                 int simple = 1;
                 for (const SubPass& sp : run.subs) if (sp.is_cost || sp.stages.size() != 1 || !sp.tdiags.empty()) simple = 0;
                 const bool direct = fused_uses_direct(run.K, in.traj ? 1 : 0, c->fused_pipeline, simple, mc, (int)run.subs.size(), run.rho_blocks);
-                fused_geometry(D >> run.K, (int)in.cols.size(), c->num_sms, direct ? 2 : pipe ? 1 : 0, in.traj, &fr.tpc, &fr.tg);
+                const int nranges = in.traj && prog.traj_ranges > 1 ? prog.traj_ranges : 1;
+                fused_geometry((D >> run.K) / (uint64_t)nranges, (int)in.cols.size(), c->num_sms, direct ? 2 : pipe ? 1 : 0, in.traj, &fr.tpc, &fr.tg);
             }
             const size_t per_item = (size_t)run.rho_blocks * 128;
             rho_doubles_max = std::max(rho_doubles_max, in.cols.size() * per_item);
@@ -854,6 +855,85 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
 
     c->psi_phys_slot = prog.psi_slot < (int)phys.size() ? phys[prog.psi_slot] : prog.psi_slot;
     // ---- execute ----------------------------------------------------------------------------------
+    // one fused launch: instruction `i`, tile range `rg` of `nrg` (nrg > 1: ranged trajectory mode, Program::traj_ranges)
+    auto fused_launch = [&](size_t i, int rg, int nrg) -> int {
+            const Instr& in = prog.instrs[i];
+            const Run& run = plan.runs[in.run];
+            const FusedRec& fr = frec[i];
+            const double Dr = (double)D / nrg;
+            const int nitems = (int)in.cols.size();
+            const size_t per_item = (size_t)run.rho_blocks * 128;
+            FusedLaunch a;
+            a.runs = (const QgtDevRun*)c->img_runs.ptr;
+            a.subs = (const QgtDevSubPass*)c->img_subs.ptr;
+            a.stages = (const QgtDevStage*)c->img_stages.ptr;
+            a.tdiags = (const QgtDevThrDiag*)c->img_tdiags.ptr;
+            a.pool = (const cplx*)c->img_pool.ptr;
+            a.run_idx = in.run;
+            a.items = (const QgtSweepItem*)c->items.ptr + item_off[i];
+            a.nitems = nitems;
+            a.phi = arena + (size_t)res[i].a * D;
+            a.ntiles = (D >> run.K) / (uint64_t)nrg;
+            a.tile_off = (uint64_t)rg * a.ntiles;
+            a.tiles_per_cta = fr.tpc; a.tile_groups = fr.tg;
+            a.gprefix = (uint64_t)c->rank << plan.nloc;
+            a.rho_partial = (double*)c->partial.ptr;
+            a.use_traj = in.traj ? 1 : 0;
+            a.debug = c->fused_debug;
+            a.pipeline = c->fused_pipeline;
+            a.all_simple = 1;
+            for (const SubPass& sp : run.subs) if (sp.is_cost || sp.stages.size() != 1 || !sp.tdiags.empty()) a.all_simple = 0;
+            for (int t = 0; t < QGT_MAX_TRAJ; t++)
+                a.traj[t] = nrg > 1 ? arena + (size_t)res[i].traj[0] * D + (size_t)t * (D / (uint64_t)nrg)
+                                    : res[i].traj[t] >= 0 ? arena + (size_t)res[i].traj[t] * D : nullptr;
+            int mat_count = 0, nstage_rho = 0, nstages = 0;
+            double flops_ab = 0.0;                  // per amplitude: one tile through every stage
+            for (const SubPass& sp : run.subs)
+                for (const Stage& stg : sp.stages) {
+                    mat_count += QGT_VARIANT_STRIDE(8) << stg.vqubits.size();
+                    // DMMA flops per amplitude of one stage application: 8 complex MACs as 4 real products (64), or the
+                    // diagonal-real form's 2 real products (32)
+                    flops_ab += c->img_stage_form[(size_t)c->img_run_stage_off[in.run] + nstages] == QGT_FORM_DIAG_REAL ? 32.0 : 64.0;
+                    nstages++;
+                    if (stg.rho_off >= 0) nstage_rho++;
+                }
+            char label[160];
+            if (c->timer.trace)
+                snprintf(label, sizeof label, "fused run=%d items=%d subs=%d rho_stages=%d rho_blocks=%d tiles=%llu chunks=%d", in.run, nitems,
+                         (int)run.subs.size(), nstage_rho, run.rho_blocks, (unsigned long long)a.ntiles, fr.tg);
+            c->timer.begin(c->stream, 0, label);
+            e = launch_fused(a, run.K, mat_count, (int)run.subs.size(), run.rho_blocks, nstages, c->stream);
+            c->timer.end(c->stream);
+            if (e != cudaSuccess) return cuda_fail(e, "fused launch");
+            c->stats.sweep_launches++; c->stats.fused_launches++;
+            if (rg == 0) c->stats.sweep_column_passes += nitems;
+            for (const SweepCol& sc : in.cols) {
+                c->stats.sweep_bytes += (sc.accumulate ? 48.0 : 32.0) * Dr;
+                int sidx = 0, nrho = 0;
+                for (const SubPass& sp : run.subs)
+                    for (const Stage& stg : sp.stages) { if (stg.rho_off >= 0 && sidx >= sc.rho_from) nrho++; sidx++; }
+                const bool use_b = !in.traj && !sc.self && sc.rho_from <= run.last_rho_stage;
+                c->stats.tensor_flops += Dr * (flops_ab * (use_b ? 2.0 : 1.0) + 48.0 * nrho);      // rho: 3M complex products
+                if (in.traj) c->stats.sweep_bytes += 16.0 * Dr * nrho;     // phi's tile images: written by the self item, fetched (L2) by the others
+            }
+            if (per_item > 0) {
+                c->timer.begin(c->stream, 1, "rho reduce + contract");
+                e = launch_rho_reduce((const double*)c->partial.ptr, fr.tg, nitems, (int)per_item, (double*)c->rho.ptr, c->stream);
+                if (e == cudaSuccess && fr.self_item >= 0) {
+                    double* self_dst = (double*)c->rho_self.ptr + fh.self_off[in.run];
+                    const double* self_src = (const double*)c->rho.ptr + (size_t)fr.self_item * per_item;
+                    if (rg == 0) e = cudaMemcpyAsync(self_dst, self_src, per_item * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+                    else e = launch_add_doubles(self_dst, self_src, per_item, c->stream);       // the ranges' shares add up
+                }
+                if (e == cudaSuccess)
+                    e = launch_rho_contract((const double*)c->rho.ptr, (int)per_item, (const double*)c->fx_pool.ptr, d_groups + fr.group_off, fr.ngroups,
+                                            d_entries, (cplx*)c->amat.ptr, c->stream);
+                c->timer.end(c->stream);
+                if (e != cudaSuccess) return cuda_fail(e, "rho reduce/contract launch");
+                c->stats.other_launches += 2;
+            }
+            return QGT_B200_OK;
+    };
     const double plus_amp = std::pow(2.0, -0.5 * plan.n);
     for (size_t i = 0; i < prog.instrs.size(); i++) {
         const Instr& in = prog.instrs[i];
@@ -889,75 +969,17 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                 c->stats.sweep_bytes += (sc.accumulate ? 48.0 : 32.0) * (double)D;
             break; }
         case INSTR_FUSED: {
-            const Run& run = plan.runs[in.run];
-            const FusedRec& fr = frec[i];
-            const int nitems = (int)in.cols.size();
-            const size_t per_item = (size_t)run.rho_blocks * 128;
-            FusedLaunch a;
-            a.runs = (const QgtDevRun*)c->img_runs.ptr;
-            a.subs = (const QgtDevSubPass*)c->img_subs.ptr;
-            a.stages = (const QgtDevStage*)c->img_stages.ptr;
-            a.tdiags = (const QgtDevThrDiag*)c->img_tdiags.ptr;
-            a.pool = (const cplx*)c->img_pool.ptr;
-            a.run_idx = in.run;
-            a.items = (const QgtSweepItem*)c->items.ptr + item_off[i];
-            a.nitems = nitems;
-            a.phi = arena + (size_t)res[i].a * D;
-            a.ntiles = D >> run.K;
-            a.tile_off = 0;
-            a.tiles_per_cta = fr.tpc; a.tile_groups = fr.tg;
-            a.gprefix = (uint64_t)c->rank << plan.nloc;
-            a.rho_partial = (double*)c->partial.ptr;
-            a.use_traj = in.traj ? 1 : 0;
-            a.debug = c->fused_debug;
-            a.pipeline = c->fused_pipeline;
-            a.all_simple = 1;
-            for (const SubPass& sp : run.subs) if (sp.is_cost || sp.stages.size() != 1 || !sp.tdiags.empty()) a.all_simple = 0;
-            for (int t = 0; t < QGT_MAX_TRAJ; t++)
-                a.traj[t] = res[i].traj[t] >= 0 ? arena + (size_t)res[i].traj[t] * D : nullptr;
-            int mat_count = 0, nstage_rho = 0, nstages = 0;
-            double flops_ab = 0.0;                  // per amplitude: one tile through every stage
-            for (const SubPass& sp : run.subs)
-                for (const Stage& stg : sp.stages) {
-                    mat_count += QGT_VARIANT_STRIDE(8) << stg.vqubits.size();
-                    // DMMA flops per amplitude of one stage application: 8 complex MACs as 4 real products (64), or the
-                    // diagonal-real form's 2 real products (32)
-                    flops_ab += c->img_stage_form[(size_t)c->img_run_stage_off[in.run] + nstages] == QGT_FORM_DIAG_REAL ? 32.0 : 64.0;
-                    nstages++;
-                    if (stg.rho_off >= 0) nstage_rho++;
-                }
-            char label[160];
-            if (c->timer.trace)
-                snprintf(label, sizeof label, "fused run=%d items=%d subs=%d rho_stages=%d rho_blocks=%d tiles=%llu chunks=%d", in.run, nitems,
-                         (int)run.subs.size(), nstage_rho, run.rho_blocks, (unsigned long long)a.ntiles, fr.tg);
-            c->timer.begin(c->stream, 0, label);
-            e = launch_fused(a, run.K, mat_count, (int)run.subs.size(), run.rho_blocks, nstages, c->stream);
-            c->timer.end(c->stream);
-            if (e != cudaSuccess) return cuda_fail(e, "fused launch");
-            c->stats.sweep_launches++; c->stats.fused_launches++;
-            c->stats.sweep_column_passes += nitems;
-            for (const SweepCol& sc : in.cols) {
-                c->stats.sweep_bytes += (sc.accumulate ? 48.0 : 32.0) * (double)D;
-                int sidx = 0, nrho = 0;
-                for (const SubPass& sp : run.subs)
-                    for (const Stage& stg : sp.stages) { if (stg.rho_off >= 0 && sidx >= sc.rho_from) nrho++; sidx++; }
-                const bool use_b = !in.traj && !sc.self && sc.rho_from <= run.last_rho_stage;
-                c->stats.tensor_flops += (double)D * (flops_ab * (use_b ? 2.0 : 1.0) + 48.0 * nrho);      // rho: 3M complex products
-                if (in.traj) c->stats.sweep_bytes += 16.0 * (double)D * nrho;     // phi's tile images: written by the self item, fetched (L2) by the others
-            }
-            if (per_item > 0) {
-                c->timer.begin(c->stream, 1, "rho reduce + contract");
-                e = launch_rho_reduce((const double*)c->partial.ptr, fr.tg, nitems, (int)per_item, (double*)c->rho.ptr, c->stream);
-                if (e == cudaSuccess && fr.self_item >= 0)
-                    e = cudaMemcpyAsync((double*)c->rho_self.ptr + fh.self_off[in.run], (const double*)c->rho.ptr + (size_t)fr.self_item * per_item,
-                                        per_item * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
-                if (e == cudaSuccess)
-                    e = launch_rho_contract((const double*)c->rho.ptr, (int)per_item, (const double*)c->fx_pool.ptr, d_groups + fr.group_off, fr.ngroups,
-                                            d_entries, (cplx*)c->amat.ptr, c->stream);
-                c->timer.end(c->stream);
-                if (e != cudaSuccess) return cuda_fail(e, "rho reduce/contract launch");
-                c->stats.other_launches += 2;
-            }
+            // ranged trajectory mode: the launches of one run (phi's, the columns', the accumulating items') form a group that
+            // is walked range by range, so that phi's images of a range are consumed before the next range overwrites them
+            const int nrg = in.traj && prog.traj_ranges > 1 ? prog.traj_ranges : 1;
+            size_t last = i;
+            if (nrg > 1)
+                while (last + 1 < prog.instrs.size() && prog.instrs[last + 1].kind == INSTR_FUSED && prog.instrs[last + 1].run == in.run &&
+                       prog.instrs[last + 1].traj) last++;
+            for (int rg = 0; rg < nrg; rg++)
+                for (size_t k = i; k <= last; k++)
+                    if ((rc = fused_launch(k, rg, nrg))) return rc;
+            i = last;
             break; }
         case INSTR_GRAM: {
             const GramRec& g = grec[i];

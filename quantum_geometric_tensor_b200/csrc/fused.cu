@@ -1241,6 +1241,17 @@ __global__ void __launch_bounds__(256) qgt_rho_reduce_warp_kernel(const double* 
     if (lane == 0) rho[i] = s;
 }
 
+__global__ void qgt_add_doubles_kernel(double* dst, const double* src, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
+cudaError_t launch_add_doubles(double* dst, const double* src, size_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    qgt_add_doubles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, src, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rho_reduce(const double* partial, int groups, int nitems, int per_item, double* rho, cudaStream_t st) {
     const size_t total = (size_t)nitems * per_item;
     if (total == 0) return cudaSuccess;

@@ -81,6 +81,7 @@ void fused_geometry(uint64_t ntiles, int nitems, int num_sms, int kind, bool use
 size_t fused_smem_bytes(int K, int mat_count, int nsub, int rho_blocks, int nstages);
 cudaError_t launch_fused(const FusedLaunch& a, int K, int mat_count, int nsub, int rho_blocks, int nstages, cudaStream_t st);
 cudaError_t launch_rho_reduce(const double* partial, int groups, int nitems, int per_item, double* rho, cudaStream_t st);
+cudaError_t launch_add_doubles(double* dst, const double* src, size_t n, cudaStream_t st);      // dst[i] += src[i]
 cudaError_t launch_rho_contract(const double* rho, int per_item, const double* xpool, const QgtContractGroup* groups, int ngroups,
                                 const QgtContractEntry* entries, cplx* A, cudaStream_t st);
 

@@ -1292,12 +1292,27 @@ int build_fused_program(const CircuitPlan& plan, size_t total_slots, bool want_p
     int Tm = 0;
     for (const Run& run : plan.runs) Tm = std::max(Tm, run.rho_stages);
     bool traj = traj_mode != 0 && Tm >= 1 && Tm <= QGT_MAX_TRAJ;
+    int ranges = 1;
     if (traj) {
         const bool fits_all = (size_t)Pa + 2 + Tm <= total_slots;
-        const long b_traj = (long)total_slots - 3 - Tm;
-        if (!fits_all && b_traj < (traj_mode == 1 ? 1 : 2)) traj = false;
+        if (!fits_all) {
+            // blocked: every column spent on images is a resident column less (30 qubits: 9 columns fit, 5 transition-matrix
+            // stages per run).  The executor then walks a run's launches range by range over the tiles - phi's launch of one
+            // eighth of the tiles, then the columns' launches of the same eighth - and the images of all stages of a range
+            // share one column.
+            int min_tiles_log2 = 64;
+            for (const Run& run : plan.runs) if (run.exchange_gbit < 0) min_tiles_log2 = std::min(min_tiles_log2, plan.nloc - run.K);
+            // ... when that buys at least a quarter more resident columns: at 28 qubits (39 columns, 4-5 stages) it would be 35
+            // instead of 31, the same 8-9 blocks, and eight times as many, shorter launches cost more than they save (8.90 s
+            // against 8.79 s per evaluation); at 30 qubits 5 columns instead of none (70.9 s -> 44.0 s)
+            const long b_full = (long)total_slots - 3 - Tm, b_ranged = (long)total_slots - 4;
+            if (min_tiles_log2 >= 3 && Tm <= 8 && (b_full < 2 || b_ranged * 4 >= b_full * 5)) ranges = 8;
+            const long b_traj = ranges > 1 ? b_ranged : b_full;
+            if (b_traj < (traj_mode == 1 ? 1 : 2)) traj = false;
+        }
     }
-    const int extra = traj ? Tm : 0;
+    if (!traj) ranges = 1;
+    const int extra = traj ? (ranges > 1 ? 1 : Tm) : 0;
     const bool blocked = (size_t)Pa + 2 + extra > total_slots;
     if (blocked && total_slots < (size_t)4 + extra) { err = "workspace too small: need at least 4 statevector-sized columns"; return QGT_B200_ERR_NO_MEMORY; }
     const int b = blocked ? (int)total_slots - 3 - extra : Pa;
@@ -1307,7 +1322,7 @@ int build_fused_program(const CircuitPlan& plan, size_t total_slots, bool want_p
     const int ckpt = blocked ? next++ : -1;
     for (int i = 0; i < extra; i++) prog.traj_slots.push_back(next++);
     for (int i = 0; i < b; i++) s.res_slots.push_back(next++);
-    prog.num_slots = next; prog.resident = b; prog.streaming = 0; prog.fused = true;
+    prog.num_slots = next; prog.resident = b; prog.streaming = 0; prog.fused = true; prog.traj_ranges = ranges;
     const int nblocks = (Pa + b - 1) / b;
     prog.blocks = nblocks;
     // block order: 1, 2, ... (the rolling checkpoint only moves forward), then block 0 from a fresh initial state - it
@@ -1555,7 +1570,7 @@ std::string dump_json(const qgt_b200_circuit& c, const CircuitPlan& plan, const 
     if (prog) {
         o << ",\"program\":{\"slots\":" << prog->num_slots << ",\"psi\":" << prog->psi_slot << ",\"resident\":" << prog->resident
           << ",\"streaming\":" << prog->streaming << ",\"blocks\":" << prog->blocks << ",\"psi_final\":" << (prog->psi_final ? 1 : 0)
-          << ",\"fused\":" << (prog->fused ? 1 : 0) << ",\"traj\":";
+          << ",\"fused\":" << (prog->fused ? 1 : 0) << ",\"traj_ranges\":" << prog->traj_ranges << ",\"traj\":";
         jarr(o, prog->traj_slots);
         o << ",\"instrs\":[";
         for (size_t i = 0; i < prog->instrs.size(); i++) {

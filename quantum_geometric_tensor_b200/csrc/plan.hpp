@@ -159,6 +159,10 @@ struct Program {
     bool fused = false;         // built by build_fused_program: no Gram instructions, Q assembled from transition matrices
     std::vector<int> traj_slots;// fused schedule, trajectory mode: columns holding phi after every transition-matrix stage of
                                 // the current run (tile images); empty = phi is recomputed next to every column
+    int traj_ranges = 1;        // > 1: the executor walks every run's trajectory launches range by range over the tiles
+                                // (phi's launch of a range, then the columns' launches of the same range), so the images of
+                                // all transition-matrix stages of a run share ONE column: traj_slots has one entry and image t
+                                // of a range lives at column + t * D / traj_ranges
     std::vector<Instr> instrs;
 };
 

@@ -78,7 +78,8 @@ def main():
     circ = K.hea_layers(22, 3)
     th = z["theta"]
     cols = [int(x) for x in z["cols"]]
-    for label, opts in (("gram schedule", {"fused": 0}), ("fused schedule, capped slots", {"fused": 1, "max_slots": 40})):
+    for label, opts in (("gram schedule", {"fused": 0}), ("fused schedule, capped slots", {"fused": 1, "max_slots": 40}),
+                        ("fused schedule, 9 slots (phi's images share one column, launches walked range by range)", {"fused": 1, "max_slots": 9})):
         for k_, v_ in opts.items():
             ctx.set_option(k_, v_)
         dist.barrier()

@@ -210,3 +210,25 @@ def test_parameter_free_circuit_applies_every_run_once(oracle):
         plan = api.plan_dump(c, np.zeros(1), tile_qubits=3, reg_qubits=2, column_slots=16)
         _, psi, _, _ = pi.run_program(plan, c)
         assert np.abs(psi - oracle.apply(c, np.zeros(1))).max() < 1e-13
+
+
+def test_blocked_fused_schedule_keeps_phi_images_in_one_column():
+    """Blocked fused schedule: the executor walks a run's launches range by range over the tiles, so the images of phi after
+    every transition-matrix stage share ONE column (traj_ranges = 8) and all other columns stay resident; when everything
+    fits, every stage keeps its own full image and a run is one launch pair."""
+    c = K.config("t30")
+    th = K.default_angles(c.num_params)
+    prog = api.plan_dump_fused(c, th, 9)["program"]
+    assert prog["fused"] == 1 and prog["traj_ranges"] == 8 and len(prog["traj"]) == 1
+    assert prog["resident"] == 9 - 4 and prog["blocks"] == -(-c.num_params // 5)
+    c2 = K.config("c2")
+    prog = api.plan_dump_fused(c2, K.default_angles(c2.num_params), 400)["program"]
+    assert prog["traj_ranges"] == 1 and len(prog["traj"]) >= 2 and prog["blocks"] == 1
+    # ... and a blocked schedule whose images cost only a small share of the columns keeps them whole (28 qubits: 39 columns)
+    c3 = K.config("c3")
+    prog = api.plan_dump_fused(c3, K.default_angles(c3.num_params), 39)["program"]
+    assert prog["traj_ranges"] == 1 and prog["blocks"] > 1 and prog["resident"] == 39 - 3 - len(prog["traj"])
+    # states with fewer than 8 tiles keep the one-image-per-stage layout even when blocked
+    small = K.hea_layers(12, 2)
+    prog = api.plan_dump_fused(small, K.default_angles(small.num_params), 12)["program"]
+    assert prog["traj_ranges"] == 1
