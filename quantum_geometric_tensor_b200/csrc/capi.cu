@@ -318,6 +318,17 @@ int qgt_b200_create(qgt_b200_ctx** out, int device) {
     if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);           // hi = numerically lowest = greatest priority
+        e = cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi);
+        if (e != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return cuda_fail(e, "cudaStreamCreateWithPriority"); }
+        for (int k = 0; k < 2; k++) {
+            cudaEventCreateWithFlags(&c->ev_side[k], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&c->ev_main[k], cudaEventDisableTiming);
+        }
+        cudaEventCreateWithFlags(&c->ev_group, cudaEventDisableTiming);
+    }
     if (const char* tr = getenv("QGT_B200_TRACE")) c->timer.trace = (tr[0] == '1');
     *out = c;
     return QGT_B200_OK;
@@ -335,6 +346,11 @@ void qgt_b200_destroy(qgt_b200_ctx* c) {
     c->fx_pool.release(); c->fx_tab.release(); c->rho.release(); c->rho_self.release(); c->amat.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    c->partial_side.release(); c->rho_side.release();
+    for (int k = 0; k < 2; k++) { cudaEventDestroy(c->ev_side[k]); cudaEventDestroy(c->ev_main[k]); }
+    cudaEventDestroy(c->ev_group);
+    cudaStreamSynchronize(c->side_stream);
+    cudaStreamDestroy(c->side_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -364,6 +380,7 @@ int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
     else if (k == "max_slots") c->max_slots = (size_t)value;
     else if (k == "fused") c->fused_mode = (int)value;
     else if (k == "fused_traj") c->fused_traj = (int)value;
+    else if (k == "fused_overlap") c->fused_overlap = (int)value;
     else if (k == "fused_debug") c->fused_debug = (int)value;
     else if (k == "fused_pipeline") c->fused_pipeline = (int)value;
     else return fail(QGT_B200_ERR_INVALID_ARG, "unknown option " + k);
@@ -702,7 +719,7 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
     std::vector<double> xpool;
     std::vector<std::vector<int>> xbase(plan.runs.size());     // per run and stage (run-relative): first X block, -1 = none
     std::vector<char> xdone(plan.runs.size(), 0);
-    size_t rho_doubles_max = 0;
+    size_t rho_doubles_max = 0, side_partial_bytes = 0;
     FusedHost& fh = c->fused_host;
     if (prog.fused) {
         fh = FusedHost();
@@ -785,6 +802,7 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             const size_t per_item = (size_t)run.rho_blocks * 128;
             rho_doubles_max = std::max(rho_doubles_max, in.cols.size() * per_item);
             partial_bytes = std::max(partial_bytes, (size_t)fr.tg * in.cols.size() * per_item * sizeof(double));
+            if (in.cols.size() == 1) side_partial_bytes = std::max(side_partial_bytes, (size_t)fr.tg * per_item * sizeof(double));
         }
     }
     // derivative (product-rule) stage matrices: independent of each other, a few microseconds each, hundreds per
@@ -837,6 +855,8 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
         if ((rc = c->fx_pool.reserve(std::max<size_t>(16, xpool.size() * sizeof(double))))) return rc;
         if ((rc = c->fx_tab.reserve(std::max<size_t>(16, entry_bytes + group_bytes)))) return rc;
         if ((rc = c->rho.reserve(std::max<size_t>(16, rho_doubles_max * sizeof(double))))) return rc;
+        if ((rc = c->rho_side.reserve(std::max<size_t>(16, rho_doubles_max * sizeof(double))))) return rc;
+        if ((rc = c->partial_side.reserve(std::max<size_t>(16, side_partial_bytes)))) return rc;
         if ((rc = c->rho_self.reserve(std::max<size_t>(16, fh.self_doubles * sizeof(double))))) return rc;
         if ((rc = c->amat.reserve(std::max<size_t>(16, (size_t)P * P * sizeof(cplx))))) return rc;
         if (e == cudaSuccess && !xpool.empty()) e = cudaMemcpyAsync(c->fx_pool.ptr, xpool.data(), xpool.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream);
@@ -856,7 +876,11 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
     c->psi_phys_slot = prog.psi_slot < (int)phys.size() ? phys[prog.psi_slot] : prog.psi_slot;
     // ---- execute ----------------------------------------------------------------------------------
     // one fused launch: instruction `i`, tile range `rg` of `nrg` (nrg > 1: ranged trajectory mode, Program::traj_ranges)
-    auto fused_launch = [&](size_t i, int rg, int nrg) -> int {
+    // `side`: on the side stream with its own partial / transition-matrix buffers (untimed); `ib`: which half of the image column
+    auto fused_launch = [&](size_t i, int rg, int nrg, bool side, int ib) -> int {
+            cudaStream_t st = side ? c->side_stream : c->stream;
+            double* partial = (double*)(side ? c->partial_side.ptr : c->partial.ptr);
+            double* rho = (double*)(side ? c->rho_side.ptr : c->rho.ptr);
             const Instr& in = prog.instrs[i];
             const Run& run = plan.runs[in.run];
             const FusedRec& fr = frec[i];
@@ -877,14 +901,14 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             a.tile_off = (uint64_t)rg * a.ntiles;
             a.tiles_per_cta = fr.tpc; a.tile_groups = fr.tg;
             a.gprefix = (uint64_t)c->rank << plan.nloc;
-            a.rho_partial = (double*)c->partial.ptr;
+            a.rho_partial = partial;
             a.use_traj = in.traj ? 1 : 0;
             a.debug = c->fused_debug;
             a.pipeline = c->fused_pipeline;
             a.all_simple = 1;
             for (const SubPass& sp : run.subs) if (sp.is_cost || sp.stages.size() != 1 || !sp.tdiags.empty()) a.all_simple = 0;
             for (int t = 0; t < QGT_MAX_TRAJ; t++)
-                a.traj[t] = nrg > 1 ? arena + (size_t)res[i].traj[0] * D + (size_t)t * (D / (uint64_t)nrg)
+                a.traj[t] = nrg > 1 ? arena + (size_t)res[i].traj[0] * D + ((size_t)ib * (size_t)(nrg / 2) + (size_t)t) * (D / (uint64_t)nrg)
                                     : res[i].traj[t] >= 0 ? arena + (size_t)res[i].traj[t] * D : nullptr;
             int mat_count = 0, nstage_rho = 0, nstages = 0;
             double flops_ab = 0.0;                  // per amplitude: one tile through every stage
@@ -901,9 +925,9 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             if (c->timer.trace)
                 snprintf(label, sizeof label, "fused run=%d items=%d subs=%d rho_stages=%d rho_blocks=%d tiles=%llu chunks=%d", in.run, nitems,
                          (int)run.subs.size(), nstage_rho, run.rho_blocks, (unsigned long long)a.ntiles, fr.tg);
-            c->timer.begin(c->stream, 0, label);
-            e = launch_fused(a, run.K, mat_count, (int)run.subs.size(), run.rho_blocks, nstages, c->stream);
-            c->timer.end(c->stream);
+            if (!side) c->timer.begin(st, 0, label);
+            e = launch_fused(a, run.K, mat_count, (int)run.subs.size(), run.rho_blocks, nstages, st);
+            if (!side) c->timer.end(st);
             if (e != cudaSuccess) return cuda_fail(e, "fused launch");
             c->stats.sweep_launches++; c->stats.fused_launches++;
             if (rg == 0) c->stats.sweep_column_passes += nitems;
@@ -917,18 +941,18 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
                 if (in.traj) c->stats.sweep_bytes += 16.0 * Dr * nrho;     // phi's tile images: written by the self item, fetched (L2) by the others
             }
             if (per_item > 0) {
-                c->timer.begin(c->stream, 1, "rho reduce + contract");
-                e = launch_rho_reduce((const double*)c->partial.ptr, fr.tg, nitems, (int)per_item, (double*)c->rho.ptr, c->stream);
+                if (!side) c->timer.begin(st, 1, "rho reduce + contract");
+                e = launch_rho_reduce(partial, fr.tg, nitems, (int)per_item, rho, st);
                 if (e == cudaSuccess && fr.self_item >= 0) {
                     double* self_dst = (double*)c->rho_self.ptr + fh.self_off[in.run];
-                    const double* self_src = (const double*)c->rho.ptr + (size_t)fr.self_item * per_item;
-                    if (rg == 0) e = cudaMemcpyAsync(self_dst, self_src, per_item * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
-                    else e = launch_add_doubles(self_dst, self_src, per_item, c->stream);       // the ranges' shares add up
+                    const double* self_src = rho + (size_t)fr.self_item * per_item;
+                    if (rg == 0) e = cudaMemcpyAsync(self_dst, self_src, per_item * sizeof(double), cudaMemcpyDeviceToDevice, st);
+                    else e = launch_add_doubles(self_dst, self_src, per_item, st);       // the ranges' shares add up
                 }
-                if (e == cudaSuccess)
-                    e = launch_rho_contract((const double*)c->rho.ptr, (int)per_item, (const double*)c->fx_pool.ptr, d_groups + fr.group_off, fr.ngroups,
-                                            d_entries, (cplx*)c->amat.ptr, c->stream);
-                c->timer.end(c->stream);
+                if (e == cudaSuccess && fr.ngroups > 0)
+                    e = launch_rho_contract(rho, (int)per_item, (const double*)c->fx_pool.ptr, d_groups + fr.group_off, fr.ngroups,
+                                            d_entries, (cplx*)c->amat.ptr, st);
+                if (!side) c->timer.end(st);
                 if (e != cudaSuccess) return cuda_fail(e, "rho reduce/contract launch");
                 c->stats.other_launches += 2;
             }
@@ -976,9 +1000,38 @@ int run_program(qgt_b200_ctx* c, const qgt_b200_circuit& circ, const CircuitPlan
             if (nrg > 1)
                 while (last + 1 < prog.instrs.size() && prog.instrs[last + 1].kind == INSTR_FUSED && prog.instrs[last + 1].run == in.run &&
                        prog.instrs[last + 1].traj) last++;
-            for (int rg = 0; rg < nrg; rg++)
-                for (size_t k = i; k <= last; k++)
-                    if ((rc = fused_launch(k, rg, nrg))) return rc;
+            // phi's launch is bound by HBM (it writes an image per stage), the columns' launches by the tensor pipe: phi's launch
+            // of range r + 1 runs on the (high-priority) side stream next to the columns' launches of range r.  The image column
+            // then holds two ranges (halves, alternating), which needs 2 x stages <= ranges.
+            const bool overlap = nrg > 1 && last > i && in.cols.size() == 1 && in.cols[0].self && c->fused_overlap != 0 &&
+                                 2 * plan.runs[in.run].rho_stages <= nrg;
+            if (!overlap) {
+                for (int rg = 0; rg < nrg; rg++)
+                    for (size_t k = i; k <= last; k++)
+                        if ((rc = fused_launch(k, rg, nrg, false, 0))) return rc;
+            } else {
+                e = cudaEventRecord(c->ev_group, c->stream);               // phi (copies, exchanges) and the previous run's readers
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(c->side_stream, c->ev_group, 0);
+                if (e != cudaSuccess) return cuda_fail(e, "side stream hand-over");
+                if ((rc = fused_launch(i, 0, nrg, true, 0))) return rc;
+                e = cudaEventRecord(c->ev_side[0], c->side_stream);
+                for (int rg = 0; rg < nrg && e == cudaSuccess; rg++) {
+                    if (rg + 1 < nrg) {
+                        const int nb = (rg + 1) & 1;
+                        if (rg >= 1) e = cudaStreamWaitEvent(c->side_stream, c->ev_main[nb], 0);      // range rg - 1 has consumed that half
+                        if (e != cudaSuccess) break;
+                        if ((rc = fused_launch(i, rg + 1, nrg, true, nb))) return rc;
+                        e = cudaEventRecord(c->ev_side[nb], c->side_stream);
+                        if (e != cudaSuccess) break;
+                    }
+                    e = cudaStreamWaitEvent(c->stream, c->ev_side[rg & 1], 0);
+                    if (e != cudaSuccess) break;
+                    for (size_t k = i + 1; k <= last; k++)
+                        if ((rc = fused_launch(k, rg, nrg, false, rg & 1))) return rc;
+                    e = cudaEventRecord(c->ev_main[rg & 1], c->stream);
+                }
+                if (e != cudaSuccess) return cuda_fail(e, "side stream ordering");
+            }
             i = last;
             break; }
         case INSTR_GRAM: {

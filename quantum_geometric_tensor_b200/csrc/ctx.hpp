@@ -57,6 +57,8 @@ struct qgt_b200_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t side_stream = nullptr;      // ranged trajectory mode: phi's launch of the next range runs here, next to the columns' launch
+    cudaEvent_t ev_side[2] = {nullptr, nullptr}, ev_main[2] = {nullptr, nullptr}, ev_group = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     size_t ws_limit = 0;
     size_t max_slots = 0;
@@ -67,10 +69,12 @@ struct qgt_b200_ctx {
     double ms_prog_pack = 0.0;
     qgt::PlanOptions opt;
     qgt::DevBuf arena, img_runs, img_subs, img_stages, img_tdiags, img_costs, img_pool, ovr_pool, items, aux, partial, cmat, outbuf, edges, vweights, scratch;
+    qgt::DevBuf partial_side, rho_side;                   // the side stream's own partial sums and reduced transition matrices
     qgt::DevBuf fx_pool, fx_tab, rho, rho_self, amat;     // fused schedule: evolved generators, contraction tables, transition matrices, A
     qgt::FusedHost fused_host;
     int psi_phys_slot = 0;       // arena column holding the program's psi slot after run_program (exchanges rotate columns through a spare)
     std::vector<int> img_stage_form, img_run_stage_off;   // QGT_FORM_* of every stage of the uploaded plan (flop accounting)
+    int fused_overlap = 1;       // ranged trajectory mode: phi's launch of the next range on the side stream (0 = everything in order)
     int fused_traj = -1;         // trajectory mode of the fused schedule: -1 automatic, 0 never, 1 whenever it fits
     int fused_debug = 0;         // timing experiments only
     int fused_pipeline = 3;      // trajectory mode at K = 11: 3 = direct kernel (fragment-order trajectory, 3 CTAs x 8 warps) where the

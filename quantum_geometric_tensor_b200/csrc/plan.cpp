@@ -1306,7 +1306,9 @@ int build_fused_program(const CircuitPlan& plan, size_t total_slots, bool want_p
             // instead of 31, the same 8-9 blocks, and eight times as many, shorter launches cost more than they save (8.90 s
             // against 8.79 s per evaluation); at 30 qubits 5 columns instead of none (70.9 s -> 44.0 s)
             const long b_full = (long)total_slots - 3 - Tm, b_ranged = (long)total_slots - 4;
-            if (min_tiles_log2 >= 3 && Tm <= 8 && (b_full < 2 || b_ranged * 4 >= b_full * 5)) ranges = 8;
+            // (16 ranges when 8 cannot hold two ranges' images at once: the executor overlaps phi's launch of the next range with
+            // the columns' launches of the current one)
+            if (min_tiles_log2 >= 3 && Tm <= 8 && (b_full < 2 || b_ranged * 4 >= b_full * 5)) ranges = (2 * Tm > 8 && min_tiles_log2 >= 4) ? 16 : 8;
             const long b_traj = ranges > 1 ? b_ranged : b_full;
             if (b_traj < (traj_mode == 1 ? 1 : 2)) traj = false;
         }
