@@ -346,7 +346,7 @@ void qgt_b200_destroy(qgt_b200_ctx* c) {
     c->fx_pool.release(); c->fx_tab.release(); c->rho.release(); c->rho_self.release(); c->amat.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-    c->partial_side.release(); c->rho_side.release();
+    c->partial_side.release(); c->rho_side.release(); c->cost_phase.release();
     for (int k = 0; k < 2; k++) { cudaEventDestroy(c->ev_side[k]); cudaEventDestroy(c->ev_main[k]); }
     cudaEventDestroy(c->ev_group);
     cudaStreamSynchronize(c->side_stream);
@@ -381,6 +381,7 @@ int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
     else if (k == "fused") c->fused_mode = (int)value;
     else if (k == "fused_traj") c->fused_traj = (int)value;
     else if (k == "fused_overlap") c->fused_overlap = (int)value;
+    else if (k == "cost_tables") c->cost_tables = (int)value;
     else if (k == "fused_debug") c->fused_debug = (int)value;
     else if (k == "fused_pipeline") c->fused_pipeline = (int)value;
     else return fail(QGT_B200_ERR_INVALID_ARG, "unknown option " + k);
@@ -561,9 +562,9 @@ static int do_sweep(qgt_b200_ctx* c, const CircuitPlan& plan, int run, const Qgt
     a.debug_skip = c->debug_skip;
     a.tiles_per_item = c->tiles_per_item;
     a.mma_only = c->use_mma && plan.R == 3 && plan.B == 0;
-    int has_cost = 0;
+    int has_cost = 0, ncost = 0;
     for (const SubPass& sp : plan.runs[run].subs) {
-        if (sp.is_cost) has_cost = 1;
+        if (sp.is_cost) { has_cost = 1; ncost++; }
         if (!sp.is_cost && !sp.mma_ok) a.mma_only = 0;     // cost passes have their own code in the tensor-only kernel
     }
     a.gprefix = (uint64_t)c->rank << plan.nloc;
@@ -580,8 +581,16 @@ static int do_sweep(qgt_b200_ctx* c, const CircuitPlan& plan, int run, const Qgt
         snprintf(label, sizeof label, "sweep run=%d items=%d subs=%d stages=%d ops=%d tiles=%llu mats=%d", run, nitems,
                  (int)plan.runs[run].subs.size(), nst, (int)plan.runs[run].ops.size(), (unsigned long long)shard_tiles, mat_count);
     }
+    a.cost_phase = nullptr; a.cost_ein = nullptr;
+    if (has_cost && c->cost_tables) {
+        int rc = c->cost_phase.reserve(((size_t)ncost << K) * sizeof(cplx) + ((size_t)1 << K) * sizeof(double));
+        if (rc) return rc;
+        a.cost_phase = (const cplx*)c->cost_phase.ptr;
+        a.cost_ein = (const double*)(a.cost_phase + ((size_t)ncost << K));
+    }
     c->timer.begin(c->stream, 0, label);
-    cudaError_t e = launch_sweep(a, K, R, plan.B, mat_count, (int)plan.runs[run].subs.size(), has_cost, c->num_sms, c->stream);
+    cudaError_t e = a.cost_phase ? launch_cost_phase_tables(a, K, ncost, (cplx*)c->cost_phase.ptr, c->stream) : cudaSuccess;
+    if (e == cudaSuccess) e = launch_sweep(a, K, R, plan.B, mat_count, (int)plan.runs[run].subs.size(), has_cost, c->num_sms, c->stream);
     c->timer.end(c->stream);
     if (e != cudaSuccess) return cuda_fail(e, "sweep launch");
     c->stats.sweep_launches++;

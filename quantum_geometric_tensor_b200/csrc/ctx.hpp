@@ -69,6 +69,8 @@ struct qgt_b200_ctx {
     double ms_prog_pack = 0.0;
     qgt::PlanOptions opt;
     qgt::DevBuf arena, img_runs, img_subs, img_stages, img_tdiags, img_costs, img_pool, ovr_pool, items, aux, partial, cmat, outbuf, edges, vweights, scratch;
+    qgt::DevBuf cost_phase;                               // per-launch phase tables of a run's cost ops
+    int cost_tables = 1;                                  // 0 = one sincos per amplitude in the cost pass (round-1 form)
     qgt::DevBuf partial_side, rho_side;                   // the side stream's own partial sums and reduced transition matrices
     qgt::DevBuf fx_pool, fx_tab, rho, rho_self, amat;     // fused schedule: evolved generators, contraction tables, transition matrices, A
     qgt::FusedHost fused_host;

@@ -246,9 +246,10 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
     cplx* sovr = spool + run.mat_count;
     QgtDevSubPass* subs = reinterpret_cast<QgtDevSubPass*>(sovr + OVR_ELEMS);
     // [sub-pass descriptors][cost tables (runs with a cost pass)][lookup tables of the tensor-only kernel]
-    QgtCostSmem cost_sm = qgt_cost_smem_carve(reinterpret_cast<double*>(subs + run.nsub), run.K, a.ct.num_edges);
+    const bool ein_smem = a.cost_phase == nullptr;         // no global tables: the energy table lives in shared memory
+    QgtCostSmem cost_sm = qgt_cost_smem_carve(reinterpret_cast<double*>(subs + run.nsub), run.K, a.ct.num_edges, ein_smem);
     QgtFastSub* fast = reinterpret_cast<QgtFastSub*>(reinterpret_cast<double*>(subs + run.nsub) +
-                                                     ((!MMA_ONLY || COST) && run.has_cost ? qgt_cost_smem_doubles(run.K, a.ct.num_edges) : 0));
+                                                     ((!MMA_ONLY || COST) && run.has_cost ? qgt_cost_smem_doubles(run.K, a.ct.num_edges, ein_smem) : 0));
     QgtFastWarp* fwarp = reinterpret_cast<QgtFastWarp*>(fast + run.nsub);
     uint32_t* flane = reinterpret_cast<uint32_t*>(fwarp + 8 * run.nsub);
     {
@@ -324,11 +325,11 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
         for (int s = 0; s < (QGT_DBG(4) ? 0 : run.nsub); ++s) {
             if (MMA_ONLY && COST && subs[s].nreg == 0) {
                 const QgtDevCost& co = (it.ovr_kind == 3 && subs[s].cost == it.ovr_index) ? it.ovr_cost : a.costs[run.cost_off + subs[s].cost];
-                for (int t2 = tid; t2 <= run.K; t2 += T) qgt_cost_tile_lin(run, a.ct, cost_sm, tileg, t2);
+                for (int t2 = tid; t2 < QGT_COST_LIN_THREADS; t2 += T) qgt_cost_tile_lin(run, a.ct, cost_sm, tileg, t2);
                 __syncthreads();
-                qgt_cost_tile_tables(run, cost_sm, tid, T);
+                qgt_cost_tile_tables(run, cost_sm, tid, T, co.angle);
                 __syncthreads();
-                qgt_phase_cost(run, co, cur, cost_sm, tid, T);
+                qgt_phase_cost(run, co, cur, cost_sm, a.cost_phase ? a.cost_phase + ((size_t)subs[s].cost << run.K) : nullptr, a.cost_ein, tid, T);
             } else if (MMA_ONLY) {
                 if (fast[s].simple)
                     qgt_warp_subpass_fast(fast[s], fwarp[s * 8 + (tid >> 5)], flane[s * 32 + (tid & 31)], cx, cur, tileg, tid & 31);
@@ -336,11 +337,11 @@ __global__ void __launch_bounds__(MAXT, MINB) qgt_sweep_kernel(SweepLaunch a) {
                     qgt_warp_subpass_mma(run, subs[s], cx, cur, tileg, tid >> 5, tid & 31);
             } else if (subs[s].nreg == 0) {
                 const QgtDevCost& co = (it.ovr_kind == 3 && subs[s].cost == it.ovr_index) ? it.ovr_cost : a.costs[run.cost_off + subs[s].cost];
-                for (int t2 = tid; t2 <= run.K; t2 += T) qgt_cost_tile_lin(run, a.ct, cost_sm, tileg, t2);
+                for (int t2 = tid; t2 < QGT_COST_LIN_THREADS; t2 += T) qgt_cost_tile_lin(run, a.ct, cost_sm, tileg, t2);
                 __syncthreads();
-                qgt_cost_tile_tables(run, cost_sm, tid, T);
+                qgt_cost_tile_tables(run, cost_sm, tid, T, co.angle);
                 __syncthreads();
-                qgt_phase_cost(run, co, cur, cost_sm, tid, T);
+                qgt_phase_cost(run, co, cur, cost_sm, a.cost_phase ? a.cost_phase + ((size_t)subs[s].cost << run.K) : nullptr, a.cost_ein, tid, T);
             } else if (R == 3 && B == 0 && a.use_mma && subs[s].mma_ok && T >= 32) {
                 qgt_warp_subpass_mma(run, subs[s], cx, cur, tileg, tid >> 5, tid & 31);
             } else {
@@ -397,13 +398,15 @@ static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, i
     const int T = 1 << (K - R - B);
     if (a.ntiles * (uint64_t)a.nitems == 0) return cudaSuccess;
     const size_t fixed0 = sizeof(cplx) * (size_t)mat_count + sizeof(cplx) * (size_t)(QGT_VARIANT_STRIDE(N) << QGT_MAX_VARIANT_BITS) +
-                         (size_t)nsub * sizeof(QgtDevSubPass) + (has_cost ? qgt_cost_smem_doubles(K, a.ct.num_edges) * sizeof(double) : 0);
+                         (size_t)nsub * sizeof(QgtDevSubPass) + (has_cost ? qgt_cost_smem_doubles(K, a.ct.num_edges, a.cost_phase == nullptr) * sizeof(double) : 0);
     const size_t tile_bytes = sizeof(cplx) << K;
     const size_t fixed = fixed0;
     if (fixed + (size_t)nsub * QGT_FAST_BYTES_PER_SUB + 2 * tile_bytes > 200 * 1024 || T > 256) return cudaErrorInvalidValue;
     if (R == 3 && B == 0 && a.mma_only && T >= 32) {
         const size_t fixed = fixed0 + (size_t)nsub * QGT_FAST_BYTES_PER_SUB;
         // single tile buffer: more resident CTAs hide the load latency instead of a second buffer
+        // with the global phase / energy tables the 16 KB energy table is gone from shared memory: four CTAs per SM again
+        if (has_cost && a.cost_phase) return launch_sweep_cfg<3, 0, true, false, 256, 4, true>(a, T, fixed + tile_bytes, num_sms, st);
         if (has_cost) return launch_sweep_cfg<3, 0, true, false, 256, 3, true>(a, T, fixed + tile_bytes, num_sms, st);
         if (a.double_buffer) return launch_sweep_cfg<3, 0, true, true, 256, 3>(a, T, fixed + 2 * tile_bytes, num_sms, st);
         return launch_sweep_cfg<3, 0, true, false, 256, 4>(a, T, fixed + tile_bytes, num_sms, st);
@@ -411,6 +414,26 @@ static cudaError_t launch_sweep_rb(const SweepLaunch& a, int K, int mat_count, i
     if (B > 0 && T <= 128) return launch_sweep_cfg<R, B, false, true, 128, 3>(a, T, fixed + 2 * tile_bytes, num_sms, st);
     if (B > 0) return launch_sweep_cfg<R, B, false, true, 256, 1>(a, T, fixed + 2 * tile_bytes, num_sms, st);
     return launch_sweep_cfg<R, B, false, true, 256, 2>(a, T, fixed + 2 * tile_bytes, num_sms, st);
+}
+
+// per-launch phase tables of a run's cost ops: out[c][idx] = exp(-i angle_c ein[idx]) (sweep_core.cuh: qgt_cost_phase_entry)
+__global__ void __launch_bounds__(256) qgt_cost_phase_kernel(const QgtDevRun* runs, int run_idx, QgtCostTable ct, const QgtDevCost* costs, cplx* out) {
+    __shared__ QgtDevRun run;
+    for (int i = threadIdx.x; i < (int)(sizeof(QgtDevRun) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(&run)[i] = reinterpret_cast<const uint32_t*>(&runs[run_idx])[i];
+    __syncthreads();
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < (1u << run.K)) {
+        out[((size_t)blockIdx.y << run.K) + idx] = qgt_cost_phase_entry(run, ct, costs[run.cost_off + blockIdx.y].angle, idx);
+        if (blockIdx.y == 0) reinterpret_cast<double*>(out + ((size_t)gridDim.y << run.K))[idx] = qgt_cost_ein(run, ct, idx);    // ein[] behind the phases
+    }
+}
+
+cudaError_t launch_cost_phase_tables(const SweepLaunch& a, int K, int ncost, cplx* out, cudaStream_t st) {
+    if (ncost <= 0) return cudaSuccess;
+    const unsigned nb = (unsigned)(((1u << K) + 255u) / 256u);
+    qgt_cost_phase_kernel<<<dim3(nb, (unsigned)ncost), 256, 0, st>>>(a.runs, a.run_idx, a.ct, a.costs, out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int has_cost, int num_sms, cudaStream_t st) {

@@ -25,6 +25,9 @@ struct SweepLaunch {
     int double_buffer;           // tensor-only kernel: two tile buffers (3 CTAs/SM) instead of one (4 CTAs/SM)
     int debug_skip;              // timing experiments only: 1 no tile load, 2 no store, 4 no sub-passes
     int use_mma;                 // dense stages on the FP64 tensor pipe (DMMA) where the sub-pass allows it
+    const double* cost_ein;      // ... and ein[2^K] behind them (derivative items need the energy itself)
+    const cplx* cost_phase;      // runs with a cost pass: [cost op of the run][2^K] phases exp(-i angle ein[idx]) built before the
+                                 // launch (launch_cost_phase_tables), or null = one sincos per amplitude
     QgtCostTable ct;
 };
 
@@ -73,6 +76,7 @@ struct GramShape { int MT, NT; int thin; };   // thin: few pairs, register accum
 
 // K, R: tile / register qubits of the run; grid is chosen inside
 cudaError_t launch_sweep(const SweepLaunch& a, int K, int R, int B, int mat_count, int nsub, int has_cost, int num_sms, cudaStream_t st);
+cudaError_t launch_cost_phase_tables(const SweepLaunch& a, int K, int ncost, cplx* out, cudaStream_t st);
 
 bool fused_uses_pipe(int K, int use_traj, int pipeline, int mat_count, int nsub, int rho_blocks, int nstages);
 bool fused_uses_direct(int K, int use_traj, int pipeline, int all_simple, int mat_count, int nsub, int rho_blocks);

@@ -302,6 +302,9 @@ struct QgtCostSmem {
     double* lo;        // [64]
     double* hi;        // [2^(K-6)] (at least 1)
     double* lin;       // [K] slopes, [K] constants, [1] outside constant
+    double* plo;       // [64][2]       exp(-i angle lo[x]) of the cost op being applied (re, im)
+    double* phi;       // [2^(K-6)][2]  exp(-i angle hi[y])
+    double* outp;      // [32] shares of the tile's outside constant (edges and vertex terms with no end in the tile)
     double* cross_w;   // cross edges (one end at a tile position) grouped by position: weights ...
     double* out_w;     // edges with both ends outside: weights ...
     int16_t* cross_start;   // [K+1] CSR offsets into cross_w / cross_q
@@ -311,20 +314,25 @@ struct QgtCostSmem {
     int* n_out;        // [1]
 };
 
-QGT_HD size_t qgt_cost_smem_doubles(int K, int num_edges) {
+// with_ein = false: the launch carries global tables (phases per cost op + ein), the 2^K energy table leaves shared memory
+QGT_HD size_t qgt_cost_smem_doubles(int K, int num_edges, bool with_ein = true) {
     const size_t ne = (size_t)(num_edges > 0 ? num_edges : 1);
     const size_t bytes_small = 2 * (QGT_MAX_TILE_QUBITS + 2) + 3 * ne + 16;     // int16 starts + three int8 arrays + count
-    return ((size_t)1 << K) + 64 + ((size_t)1 << (K > QGT_COST_LO_BITS ? K - QGT_COST_LO_BITS : 0)) + 2 * QGT_MAX_TILE_QUBITS + 8 +
+    return (with_ein ? ((size_t)1 << K) : 0) + 3 * (64 + ((size_t)1 << (K > QGT_COST_LO_BITS ? K - QGT_COST_LO_BITS : 0))) + 32 + 2 * QGT_MAX_TILE_QUBITS + 8 +
            2 * ne + (bytes_small + 7) / 8;
 }
 
-QGT_HD QgtCostSmem qgt_cost_smem_carve(double* base, int K, int num_edges) {
+QGT_HD QgtCostSmem qgt_cost_smem_carve(double* base, int K, int num_edges, bool with_ein = true) {
     const size_t ne = (size_t)(num_edges > 0 ? num_edges : 1);
     QgtCostSmem c;
-    c.ein = base;
-    c.lo = c.ein + ((size_t)1 << K);
+    c.ein = with_ein ? base : nullptr;
+    c.lo = base + (with_ein ? ((size_t)1 << K) : 0);
     c.hi = c.lo + 64;
-    c.lin = c.hi + ((size_t)1 << (K > QGT_COST_LO_BITS ? K - QGT_COST_LO_BITS : 0));
+    const size_t nhi = (size_t)1 << (K > QGT_COST_LO_BITS ? K - QGT_COST_LO_BITS : 0);
+    c.plo = c.hi + nhi;
+    c.phi = c.plo + 128;
+    c.outp = c.phi + 2 * nhi;
+    c.lin = c.outp + 32;
     c.cross_w = c.lin + 2 * QGT_MAX_TILE_QUBITS + 8;
     c.out_w = c.cross_w + ne;
     c.cross_start = reinterpret_cast<int16_t*>(c.out_w + ne);
@@ -342,18 +350,37 @@ QGT_HD int qgt_local_pos(const QgtDevRun& run, int q) {
 
 // once per CTA: thread `tid` of T fills its share of ein[]; thread 0 also sorts the edges into the cross
 // lists (by tile position) and the outside list
+QGT_HD double qgt_cost_ein(const QgtDevRun& run, const QgtCostTable& ct, uint32_t idx) {
+    double e = 0.0;
+    for (int k = 0; k < ct.num_edges; k++) {
+        const int li = qgt_local_pos(run, ct.edges[k].i), lj = qgt_local_pos(run, ct.edges[k].j);
+        if (li >= 0 && lj >= 0 && (((idx >> li) ^ (idx >> lj)) & 1u)) e += ct.edges[k].w;
+    }
+    if (ct.vertex_weights)
+        for (int j = 0; j < run.K; j++) e += ct.vertex_weights[run.tq[j]] * (double)(1 - 2 * (int)((idx >> j) & 1u));
+    return e;
+}
+
+QGT_HD void qgt_sincos(double x, double* sn, double* cs_) {
+#if defined(__CUDA_ARCH__)
+    sincos(x, sn, cs_);
+#else
+    *sn = std::sin(x); *cs_ = std::cos(x);
+#endif
+}
+
+// entry idx of the per-launch phase table of one cost op: exp(-i angle ein[idx]) (filled by a small kernel before the sweep,
+// read per amplitude instead of a sincos: the tile part of the phase then comes from two small per-tile tables)
+QGT_HD cplx qgt_cost_phase_entry(const QgtDevRun& run, const QgtCostTable& ct, double angle, uint32_t idx) {
+    cplx p;
+    qgt_sincos(-angle * qgt_cost_ein(run, ct, idx), &p.y, &p.x);
+    return p;
+}
+
 QGT_HD void qgt_cost_build_ein(const QgtDevRun& run, const QgtCostTable& ct, const QgtCostSmem& cs, int tid, int T) {
     const uint32_t count = 1u << run.K;
-    for (uint32_t idx = (uint32_t)tid; idx < count; idx += (uint32_t)T) {
-        double e = 0.0;
-        for (int k = 0; k < ct.num_edges; k++) {
-            const int li = qgt_local_pos(run, ct.edges[k].i), lj = qgt_local_pos(run, ct.edges[k].j);
-            if (li >= 0 && lj >= 0 && (((idx >> li) ^ (idx >> lj)) & 1u)) e += ct.edges[k].w;
-        }
-        if (ct.vertex_weights)
-            for (int j = 0; j < run.K; j++) e += ct.vertex_weights[run.tq[j]] * (double)(1 - 2 * (int)((idx >> j) & 1u));
-        cs.ein[idx] = e;
-    }
+    if (cs.ein)
+        for (uint32_t idx = (uint32_t)tid; idx < count; idx += (uint32_t)T) cs.ein[idx] = qgt_cost_ein(run, ct, idx);
     if (tid == 0) {
         int nc = 0, no = 0;
         for (int p = 0; p < run.K; p++) {
@@ -376,8 +403,10 @@ QGT_HD void qgt_cost_build_ein(const QgtDevRun& run, const QgtCostTable& ct, con
     }
 }
 
-// per tile, step 1: thread p < K computes lin[p] and its constant from its own cross list; thread K the
-// outside constant
+// per tile, step 1, threads 0..31: thread p < K computes lin[p] and its constant from its own cross list; every one of the
+// 32 takes its share (edges / qubits p, p + 32, ...) of the outside constant - one thread walking all outside edges and
+// qubits was a serial chain as long as the tile's whole HBM time
+#define QGT_COST_LIN_THREADS 32
 QGT_HD void qgt_cost_tile_lin(const QgtDevRun& run, const QgtCostTable& ct, const QgtCostSmem& cs, uint64_t tileg, int tid) {
     if (tid < run.K) {
         double lin = 0.0, c0 = 0.0;
@@ -388,49 +417,63 @@ QGT_HD void qgt_cost_tile_lin(const QgtDevRun& run, const QgtCostTable& ct, cons
         }
         cs.lin[tid] = lin;
         cs.lin[QGT_MAX_TILE_QUBITS + tid] = c0;
-    } else if (tid == run.K) {
+    }
+    if (tid < QGT_COST_LIN_THREADS) {
         double e = 0.0;
         const int no = *cs.n_out;
-        for (int k = 0; k < no; k++)
+        for (int k = tid; k < no; k += QGT_COST_LIN_THREADS)
             if (((tileg >> cs.out_i[k]) ^ (tileg >> cs.out_j[k])) & 1ull) e += cs.out_w[k];
         if (ct.vertex_weights)
-            for (int q = 0; q < ct.n; q++)
+            for (int q = tid; q < ct.n; q += QGT_COST_LIN_THREADS)
                 if (qgt_local_pos(run, q) < 0) e += ct.vertex_weights[q] * (double)(1 - 2 * (int)((tileg >> q) & 1ull));
-        cs.lin[2 * QGT_MAX_TILE_QUBITS] = e;
+        cs.outp[tid] = e;
     }
 }
 
 // per tile, step 2 (after a barrier): the two small tables; the constants are folded into lo[]
-QGT_HD void qgt_cost_tile_tables(const QgtDevRun& run, const QgtCostSmem& cs, int tid, int T) {
+// (`angle`: of the cost op being applied; the phases of the two tables go next to their energies)
+QGT_HD void qgt_cost_tile_tables(const QgtDevRun& run, const QgtCostSmem& cs, int tid, int T, double angle) {
     const int lo_bits = run.K < QGT_COST_LO_BITS ? run.K : QGT_COST_LO_BITS;
     const int hi_bits = run.K - lo_bits;
     for (int x = tid; x < (1 << lo_bits) + (1 << hi_bits); x += T) {
         if (x < (1 << lo_bits)) {
-            double e = cs.lin[2 * QGT_MAX_TILE_QUBITS];
+            double e = 0.0;
+            for (int p = 0; p < QGT_COST_LIN_THREADS; p++) e += cs.outp[p];          // fixed order
             for (int p = 0; p < run.K; p++) e += cs.lin[QGT_MAX_TILE_QUBITS + p];
             for (int p = 0; p < lo_bits; p++) if ((x >> p) & 1) e += cs.lin[p];
             cs.lo[x] = e;
+            qgt_sincos(-angle * e, &cs.plo[2 * x + 1], &cs.plo[2 * x]);
         } else {
             const int y = x - (1 << lo_bits);
             double e = 0.0;
             for (int p = 0; p < hi_bits; p++) if ((y >> p) & 1) e += cs.lin[lo_bits + p];
             cs.hi[y] = e;
+            qgt_sincos(-angle * e, &cs.phi[2 * y + 1], &cs.phi[2 * y]);
         }
     }
 }
 
 // per tile, step 3 (after a barrier): thread `tid` of T handles local indices tid, tid+T, ... in shared memory
-QGT_HD void qgt_phase_cost(const QgtDevRun& run, const QgtDevCost& op, cplx* tile, const QgtCostSmem& cs, int tid, int T) {
+// `ptab`: the op's phase table exp(-i angle ein[idx]) (qgt_cost_phase_entry), or null = one sincos per amplitude
+// (then `etab` = ein[] in global memory, read by derivative items only)
+QGT_HD void qgt_phase_cost(const QgtDevRun& run, const QgtDevCost& op, cplx* tile, const QgtCostSmem& cs, const cplx* ptab, const double* etab,
+                           int tid, int T) {
     const uint32_t count = 1u << run.K;
     const int lo_bits = run.K < QGT_COST_LO_BITS ? run.K : QGT_COST_LO_BITS;
+    const bool need_e = !ptab || (op.flags & QGT_FLAG_COST_DERIV);
     for (uint32_t idx = (uint32_t)tid; idx < count; idx += (uint32_t)T) {
-        const double e = cs.ein[idx] + cs.lo[idx & ((1u << lo_bits) - 1u)] + cs.hi[idx >> lo_bits];
+        const uint32_t xl = idx & ((1u << lo_bits) - 1u), xh = idx >> lo_bits;
+        const double e = need_e ? (cs.ein ? cs.ein[idx] : etab[idx]) + cs.lo[xl] + cs.hi[xh] : 0.0;
         double sn, cs_;
-#if defined(__CUDA_ARCH__)
-        sincos(-op.angle * e, &sn, &cs_);
-#else
-        sn = std::sin(-op.angle * e); cs_ = std::cos(-op.angle * e);
-#endif
+        if (ptab) {
+            // exp(-i angle e) = table entry x phase of the low tile bits x phase of the high tile bits
+            const cplx p = ptab[idx];
+            const double lr = cs.plo[2 * xl], li = cs.plo[2 * xl + 1], hr = cs.phi[2 * xh], hi_ = cs.phi[2 * xh + 1];
+            const double tr = lr * hr - li * hi_, ti = lr * hi_ + li * hr;
+            cs_ = p.x * tr - p.y * ti; sn = p.x * ti + p.y * tr;
+        } else {
+            qgt_sincos(-op.angle * e, &sn, &cs_);
+        }
         const cplx a = tile[qgt_swz(idx)];
         cplx b; b.x = cs_ * a.x - sn * a.y; b.y = cs_ * a.y + sn * a.x;
         if (op.flags & QGT_FLAG_COST_DERIV) {   // times (-i * scale * E)

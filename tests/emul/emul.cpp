@@ -16,6 +16,8 @@ using namespace qgt;
 
 static int g_emul_batch = 0;
 extern "C" void emul_set_batch(int b) { g_emul_batch = b; }
+static int g_emul_cost_tables = 1;      // the cost pass through the phase tables (the device default) or one sincos per amplitude
+extern "C" void emul_set_cost_tables(int v) { g_emul_cost_tables = v; }
 
 template <int R, int B>
 static void emul_item(const QgtDevRun& run, const PlanImage& img, const QgtSweepItem& it, const QgtCostTable& ct, uint64_t D) {
@@ -35,8 +37,14 @@ static void emul_item(const QgtDevRun& run, const PlanImage& img, const QgtSweep
     cx.ovr_mat_off = run.mat_count;
     cx.ovr_kind = it.ovr_kind; cx.ovr_index = it.ovr_index; cx.ovr_form = it.ovr_form;
     cx.ovr_tdiag = &it.ovr_tdiag;
-    std::vector<double> cost_buf(qgt_cost_smem_doubles(run.K, ct.num_edges));
-    QgtCostSmem cost_sm = qgt_cost_smem_carve(cost_buf.data(), run.K, ct.num_edges);
+    std::vector<cplx> ptab;
+    std::vector<double> etab;
+    if (run.has_cost && g_emul_cost_tables) {
+        etab.resize((size_t)1 << run.K);
+        for (uint32_t idx = 0; idx < (1u << run.K); idx++) etab[idx] = qgt_cost_ein(run, ct, idx);
+    }
+    std::vector<double> cost_buf(qgt_cost_smem_doubles(run.K, ct.num_edges, !g_emul_cost_tables));
+    QgtCostSmem cost_sm = qgt_cost_smem_carve(cost_buf.data(), run.K, ct.num_edges, !g_emul_cost_tables);
     if (run.has_cost) for (int tid = 0; tid < T; tid++) qgt_cost_build_ein(run, ct, cost_sm, tid, T);
     for (uint64_t tau = 0; tau < ntiles; tau++) {
         const uint64_t tilebase = qgt_tile_base(run, tau);
@@ -47,13 +55,17 @@ static void emul_item(const QgtDevRun& run, const PlanImage& img, const QgtSweep
         for (int s = 0; s < run.nsub; s++)
             for (int tid = 0; tid < T; tid++) {
                 if (subs[s].nreg == 0) {
+                    const QgtDevCost& co = (it.ovr_kind == 3 && subs[s].cost == it.ovr_index) ? it.ovr_cost : img.costs[run.cost_off + subs[s].cost];
                     if (tid == 0) {          // the kernel's three barrier-separated steps, all threads of each step in turn
                         for (int t1 = 0; t1 < T; t1++)
-                            for (int t2 = t1; t2 <= run.K; t2 += T) qgt_cost_tile_lin(run, ct, cost_sm, tilebase, t2);
-                        for (int t2 = 0; t2 < T; t2++) qgt_cost_tile_tables(run, cost_sm, t2, T);
+                            for (int t2 = t1; t2 < QGT_COST_LIN_THREADS; t2 += T) qgt_cost_tile_lin(run, ct, cost_sm, tilebase, t2);
+                        for (int t2 = 0; t2 < T; t2++) qgt_cost_tile_tables(run, cost_sm, t2, T, co.angle);
+                        // the per-launch phase table of this cost op (a small kernel on the device)
+                        ptab.resize((size_t)1 << run.K);
+                        for (uint32_t idx = 0; idx < (1u << run.K); idx++)
+                            ptab[idx] = qgt_cost_phase_entry(run, ct, img.costs[run.cost_off + subs[s].cost].angle, idx);
                     }
-                    const QgtDevCost& co = (it.ovr_kind == 3 && subs[s].cost == it.ovr_index) ? it.ovr_cost : img.costs[run.cost_off + subs[s].cost];
-                    qgt_phase_cost(run, co, tile.data(), cost_sm, tid, T);
+                    qgt_phase_cost(run, co, tile.data(), cost_sm, g_emul_cost_tables ? ptab.data() : nullptr, etab.data(), tid, T);
                 } else {
                     qgt_phase_subpass<R, B>(run, subs[s], cx, tile.data(), tilebase, tid);
                 }
