@@ -367,6 +367,7 @@ int qgt_b200_set_option(qgt_b200_ctx* c, const char* key, double value) {
     if (k == "tile_qubits") { if (value) c->opt.tile_qubits = (int)value; }
     else if (k == "low_qubits") c->opt.low_qubits = (int)value;
     else if (k == "birth_cut") c->opt.birth_cut = (int)value;
+    else if (k == "parity_form") c->opt.parity_form = (int)value;
     else if (k == "wavefront") c->opt.wavefront = (int)value;
     else if (k == "max_ops_per_run") c->opt.max_ops_per_run = (int)value;
     else if (k == "reg_qubits") c->opt.reg_qubits = (int)value;

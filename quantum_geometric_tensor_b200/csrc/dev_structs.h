@@ -43,6 +43,15 @@ enum QgtOpFlags {
 // instead of 8 and one complex multiply per result.
 #define QGT_FORM_DENSE 0
 #define QGT_FORM_DIAG_REAL 1
+// QGT_FORM_PARITY (8x8, plans with a cost pass = sweep kernel only): the real part lives on the elements with an even
+// number of differing index bits, the imaginary part on the odd ones - any product of X rotations on the stage's qubits
+// (the QAOA mixer).  In the basis ordered (parity, bit 1, bit 0) the matrix is [[A_ee, i B_eo], [i B_oe, A_oo]] with
+// real 4x4 blocks, and with the inputs split into even / odd components v_e, v_o
+//     X = [A_ee; B_oe] v_e.re + [-B_eo; A_oo] v_o.im = [y_e.re; y_o.im],   Y = [A_ee; -B_oe] v_e.im + [B_eo; A_oo] v_o.re = [y_e.im; y_o.re]
+// takes 4 DMMAs per 8 vectors and no other arithmetic.  Slot QGT_MIDX(8, q, k) of the variant holds (x, y) = the two
+// stacked matrices' element (row q, even column k); slot QGT_MIDX(8, q, 4 + k) those of the odd column k (q, k in the
+// parity basis: index (p, b1, b0) is component ((p ^ b1 ^ b0) << 2) | (b1 << 1) | b0).
+#define QGT_FORM_PARITY 2
 // element (i, j) of a stage matrix inside its variant.  8x8 matrices are stored in DMMA A-fragment order
 // (lane (r, k) reads M[r][k] and M[r][4+k]: 32 consecutive elements per load, conflict-free); smaller
 // ones row-major.

@@ -82,6 +82,40 @@ __device__ __forceinline__ void qgt_warp_subpass_fast(const QgtFastSub& f, const
         return;
     }
     const cplx m0 = M[lane], m1 = M[32 + lane];           // A fragments: QGT_MIDX(8, q, k) == lane
+    if ((ovr ? (uint32_t)cx.ovr_form : f.form) == QGT_FORM_PARITY) {
+        // real part on even, imaginary part on odd index distance (dev_structs.h): inputs and results are taken in the
+        // (parity, bit 1, bit 0) order of the component index - which only changes the slots this lane reads and writes -
+        // and 4 DMMAs give [y_e.re; y_o.im] and [y_e.im; y_o.re]
+        const uint32_t pb = (__popc(lane & 3) & 1) ? sr2 : 0u;             // B operand: the even-parity component of column pair k first
+        const uint32_t pc = (__popc((lane >> 2) & 3) & 1) ? sr2 : 0u;      // C rows: (p, b1, b0) -> component bit 2 = p ^ b1 ^ b0
+        const bool odd_row = lane >= 16;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            cplx v0[2], v1[2];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const uint32_t gx = (g ? gx1 : 0u) ^ (h ? gx2 : 0u);
+                v0[g] = tile[baseB ^ gx ^ pb];
+                v1[g] = tile[baseB ^ gx ^ pb ^ sr2];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const uint32_t gx = (g ? gx1 : 0u) ^ (h ? gx2 : 0u);
+                double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+                dmma884(x0, x1, m0.x, v0[g].x);
+                dmma884(y0, y1, m0.y, v0[g].y);
+                dmma884(x0, x1, m1.x, v1[g].y);
+                dmma884(y0, y1, m1.y, v1[g].x);
+                cplx o0, o1;
+                o0.x = odd_row ? y0 : x0; o0.y = odd_row ? x0 : y0;
+                o1.x = odd_row ? y1 : x1; o1.y = odd_row ? x1 : y1;
+                tile[baseC ^ gx ^ pc] = o0;
+                tile[baseC ^ gx ^ pc ^ st0] = o1;
+            }
+        }
+        return;
+    }
     const double nm0y = -m0.y, nm1y = -m1.y;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {     // two groups of 8 vectors at a time: operand loads first, then the DMMAs
@@ -175,6 +209,8 @@ __device__ __forceinline__ void qgt_warp_subpass_mma(const QgtDevRun& run, const
             m0.x = reinterpret_cast<const double*>(M)[QGT_MIDX(N, q, k)]; m1.x = reinterpret_cast<const double*>(M)[QGT_MIDX(N, q, 4 + k)];
             m0.y = 0.0; m1.y = 0.0;
             dq = M[N * N + q];
+        } else if ((ovr ? cx.ovr_form : (int)st.form) == QGT_FORM_PARITY) {
+            m0 = qgt_parity_elem(M, q, k); m1 = qgt_parity_elem(M, q, 4 + k);      // (multi-stage sub-passes: plain 8-DMMA form)
         } else {
             m0 = M[QGT_MIDX(N, q, k)]; m1 = M[QGT_MIDX(N, q, 4 + k)];
         }

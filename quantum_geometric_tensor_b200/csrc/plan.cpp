@@ -369,7 +369,7 @@ static void stage_dense(const Run& run, const SubPass& sp, const Stage& st, int 
 // Device layout of a stage's variants (see dev_structs.h).  8x8 matrices whose rows all have a constant
 // phase, M[i][j] = d_i * r_ij with r real, are stored in QGT_FORM_DIAG_REAL (decided for all variants of
 // the stage together); everything else dense.
-static int pack_stage(int N, int nvariants, const std::vector<double>& dense, std::vector<double>& out) {
+static int pack_stage(int N, int nvariants, const std::vector<double>& dense, std::vector<double>& out, bool allow_parity) {
     const size_t vstride = (size_t)QGT_VARIANT_STRIDE(N) * 2;      // doubles per variant
     out.assign((size_t)nvariants * vstride, 0.0);
     bool diag_real = (N == 8);
@@ -394,6 +394,37 @@ static int pack_stage(int N, int nvariants, const std::vector<double>& dense, st
             }
         }
     }
+    // the X-rotation structure (dev_structs.h, QGT_FORM_PARITY): real part on even, imaginary part on odd index distance
+    bool parity = !diag_real && allow_parity && N == 8;
+    for (int p = 0; p < nvariants && parity; p++) {
+        const double* M = &dense[(size_t)p * N * N * 2];
+        double big = 0.0;
+        for (int e = 0; e < N * N * 2; e++) big = std::max(big, std::fabs(M[e]));
+        for (int i = 0; i < N && parity; i++)
+            for (int j = 0; j < N; j++) {
+                const int odd = __builtin_popcount((unsigned)(i ^ j)) & 1;
+                if (std::fabs(M[2 * (i * N + j) + (odd ? 0 : 1)]) > 1e-14 * big) { parity = false; break; }
+            }
+    }
+    if (parity) {
+        for (int p = 0; p < nvariants; p++) {
+            double* dst = &out[(size_t)p * vstride];
+            const double* M = &dense[(size_t)p * N * N * 2];
+            auto comp = [](int idx) { return ((((idx >> 2) ^ (idx >> 1) ^ idx) & 1) << 2) | (idx & 3); };     // (p, b1, b0) -> component
+            for (int q = 0; q < 8; q++)
+                for (int k = 0; k < 4; k++) {
+                    const int r = comp(q), ce = comp(k), co = comp(4 + k);
+                    const double re_e = M[2 * (r * N + ce)], im_e = M[2 * (r * N + ce) + 1];
+                    const double re_o = M[2 * (r * N + co)], im_o = M[2 * (r * N + co) + 1];
+                    // even rows (q < 4): [A_ee | -B_eo] for X, [A_ee | B_eo] for Y; odd rows: [B_oe | A_oo] for X, [-B_oe | A_oo] for Y
+                    dst[2 * QGT_MIDX(N, q, k)] = q < 4 ? re_e : im_e;
+                    dst[2 * QGT_MIDX(N, q, k) + 1] = q < 4 ? re_e : -im_e;
+                    dst[2 * QGT_MIDX(N, q, 4 + k)] = q < 4 ? -im_o : re_o;
+                    dst[2 * QGT_MIDX(N, q, 4 + k) + 1] = q < 4 ? im_o : re_o;
+                }
+        }
+        return QGT_FORM_PARITY;
+    }
     for (int p = 0; p < nvariants; p++) {
         double* dst = &out[(size_t)p * vstride];
         const double* M = &dense[(size_t)p * N * N * 2];
@@ -411,7 +442,7 @@ static int pack_stage(int N, int nvariants, const std::vector<double>& dense, st
 int stage_matrices(const Run& run, const SubPass& sp, const Stage& st, int deriv_op, std::vector<double>& out) {
     std::vector<double> dense;
     stage_dense(run, sp, st, deriv_op, dense);
-    return pack_stage(1 << (int)sp.reg_local.size(), 1 << (int)st.vqubits.size(), dense, out);
+    return pack_stage(1 << (int)sp.reg_local.size(), 1 << (int)st.vqubits.size(), dense, out, run.parity_form);
 }
 
 int stage_matrices_sum(const Run& run, const SubPass& sp, const Stage& st, const std::vector<int>& deriv_ops, std::vector<double>& out) {
@@ -421,7 +452,7 @@ int stage_matrices_sum(const Run& run, const SubPass& sp, const Stage& st, const
         if (sum.empty()) sum = one;
         else for (size_t i = 0; i < sum.size(); i++) sum[i] += one[i];
     }
-    return pack_stage(1 << (int)sp.reg_local.size(), 1 << (int)st.vqubits.size(), sum, out);
+    return pack_stage(1 << (int)sp.reg_local.size(), 1 << (int)st.vqubits.size(), sum, out, run.parity_form);
 }
 
 // A derivative column spawned at sub-pass s of a run recomputes the s earlier sub-passes phi has been through (the
@@ -676,6 +707,10 @@ int build_plan(const qgt_b200_circuit& c, const double* theta, const PlanOptions
             plan.runs.push_back(std::move(piece));
         }
     }
+    // circuits with a cost pass stay in the sweep kernel (plan_supports_fused), which knows the X-rotation matrix form
+    bool any_cost = false;
+    for (const Run& run : plan.runs) for (const SubPass& sp : run.subs) any_cost = any_cost || sp.is_cost;
+    for (Run& run : plan.runs) run.parity_form = any_cost && opt.parity_form != 0;
     return QGT_B200_OK;
 }
 

@@ -21,6 +21,7 @@ struct PlanOptions {
     int wavefront = 2;      // unsharded plans: lower the gates in the order the sharded mapper would emit them with this many
                             // virtual rank qubits (gates that wait for them are deferred, the rest runs ahead): a dependency-
                             // respecting reordering that lets the run builder work deep before it works wide
+    int parity_form = 1;    // plans with a cost pass: pack X-rotation stage matrices in QGT_FORM_PARITY (4 DMMAs per 8 vectors instead of 8)
     int local_qubits = 0;   // sharded states: qubits >= local_qubits are rank bits (diagonal use / controls only); 0 = all local
 };
 
@@ -75,6 +76,8 @@ struct Run {
     unsigned exchange_mask = 0;     // rank bits b_0 < b_1 < ... swapped, in ONE grouped all-to-all, with the top local qubits
                                     // nloc-k, ..., nloc-1 (b_i <-> nloc-k+i); k = popcount
     int segment = 0;                // index of the mapped segment the run belongs to (selects the cost table)
+    bool parity_form = false;       // 8x8 stage matrices with the X-rotation structure are packed in QGT_FORM_PARITY (plans with a cost
+                                    // pass: they run in the sweep kernel, the only one that knows the form)
     int rho_blocks = 0;             // fused schedule: 64-element transition-matrix blocks per item (sum of 2^nvar over stages with parameters)
     int last_rho_stage = -1;        // run-relative index of the last stage with a parameter occurrence
     int rho_stages = 0;             // number of stages with a parameter occurrence

@@ -99,6 +99,16 @@ QGT_HD int qgt_variant_index(const QgtDevStage& st, uint64_t g) {
     return v;
 }
 
+// element (i, j) of an 8x8 stage matrix stored in QGT_FORM_PARITY (dev_structs.h), for the paths that do plain arithmetic
+QGT_HD cplx qgt_parity_elem(const cplx* M, int i, int j) {
+    const int pi = (i ^ (i >> 1) ^ (i >> 2)) & 1, pj = (j ^ (j >> 1) ^ (j >> 2)) & 1;
+    const cplx slot = M[QGT_MIDX(8, (pi << 2) | (i & 3), (pj << 2) | (j & 3))];
+    cplx m; m.x = 0.0; m.y = 0.0;
+    if (!pj) { if (!pi) m.x = slot.x; else m.y = slot.x; }       // even column: x = (row even ? Re : Im)
+    else { if (!pi) m.y = slot.y; else m.x = slot.y; }           // odd column:  y = (row even ? Im : Re)
+    return m;
+}
+
 // ---- per-thread phases --------------------------------------------------------------------------------
 // Per-thread constants of the load/store phases (independent of the tile): thread `tid` of T moves the
 // amplitudes with local index idx = tid + i*T, i < 2^R, i.e. thread bits occupy local positions 0..K-R-1
@@ -209,6 +219,7 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
         const bool ovr = (cx.ovr_kind == 1 && s == cx.ovr_index);
         const int off = ovr ? cx.ovr_mat_off : st.mat_off;
         const bool diag_real = (ovr ? cx.ovr_form : (int)st.form) == QGT_FORM_DIAG_REAL;   // M = D * Rm: rows scaled afterwards
+        const bool parity = (ovr ? cx.ovr_form : (int)st.form) == QGT_FORM_PARITY;
         const bool last = (s == sp.stage_end - 1);
         cplx v[NB][N];
 #pragma unroll
@@ -232,6 +243,7 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
                 for (int j = 0; j < N; ++j) {
                     cplx m;
                     if (diag_real) { m.x = reinterpret_cast<const double*>(M[0])[QGT_MIDX(N, i, j)]; m.y = 0.0; }
+                    else if (N == 8 && parity) m = qgt_parity_elem(M[0], i, j);
                     else m = M[0][QGT_MIDX(N, i, j)];
 #pragma unroll
                     for (int h = 0; h < NB; ++h) {
@@ -257,6 +269,7 @@ QGT_HD void qgt_phase_subpass(const QgtDevRun& run, const QgtDevSubPass& sp, con
                     for (int j = 0; j < N; ++j) {
                         cplx m;
                         if (diag_real) { m.x = reinterpret_cast<const double*>(M[h])[QGT_MIDX(N, i, j)]; m.y = 0.0; }
+                        else if (N == 8 && parity) m = qgt_parity_elem(M[h], i, j);
                         else m = M[h][QGT_MIDX(N, i, j)];
                         xr = qgt_fma(m.x, v[h][j].x, xr); xr = qgt_fma(-m.y, v[h][j].y, xr);
                         xi = qgt_fma(m.x, v[h][j].y, xi); xi = qgt_fma(m.y, v[h][j].x, xi);

@@ -165,7 +165,8 @@ def test_fusion_depth_on_hea():
 
 
 def test_stage_matrix_forms_are_detected():
-    """One ansatz layer per stage factors as (diagonal) x (real); RX layers (QAOA mixer) and two fused layers are dense."""
+    """One ansatz layer per stage factors as (diagonal) x (real); RX layers next to a cost pass (QAOA mixer) take the parity form
+    (real part on even, imaginary part on odd index distance; 2), RX layers of other circuits and two fused layers are dense."""
     def forms(circ):
         d = api.plan_dump(circ, K.default_angles(max(1, circ.num_params)))
         return [f for r in d["runs"] for s in r["subs"] for f in s["forms"]]
@@ -173,7 +174,12 @@ def test_stage_matrix_forms_are_detected():
     one_layer = forms(K.hea_layers(12, 1))
     assert one_layer and all(f == 1 for f in one_layer)
     qaoa = forms(K.qaoa_maxcut(12, 2))
-    assert qaoa and all(f == 0 for f in qaoa)
+    assert qaoa and all(f == 2 for f in qaoa)
+    rx_only = K.Circuit(12)
+    for q in range(12):
+        rx_only.rot(K.RX, q, q)
+    plain = forms(rx_only)
+    assert plain and all(f == 0 for f in plain)   # no cost pass: the plan may run in the fused kernels, which do not know the form
     deep = forms(K.config("c2"))
     assert 0 in deep and 1 in deep              # two fused layers are dense
 
