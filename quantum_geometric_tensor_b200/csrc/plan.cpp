@@ -1197,7 +1197,43 @@ void select_fit(const CircuitPlan& plan, const std::vector<int>& pending, int c,
 
 }  // namespace
 
+// HBM traffic of a Gram-schedule program in column reads / writes of 16 bytes per amplitude (a sweep item reads and writes
+// its column, a Gram reads each operand once, a copy reads and writes)
+static double program_traffic(const Program& prog) {
+    double t = 0.0;
+    for (const Instr& in : prog.instrs) {
+        if (in.kind == INSTR_SWEEP || in.kind == INSTR_FUSED) t += 2.0 * (double)in.cols.size();
+        else if (in.kind == INSTR_GRAM) t += (double)in.a_slots.size() + (double)in.b_slots.size();
+        else if (in.kind == INSTR_COPY) t += 2.0;
+    }
+    return t;
+}
+
+static int build_qgt_program_split(const CircuitPlan& plan, size_t total_slots, bool want_psi, Program& prog, std::string& err, int c_forced);
+
 int build_qgt_program(const CircuitPlan& plan, size_t total_slots, bool want_psi, Program& prog, std::string& err) {
+    int Pa = 0;
+    for (int p = 0; p < plan.P; p++) if (plan.first_run[p] >= 0) Pa++;
+    const bool blocked = !((size_t)Pa + 1 <= total_slots);
+    if (!blocked || total_slots < 5 || Pa > 64) return build_qgt_program_split(plan, total_slots, want_psi, prog, err, 0);
+    // few parameters on a state that leaves room for a handful of columns (30-qubit QAOA: 16 parameters, 9 columns): how the
+    // columns are split between the resident block and the streaming ones decides how often the block is marched again
+    // (every march serves c - 1 long-lived streaming columns).  The programs are small: build one per split, keep the one
+    // that moves the fewest bytes.
+    const int avail = (int)total_slots - 2;
+    int rc = QGT_B200_ERR_NO_MEMORY;
+    double best = -1.0;
+    for (int c = 2; c <= avail - 1; c++) {
+        Program trial; std::string terr;
+        const int trc = build_qgt_program_split(plan, total_slots, want_psi, trial, terr, c);
+        if (trc != QGT_B200_OK) { if (best < 0.0) { rc = trc; err = terr; } continue; }
+        const double t = program_traffic(trial);
+        if (best < 0.0 || t < best) { best = t; prog = std::move(trial); rc = QGT_B200_OK; }
+    }
+    return rc;
+}
+
+static int build_qgt_program_split(const CircuitPlan& plan, size_t total_slots, bool want_psi, Program& prog, std::string& err, int c_forced) {
     prog = Program();
     const int P = plan.P;
     const int R = (int)plan.runs.size();
@@ -1212,7 +1248,7 @@ int build_qgt_program(const CircuitPlan& plan, size_t total_slots, bool want_psi
     else {
         if (total_slots < 5) { err = "workspace too small: need at least 5 statevector-sized columns"; return QGT_B200_ERR_NO_MEMORY; }
         const int avail = (int)total_slots - 2;             // phi + rolling checkpoint
-        c = std::max(2, std::min(avail / 3, 16));
+        c = c_forced > 0 ? std::min(c_forced, avail - 1) : std::max(2, std::min(avail / 3, 16));
         b = avail - c;
     }
     const bool blocked = (c > 0);
