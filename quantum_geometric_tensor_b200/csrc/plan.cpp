@@ -1183,12 +1183,16 @@ void select_fit(const CircuitPlan& plan, const std::vector<int>& pending, int c,
     const int R = (int)plan.runs.size();
     std::vector<int> occ(R + 1, 0);
     take.clear(); rest.clear();
+    // one slot stays free for the transient parameters (born and ready in the same run) - when there are any
+    bool any_transient = false;
+    for (int p : pending) any_transient = any_transient || std::max(plan.last_run[p], T_res) == plan.first_run[p];
+    const int cap = any_transient ? c - 1 : c;
     for (int p : pending) {
         const int f = plan.first_run[p];
         const int ready = std::max(plan.last_run[p], T_res);
         if (ready == f) { take.push_back(p); continue; }     // transient: uses the reserved slot
         bool ok = true;
-        for (int r = f; r <= ready; r++) if (occ[r] >= c - 1) { ok = false; break; }
+        for (int r = f; r <= ready; r++) if (occ[r] >= cap) { ok = false; break; }
         if (ok) { for (int r = f; r <= ready; r++) occ[r]++; take.push_back(p); }
         else rest.push_back(p);
     }
