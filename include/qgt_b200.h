@@ -162,6 +162,13 @@ int  qgt_b200_set_workspace_limit(qgt_b200_ctx* ctx, size_t bytes);
  *   use_mma (1)            dense stages on the FP64 tensor pipe             double_buffer (0) two tile buffers per CTA
  *   tiles_per_item (0)     tiles per work unit, 0 = automatic               gram_tile (0)    force 32 or 64 square Gram tiles
  *   max_slots (0)          cap on statevector-sized columns (forces the blocked schedule; tests)
+ *   fused (-1)             schedule: -1 automatic (Gram while every column is resident, fused otherwise), 0 Gram, 1 fused
+ *   fused_traj (-1)        fused schedule: phi's stage images (-1 automatic, 0 never: phi recomputed per column, 1 whenever they fit)
+ *   fused_pipeline (3)     trajectory kernel: 3 direct (3 CTAs x 8 warps), 1 persistent 16-warp, 2 lean 2 x 16-warp, 0 generic
+ *   fused_overlap (1)      ranged trajectory images: phi's launch of the next tile range on a side stream
+ *   cost_tables (1)        QAOA cost pass through per-launch phase tables (0 = one sincos per amplitude)
+ *   parity_form (1)        X-rotation stage matrices next to a cost pass in the 4-DMMA parity form
+ *   wavefront (2)          gate order of unsharded plans (virtual rank qubits of the DAG walk)
  *   profile (0)            per-category CUDA-event timing into qgt_b200_stats
  *   debug_skip (0)         timing experiments in builds with -DQGT_DEBUG_SKIP only
  * Unknown keys return QGT_B200_ERR_INVALID_ARG. */
