@@ -239,3 +239,26 @@ def test_blocked_fused_schedule_keeps_phi_images_in_one_column():
     small = K.hea_layers(12, 2)
     prog = api.plan_dump_fused(small, K.default_angles(small.num_params), 12)["program"]
     assert prog["traj_ranges"] == 1
+
+
+def test_blocked_gram_split_is_chosen_by_traffic():
+    """Few parameters on a state that leaves room for a handful of columns (BASELINE config 3: 30-qubit QAOA, 16 parameters,
+    9 columns): the planner builds the blocked Gram program for every resident / streaming split and keeps the one that moves
+    the fewest bytes - 4 + 3 instead of the 5 + 2 of the fixed rule (601 instead of 810 column passes)."""
+    c = K.config("c4")
+    prog = api.plan_dump(c, K.default_angles(c.num_params), column_slots=9)["program"]
+    assert prog["fused"] == 0 and prog["resident"] + prog["streaming"] == 9 - 2
+    passes = sum(len(i["cols"]) for i in prog["instrs"] if i["k"] == "sweep")
+    assert prog["streaming"] >= 3 and passes <= 601
+    # every pair of parameters (and every parameter with psi) is covered exactly by the union of the Gram instructions:
+    # the choice of the split must not change what is computed
+    P = c.num_params
+    seen = set()
+    for i in prog["instrs"]:
+        if i["k"] != "gram":
+            continue
+        for a in i["aid"]:
+            for b in i["bid"]:
+                seen.add((min(a, b), max(a, b)))
+    want = {(a, b) for a in range(P) for b in range(a, P + 1)}
+    assert want <= seen
